@@ -1,0 +1,86 @@
+"""The CPU oracle (oracle/yolo_oracle.py) against the golden fixtures produced by the reference itself
+(tests/golden/make_golden.py).  Runs everywhere (no GPU, no /root/reference)."""
+import ast
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import yolo_oracle as O
+
+G = Path(__file__).parent / "golden"
+CFG = Path(__file__).resolve().parents[1] / "yolov3_b200" / "cfg"
+
+
+@pytest.mark.parametrize("name", ["yolov3-tiny", "yolov3", "yolov3-spp"])
+def test_forward_matches_reference(name):
+    g = np.load(G / f"forward_{name}.npz")
+    params = O.init_params(CFG / f"{name}.yaml", seed=int(g["param_seed"]))
+    om = O.OracleModel(CFG / f"{name}.yaml", params=params, fused=True)
+    assert om.save == list(g["save"]) and np.array_equal(om.stride.numpy(), g["stride"])
+    ci = 0
+    while f"z{ci}" in g:
+        bs, c, h, w = g[f"x{ci}_shape"]
+        x = torch.rand(int(bs), int(c), int(h), int(w), generator=torch.Generator().manual_seed(int(g[f"x{ci}_seed"])))
+        taps = {int(k.split("_")[1]): None for k in g.files if k.startswith(f"tap{ci}_")}
+        with torch.no_grad():
+            z, raw = om(x, taps)
+        assert np.allclose(z.numpy(), g[f"z{ci}"], atol=2e-4, rtol=2e-4)
+        for li, r in enumerate(raw):
+            assert np.allclose(r.numpy(), g[f"raw{ci}_{li}"], atol=2e-4, rtol=2e-4)
+        for i, t in taps.items():
+            ref = g[f"tap{ci}_{i}"]
+            flat = t.flatten()
+            idx = torch.linspace(0, flat.numel() - 1, 64).long()
+            got = np.concatenate([[t.mean().item(), t.std().item(), t.abs().max().item()], flat[idx].numpy()])
+            assert np.allclose(got, ref, atol=2e-4, rtol=2e-4), (name, ci, i)
+        ci += 1
+    assert ci >= 1
+
+
+def _nms_cases():
+    g = np.load(G / "nms_cases.npz")
+    return sorted({k.split("/")[0] for k in g.files if "/" in k})
+
+
+@pytest.mark.parametrize("case", _nms_cases())
+def test_nms_bit_exact(case):
+    g = np.load(G / "nms_cases.npz")
+    kw = ast.literal_eval(str(g[f"{case}/kw"]))
+    pred = g[str(g[f"{case}/pred_key"])]
+    outs, srcs = O.non_max_suppression(torch.from_numpy(pred), **kw)
+    for xi, (o, s) in enumerate(zip(outs, srcs)):
+        assert np.array_equal(o, g[f"{case}/out{xi}"])
+        assert np.array_equal(s, g[f"{case}/src{xi}"])
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_loss_matches_reference(case):
+    import sys
+    sys.path.insert(0, str(G))
+    from make_golden import loss_inputs
+
+    g = np.load(G / "loss_cases.npz")
+    hyp = ast.literal_eval(str(g["hyp"]))
+    anchors = torch.from_numpy(g["anchors"])
+    p, t = loss_inputs(case)
+    assert np.array_equal(t.numpy(), g[f"c{case}/targets"])
+    p = [x.requires_grad_(True) for x in p]
+    loss, items = O.compute_loss(p, t, anchors, hyp)
+    loss.backward()
+    assert np.allclose(loss.detach().numpy(), g[f"c{case}/loss"], rtol=1e-5)
+    assert np.allclose(items.numpy(), g[f"c{case}/items"], rtol=1e-5, atol=1e-7)
+    for i, x in enumerate(p):
+        assert np.allclose(x.grad.numpy(), g[f"c{case}/grad{i}"], rtol=1e-4, atol=1e-7)
+    bt = O.build_targets([tuple(x.shape) for x in p], t, anchors, hyp["anchor_t"])
+    for i in range(3):
+        got = torch.cat((torch.stack([bt[i][k].float() for k in ("b", "a", "gj", "gi")], 1), bt[i]["tbox"], bt[i]["anch"],
+                         bt[i]["tcls"][:, None].float()), 1).numpy()
+        assert np.allclose(got, g[f"c{case}/bt{i}"], atol=1e-6)
+
+
+def test_iou():
+    g = np.load(G / "iou_cases.npz")
+    assert np.array_equal(O.box_iou(g["a"], g["b"]).numpy(), g["iou"])
+    assert np.allclose(O.ciou_xywh(torch.from_numpy(g["p1"]), torch.from_numpy(g["p2"])).numpy(), g["ciou"], atol=1e-6)
