@@ -1,0 +1,452 @@
+// yolov3_b200 — implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM),
+// operands staged by TMA, folded-BN bias + SiLU (+ residual, + nearest-2x upsample, + concat-offset / Detect store)
+// fused into the epilogue.  Replaces Conv.forward_fuse (reference models/common.py:77-81) and the adds/copies around it.
+//
+// GEMM view:  D[pixel, cout] = sum_{tap, c} A[pixel shifted by tap, c] * W[cout, tap, c]
+//   * activations are bf16 "padded NHWC" [n, h+2, w+2, ld] with an all-zero halo, so for a stride-1 conv the A tile
+//     of filter tap (r,s) is simply the [128 pixels x BLOCK_K channels] box of the flat pixel list shifted by
+//     (r-1)*(w+2)+(s-1) rows: one 2-D TMA box per (tap, k-block), zero quantisation waste, no im2col buffer
+//     ("flat" mode; halo pixels are computed but never stored).
+//   * a stride-2 conv reads the same buffer through a 5-D view (2*ld, (w+2)/2, 2, (h+2)/2, n) that splits rows and
+//     columns by parity; the A tile of tap (r,s) for a TH x TW patch of output pixels is one 5-D TMA box ("patch").
+//   * weights are bf16 [cout_pad, taps*cin] (K-major); B tile = [BLOCK_N x BLOCK_K] box.
+// Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread
+// MMA issuer, warps 2-5 = epilogue (TMEM -> registers -> global).  smem ring of STAGES {A,B} tiles; two accumulator
+// buffers in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <cuda_bf16.h>
+
+#include "y3_common.cuh"
+#include "y3_internal.h"
+
+namespace y3 {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;  // ring buffers; barriers + alignment slack come on top (227 KB max per CTA)
+
+template <int BLOCK_N, int BLOCK_K>
+struct Cfg {
+  static constexpr uint32_t kABytes = kBlockM * BLOCK_K * 2;
+  static constexpr uint32_t kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // power of two for N in {32,64,128,256}
+  static constexpr uint32_t kSwizzleBytes = BLOCK_K * 2;                       // 32 / 64 / 128
+  static constexpr uint32_t kLayout = BLOCK_K == 64 ? 2u : (BLOCK_K == 32 ? 4u : 6u);
+  static constexpr uint32_t kSbo = 8 * kSwizzleBytes;
+  static constexpr size_t kSmemBytes = size_t(kStages) * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(kStages >= 2, "pipeline needs at least two stages");
+};
+
+template <int BLOCK_N, int BLOCK_K>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const ConvTcArgs p) {
+  using C = Cfg<BLOCK_N, BLOCK_K>;
+  constexpr int STAGES = C::kStages;
+  constexpr uint32_t IDESC = umma_idesc_bf16_m128(BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // swizzled TMA/UMMA tiles need 1 KB alignment
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * C::kABytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int k_iters = p.taps * p.kblocks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one thread)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int n0 = nt * BLOCK_N;
+        int row0 = 0, img = 0, oh0 = 0, ow0 = 0;
+        if (p.mode == 0) {
+          row0 = mt * kBlockM;
+        } else {
+          const int per_img = p.tiles_w * p.tiles_h;
+          img = mt / per_img;
+          const int t = mt - img * per_img;
+          oh0 = (t / p.tiles_w) * p.th;
+          ow0 = (t % p.tiles_w) * p.tw;
+        }
+        for (int it = 0; it < k_iters; ++it) {
+          const int kb = it / p.taps, tap = it - kb * p.taps;
+          mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 1);
+          mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + C::kBBytes);
+          uint8_t* a_dst = smem_a + stage * C::kABytes;
+          uint8_t* b_dst = smem_b + stage * C::kBBytes;
+          if (p.mode == 0) {
+            const int shift = (p.taps == 9) ? ((tap / 3 - 1) * p.wp + (tap % 3 - 1)) : 0;
+            tma_load_2d(a_dst, &map_a, &full_bar[stage], p.a_coff + kb * BLOCK_K, row0 + shift);
+          } else {
+            const int r = tap / 3, s = tap - r * 3;
+            tma_load_5d(a_dst, &map_a, &full_bar[stage], (s & 1) * p.a_ld + p.a_coff + kb * BLOCK_K, ow0 + (s >> 1),
+                        r & 1, oh0 + (r >> 1), img);
+          }
+          tma_load_2d(b_dst, &map_b, &full_bar[stage], tap * p.cin + kb * BLOCK_K, n0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+        const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1u, p.err, 2);  // epilogue has drained this accumulator buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase, p.err, 3);  // TMA bytes have landed
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * C::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * C::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t adesc = umma_smem_desc(a_addr + k * 32, C::kSbo, C::kLayout);
+            const uint64_t bdesc = umma_smem_desc(b_addr + k * 32, C::kSbo, C::kLayout);
+            umma_bf16_ss(d_tmem, adesc, bdesc, IDESC, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
+          if (it == k_iters - 1) umma_commit(&tfull_bar[as]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5 = 128 threads)
+    const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int m = quarter * 32 + lane;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int n0 = nt * BLOCK_N;
+
+      // ---- which output pixel does accumulator row m belong to?
+      bool valid;
+      int img, oy, ox;  // image, UNPADDED output coordinates
+      if (p.mode == 0) {
+        const int row = mt * kBlockM + m;
+        const int plane = p.hp * p.wp;
+        img = row / plane;
+        const int rem = row - img * plane;
+        const int yp = rem / p.wp, xp = rem - yp * p.wp;
+        valid = row < p.rows_total && yp >= 1 && yp <= p.hp - 2 && xp >= 1 && xp <= p.wp - 2;
+        oy = yp - 1;
+        ox = xp - 1;
+      } else {
+        const int per_img = p.tiles_w * p.tiles_h;
+        img = mt / per_img;
+        const int t = mt - img * per_img;
+        const int ty = m / p.tw, tx = m - ty * p.tw;
+        oy = (t / p.tiles_w) * p.th + ty;
+        ox = (t % p.tiles_w) * p.tw + tx;
+        valid = ty < p.th && oy < p.ho && ox < p.wo;
+      }
+      const int oh = p.mode == 0 ? p.hp - 2 : p.ho;  // conv-output height/width (unpadded)
+      const int ow = p.mode == 0 ? p.wp - 2 : p.wo;
+      const long long conv_row = (static_cast<long long>(img) * (oh + 2) + oy + 1) * (ow + 2) + ox + 1;
+      const __nv_bfloat16* res_ptr = p.res ? p.res + conv_row * p.res_ld + p.res_coff + n0 : nullptr;
+      __nv_bfloat16* out_ptr = nullptr;
+      long long up_row_stride = 0;
+      if (p.out) {
+        if (p.upsample) {
+          const int w2 = 2 * ow + 2;
+          const long long r00 = (static_cast<long long>(img) * (2 * oh + 2) + 2 * oy + 1) * w2 + 2 * ox + 1;
+          out_ptr = p.out + r00 * p.out_ld + p.out_coff + n0;
+          up_row_stride = static_cast<long long>(w2) * p.out_ld;
+        } else {
+          out_ptr = p.out + conv_row * p.out_ld + p.out_coff + n0;
+        }
+      }
+
+      mbar_wait(&tfull_bar[as], aphase, p.err, 4);  // accumulator complete
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(t_addr + c, v);
+        tmem_ld_wait();
+        if (!valid) continue;
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
+          x[j + 0] = __uint_as_float(v[j + 0]) + b.x;
+          x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
+          x[j + 2] = __uint_as_float(v[j + 2]) + b.z;
+          x[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+        }
+        if (p.act == Y3_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = silu_f(x[j]);
+        }
+        if (p.raw) {
+          // Detect head: fp32 logits in the reference's [n, na, ny, nx, no] layout (models/yolo.py:98)
+#pragma unroll 1
+          for (int j = 0; j < 32; ++j) {
+            const int co = n0 + c + j;
+            if (co < p.cout) {
+              const int a = co / p.no, k = co - a * p.no;
+              p.raw[(((static_cast<long long>(img) * p.na + a) * oh + oy) * ow + ox) * p.no + k] = x[j];
+            }
+          }
+          continue;
+        }
+        if (res_ptr) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 r = __ldg(reinterpret_cast<const uint4*>(res_ptr + c) + q);
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = unpack_bf16x2(rr[e]);
+              x[q * 8 + e * 2 + 0] += f.x;
+              x[q * 8 + e * 2 + 1] += f.y;
+            }
+          }
+        }
+        uint4 o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          o[q].x = pack_bf16x2(x[q * 8 + 0], x[q * 8 + 1]);
+          o[q].y = pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]);
+          o[q].z = pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]);
+          o[q].w = pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]);
+        }
+        const int reps = p.upsample ? 4 : 1;
+        for (int rep = 0; rep < reps; ++rep) {
+          uint4* dst = reinterpret_cast<uint4*>(out_ptr + (rep >> 1) * up_row_stride + (rep & 1) * p.out_ld + c);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q] = o[q];
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+template <int BLOCK_N, int BLOCK_K>
+int launch_cfg(const ConvTcPlan& plan, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N, BLOCK_K>;
+  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K>;
+  static bool attr_set = false;  // benign race: idempotent attribute
+  if (!attr_set) {
+    Y3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::kSmemBytes)));
+    attr_set = true;
+  }
+  kern<<<plan.grid, kThreads, C::kSmemBytes, stream>>>(plan.map_a, plan.map_b, plan.args);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+int pick_block_n(int cout) { return cout <= 32 ? 32 : (cout <= 64 ? 64 : (cout <= 128 ? 128 : 256)); }
+
+}  // namespace
+
+int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream) {
+#define Y3_DISPATCH_K(BN)                                        \
+  switch (plan.block_k) {                                        \
+    case 64: return launch_cfg<BN, 64>(plan, stream);            \
+    case 32: return launch_cfg<BN, 32>(plan, stream);            \
+    case 16: return launch_cfg<BN, 16>(plan, stream);            \
+  }                                                              \
+  break;
+  switch (plan.block_n) {
+    case 32: Y3_DISPATCH_K(32)
+    case 64: Y3_DISPATCH_K(64)
+    case 128: Y3_DISPATCH_K(128)
+    case 256: Y3_DISPATCH_K(256)
+  }
+#undef Y3_DISPATCH_K
+  return set_error(Y3_ERR_BAD_ARG, "conv_tc: no kernel for tile N=%d K=%d", plan.block_n, plan.block_k);
+}
+
+int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
+  Y3_REQUIRE(d.n > 0 && d.h > 0 && d.w > 0, "conv: empty shape");
+  Y3_REQUIRE((d.ksize == 1 && d.stride == 1) || (d.ksize == 3 && (d.stride == 1 || d.stride == 2)),
+             "conv: ksize/stride %d/%d unsupported (1x1 s1, 3x3 s1, 3x3 s2)", d.ksize, d.stride);
+  Y3_REQUIRE(d.c_in % 16 == 0 && d.c_in >= 16, "conv: c_in=%d must be a multiple of 16", d.c_in);
+  Y3_REQUIRE(d.in_ld % 8 == 0 && d.in_coff % 8 == 0 && d.in_coff + d.c_in <= d.in_ld, "conv: bad input slice");
+  Y3_REQUIRE(d.in && d.weight && d.bias, "conv: null pointer");
+  Y3_REQUIRE((reinterpret_cast<uintptr_t>(d.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.weight) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0,
+             "conv: pointers must be 16-byte aligned");
+  const bool head = d.raw != nullptr;
+  if (head) {
+    Y3_REQUIRE(d.na * d.no == d.c_out && d.stride == 1 && !d.upsample && !d.res, "conv: bad Detect-head description");
+  } else {
+    Y3_REQUIRE(d.out != nullptr, "conv: null output");
+    Y3_REQUIRE(d.c_out % 32 == 0, "conv: c_out=%d must be a multiple of 32", d.c_out);
+    Y3_REQUIRE(d.out_ld % 8 == 0 && d.out_coff % 8 == 0 && d.out_coff + d.c_out <= d.out_ld, "conv: bad output slice");
+    Y3_REQUIRE((reinterpret_cast<uintptr_t>(d.out) & 15) == 0, "conv: out must be 16-byte aligned");
+    if (d.res)
+      Y3_REQUIRE(d.res_ld % 8 == 0 && d.res_coff % 8 == 0 && (reinterpret_cast<uintptr_t>(d.res) & 15) == 0,
+                 "conv: bad residual slice");
+  }
+  if (d.stride == 2) Y3_REQUIRE(d.h % 2 == 0 && d.w % 2 == 0, "conv: stride-2 needs even h, w");
+
+  const int bn = pick_block_n(d.c_out);
+  const int bk = d.c_in % 64 == 0 ? 64 : (d.c_in % 32 == 0 ? 32 : 16);
+  const int cout_pad = (d.c_out + bn - 1) / bn * bn;
+  const int taps = d.ksize * d.ksize;
+  const int hp = d.h + 2, wp = d.w + 2;
+
+  ConvTcArgs& a = plan->args;
+  a = ConvTcArgs{};
+  plan->block_n = bn;
+  plan->block_k = bk;
+  a.taps = taps;
+  a.kblocks = d.c_in / bk;
+  a.cin = d.c_in;
+  a.a_coff = d.in_coff;
+  a.a_ld = d.in_ld;
+  a.n_tiles = cout_pad / bn;
+  a.bias = d.bias;
+  a.cout = d.c_out;
+  a.act = d.act;
+  a.out = static_cast<__nv_bfloat16*>(d.out);
+  a.out_ld = d.out_ld;
+  a.out_coff = d.out_coff;
+  a.upsample = d.upsample;
+  a.res = static_cast<const __nv_bfloat16*>(d.res);
+  a.res_ld = d.res_ld;
+  a.res_coff = d.res_coff;
+  a.raw = d.raw;
+  a.na = d.na;
+  a.no = d.no > 0 ? d.no : 1;
+  a.err = d.err;
+  if (head) a.out = nullptr;
+
+  int rc;
+  if (d.stride == 1) {
+    a.mode = 0;
+    a.hp = hp;
+    a.wp = wp;
+    const long long rows = static_cast<long long>(d.n) * hp * wp;
+    Y3_REQUIRE(rows < (1ll << 31) - 4096, "conv: too many pixels");
+    a.rows_total = static_cast<int>(rows);
+    a.m_tiles = static_cast<int>((rows + kBlockM - 1) / kBlockM);
+    a.a_tx_bytes = kBlockM * bk * 2;
+    const uint64_t dims[2] = {static_cast<uint64_t>(d.in_ld), static_cast<uint64_t>(rows)};
+    const uint64_t strides[2] = {0, static_cast<uint64_t>(d.in_ld) * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(bk), kBlockM};
+    rc = encode_tensor_map_bf16(&plan->map_a, d.in, 2, dims, strides, box, bk * 2);
+    if (rc) return rc;
+  } else {
+    a.mode = 1;
+    a.ho = d.h / 2;
+    a.wo = d.w / 2;
+    // pick the TH x TW (<=128 pixels) output patch that wastes the least MMA rows
+    int best_tw = 1, best_th = 1;
+    long long best_tiles = -1;
+    for (int tw = 1; tw <= 128 && tw <= 256; ++tw) {
+      const int th = 128 / tw;
+      if (th < 1) break;
+      const int thc = th > a.ho ? a.ho : th;
+      const long long tiles = static_cast<long long>((a.wo + tw - 1) / tw) * ((a.ho + thc - 1) / thc);
+      if (best_tiles < 0 || tiles < best_tiles || (tiles == best_tiles && tw > best_tw)) {
+        best_tiles = tiles;
+        best_tw = tw;
+        best_th = thc;
+      }
+    }
+    a.tw = best_tw;
+    a.th = best_th;
+    a.tiles_w = (a.wo + a.tw - 1) / a.tw;
+    a.tiles_h = (a.ho + a.th - 1) / a.th;
+    a.m_tiles = d.n * a.tiles_w * a.tiles_h;
+    a.a_tx_bytes = static_cast<uint32_t>(a.tw) * a.th * bk * 2;
+    const uint64_t ld = static_cast<uint64_t>(d.in_ld);
+    const uint64_t dims[5] = {2 * ld, static_cast<uint64_t>(wp / 2), 2, static_cast<uint64_t>(hp / 2),
+                              static_cast<uint64_t>(d.n)};
+    const uint64_t strides[5] = {0, 2 * ld * 2, static_cast<uint64_t>(wp) * ld * 2, 2ull * wp * ld * 2,
+                                 static_cast<uint64_t>(hp) * wp * ld * 2};
+    const uint32_t box[5] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(a.tw), 1, static_cast<uint32_t>(a.th), 1};
+    rc = encode_tensor_map_bf16(&plan->map_a, d.in, 5, dims, strides, box, bk * 2);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t ktot = static_cast<uint64_t>(taps) * d.c_in;
+    const uint64_t dims[2] = {ktot, static_cast<uint64_t>(cout_pad)};
+    const uint64_t strides[2] = {0, ktot * 2};
+    const uint32_t box[2] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(bn)};
+    rc = encode_tensor_map_bf16(&plan->map_b, d.weight, 2, dims, strides, box, bk * 2);
+    if (rc) return rc;
+  }
+  const long long total = static_cast<long long>(a.m_tiles) * a.n_tiles;
+  const int sms = num_sms();
+  plan->grid = static_cast<int>(total < sms ? total : sms);
+  plan->smem_bytes = 0;
+  return Y3_OK;
+}
+
+}  // namespace y3
+
+extern "C" int y3_conv_cout_pad(int32_t c_out) {
+  const int bn = y3::pick_block_n(c_out);
+  return (c_out + bn - 1) / bn * bn;
+}
+
+extern "C" int y3_conv_bn_act_fwd(const y3_conv_desc* d, y3_stream_t stream) {
+  if (!d) return y3::set_error(Y3_ERR_BAD_ARG, "conv: null descriptor");
+  y3::ConvTcPlan plan;
+  int rc = y3::conv_tc_prepare(*d, &plan);
+  if (rc) return rc;
+  return y3::conv_tc_launch(plan, static_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,68 @@
+// yolov3_b200 — host-side internals shared by the translation units behind the C ABI.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/yolov3_b200.h"
+
+namespace y3 {
+
+// ---- error plumbing (thread-local last-error string)
+int set_error(int code, const char* fmt, ...);
+#define Y3_CHECK_CUDA(expr)                                                                            \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess)                                                                             \
+      return ::y3::set_error(Y3_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define Y3_REQUIRE(cond, ...)                                       \
+  do {                                                              \
+    if (!(cond)) return ::y3::set_error(Y3_ERR_BAD_ARG, __VA_ARGS__); \
+  } while (0)
+
+// ---- TMA descriptor encoding through the driver entry point (no link-time libcuda dependency)
+// dims/strides innermost first; strides in BYTES for dims 1..rank-1; swizzle_bytes in {32,64,128}.
+int encode_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                           const uint32_t* box, int swizzle_bytes);
+
+int num_sms();
+
+// ---- tcgen05 conv: kernel arguments (device view) and a prepared launch
+struct ConvTcArgs {
+  int mode;  // 0: "flat" stride-1 (1x1 / 3x3) on the padded pixel list; 1: "patch" stride-2 3x3
+  int taps, kblocks, cin;
+  int a_coff, a_ld;
+  uint32_t a_tx_bytes;   // bytes one A box delivers
+  int m_tiles, n_tiles;
+  // flat geometry (input and conv-output share it)
+  int hp, wp, rows_total;
+  // patch geometry
+  int tw, th, tiles_w, tiles_h, ho, wo;
+  // epilogue
+  const float* bias;
+  int cout, act;
+  __nv_bfloat16* out;
+  int out_ld, out_coff, upsample;
+  const __nv_bfloat16* res;
+  int res_ld, res_coff;
+  float* raw;
+  int na, no;
+  int* err;
+};
+
+struct ConvTcPlan {
+  CUtensorMap map_a, map_b;
+  ConvTcArgs args;
+  int block_n, block_k;
+  int grid;
+  size_t smem_bytes;
+};
+int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan);
+int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);
+
+}  // namespace y3

@@ -1,0 +1,75 @@
+"""Thin Python adapters over the C ABI (include/yolov3_b200.h): they pass raw device pointers and the current
+CUDA stream, never compute anything themselves, and raise on any non-zero return code."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .tensors import PaddedNHWC, _stream
+
+ACT_NONE, ACT_SILU = 0, 1
+
+
+def cout_pad(c_out: int) -> int:
+    return _lib.lib().y3_conv_cout_pad(c_out)
+
+
+def pack_conv_weight(w: torch.Tensor, b: torch.Tensor, device="cuda"):
+    """[c_out, c_in, k, k] fp32 (BN already folded) + bias -> (bf16 [c_out_pad, k*k*c_in] tap-major, fp32 [c_out_pad])."""
+    c_out, c_in, k, _ = w.shape
+    cp = cout_pad(c_out)
+    wp = torch.zeros(cp, k * k * c_in, dtype=torch.float32)
+    wp[:c_out] = w.detach().float().cpu().permute(0, 2, 3, 1).reshape(c_out, -1)
+    bp = torch.zeros(cp, dtype=torch.float32)
+    bp[:c_out] = b.detach().float().cpu()
+    return wp.to(device=device, dtype=torch.bfloat16).contiguous(), bp.to(device).contiguous()
+
+
+def pack_first_weight(w: torch.Tensor, b: torch.Tensor, device="cuda"):
+    """[c_out, 3, 3, 3] fp32 -> fp32 [27, c_out] with k = (c*3+kh)*3+kw."""
+    c_out = w.shape[0]
+    return (w.detach().float().cpu().reshape(c_out, 27).t().contiguous().to(device),
+            b.detach().float().cpu().contiguous().to(device))
+
+
+def conv_desc(x: PaddedNHWC, weight, bias, c_out, k, s, act, out: PaddedNHWC | None, res: PaddedNHWC | None = None,
+              upsample=False, raw: torch.Tensor | None = None, na=0, no=0, err: torch.Tensor | None = None):
+    d = _lib.ConvDesc()
+    d.n, d.h, d.w, d.c_in, d.c_out, d.ksize, d.stride, d.act = x.n, x.h, x.w, x.c, c_out, k, s, act
+    d.in_, d.in_ld, d.in_coff = x.ptr, x.ld, x.coff
+    d.weight, d.bias = weight.data_ptr(), bias.data_ptr()
+    if out is not None:
+        d.out, d.out_ld, d.out_coff = out.ptr, out.ld, out.coff
+    if res is not None:
+        d.res, d.res_ld, d.res_coff = res.ptr, res.ld, res.coff
+    d.upsample = int(bool(upsample))
+    if raw is not None:
+        d.raw, d.na, d.no = raw.data_ptr(), na, no
+    if err is not None:
+        d.err = err.data_ptr()
+    return d
+
+
+def conv_bn_act(x: PaddedNHWC, weight, bias, c_out, k=1, s=1, act=ACT_SILU, out=None, res=None, upsample=False,
+                raw=None, na=0, no=0, err=None):
+    """y3_conv_bn_act_fwd.  Allocates ``out`` when not given (tests); the model executor always passes buffers."""
+    ho, wo = x.h // s, x.w // s
+    if out is None and raw is None:
+        u = 2 if upsample else 1
+        out = PaddedNHWC.zeros(x.n, ho * u, wo * u, c_out, device=x.buf.device)
+    d = conv_desc(x, weight, bias, c_out, k, s, act, out, res, upsample, raw, na, no, err)
+    _lib.check(_lib.lib().y3_conv_bn_act_fwd(C.byref(d), _stream()), "y3_conv_bn_act_fwd")
+    return out if raw is None else raw
+
+
+def conv_first(x_nchw: torch.Tensor, weight27, bias, c_out, out: PaddedNHWC | None = None):
+    x = x_nchw.contiguous()
+    assert x.dtype == torch.float32 and x.shape[1] == 3
+    n, _, h, w = x.shape
+    if out is None:
+        out = PaddedNHWC.zeros(n, h, w, c_out, device=x.device)
+    _lib.check(_lib.lib().y3_conv_first_fwd(x.data_ptr(), n, h, w, weight27.data_ptr(), bias.data_ptr(), c_out, out.ptr,
+                                            out.ld, out.coff, _stream()), "y3_conv_first_fwd")
+    return out
