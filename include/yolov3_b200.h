@@ -37,6 +37,9 @@ int y3_version(void);
 int y3_last_error(char* buf, size_t n);
 /* Y3_OK iff the current CUDA device is compute capability 10.x. */
 int y3_device_check(void);
+/* sizeof() of the ABI structs, for bindings to verify their mirror definitions:
+ * 0 y3_conv_desc, 1 y3_first_desc, 2 y3_pool_desc, 3 y3_detect_level, 4 y3_decode_desc, 5 y3_op, 6 y3_nms_params. */
+int64_t y3_abi_sizeof(int32_t which);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Conv + folded-BN + SiLU (+ residual add, + nearest-2x upsample, + concat-offset store, or Detect raw store).
@@ -67,17 +70,117 @@ int y3_conv_bn_act_fwd(const y3_conv_desc* d, y3_stream_t stream);
 /* Tile N the kernel will use for c_out (weights/bias must be padded to a multiple of it). */
 int y3_conv_cout_pad(int32_t c_out);
 
-/* First layer: 3x3 stride-1 conv on the fp32 NCHW image (c_in = 3), folded BN + SiLU, writing padded NHWC bf16.
- * Replaces Conv.forward_fuse for layer 0 together with the NCHW->NHWC/bf16 conversion.  c_out in {16, 32}.
+/* First layer: 3x3 stride-1 pad-1 conv on the NCHW image (c_in = 3), folded BN + SiLU, writing padded NHWC bf16.
+ * Replaces Conv.forward_fuse for layer 0 together with the caller-side `im.float() / 255` (detect.py:187-191,
+ * val.py:358-359) and the NCHW->NHWC/bf16 conversion.  c_out in {16, 32}.
  * weight: fp32 [27, c_out] (k = (c*3+kh)*3+kw), bias fp32 [c_out]. */
-int y3_conv_first_fwd(const float* in_nchw, int32_t n, int32_t h, int32_t w, const float* weight, const float* bias,
-                      int32_t c_out, void* out, int32_t out_ld, int32_t out_coff, y3_stream_t stream);
+#define Y3_IN_F32 0
+#define Y3_IN_U8 1
+typedef struct y3_first_desc {
+  const void* in;        /* [n, 3, h, w] fp32 or uint8 */
+  int32_t in_dtype;      /* Y3_IN_* */
+  float in_div;          /* > 0: pixel = value / in_div (255 for uint8 images); 0: use as is */
+  int32_t n, h, w;
+  const float* weight;
+  const float* bias;
+  int32_t c_out;
+  void* out;             /* padded NHWC bf16 [n, h+2, w+2, out_ld] */
+  int32_t out_ld, out_coff;
+} y3_first_desc;
+int y3_conv_first_fwd(const y3_first_desc* d, y3_stream_t stream);
+
+/* Max-pool on padded NHWC bf16 (nn.MaxPool2d of yolov3-tiny.yaml; SPP pools, models/common.py:279,290).
+ * Window of output (y,x) = input rows [y*stride+off, +k) x cols [x*stride+off, +k); out-of-image elements are ignored
+ * (-inf padding) unless oob_zero, where they count as 0 (ZeroPad2d followed by MaxPool2d). */
+typedef struct y3_pool_desc {
+  const void* in;
+  int32_t in_ld, in_coff;
+  void* out;
+  int32_t out_ld, out_coff;
+  int32_t n, h, w, c;    /* input size (unpadded), channels (multiple of 8) */
+  int32_t ho, wo;
+  int32_t k, stride, off, oob_zero;
+} y3_pool_desc;
+int y3_maxpool_fwd(const y3_pool_desc* d, y3_stream_t stream);
 
 /* Layout helpers (tests / feeding intermediate tensors): NCHW fp32 <-> padded NHWC bf16 channel slice. */
 int y3_nchw_to_padded_nhwc(const float* src, int32_t n, int32_t c, int32_t h, int32_t w, void* dst, int32_t dst_ld,
                            int32_t dst_coff, y3_stream_t stream);
 int y3_padded_nhwc_to_nchw(const void* src, int32_t src_ld, int32_t src_coff, int32_t n, int32_t c, int32_t h,
                            int32_t w, float* dst, y3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Detect decode.  Replaces the eval branch of Detect.forward and _make_grid (models/yolo.py:100-123):
+ * z[b, off_l + (a*ny + y)*nx + x, :] = (xy: (2*sig + grid - 0.5)*stride, wh: (2*sig)^2 * anchor_px, rest: sig).
+ */
+#define Y3_MAX_LEVELS 5
+#define Y3_MAX_ANCHORS 6
+typedef struct y3_detect_level {
+  const float* raw;                 /* fp32 [bs, na, ny, nx, no] logits (the reference's x[i], models/yolo.py:98) */
+  int32_t ny, nx;
+  float stride;                     /* Detect.stride[i] */
+  float anchor_w[Y3_MAX_ANCHORS];   /* anchors[i] * stride[i], pixels (anchor_grid, models/yolo.py:122) */
+  float anchor_h[Y3_MAX_ANCHORS];
+} y3_detect_level;
+int y3_detect_decode_fwd(const y3_detect_level* levels, int32_t nl, int32_t bs, int32_t na, int32_t no, float* z,
+                         y3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Batched NMS.  Replaces non_max_suppression (utils/general.py:630-750) incl. torchvision.ops.nms (:733) for nm=0,
+ * labels=().  Sync-free: results are padded device arrays plus per-image counts.
+ *   pred      fp32 [bs, n_rows, 5+nc]  (xywh, obj, cls...)
+ *   out       fp32 [bs, max_det, 6]    rows (x1,y1,x2,y2,conf,cls) sorted by conf desc, zero beyond out_count[b]
+ *   out_src   int32 [bs, max_det, 2]   optional (pred row, class) of every kept detection
+ *   out_count int32 [bs]
+ *   overflow  int32 [bs]               optional; non-zero = candidates found (> cap): rerun with a larger capacity
+ * The wall-clock time_limit break of the reference (:675,746-748) is intentionally not reproduced.
+ */
+typedef struct y3_nms_params {
+  int32_t bs, n_rows, nc;
+  float conf_thres, iou_thres;      /* must lie in [0,1] (the reference asserts, :658-659) */
+  int32_t multi_label, agnostic;
+  int32_t max_det;                  /* :734 */
+  int32_t max_nms;                  /* 30000 (:674); <= 32768 */
+  float max_wh;                     /* 7680 (:673) */
+  int32_t cap;                      /* per-image candidate capacity, power of two >= 4096 */
+  const int32_t* classes;           /* HOST array of class ids to keep (:717-718), or NULL */
+  int32_t n_classes;
+} y3_nms_params;
+int32_t y3_nms_default_capacity(int32_t n_rows, int32_t nc, int32_t multi_label);
+int64_t y3_nms_workspace_bytes(int32_t bs, int32_t cap);
+int y3_nms_batched(const float* pred, const y3_nms_params* params, void* workspace, int64_t workspace_bytes, float* out,
+                   int32_t* out_src, int32_t* out_count, int32_t* overflow, y3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Whole-graph executor.  Replaces BaseModel._forward_once (models/yolo.py:135-147): the Python loop over nn.Modules
+ * becomes an immutable list of prepared launches (TMA descriptors encoded once at create) replayed on one stream.
+ * All buffers belong to the caller; y3_model_forward is CUDA-graph capturable.
+ */
+#define Y3_OP_CONV_FIRST 1
+#define Y3_OP_CONV 2
+#define Y3_OP_MAXPOOL 3
+#define Y3_OP_DECODE 4
+typedef struct y3_decode_desc {
+  y3_detect_level levels[Y3_MAX_LEVELS];
+  int32_t nl, bs, na, no;
+  float* z;
+} y3_decode_desc;
+typedef struct y3_op {
+  int32_t kind;          /* Y3_OP_*: selects which member below is read */
+  y3_conv_desc conv;
+  y3_first_desc first;
+  y3_pool_desc pool;
+  y3_decode_desc decode;
+} y3_op;
+typedef struct y3_model y3_model;
+int y3_model_create(const y3_op* ops, int32_t n_ops, y3_model** out);
+/* input: optional override of the first op's image pointer (NULL = the pointer given at create). */
+int y3_model_forward(const y3_model* m, const void* input, y3_stream_t stream);
+int32_t y3_model_num_launches(const y3_model* m);
+/* Profiling aid (synchronises; not capturable): average device time of every launch over `iters` passes, measured
+ * with CUDA events on `stream`; ms_out is a HOST array of y3_model_num_launches() floats. */
+int y3_model_forward_timed(const y3_model* m, const void* input, y3_stream_t stream, float* ms_out, int32_t iters);
+void y3_model_destroy(y3_model* m);
 
 #ifdef __cplusplus
 }

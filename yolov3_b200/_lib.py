@@ -32,6 +32,63 @@ class ConvDesc(C.Structure):
     ]
 
 
+MAX_LEVELS, MAX_ANCHORS = 5, 6
+
+
+class DetectLevel(C.Structure):
+    """struct y3_detect_level."""
+
+    _fields_ = [("raw", C.c_void_p), ("ny", C.c_int32), ("nx", C.c_int32), ("stride", C.c_float),
+                ("anchor_w", C.c_float * MAX_ANCHORS), ("anchor_h", C.c_float * MAX_ANCHORS)]
+
+
+class FirstDesc(C.Structure):
+    """struct y3_first_desc."""
+
+    _fields_ = [("in_", C.c_void_p), ("in_dtype", C.c_int32), ("in_div", C.c_float),
+                ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("weight", C.c_void_p), ("bias", C.c_void_p), ("c_out", C.c_int32),
+                ("out", C.c_void_p), ("out_ld", C.c_int32), ("out_coff", C.c_int32)]
+
+
+class PoolDesc(C.Structure):
+    """struct y3_pool_desc."""
+
+    _fields_ = [("in_", C.c_void_p), ("in_ld", C.c_int32), ("in_coff", C.c_int32),
+                ("out", C.c_void_p), ("out_ld", C.c_int32), ("out_coff", C.c_int32),
+                ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32),
+                ("ho", C.c_int32), ("wo", C.c_int32),
+                ("k", C.c_int32), ("stride", C.c_int32), ("off", C.c_int32), ("oob_zero", C.c_int32)]
+
+
+class DecodeDesc(C.Structure):
+    """struct y3_decode_desc."""
+
+    _fields_ = [("levels", DetectLevel * MAX_LEVELS), ("nl", C.c_int32), ("bs", C.c_int32), ("na", C.c_int32),
+                ("no", C.c_int32), ("z", C.c_void_p)]
+
+
+OP_CONV_FIRST, OP_CONV, OP_MAXPOOL, OP_DECODE = 1, 2, 3, 4
+IN_F32, IN_U8 = 0, 1
+
+
+class Op(C.Structure):
+    """struct y3_op."""
+
+    _fields_ = [("kind", C.c_int32), ("conv", ConvDesc), ("first", FirstDesc), ("pool", PoolDesc),
+                ("decode", DecodeDesc)]
+
+
+class NmsParams(C.Structure):
+    """struct y3_nms_params."""
+
+    _fields_ = [("bs", C.c_int32), ("n_rows", C.c_int32), ("nc", C.c_int32),
+                ("conf_thres", C.c_float), ("iou_thres", C.c_float),
+                ("multi_label", C.c_int32), ("agnostic", C.c_int32),
+                ("max_det", C.c_int32), ("max_nms", C.c_int32), ("max_wh", C.c_float),
+                ("cap", C.c_int32), ("classes", C.POINTER(C.c_int32)), ("n_classes", C.c_int32)]
+
+
 def _declare(lib):
     i32, vp, sz = C.c_int32, C.c_void_p, C.c_size_t
     sigs = {
@@ -40,9 +97,20 @@ def _declare(lib):
         "y3_device_check": ([], C.c_int),
         "y3_conv_bn_act_fwd": ([C.POINTER(ConvDesc), vp], C.c_int),
         "y3_conv_cout_pad": ([i32], C.c_int),
-        "y3_conv_first_fwd": ([vp, i32, i32, i32, vp, vp, i32, vp, i32, i32, vp], C.c_int),
+        "y3_abi_sizeof": ([i32], C.c_int64),
+        "y3_conv_first_fwd": ([C.POINTER(FirstDesc), vp], C.c_int),
+        "y3_maxpool_fwd": ([C.POINTER(PoolDesc), vp], C.c_int),
+        "y3_model_create": ([C.POINTER(Op), i32, C.POINTER(vp)], C.c_int),
+        "y3_model_forward": ([vp, vp, vp], C.c_int),
+        "y3_model_num_launches": ([vp], i32),
+        "y3_model_forward_timed": ([vp, vp, vp, C.POINTER(C.c_float), i32], C.c_int),
+        "y3_model_destroy": ([vp], None),
         "y3_nchw_to_padded_nhwc": ([vp, i32, i32, i32, i32, vp, i32, i32, vp], C.c_int),
         "y3_padded_nhwc_to_nchw": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], C.c_int),
+        "y3_detect_decode_fwd": ([C.POINTER(DetectLevel), i32, i32, i32, i32, vp, vp], C.c_int),
+        "y3_nms_default_capacity": ([i32, i32, i32], i32),
+        "y3_nms_workspace_bytes": ([i32, i32], C.c_int64),
+        "y3_nms_batched": ([vp, C.POINTER(NmsParams), vp, C.c_int64, vp, vp, vp, vp, vp], C.c_int),
     }
     for name, (argtypes, restype) in sigs.items():
         fn = getattr(lib, name)
@@ -64,6 +132,10 @@ def lib():
             )
         _lib = C.CDLL(str(_LIB_PATH))
         SYMBOLS.update(_declare(_lib))
+        for which, st in enumerate((ConvDesc, FirstDesc, PoolDesc, DetectLevel, DecodeDesc, Op, NmsParams)):
+            if _lib.y3_abi_sizeof(which) != C.sizeof(st):
+                raise Y3Error(f"ABI mismatch: sizeof({st.__name__}) is {C.sizeof(st)} here, "
+                              f"{_lib.y3_abi_sizeof(which)} in {_LIB_PATH.name}; rebuild the library")
     return _lib
 
 

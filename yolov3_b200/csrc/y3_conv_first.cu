@@ -9,8 +9,21 @@
 namespace y3 {
 namespace {
 
-template <int COUT>
-__global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict__ in, int H, int W,
+template <typename TIN>
+__device__ __forceinline__ float load_px(const TIN* p, float div);
+template <>
+__device__ __forceinline__ float load_px<float>(const float* p, float div) {
+  const float v = __ldg(p);
+  return div > 0.f ? __fdiv_rn(v, div) : v;
+}
+template <>
+__device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p, float div) {
+  const float v = static_cast<float>(__ldg(p));
+  return div > 0.f ? __fdiv_rn(v, div) : v;
+}
+
+template <int COUT, typename TIN>
+__global__ void __launch_bounds__(128) conv_first_kernel(const TIN* __restrict__ in, float in_div, int H, int W,
                                                          const float* __restrict__ wgt, const float* __restrict__ bias,
                                                          __nv_bfloat16* __restrict__ out, int out_ld, int out_coff) {
   __shared__ __align__(16) float sw[27 * COUT];
@@ -25,7 +38,7 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict
   float x[27];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const float* plane = in + (static_cast<size_t>(n) * 3 + c) * H * W;
+    const TIN* plane = in + (static_cast<size_t>(n) * 3 + c) * H * W;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int hh = h + kh - 1;
@@ -33,7 +46,7 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const float* __restrict
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
         const int ww = w + kw - 1;
-        x[(c * 3 + kh) * 3 + kw] = (row_ok && ww >= 0 && ww < W) ? __ldg(plane + static_cast<size_t>(hh) * W + ww) : 0.f;
+        x[(c * 3 + kh) * 3 + kw] = (row_ok && ww >= 0 && ww < W) ? load_px<TIN>(plane + static_cast<size_t>(hh) * W + ww, in_div) : 0.f;
       }
     }
   }
@@ -89,23 +102,26 @@ __global__ void padded_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int
 }  // namespace
 }  // namespace y3
 
-extern "C" int y3_conv_first_fwd(const float* in_nchw, int32_t n, int32_t h, int32_t w, const float* weight,
-                                 const float* bias, int32_t c_out, void* out, int32_t out_ld, int32_t out_coff,
-                                 y3_stream_t stream) {
-  Y3_REQUIRE(in_nchw && weight && bias && out, "conv_first: null pointer");
-  Y3_REQUIRE(n > 0 && h > 0 && w > 0 && n <= 65535 && h <= 65535, "conv_first: bad shape");
-  Y3_REQUIRE(out_ld % 8 == 0 && out_coff % 8 == 0 && out_coff + c_out <= out_ld &&
-                 (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+extern "C" int y3_conv_first_fwd(const y3_first_desc* d, y3_stream_t stream) {
+  Y3_REQUIRE(d && d->in && d->weight && d->bias && d->out, "conv_first: null pointer");
+  Y3_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0 && d->n <= 65535 && d->h <= 65535, "conv_first: bad shape");
+  Y3_REQUIRE(d->out_ld % 8 == 0 && d->out_coff % 8 == 0 && d->out_coff + d->c_out <= d->out_ld &&
+                 (reinterpret_cast<uintptr_t>(d->out) & 15) == 0,
              "conv_first: bad output slice");
-  const dim3 grid((w + 127) / 128, h, n), block(128);
-  auto* o = static_cast<__nv_bfloat16*>(out);
+  Y3_REQUIRE(d->c_out == 16 || d->c_out == 32, "conv_first: c_out=%d unsupported (16 or 32)", d->c_out);
+  Y3_REQUIRE(d->in_dtype == Y3_IN_F32 || d->in_dtype == Y3_IN_U8, "conv_first: bad input dtype %d", d->in_dtype);
+  const dim3 grid((d->w + 127) / 128, d->h, d->n), block(128);
+  auto* o = static_cast<__nv_bfloat16*>(d->out);
   auto s = static_cast<cudaStream_t>(stream);
-  if (c_out == 32)
-    y3::conv_first_kernel<32><<<grid, block, 0, s>>>(in_nchw, h, w, weight, bias, o, out_ld, out_coff);
-  else if (c_out == 16)
-    y3::conv_first_kernel<16><<<grid, block, 0, s>>>(in_nchw, h, w, weight, bias, o, out_ld, out_coff);
-  else
-    return y3::set_error(Y3_ERR_BAD_ARG, "conv_first: c_out=%d unsupported (16 or 32)", c_out);
+#define Y3_FIRST(CO, T)                                                                                            \
+  y3::conv_first_kernel<CO, T><<<grid, block, 0, s>>>(static_cast<const T*>(d->in), d->in_div, d->h, d->w, d->weight, \
+                                                      d->bias, o, d->out_ld, d->out_coff)
+  if (d->c_out == 32) {
+    if (d->in_dtype == Y3_IN_F32) Y3_FIRST(32, float); else Y3_FIRST(32, uint8_t);
+  } else {
+    if (d->in_dtype == Y3_IN_F32) Y3_FIRST(16, float); else Y3_FIRST(16, uint8_t);
+  }
+#undef Y3_FIRST
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }

@@ -1,0 +1,90 @@
+// yolov3_b200 — Detect-head decode: sigmoid + anchor-grid transform of all pyramid levels in ONE coalesced pass.
+// Replaces Detect.forward's eval branch and _make_grid (reference models/yolo.py:100-123): no grid / anchor_grid
+// tensors, no split/cat; grid offsets come from the element index.  raw level l is fp32 [bs, na, ny, nx, no]
+// (= the reference's x[i]); z is fp32 [bs, sum_l na*ny*nx, no] with row = off_l + (a*ny + y)*nx + x, i.e. exactly
+// torch.cat(z, 1) of models/yolo.py:110.  Compiled without fast-math/FMA contraction: (2*s + g) * stride is evaluated
+// with the reference's operation order and rounding.
+#include "y3_common.cuh"
+#include "y3_internal.h"
+
+namespace y3 {
+namespace {
+
+struct DecodeArgs {
+  const float* raw[Y3_MAX_LEVELS];
+  int ny[Y3_MAX_LEVELS], nx[Y3_MAX_LEVELS];
+  int row_off[Y3_MAX_LEVELS + 1];  // first z row of each level; [nl] = total rows
+  float stride[Y3_MAX_LEVELS];
+  float anchor_w[Y3_MAX_LEVELS][Y3_MAX_ANCHORS], anchor_h[Y3_MAX_LEVELS][Y3_MAX_ANCHORS];  // pixels
+  int nl, bs, na, no;
+  float* z;
+};
+
+__global__ void __launch_bounds__(256) decode_kernel(const DecodeArgs p) {
+  const long long per_img = static_cast<long long>(p.row_off[p.nl]) * p.no;
+  const long long total = per_img * p.bs;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / per_img);
+    const long long e = i - b * per_img;
+    const int row = static_cast<int>(e / p.no);
+    const int k = static_cast<int>(e - static_cast<long long>(row) * p.no);
+    int l = 0;
+    while (l + 1 < p.nl && row >= p.row_off[l + 1]) ++l;
+    const int r = row - p.row_off[l];
+    const int plane = p.ny[l] * p.nx[l];
+    const float v = p.raw[l][(static_cast<long long>(b) * p.na * plane + r) * p.no + k];
+    const float s = 1.0f / (1.0f + expf(-v));
+    float o = s;
+    if (k < 4) {
+      const int a = r / plane, cell = r - a * plane;
+      const int y = cell / p.nx[l], x = cell - y * p.nx[l];
+      if (k == 0)
+        o = (s * 2.0f + (static_cast<float>(x) - 0.5f)) * p.stride[l];
+      else if (k == 1)
+        o = (s * 2.0f + (static_cast<float>(y) - 0.5f)) * p.stride[l];
+      else {
+        const float t = s * 2.0f;
+        o = (t * t) * (k == 2 ? p.anchor_w[l][a] : p.anchor_h[l][a]);
+      }
+    }
+    p.z[i] = o;
+  }
+}
+
+}  // namespace
+}  // namespace y3
+
+extern "C" int y3_detect_decode_fwd(const y3_detect_level* levels, int32_t nl, int32_t bs, int32_t na, int32_t no,
+                                    float* z, y3_stream_t stream) {
+  Y3_REQUIRE(levels && z && nl >= 1 && nl <= Y3_MAX_LEVELS && na >= 1 && na <= Y3_MAX_ANCHORS && bs > 0 && no >= 5,
+             "decode: bad arguments (nl=%d na=%d bs=%d no=%d)", nl, na, bs, no);
+  y3::DecodeArgs a{};
+  a.nl = nl;
+  a.bs = bs;
+  a.na = na;
+  a.no = no;
+  a.z = z;
+  int off = 0;
+  for (int l = 0; l < nl; ++l) {
+    Y3_REQUIRE(levels[l].raw && levels[l].ny > 0 && levels[l].nx > 0, "decode: bad level %d", l);
+    a.raw[l] = levels[l].raw;
+    a.ny[l] = levels[l].ny;
+    a.nx[l] = levels[l].nx;
+    a.stride[l] = levels[l].stride;
+    a.row_off[l] = off;
+    off += na * levels[l].ny * levels[l].nx;
+    for (int j = 0; j < na; ++j) {
+      a.anchor_w[l][j] = levels[l].anchor_w[j];
+      a.anchor_h[l][j] = levels[l].anchor_h[j];
+    }
+  }
+  a.row_off[nl] = off;
+  const long long total = static_cast<long long>(off) * no * bs;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(y3::num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  y3::decode_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}

@@ -64,5 +64,6 @@ struct ConvTcPlan {
 };
 int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan);
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);
+int pool_launch(const y3_pool_desc& d, cudaStream_t stream);
 
 }  // namespace y3

@@ -1,0 +1,531 @@
+// yolov3_b200 — batched non-maximum suppression entirely on the device, no host synchronisation.
+// Replaces non_max_suppression (reference utils/general.py:630-750) together with torchvision.ops.nms (:733):
+//   K1 candidates : obj > thr, conf = obj*cls, best class (or every class > thr when multi_label), class filter
+//                   -> 64-bit key (conf bits | ~candidate id) appended per image               (general.py:669-718)
+//   K2 sort       : bitonic sort of the keys, descending == stable sort by conf               (general.py:728)
+//   K3 gather     : rank r < min(count, max_nms): xywh -> xyxy, class-offset boxes            (general.py:705,731-732)
+//   K4 sort       : (class, rank) keys ascending -> per-class segments in confidence order
+//   K5 segments   : greedy suppression inside each (image, class) segment, strict IoU > thr   (torchvision nms)
+//   K6 compact    : first max_det kept ranks in confidence order -> out rows + counts         (general.py:734,743)
+// Exactness: every floating-point step is a separately rounded fp32 operation in the reference's order (this file is
+// compiled with -fmad=false and without fast-math), so kept sets and output rows are bit-identical to the reference on
+// identical inputs whenever confidences are tie-free (ties: lower candidate index first, i.e. a stable sort; the
+// reference's argsort is unstable there).  Splitting the greedy pass by class is exact because boxes offset by
+// class*max_wh cannot intersect across classes while all coordinates lie inside (-max_wh/2, max_wh/2); images that
+// violate that bound (or agnostic=True) take the single-segment path over all candidates.
+// The reference's wall-clock time_limit break (general.py:675,746-748) is deliberately not reproduced.
+#include "y3_common.cuh"
+#include "y3_internal.h"
+
+namespace y3 {
+namespace {
+
+constexpr int kSortTile = 4096;   // keys sorted per CTA in shared memory
+constexpr int kRankCap = 32768;   // >= max_nms (30000), power of two
+constexpr int kSegSmemBoxes = 2048;
+
+struct NmsArgs {
+  const float* pred;  // [bs, n_rows, no]
+  int bs, n_rows, nc, no;
+  float conf_thres, iou_thres, max_wh;
+  int multi_label, agnostic, max_det, max_nms;
+  int cap;  // candidate capacity per image (power of two >= kSortTile)
+  uint32_t cls_mask[32];
+  int use_mask;
+  // workspace
+  unsigned long long* keys;  // [bs, cap]
+  int* count;                // [bs] candidates found (may exceed cap)
+  int* flags;                // [bs] bit0: needs single-segment path
+  float* det;                // [bs, kRankCap, 6]
+  uint32_t* seg_keys;        // [bs, kRankCap]
+  uint8_t* keep;             // [bs, kRankCap]
+  // outputs
+  float* out;     // [bs, max_det, 6]
+  int* out_src;   // [bs, max_det, 2] or null
+  int* out_count; // [bs]
+  int* overflow;  // [bs] or null
+};
+
+__device__ __forceinline__ int next_pow2(int v) { return v <= 1 ? 1 : 1 << (32 - __clz(v - 1)); }
+
+// ------------------------------------------------------------------------------------------------ K1 candidates
+// one warp per prediction row, 32 rows per block; one global atomic per block
+__global__ void __launch_bounds__(1024) nms_candidates_kernel(const NmsArgs p) {
+  __shared__ int s_cnt[32];
+  __shared__ int s_base;
+  const int img = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 32 + warp;
+  const float* x = p.pred + (static_cast<size_t>(img) * p.n_rows + (row < p.n_rows ? row : 0)) * p.no;
+  float obj = 0.f;
+  bool row_ok = false;
+  if (row < p.n_rows) {
+    obj = __ldg(x + 4);
+    row_ok = obj > p.conf_thres;
+  }
+  int my_cnt = 0;          // candidates this LANE contributes
+  float best = 0.f;        // single-label: best conf / class (valid in all lanes after the reduce)
+  int best_c = 0;
+  if (row_ok) {
+    if (p.multi_label) {
+      for (int c = lane; c < p.nc; c += 32) {
+        const float conf = __fmul_rn(__ldg(x + 5 + c), obj);
+        const bool in_set = !p.use_mask || ((p.cls_mask[c >> 5] >> (c & 31)) & 1u);
+        my_cnt += (conf > p.conf_thres) && in_set;
+      }
+    } else {
+      float bv = -INFINITY;
+      int bc = 0x7fffffff;
+      bool any_nan = false;
+      for (int c = lane; c < p.nc; c += 32) {
+        const float conf = __fmul_rn(__ldg(x + 5 + c), obj);
+        any_nan |= (conf != conf);
+        if (conf > bv) {  // first maximum wins inside a lane (ascending c)
+          bv = conf;
+          bc = c;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+        if (ov > bv || (ov == bv && oc < bc)) {
+          bv = ov;
+          bc = oc;
+        }
+      }
+      best = __any_sync(0xffffffffu, any_nan) ? __int_as_float(0x7fc00000) : bv;  // torch.max propagates NaN
+      best_c = bc;
+      const bool in_set = !p.use_mask || ((p.cls_mask[(best_c & 1023) >> 5] >> (best_c & 31)) & 1u);
+      my_cnt = (lane == 0 && best > p.conf_thres && in_set) ? 1 : 0;
+    }
+  }
+  // warp total + exclusive prefix over lanes
+  int incl = my_cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+  if (lane == 0) s_cnt[warp] = warp_total;
+  __syncthreads();
+  if (warp == 0) {
+    int v = s_cnt[lane];
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    s_cnt[lane] = inc - v;  // exclusive offset of each warp
+    if (lane == 31) s_base = inc > 0 ? atomicAdd(&p.count[img], inc) : 0;
+  }
+  __syncthreads();
+  if (my_cnt == 0) return;
+  int slot = s_base + s_cnt[warp] + (incl - my_cnt);
+  unsigned long long* keys = p.keys + static_cast<size_t>(img) * p.cap;
+  if (p.multi_label) {
+    for (int c = lane; c < p.nc; c += 32) {
+      const float conf = __fmul_rn(__ldg(x + 5 + c), obj);
+      const bool in_set = !p.use_mask || ((p.cls_mask[c >> 5] >> (c & 31)) & 1u);
+      if ((conf > p.conf_thres) && in_set) {
+        if (slot < p.cap) {
+          const uint32_t id = static_cast<uint32_t>(row) * p.nc + c;
+          keys[slot] = (static_cast<unsigned long long>(__float_as_uint(conf)) << 32) | (0xFFFFFFFFu - id);
+        }
+        ++slot;
+      }
+    }
+  } else if (slot < p.cap) {
+    const uint32_t id = static_cast<uint32_t>(row) * p.nc + best_c;
+    keys[slot] = (static_cast<unsigned long long>(__float_as_uint(best)) << 32) | (0xFFFFFFFFu - id);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ bitonic sort
+// Sorts, per image, the first npow2(count) keys (padding written by the caller).  DESC=true: descending.
+template <typename T, bool DESC>
+__device__ __forceinline__ void cmp_swap(T& a, T& b, bool up) {
+  // `up` = this pair must end ascending (a <= b) in the un-flipped network
+  const bool swap = DESC ? (up ? a < b : a > b) : (up ? a > b : a < b);
+  if (swap) {
+    const T t = a;
+    a = b;
+    b = t;
+  }
+}
+
+__device__ __forceinline__ int sort_len(const NmsArgs& p, int img, bool second) {
+  int c = p.count[img];
+  if (!second) {
+    c = c < p.cap ? c : p.cap;
+  } else {
+    c = c < p.cap ? c : p.cap;
+    c = c < p.max_nms ? c : p.max_nms;
+  }
+  return next_pow2(c);
+}
+
+// full sort of each kSortTile-sized tile in shared memory (k = 2 .. kSortTile)
+template <typename T, bool DESC>
+__global__ void __launch_bounds__(1024) bitonic_local_kernel(const NmsArgs p, T* base, int stride, bool second) {
+  __shared__ T s[kSortTile];
+  const int img = blockIdx.y;
+  const int n = sort_len(p, img, second);
+  const int t0 = blockIdx.x * kSortTile;
+  if (t0 >= n) return;
+  T* g = base + static_cast<size_t>(img) * stride + t0;
+  for (int i = threadIdx.x; i < kSortTile; i += blockDim.x) s[i] = g[i];
+  __syncthreads();
+  for (int k = 2; k <= kSortTile; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < kSortTile / 2; t += blockDim.x) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const bool up = (((t0 + i) & k) == 0);
+        cmp_swap<T, DESC>(s[i], s[i | j], up);
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < kSortTile; i += blockDim.x) g[i] = s[i];
+}
+
+// one global compare-exchange step (k > kSortTile, j >= kSortTile)
+template <typename T, bool DESC>
+__global__ void __launch_bounds__(256) bitonic_global_kernel(const NmsArgs p, T* base, int stride, bool second, int k,
+                                                             int j) {
+  const int img = blockIdx.y;
+  const int n = sort_len(p, img, second);
+  if (k > n) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n / 2) return;
+  const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+  T* g = base + static_cast<size_t>(img) * stride;
+  T a = g[i], b = g[i | j];
+  const bool up = ((i & k) == 0);
+  const T a0 = a, b0 = b;
+  cmp_swap<T, DESC>(a, b, up);
+  if (a != a0) {
+    g[i] = a;
+    g[i | j] = b;
+  }
+  (void)b0;
+}
+
+// finish merge level k inside each tile (j = kSortTile/2 .. 1)
+template <typename T, bool DESC>
+__global__ void __launch_bounds__(1024) bitonic_merge_kernel(const NmsArgs p, T* base, int stride, bool second, int k) {
+  __shared__ T s[kSortTile];
+  const int img = blockIdx.y;
+  const int n = sort_len(p, img, second);
+  if (k > n) return;
+  const int t0 = blockIdx.x * kSortTile;
+  if (t0 >= n) return;
+  T* g = base + static_cast<size_t>(img) * stride + t0;
+  for (int i = threadIdx.x; i < kSortTile; i += blockDim.x) s[i] = g[i];
+  __syncthreads();
+  for (int j = kSortTile >> 1; j > 0; j >>= 1) {
+    for (int t = threadIdx.x; t < kSortTile / 2; t += blockDim.x) {
+      const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+      const bool up = (((t0 + i) & k) == 0);
+      cmp_swap<T, DESC>(s[i], s[i | j], up);
+    }
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < kSortTile; i += blockDim.x) g[i] = s[i];
+}
+
+// write padding so that the sort networks see a full power-of-two array (at least one tile)
+__global__ void __launch_bounds__(256) pad_keys_kernel(const NmsArgs p) {
+  const int img = blockIdx.y;
+  int c = p.count[img];
+  c = c < p.cap ? c : p.cap;
+  int n = next_pow2(c);
+  n = n < kSortTile ? kSortTile : n;
+  unsigned long long* keys = p.keys + static_cast<size_t>(img) * p.cap;
+  for (int i = c + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) keys[i] = 0ull;
+}
+
+// ------------------------------------------------------------------------------------------------ K3 gather
+__global__ void __launch_bounds__(256) nms_gather_kernel(const NmsArgs p) {
+  const int img = blockIdx.y;
+  int c = p.count[img];
+  c = c < p.cap ? c : p.cap;
+  const int n = c < p.max_nms ? c : p.max_nms;
+  int npad = next_pow2(n);
+  npad = npad < kSortTile ? kSortTile : npad;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= npad) return;
+  uint32_t* sk = p.seg_keys + static_cast<size_t>(img) * kRankCap;
+  if (r >= n) {
+    sk[r] = 0xFFFFFFFFu;
+    return;
+  }
+  const unsigned long long key = p.keys[static_cast<size_t>(img) * p.cap + r];
+  const uint32_t id = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+  const float conf = __uint_as_float(static_cast<uint32_t>(key >> 32));
+  const int row = id / p.nc, cls = id - row * p.nc;
+  const float* x = p.pred + (static_cast<size_t>(img) * p.n_rows + row) * p.no;
+  const float cx = __ldg(x), cy = __ldg(x + 1), w = __ldg(x + 2), h = __ldg(x + 3);
+  const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+  const float x1 = __fsub_rn(cx, hw), y1 = __fsub_rn(cy, hh), x2 = __fadd_rn(cx, hw), y2 = __fadd_rn(cy, hh);
+  float* d = p.det + (static_cast<size_t>(img) * kRankCap + r) * 6;
+  d[0] = x1;
+  d[1] = y1;
+  d[2] = x2;
+  d[3] = y2;
+  d[4] = conf;
+  d[5] = static_cast<float>(cls);
+  p.keep[static_cast<size_t>(img) * kRankCap + r] = 0;
+  sk[r] = p.agnostic ? static_cast<uint32_t>(r) : ((static_cast<uint32_t>(cls) << 15) | static_cast<uint32_t>(r));
+  // class-split greedy NMS is only exact while offset boxes of different classes cannot intersect
+  const float lim = p.max_wh * 0.5f;
+  const bool inside = (x1 > -lim) && (x2 < lim) && (x1 <= x2);
+  if (!inside && !p.agnostic) atomicOr(&p.flags[img], 1);
+}
+
+// ------------------------------------------------------------------------------------------------ K5 segments
+__device__ __forceinline__ int lower_bound_u32(const uint32_t* a, int n, uint32_t v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) nms_segments_kernel(const NmsArgs p) {
+  __shared__ float4 s_box[kSegSmemBoxes];
+  __shared__ float s_area[kSegSmemBoxes];
+  __shared__ uint32_t s_supp[(kRankCap + 31) / 32];
+  const int img = blockIdx.y, seg = blockIdx.x;
+  int c = p.count[img];
+  c = c < p.cap ? c : p.cap;
+  const int n = c < p.max_nms ? c : p.max_nms;
+  if (n == 0) return;
+  const bool single = p.agnostic || (p.flags[img] & 1);
+  if (single && seg != 0) return;
+  const uint32_t* sk = p.seg_keys + static_cast<size_t>(img) * kRankCap;
+  int lo = 0, hi = n;
+  if (!single) {
+    lo = lower_bound_u32(sk, n, static_cast<uint32_t>(seg) << 15);
+    hi = lower_bound_u32(sk, n, static_cast<uint32_t>(seg + 1) << 15);
+  }
+  const int m = hi - lo;
+  if (m <= 0) return;
+  const float* det = p.det + static_cast<size_t>(img) * kRankCap * 6;
+  uint8_t* keep = p.keep + static_cast<size_t>(img) * kRankCap;
+  // member j of the segment (confidence order) -> rank
+  auto rank_of = [&](int j) -> int { return single ? j : static_cast<int>(sk[lo + j] & 0x7FFFu); };
+  auto load_box = [&](int j) -> float4 {
+    const float* d = det + static_cast<size_t>(rank_of(j)) * 6;
+    const float off = p.agnostic ? 0.0f : __fmul_rn(d[5], p.max_wh);
+    return make_float4(__fadd_rn(d[0], off), __fadd_rn(d[1], off), __fadd_rn(d[2], off), __fadd_rn(d[3], off));
+  };
+  const bool in_smem = m <= kSegSmemBoxes;
+  for (int j = threadIdx.x; j < (m + 31) / 32; j += blockDim.x) s_supp[j] = 0;
+  if (in_smem) {
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+      const float4 b = load_box(j);
+      s_box[j] = b;
+      s_area[j] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    }
+  }
+  __syncthreads();
+  for (int i = 0; i < m; ++i) {
+    if ((s_supp[i >> 5] >> (i & 31)) & 1u) continue;  // uniform: every thread reads the same word
+    if (threadIdx.x == 0) keep[rank_of(i)] = 1;
+    float4 bi;
+    float ai;
+    if (in_smem) {
+      bi = s_box[i];
+      ai = s_area[i];
+    } else {
+      bi = load_box(i);
+      ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+    }
+    for (int j = i + 1 + threadIdx.x; j < m; j += blockDim.x) {
+      if ((s_supp[j >> 5] >> (j & 31)) & 1u) continue;
+      float4 bj;
+      float aj;
+      if (in_smem) {
+        bj = s_box[j];
+        aj = s_area[j];
+      } else {
+        bj = load_box(j);
+        aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+      }
+      const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+      const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+      const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+      const float inter = __fmul_rn(w, h);
+      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
+      if (ovr > p.iou_thres) atomicOr(&s_supp[j >> 5], 1u << (j & 31));
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K6 compact
+__global__ void __launch_bounds__(1024) nms_compact_kernel(const NmsArgs p) {
+  __shared__ int s_warp[32];
+  __shared__ int s_run;
+  const int img = blockIdx.x;
+  int c = p.count[img];
+  if (p.overflow && threadIdx.x == 0) p.overflow[img] = c > p.cap ? c : 0;
+  c = c < p.cap ? c : p.cap;
+  const int n = c < p.max_nms ? c : p.max_nms;
+  const uint8_t* keep = p.keep + static_cast<size_t>(img) * kRankCap;
+  const float* det = p.det + static_cast<size_t>(img) * kRankCap * 6;
+  float* out = p.out + static_cast<size_t>(img) * p.max_det * 6;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) s_run = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int run = s_run;
+    if (run >= p.max_det) break;
+    const int r = base + threadIdx.x;
+    const int k = (r < n) ? keep[r] : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, k);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int woff = 0, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int v = s_warp[w];
+      if (w < warp) woff += v;
+      tot += v;
+    }
+    const int pos = run + woff + __popc(bal & ((1u << lane) - 1u));
+    if (k && pos < p.max_det) {
+      const float* d = det + static_cast<size_t>(r) * 6;
+      float* o = out + static_cast<size_t>(pos) * 6;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) o[q] = d[q];
+      if (p.out_src) {
+        const unsigned long long key = p.keys[static_cast<size_t>(img) * p.cap + r];
+        const uint32_t id = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+        p.out_src[(static_cast<size_t>(img) * p.max_det + pos) * 2 + 0] = id / p.nc;
+        p.out_src[(static_cast<size_t>(img) * p.max_det + pos) * 2 + 1] = id % p.nc;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_run = run + tot;
+    __syncthreads();
+  }
+  const int total = s_run < p.max_det ? s_run : p.max_det;
+  if (threadIdx.x == 0) p.out_count[img] = total;
+  for (int i = total * 6 + threadIdx.x; i < p.max_det * 6; i += blockDim.x) out[i] = 0.f;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+}  // namespace y3
+
+extern "C" int64_t y3_nms_workspace_bytes(int32_t bs, int32_t cap) {
+  if (bs <= 0 || cap <= 0) return -1;
+  size_t b = 0;
+  b += y3::align_up(sizeof(unsigned long long) * size_t(bs) * cap, 256);
+  b += y3::align_up(sizeof(int) * size_t(bs) * 2, 256);
+  b += y3::align_up(sizeof(float) * size_t(bs) * y3::kRankCap * 6, 256);
+  b += y3::align_up(sizeof(uint32_t) * size_t(bs) * y3::kRankCap, 256);
+  b += y3::align_up(size_t(bs) * y3::kRankCap, 256);
+  return static_cast<int64_t>(b);
+}
+
+extern "C" int32_t y3_nms_default_capacity(int32_t n_rows, int32_t nc, int32_t multi_label) {
+  long long want = multi_label ? 4ll * n_rows : n_rows;  // multi-label: room for 4 labels/row before an exact retry
+  if (want < y3::kSortTile) want = y3::kSortTile;
+  long long cap = y3::kSortTile;
+  while (cap < want) cap <<= 1;
+  (void)nc;
+  return static_cast<int32_t>(cap);
+}
+
+extern "C" int y3_nms_batched(const float* pred, const y3_nms_params* q, void* workspace, int64_t workspace_bytes,
+                              float* out, int32_t* out_src, int32_t* out_count, int32_t* overflow,
+                              y3_stream_t stream_) {
+  using namespace y3;
+  Y3_REQUIRE(pred && q && workspace && out && out_count, "nms: null pointer");
+  Y3_REQUIRE(q->bs > 0 && q->n_rows > 0 && q->nc >= 1 && q->nc <= 1024, "nms: bad shape bs=%d rows=%d nc=%d", q->bs,
+             q->n_rows, q->nc);
+  Y3_REQUIRE(q->conf_thres >= 0.f && q->conf_thres <= 1.f, "nms: invalid confidence threshold %f", q->conf_thres);
+  Y3_REQUIRE(q->iou_thres >= 0.f && q->iou_thres <= 1.f, "nms: invalid IoU threshold %f", q->iou_thres);
+  Y3_REQUIRE(q->max_det > 0 && q->max_nms > 0 && q->max_nms <= kRankCap, "nms: max_det/max_nms out of range");
+  Y3_REQUIRE(q->cap >= kSortTile && (q->cap & (q->cap - 1)) == 0, "nms: capacity must be a power of two >= %d",
+             kSortTile);
+  Y3_REQUIRE(static_cast<long long>(q->n_rows) * q->nc < (1ll << 32), "nms: n_rows*nc overflows the candidate id");
+  Y3_REQUIRE(workspace_bytes >= y3_nms_workspace_bytes(q->bs, q->cap), "nms: workspace too small");
+  Y3_REQUIRE(q->bs <= 65535, "nms: batch too large");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+  NmsArgs a{};
+  a.pred = pred;
+  a.bs = q->bs;
+  a.n_rows = q->n_rows;
+  a.nc = q->nc;
+  a.no = q->nc + 5;
+  a.conf_thres = q->conf_thres;
+  a.iou_thres = q->iou_thres;
+  a.max_wh = q->max_wh > 0 ? q->max_wh : 7680.f;
+  a.multi_label = (q->multi_label && q->nc > 1) ? 1 : 0;  // general.py:677
+  a.agnostic = q->agnostic ? 1 : 0;
+  a.max_det = q->max_det;
+  a.max_nms = q->max_nms;
+  a.cap = q->cap;
+  a.use_mask = q->n_classes > 0;
+  for (int i = 0; i < q->n_classes; ++i) {
+    const int c = q->classes[i];
+    if (c >= 0 && c < 1024) a.cls_mask[c >> 5] |= 1u << (c & 31);
+  }
+  uint8_t* w = static_cast<uint8_t*>(workspace);
+  a.keys = reinterpret_cast<unsigned long long*>(w);
+  w += align_up(sizeof(unsigned long long) * size_t(a.bs) * a.cap, 256);
+  a.count = reinterpret_cast<int*>(w);
+  a.flags = a.count + a.bs;
+  w += align_up(sizeof(int) * size_t(a.bs) * 2, 256);
+  a.det = reinterpret_cast<float*>(w);
+  w += align_up(sizeof(float) * size_t(a.bs) * kRankCap * 6, 256);
+  a.seg_keys = reinterpret_cast<uint32_t*>(w);
+  w += align_up(sizeof(uint32_t) * size_t(a.bs) * kRankCap, 256);
+  a.keep = w;
+  a.out = out;
+  a.out_src = out_src;
+  a.out_count = out_count;
+  a.overflow = overflow;
+
+  Y3_CHECK_CUDA(cudaMemsetAsync(a.count, 0, sizeof(int) * size_t(a.bs) * 2, stream));
+  // K1
+  nms_candidates_kernel<<<dim3((a.n_rows + 31) / 32, a.bs), 1024, 0, stream>>>(a);
+  pad_keys_kernel<<<dim3(8, a.bs), 256, 0, stream>>>(a);
+  // K2: sort candidates by confidence (descending)
+  {
+    using T = unsigned long long;
+    const int tiles = a.cap / kSortTile;
+    bitonic_local_kernel<T, true><<<dim3(tiles, a.bs), 1024, 0, stream>>>(a, a.keys, a.cap, false);
+    for (int k = 2 * kSortTile; k <= a.cap; k <<= 1) {
+      for (int j = k >> 1; j >= kSortTile; j >>= 1)
+        bitonic_global_kernel<T, true><<<dim3(a.cap / 2 / 256, a.bs), 256, 0, stream>>>(a, a.keys, a.cap, false, k, j);
+      bitonic_merge_kernel<T, true><<<dim3(tiles, a.bs), 1024, 0, stream>>>(a, a.keys, a.cap, false, k);
+    }
+  }
+  // K3
+  nms_gather_kernel<<<dim3(kRankCap / 256, a.bs), 256, 0, stream>>>(a);
+  // K4: (class, rank) ascending
+  {
+    using T = uint32_t;
+    const int tiles = kRankCap / kSortTile;
+    bitonic_local_kernel<T, false><<<dim3(tiles, a.bs), 1024, 0, stream>>>(a, a.seg_keys, kRankCap, true);
+    for (int k = 2 * kSortTile; k <= kRankCap; k <<= 1) {
+      for (int j = k >> 1; j >= kSortTile; j >>= 1)
+        bitonic_global_kernel<T, false><<<dim3(kRankCap / 2 / 256, a.bs), 256, 0, stream>>>(a, a.seg_keys, kRankCap, true, k, j);
+      bitonic_merge_kernel<T, false><<<dim3(tiles, a.bs), 1024, 0, stream>>>(a, a.seg_keys, kRankCap, true, k);
+    }
+  }
+  // K5, K6
+  nms_segments_kernel<<<dim3(a.nc, a.bs), 256, 0, stream>>>(a);
+  nms_compact_kernel<<<a.bs, 1024, 0, stream>>>(a);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}

@@ -1,0 +1,107 @@
+// yolov3_b200 — max-pool on padded NHWC bf16 (8 channels / 16 bytes per thread, coalesced along channels).
+// Covers the three pooling uses of the shipped YAMLs:
+//   * nn.MaxPool2d(2, 2, 0)                         (yolov3-tiny.yaml backbone)        k=2 stride=2 off=0
+//   * nn.ZeroPad2d([0,1,0,1]) + nn.MaxPool2d(2,1,0) (yolov3-tiny.yaml layers 11-12)    k=2 stride=1 off=0 oob_zero=1
+//   * SPP's MaxPool2d(k, 1, k//2), -inf padding     (reference models/common.py:279)   k=5 stride=1 off=-2 oob_zero=0
+//     (9x9 and 13x13 are produced by cascading the 5x5 pool, which is exact for max with -inf padding)
+#include "y3_common.cuh"
+#include "y3_internal.h"
+
+namespace y3 {
+namespace {
+
+struct PoolArgs {
+  const __nv_bfloat16* in;
+  __nv_bfloat16* out;
+  int in_ld, in_coff, out_ld, out_coff;
+  int n, h, w, c8;  // input size (unpadded), channel groups of 8
+  int ho, wo;
+  int k, stride, off, oob_zero;
+};
+
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&a), y = *reinterpret_cast<__nv_bfloat162*>(&b);
+  __nv_bfloat162 m = __hmax2(x, y);
+  return *reinterpret_cast<uint32_t*>(&m);
+}
+
+__global__ void __launch_bounds__(256) maxpool_kernel(const PoolArgs p) {
+  const long long total = static_cast<long long>(p.n) * p.ho * p.wo * p.c8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % p.c8);
+    long long t = i / p.c8;
+    const int x = static_cast<int>(t % p.wo);
+    t /= p.wo;
+    const int y = static_cast<int>(t % p.ho);
+    const int n = static_cast<int>(t / p.ho);
+    const uint32_t ninf = 0xFF80FF80u;  // two bf16 -inf
+    uint4 m = make_uint4(ninf, ninf, ninf, ninf);
+    bool saw_oob = false;
+    for (int dy = 0; dy < p.k; ++dy) {
+      const int yy = y * p.stride + p.off + dy;
+      for (int dx = 0; dx < p.k; ++dx) {
+        const int xx = x * p.stride + p.off + dx;
+        if (yy < 0 || yy >= p.h || xx < 0 || xx >= p.w) {
+          saw_oob = true;
+          continue;
+        }
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+            p.in + ((static_cast<long long>(n) * (p.h + 2) + yy + 1) * (p.w + 2) + xx + 1) * p.in_ld + p.in_coff + cg * 8));
+        m.x = bf16x2_max(m.x, v.x);
+        m.y = bf16x2_max(m.y, v.y);
+        m.z = bf16x2_max(m.z, v.z);
+        m.w = bf16x2_max(m.w, v.w);
+      }
+    }
+    if (saw_oob && p.oob_zero) {
+      m.x = bf16x2_max(m.x, 0u);
+      m.y = bf16x2_max(m.y, 0u);
+      m.z = bf16x2_max(m.z, 0u);
+      m.w = bf16x2_max(m.w, 0u);
+    }
+    *reinterpret_cast<uint4*>(p.out + ((static_cast<long long>(n) * (p.ho + 2) + y + 1) * (p.wo + 2) + x + 1) * p.out_ld +
+                              p.out_coff + cg * 8) = m;
+  }
+}
+
+}  // namespace
+
+int pool_launch(const y3_pool_desc& d, cudaStream_t stream) {
+  Y3_REQUIRE(d.in && d.out && d.n > 0 && d.h > 0 && d.w > 0 && d.c > 0 && d.c % 8 == 0, "pool: bad shape");
+  Y3_REQUIRE(d.in_ld % 8 == 0 && d.in_coff % 8 == 0 && d.out_ld % 8 == 0 && d.out_coff % 8 == 0 &&
+                 d.in_coff + d.c <= d.in_ld && d.out_coff + d.c <= d.out_ld,
+             "pool: bad channel slice");
+  Y3_REQUIRE(d.k >= 1 && d.k <= 13 && d.stride >= 1 && d.ho > 0 && d.wo > 0, "pool: bad window");
+  PoolArgs a;
+  a.in = static_cast<const __nv_bfloat16*>(d.in);
+  a.out = static_cast<__nv_bfloat16*>(d.out);
+  a.in_ld = d.in_ld;
+  a.in_coff = d.in_coff;
+  a.out_ld = d.out_ld;
+  a.out_coff = d.out_coff;
+  a.n = d.n;
+  a.h = d.h;
+  a.w = d.w;
+  a.c8 = d.c / 8;
+  a.ho = d.ho;
+  a.wo = d.wo;
+  a.k = d.k;
+  a.stride = d.stride;
+  a.off = d.off;
+  a.oob_zero = d.oob_zero;
+  const long long total = static_cast<long long>(a.n) * a.ho * a.wo * a.c8;
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  maxpool_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(a);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+}  // namespace y3
+
+extern "C" int y3_maxpool_fwd(const y3_pool_desc* d, y3_stream_t stream) {
+  if (!d) return y3::set_error(Y3_ERR_BAD_ARG, "pool: null descriptor");
+  return y3::pool_launch(*d, static_cast<cudaStream_t>(stream));
+}

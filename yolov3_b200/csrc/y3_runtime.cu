@@ -101,3 +101,16 @@ extern "C" int y3_device_check(void) {
   if (major != 10) return y3::set_error(Y3_ERR_UNSUPPORTED, "device compute capability %d.x is not sm_100", major);
   return Y3_OK;
 }
+
+extern "C" int64_t y3_abi_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(y3_conv_desc);
+    case 1: return sizeof(y3_first_desc);
+    case 2: return sizeof(y3_pool_desc);
+    case 3: return sizeof(y3_detect_level);
+    case 4: return sizeof(y3_decode_desc);
+    case 5: return sizeof(y3_op);
+    case 6: return sizeof(y3_nms_params);
+  }
+  return -1;
+}

@@ -64,12 +64,40 @@ def conv_bn_act(x: PaddedNHWC, weight, bias, c_out, k=1, s=1, act=ACT_SILU, out=
     return out if raw is None else raw
 
 
-def conv_first(x_nchw: torch.Tensor, weight27, bias, c_out, out: PaddedNHWC | None = None):
+def first_desc(x: torch.Tensor, weight27, bias, c_out, out: PaddedNHWC, in_div=0.0):
+    from . import tensors as _t
+
+    assert (x.is_cuda or _t.DRY_RUN) and x.is_contiguous() and x.dim() == 4 and x.shape[1] == 3
+    assert x.dtype in (torch.float32, torch.uint8), "first conv takes fp32 or uint8 NCHW images"
+    d = _lib.FirstDesc()
+    d.in_, d.in_dtype, d.in_div = x.data_ptr(), (_lib.IN_U8 if x.dtype == torch.uint8 else _lib.IN_F32), float(in_div)
+    d.n, d.h, d.w = x.shape[0], x.shape[2], x.shape[3]
+    d.weight, d.bias, d.c_out = weight27.data_ptr(), bias.data_ptr(), c_out
+    d.out, d.out_ld, d.out_coff = out.ptr, out.ld, out.coff
+    return d
+
+
+def conv_first(x_nchw: torch.Tensor, weight27, bias, c_out, out: PaddedNHWC | None = None, in_div=0.0):
     x = x_nchw.contiguous()
-    assert x.dtype == torch.float32 and x.shape[1] == 3
     n, _, h, w = x.shape
     if out is None:
         out = PaddedNHWC.zeros(n, h, w, c_out, device=x.device)
-    _lib.check(_lib.lib().y3_conv_first_fwd(x.data_ptr(), n, h, w, weight27.data_ptr(), bias.data_ptr(), c_out, out.ptr,
-                                            out.ld, out.coff, _stream()), "y3_conv_first_fwd")
+    d = first_desc(x, weight27, bias, c_out, out, in_div)
+    _lib.check(_lib.lib().y3_conv_first_fwd(C.byref(d), _stream()), "y3_conv_first_fwd")
+    return out
+
+
+def pool_desc(x: PaddedNHWC, out: PaddedNHWC, k, stride, off, oob_zero=False):
+    d = _lib.PoolDesc()
+    d.in_, d.in_ld, d.in_coff = x.ptr, x.ld, x.coff
+    d.out, d.out_ld, d.out_coff = out.ptr, out.ld, out.coff
+    d.n, d.h, d.w, d.c = x.n, x.h, x.w, x.c
+    d.ho, d.wo = out.h, out.w
+    d.k, d.stride, d.off, d.oob_zero = k, stride, off, int(bool(oob_zero))
+    return d
+
+
+def maxpool(x: PaddedNHWC, out: PaddedNHWC, k, stride, off, oob_zero=False):
+    d = pool_desc(x, out, k, stride, off, oob_zero)
+    _lib.check(_lib.lib().y3_maxpool_fwd(C.byref(d), _stream()), "y3_maxpool_fwd")
     return out

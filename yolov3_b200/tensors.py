@@ -16,11 +16,14 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+DRY_RUN = False  # set only by Engine(dry_run=True): lets the lowering logic be exercised without a GPU (no launches)
+
+
 class PaddedNHWC:
     __slots__ = ("buf", "coff", "c")
 
     def __init__(self, buf: torch.Tensor, coff: int = 0, c: int | None = None):
-        assert buf.dtype == torch.bfloat16 and buf.dim() == 4 and buf.is_contiguous() and buf.is_cuda
+        assert buf.dtype == torch.bfloat16 and buf.dim() == 4 and buf.is_contiguous() and (buf.is_cuda or DRY_RUN)
         self.buf, self.coff = buf, coff
         self.c = buf.shape[3] - coff if c is None else c
         assert 0 <= coff and coff + self.c <= buf.shape[3]
