@@ -84,6 +84,18 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def aggregate(ms_local: float, dev) -> float:
+    """Max over ranks of a locally event-timed duration (one process per GPU; NCCL on GPUs, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return ms_local
+    t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def build_model(device):
     import torch
 
@@ -221,10 +233,8 @@ def main():
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    ms_total = aggregate(ms_total, dev)
     if world > 1:
-        t = torch.tensor([ms_total], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
         dist.barrier()
     value = world * BS * args.steps / (ms_total / 1e3)
 
@@ -243,10 +253,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+    ms_e2e = aggregate(ms_e2e, dev)
     e2e = world * BS * args.steps / (ms_e2e / 1e3)
 
     if rank != 0:

@@ -38,7 +38,8 @@ int y3_last_error(char* buf, size_t n);
 /* Y3_OK iff the current CUDA device is compute capability 10.x. */
 int y3_device_check(void);
 /* sizeof() of the ABI structs, for bindings to verify their mirror definitions:
- * 0 y3_conv_desc, 1 y3_first_desc, 2 y3_pool_desc, 3 y3_detect_level, 4 y3_decode_desc, 5 y3_op, 6 y3_nms_params. */
+ * 0 y3_conv_desc, 1 y3_first_desc, 2 y3_pool_desc, 3 y3_detect_level, 4 y3_decode_desc, 5 y3_op, 6 y3_nms_params,
+ * 7 y3_loss_desc. */
 int64_t y3_abi_sizeof(int32_t which);
 
 /* ---------------------------------------------------------------------------------------------------------------
@@ -150,6 +151,37 @@ int32_t y3_nms_default_capacity(int32_t n_rows, int32_t nc, int32_t multi_label)
 int64_t y3_nms_workspace_bytes(int32_t bs, int32_t cap);
 int y3_nms_batched(const float* pred, const y3_nms_params* params, void* workspace, int64_t workspace_bytes, float* out,
                    int32_t* out_src, int32_t* out_count, int32_t* overflow, y3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Pairwise IoU.  Replaces box_iou (ultralytics; re-exported utils/metrics.py:10, used val.py:176): xyxy boxes,
+ * out[i*m + j] = inter / (area1 + area2 - inter + eps).  box1 [n,4], box2 [m,4] fp32, 16-byte aligned. */
+int y3_box_iou(const float* box1, int32_t n, const float* box2, int32_t m, float eps, float* out, y3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Training loss, forward + backward.  Replaces ComputeLoss.__call__ / build_targets (utils/loss.py:131-244) with
+ * bbox_iou(CIoU) and BCEWithLogitsLoss(pos_weight), for fl_gamma = 0, autobalance off, gr = 1 (the shipped hyps).
+ *   p[l]     fp32 [bs, na, ny_l, nx_l, nc+5] raw logits (train-mode Detect output, models/yolo.py:110)
+ *   grad[l]  same shape (or NULL): receives d(out[0])/dp[l] * grad_scale
+ *   targets  fp32 [nt, 6] = (image, class, x, y, w, h) normalised (collate_fn, utils/dataloaders.py:825-830)
+ *   out      fp32 [4] = ((lbox+lobj+lcls)*bs, lbox, lobj, lcls)   (loss.py:181)
+ */
+typedef struct y3_loss_desc {
+  int32_t nl, bs, na, nc;
+  const float* p[Y3_MAX_LEVELS];
+  float* grad[Y3_MAX_LEVELS];
+  int32_t ny[Y3_MAX_LEVELS], nx[Y3_MAX_LEVELS];
+  float anchors[Y3_MAX_LEVELS][Y3_MAX_ANCHORS][2]; /* Detect.anchors, grid units */
+  const float* targets;
+  int32_t nt;
+  float box, obj, cls;       /* hyp gains (already rescaled as train.py:326-329) */
+  float cls_pw, obj_pw;      /* BCE pos_weight */
+  float anchor_t;
+  float cp, cn;              /* smooth_bce(label_smoothing) targets */
+  float balance[Y3_MAX_LEVELS];
+  float grad_scale;          /* upstream gradient of out[0] (1 for loss.backward()) */
+} y3_loss_desc;
+int64_t y3_loss_workspace_bytes(const y3_loss_desc* d);
+int y3_loss_fwd_bwd(const y3_loss_desc* d, void* workspace, int64_t workspace_bytes, float* out, y3_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Whole-graph executor.  Replaces BaseModel._forward_once (models/yolo.py:135-147): the Python loop over nn.Modules

@@ -1,0 +1,134 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every symbol include/yolov3_b200.h
+declares, the ctypes mirrors match the C structs, the YAML lowering reproduces the reference graph contract, the
+Python seams keep the reference's error behaviour, and the multi-rank aggregation works over gloo."""
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+import yolo_oracle as O
+
+ROOT = Path(__file__).resolve().parents[1]
+CFG = ROOT / "yolov3_b200" / "cfg"
+
+
+def test_library_exports_every_declared_symbol():
+    from yolov3_b200 import _lib
+
+    L = _lib.lib()
+    hdr = (ROOT / "include" / "yolov3_b200.h").read_text()
+    names = set(re.findall(r"^\s*(?:int|int32_t|int64_t|void)\s+(y3_\w+)\s*\(", hdr, flags=re.M))
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+    assert set(_lib.SYMBOLS) == names, (set(_lib.SYMBOLS) ^ names)
+    assert L.y3_version() >= 100
+    assert L.y3_conv_cout_pad(255) == 256 and L.y3_conv_cout_pad(32) == 32 and L.y3_conv_cout_pad(1024) == 1024
+    assert L.y3_nms_default_capacity(25200, 80, 0) == 32768
+    assert L.y3_nms_workspace_bytes(32, 32768) > 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from yolov3_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "_LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(_lib.Y3Error, match="no CPU or PyTorch fallback"):
+        _lib.lib()
+
+
+@pytest.mark.parametrize("name", ["yolov3", "yolov3-spp", "yolov3-tiny"])
+def test_graph_contract(name):
+    from yolov3_b200 import graph
+    from yolov3_b200.model import Model
+
+    cfg, _ = graph.resolve_cfg(CFG / f"{name}.yaml")
+    nodes, save = graph.parse(cfg)
+    onodes, osave = O.parse_graph(CFG / f"{name}.yaml")
+    assert save == osave
+    assert [(n.type, n.n, n.c_out) for n in nodes] == [(n["type"], n["n"], n["c_out"]) for n in onodes]
+    assert graph.strides(nodes) == O.detect_strides(onodes)
+    assert [(c.prefix, c.c1, c.c2, c.k, c.s) for c in graph.conv_specs(nodes)] == O.conv_prefixes(onodes)
+    m = Model(CFG / f"{name}.yaml", device="cpu")
+    params = O.init_params(CFG / f"{name}.yaml", seed=0)
+    assert list(m.state_dict().keys()) == list(params.keys())
+    assert torch.allclose(m.detect.anchors, params[f"model.{m.detect.i}.anchors"])
+    missing, unexpected = m.load_state_dict(params)
+    assert not missing and not unexpected
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({"bogus": torch.zeros(1)})
+    n_params = sum(v.numel() for k, v in m.params.items() if "running" not in k and not k.endswith("anchors"))
+    assert n_params == {"yolov3": 61949149, "yolov3-spp": 62998749, "yolov3-tiny": 8852366}[name]
+
+
+def test_lowering_zero_copy_concat_and_fused_upsample():
+    from yolov3_b200 import _lib
+    from yolov3_b200.model import Engine, Model
+
+    m = Model(CFG / "yolov3.yaml", device="cpu")
+    e = Engine(m, 2, 64, 96, dry_run=True)
+    kinds = [o.kind for o in e.op_list]
+    assert kinds.count(_lib.OP_CONV) == 74 and kinds.count(_lib.OP_CONV_FIRST) == 1 and kinds[-1] == _lib.OP_DECODE
+    convs = [o.conv for o in e.op_list if o.kind == _lib.OP_CONV]
+    ups = [c for c in convs if c.upsample]
+    assert [(c.c_in, c.c_out, c.out_ld, c.out_coff) for c in ups] == [(512, 256, 768, 0), (256, 128, 384, 0)]
+    cat18 = e.bufs[18]
+    # node 8's last bottleneck writes channels [256,768) of the node-18 buffer; node 9 reads them back from there
+    w = [c for c in convs if c.out == cat18.ptr and not c.upsample]
+    assert [(c.out_ld, c.out_coff, c.c_out) for c in w] == [(768, 256, 512)] and w[0].res
+    r = [c for c in convs if c.in_ == cat18.ptr]
+    assert sorted((c.in_coff, c.c_in, c.stride) for c in r) == [(0, 768, 1), (256, 512, 2)]
+    heads = [c for c in convs if c.raw]
+    assert [(c.c_in, c.c_out, c.act) for c in heads] == [(256, 255, 0), (512, 255, 0), (1024, 255, 0)]
+    assert e.z.shape == (2, 3 * (8 * 12 + 4 * 6 + 2 * 3), 85)
+    with pytest.raises(_lib.Y3Error):
+        e.run(None)
+    with pytest.raises(ValueError):
+        Engine(m, 1, 100, 64, dry_run=True)  # not a multiple of the max stride
+
+
+def test_reference_error_behaviour_at_the_seams():
+    from yolov3_b200.model import Model
+    from yolov3_b200.nms import non_max_suppression
+
+    with pytest.raises(AssertionError):
+        non_max_suppression(torch.zeros(1, 10, 85), conf_thres=1.2)
+    with pytest.raises(AssertionError):
+        non_max_suppression(torch.zeros(1, 10, 85), iou_thres=-1)
+    with pytest.raises(AssertionError, match="no CPU path"):
+        non_max_suppression(torch.zeros(1, 10, 85))
+    m = Model(CFG / "yolov3-tiny.yaml", device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 64, 64), augment=True)
+
+
+WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from bench import aggregate
+dist.init_process_group("gloo")
+r = dist.get_rank()
+ms = aggregate(100.0 + 50.0 * r, torch.device("cpu"))       # max over ranks
+assert ms == 150.0, ms
+if r == 0:
+    print("AGG", ms, dist.get_world_size() * 32 * 10 / (ms / 1e3))
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_multi_rank_aggregation_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29653", str(script), str(ROOT)], capture_output=True, text=True,
+                       timeout=240, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("AGG")][0].split()
+    assert float(line[1]) == 150.0 and abs(float(line[2]) - 2 * 32 * 10 / 0.15) < 1e-6

@@ -89,6 +89,20 @@ class NmsParams(C.Structure):
                 ("cap", C.c_int32), ("classes", C.POINTER(C.c_int32)), ("n_classes", C.c_int32)]
 
 
+class LossDesc(C.Structure):
+    """struct y3_loss_desc."""
+
+    _fields_ = [("nl", C.c_int32), ("bs", C.c_int32), ("na", C.c_int32), ("nc", C.c_int32),
+                ("p", C.c_void_p * MAX_LEVELS), ("grad", C.c_void_p * MAX_LEVELS),
+                ("ny", C.c_int32 * MAX_LEVELS), ("nx", C.c_int32 * MAX_LEVELS),
+                ("anchors", ((C.c_float * 2) * MAX_ANCHORS) * MAX_LEVELS),
+                ("targets", C.c_void_p), ("nt", C.c_int32),
+                ("box", C.c_float), ("obj", C.c_float), ("cls", C.c_float),
+                ("cls_pw", C.c_float), ("obj_pw", C.c_float), ("anchor_t", C.c_float),
+                ("cp", C.c_float), ("cn", C.c_float),
+                ("balance", C.c_float * MAX_LEVELS), ("grad_scale", C.c_float)]
+
+
 def _declare(lib):
     i32, vp, sz = C.c_int32, C.c_void_p, C.c_size_t
     sigs = {
@@ -100,6 +114,9 @@ def _declare(lib):
         "y3_abi_sizeof": ([i32], C.c_int64),
         "y3_conv_first_fwd": ([C.POINTER(FirstDesc), vp], C.c_int),
         "y3_maxpool_fwd": ([C.POINTER(PoolDesc), vp], C.c_int),
+        "y3_box_iou": ([vp, i32, vp, i32, C.c_float, vp, vp], C.c_int),
+        "y3_loss_workspace_bytes": ([C.POINTER(LossDesc)], C.c_int64),
+        "y3_loss_fwd_bwd": ([C.POINTER(LossDesc), vp, C.c_int64, vp, vp], C.c_int),
         "y3_model_create": ([C.POINTER(Op), i32, C.POINTER(vp)], C.c_int),
         "y3_model_forward": ([vp, vp, vp], C.c_int),
         "y3_model_num_launches": ([vp], i32),
@@ -132,7 +149,7 @@ def lib():
             )
         _lib = C.CDLL(str(_LIB_PATH))
         SYMBOLS.update(_declare(_lib))
-        for which, st in enumerate((ConvDesc, FirstDesc, PoolDesc, DetectLevel, DecodeDesc, Op, NmsParams)):
+        for which, st in enumerate((ConvDesc, FirstDesc, PoolDesc, DetectLevel, DecodeDesc, Op, NmsParams, LossDesc)):
             if _lib.y3_abi_sizeof(which) != C.sizeof(st):
                 raise Y3Error(f"ABI mismatch: sizeof({st.__name__}) is {C.sizeof(st)} here, "
                               f"{_lib.y3_abi_sizeof(which)} in {_LIB_PATH.name}; rebuild the library")

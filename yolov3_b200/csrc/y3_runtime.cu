@@ -111,6 +111,7 @@ extern "C" int64_t y3_abi_sizeof(int32_t which) {
     case 4: return sizeof(y3_decode_desc);
     case 5: return sizeof(y3_op);
     case 6: return sizeof(y3_nms_params);
+    case 7: return sizeof(y3_loss_desc);
   }
   return -1;
 }
