@@ -43,7 +43,7 @@ int y3_device_check(void);
 int64_t y3_abi_sizeof(int32_t which);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Conv + folded-BN + SiLU (+ residual add, + nearest-2x upsample, + concat-offset store, or Detect raw store).
+ * Conv + folded-BN + SiLU (+ residual add, + nearest-2x upsample, + concat-offset store, or fp32 head store).
  * Replaces Conv.forward_fuse (models/common.py:77-81) after BaseModel.fuse (models/yolo.py:163-172), the shortcut add
  * of Bottleneck.forward (common.py:163-165), nn.Upsample+Concat (models/yolov3.yaml:43-44,51-52) and Detect.m[i]
  * (models/yolo.py:96-98).  tcgen05 implicit GEMM; c_in % 16 == 0, c_out_pad = c_out rounded up to the tile N.
@@ -63,8 +63,9 @@ typedef struct y3_conv_desc {
   const void* res;       /* optional residual (NULL = none): padded NHWC bf16 with the conv-output geometry */
   int32_t res_ld, res_coff;
   int32_t upsample;      /* 1: replicate every output pixel 2x2 into `out` */
-  float* raw;            /* Detect head (NULL = off): fp32 [n, na, ho, wo, no] logits, c_out == na*no; `out` unused */
-  int32_t na, no;
+  float* out_f32;        /* Detect heads (NULL = off): fp32 pixel-major [n*ho*wo, out_f32_ld] instead of `out`;
+                            columns [0, c_out_pad) of every row are written (pad columns = 0) */
+  int32_t out_f32_ld;    /* >= c_out_pad, multiple of 4 */
   int32_t* err;          /* optional device int32 error word written by the in-kernel watchdog */
 } y3_conv_desc;
 int y3_conv_bn_act_fwd(const y3_conv_desc* d, y3_stream_t stream);
@@ -117,7 +118,11 @@ int y3_padded_nhwc_to_nchw(const void* src, int32_t src_ld, int32_t src_coff, in
 #define Y3_MAX_LEVELS 5
 #define Y3_MAX_ANCHORS 6
 typedef struct y3_detect_level {
-  const float* raw;                 /* fp32 [bs, na, ny, nx, no] logits (the reference's x[i], models/yolo.py:98) */
+  const float* raw;                 /* y3_detect_decode_fwd: fp32 [bs, na, ny, nx, no] logits (the reference's x[i]) */
+  const float* head;                /* y3_detect_head_decode_fwd: head-conv output, fp32 [bs*ny*nx, head_ld],
+                                       column a*no + k (y3_conv_desc.out_f32) */
+  int32_t head_ld;
+  float* raw_out;                   /* y3_detect_head_decode_fwd: optional fp32 [bs, na, ny, nx, no] (models/yolo.py:98) */
   int32_t ny, nx;
   float stride;                     /* Detect.stride[i] */
   float anchor_w[Y3_MAX_ANCHORS];   /* anchors[i] * stride[i], pixels (anchor_grid, models/yolo.py:122) */
@@ -125,6 +130,14 @@ typedef struct y3_detect_level {
 } y3_detect_level;
 int y3_detect_decode_fwd(const y3_detect_level* levels, int32_t nl, int32_t bs, int32_t na, int32_t no, float* z,
                          y3_stream_t stream);
+typedef struct y3_decode_desc {
+  y3_detect_level levels[Y3_MAX_LEVELS];
+  int32_t nl, bs, na, no;
+  float* z;                         /* [bs, sum_l na*ny*nx, no] or NULL (training: logits only) */
+} y3_decode_desc;
+/* Fused head transpose + decode used by the graph executor: one pass from the head convs' pixel-major fp32 output to
+ * z and to the reference-layout logits. */
+int y3_detect_head_decode_fwd(const y3_decode_desc* d, y3_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Batched NMS.  Replaces non_max_suppression (utils/general.py:630-750) incl. torchvision.ops.nms (:733) for nm=0,
@@ -192,11 +205,6 @@ int y3_loss_fwd_bwd(const y3_loss_desc* d, void* workspace, int64_t workspace_by
 #define Y3_OP_CONV 2
 #define Y3_OP_MAXPOOL 3
 #define Y3_OP_DECODE 4
-typedef struct y3_decode_desc {
-  y3_detect_level levels[Y3_MAX_LEVELS];
-  int32_t nl, bs, na, no;
-  float* z;
-} y3_decode_desc;
 typedef struct y3_op {
   int32_t kind;          /* Y3_OP_*: selects which member below is read */
   y3_conv_desc conv;

@@ -212,7 +212,7 @@ class OracleModel:
         bn = [P[prefix + ".bn." + n] for n in ("weight", "bias", "running_mean", "running_var")]
         if self.fused:
             w, b = fold_bn(w, *bn)
-            if self.weight_dtype is not None and w.shape[1] != 3:  # the CUDA path keeps layer 0 (c_in=3) in fp32
+            if self.weight_dtype is not None:
                 w = w.to(self.weight_dtype).float()
             y = F.conv2d(x, w, b, stride=s, padding=k // 2)
         else:
@@ -229,6 +229,7 @@ class OracleModel:
     def forward_features(self, x, taps=None):
         """_forward_once, models/yolo.py:135-147.  Returns the list fed to Detect; fills ``taps`` {layer: tensor}."""
         y = []
+        x = self._round(x)  # layer 0 of the CUDA path feeds bf16 MMAs: the image itself is rounded to bf16
         for nd in self.nodes:
             i, f, t = nd["i"], nd["f"], nd["type"]
             if t == "Detect":

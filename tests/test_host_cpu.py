@@ -82,7 +82,7 @@ def test_lowering_zero_copy_concat_and_fused_upsample():
     assert [(c.out_ld, c.out_coff, c.c_out) for c in w] == [(768, 256, 512)] and w[0].res
     r = [c for c in convs if c.in_ == cat18.ptr]
     assert sorted((c.in_coff, c.c_in, c.stride) for c in r) == [(0, 768, 1), (256, 512, 2)]
-    heads = [c for c in convs if c.raw]
+    heads = [c for c in convs if c.out_f32]
     assert [(c.c_in, c.c_out, c.act) for c in heads] == [(256, 255, 0), (512, 255, 0), (1024, 255, 0)]
     assert e.z.shape == (2, 3 * (8 * 12 + 4 * 6 + 2 * 3), 85)
     with pytest.raises(_lib.Y3Error):

@@ -27,7 +27,7 @@ class ConvDesc(C.Structure):
         ("out", C.c_void_p), ("out_ld", C.c_int32), ("out_coff", C.c_int32),
         ("res", C.c_void_p), ("res_ld", C.c_int32), ("res_coff", C.c_int32),
         ("upsample", C.c_int32),
-        ("raw", C.c_void_p), ("na", C.c_int32), ("no", C.c_int32),
+        ("out_f32", C.c_void_p), ("out_f32_ld", C.c_int32),
         ("err", C.c_void_p),
     ]
 
@@ -38,7 +38,8 @@ MAX_LEVELS, MAX_ANCHORS = 5, 6
 class DetectLevel(C.Structure):
     """struct y3_detect_level."""
 
-    _fields_ = [("raw", C.c_void_p), ("ny", C.c_int32), ("nx", C.c_int32), ("stride", C.c_float),
+    _fields_ = [("raw", C.c_void_p), ("head", C.c_void_p), ("head_ld", C.c_int32), ("raw_out", C.c_void_p),
+                ("ny", C.c_int32), ("nx", C.c_int32), ("stride", C.c_float),
                 ("anchor_w", C.c_float * MAX_ANCHORS), ("anchor_h", C.c_float * MAX_ANCHORS)]
 
 
@@ -125,6 +126,7 @@ def _declare(lib):
         "y3_nchw_to_padded_nhwc": ([vp, i32, i32, i32, i32, vp, i32, i32, vp], C.c_int),
         "y3_padded_nhwc_to_nchw": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], C.c_int),
         "y3_detect_decode_fwd": ([C.POINTER(DetectLevel), i32, i32, i32, i32, vp, vp], C.c_int),
+        "y3_detect_head_decode_fwd": ([C.POINTER(DecodeDesc), vp], C.c_int),
         "y3_nms_default_capacity": ([i32, i32, i32], i32),
         "y3_nms_workspace_bytes": ([i32, i32], C.c_int64),
         "y3_nms_batched": ([vp, C.POINTER(NmsParams), vp, C.c_int64, vp, vp, vp, vp, vp], C.c_int),

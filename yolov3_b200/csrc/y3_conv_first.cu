@@ -1,7 +1,8 @@
-// yolov3_b200 — layer-0 convolution (c_in = 3): 3x3 stride-1 pad-1 on the fp32 NCHW image with folded BN + SiLU,
-// fused with the NCHW-fp32 -> padded-NHWC-bf16 conversion.  K = 27 is too thin for an MMA tile, and the layer is
-// bandwidth-bound (24.7 FLOP/B): one thread per output pixel, fp32 FMAs against smem-broadcast weights,
-// one contiguous 2*c_out-byte store per pixel.  Also the test-only layout converters.
+// yolov3_b200 — layer-0 convolution (c_in = 3): 3x3 stride-1 pad-1 on the NCHW image (fp32, or uint8 with the /255 of
+// detect.py:190 fused) with folded BN + SiLU, fused with the NCHW -> padded-NHWC-bf16 conversion.  Bandwidth-bound
+// (24.7 FLOP/B).  v1 was one thread per pixel with fp32 FMAs (970 us @bs32, LDS/FMA-bound, see
+// profiles/r01_per_op_v1_baseline.json); this version feeds warp-level bf16 MMAs from a shared-memory patch.
+// Also the test-only layout converters.
 // Replaces Conv.forward_fuse for model.0 (reference models/common.py:77-81, models/yolov3.yaml:18).
 #include "y3_common.cuh"
 #include "y3_internal.h"
@@ -22,58 +23,97 @@ __device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p, float div) {
   return div > 0.f ? __fdiv_rn(v, div) : v;
 }
 
+// Tensor-core version (legacy warp-level mma.sync m16n8k16: K = 27 padded to 32 is far too thin for a tcgen05 tile and
+// the layer is bandwidth-bound anyway).  One block = 128 consecutive pixels of one image row; the 3x3x(128+2) input
+// patch is staged in shared memory with coalesced loads, each warp then builds the im2col A fragments for its 32 pixels
+// straight from smem, multiplies by the [32 x COUT] bf16 weight fragments held in registers, and stores bf16 NHWC.
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 template <int COUT, typename TIN>
 __global__ void __launch_bounds__(128) conv_first_kernel(const TIN* __restrict__ in, float in_div, int H, int W,
                                                          const float* __restrict__ wgt, const float* __restrict__ bias,
                                                          __nv_bfloat16* __restrict__ out, int out_ld, int out_coff) {
-  __shared__ __align__(16) float sw[27 * COUT];
-  __shared__ __align__(16) float sb[COUT];
-  for (int i = threadIdx.x; i < 27 * COUT; i += blockDim.x) sw[i] = wgt[i];
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) sb[i] = bias[i];
-  __syncthreads();
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
-  const int h = blockIdx.y, n = blockIdx.z;
-  if (w >= W) return;
-
-  float x[27];
+  constexpr int TW = 128, NT = COUT / 8;
+  __shared__ float s_in[3][3][TW + 2];
+  const int w0 = blockIdx.x * TW, h = blockIdx.y, n = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  // ---- stage the input patch (zero outside the image = the conv's padding)
+  for (int i = threadIdx.x; i < 9 * (TW + 2); i += blockDim.x) {
+    const int col = i % (TW + 2), rc = i / (TW + 2);
+    const int c = rc / 3, kh = rc - c * 3;
+    const int hh = h + kh - 1, ww = w0 + col - 1;
+    float v = 0.f;
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+      v = load_px<TIN>(in + ((static_cast<size_t>(n) * 3 + c) * H + hh) * W + ww, in_div);
+    s_in[c][kh][col] = v;
+  }
+  // ---- weight fragments: B[k][n], k = (c*3+kh)*3+kw (27 real rows, zero padded to 32)
+  uint32_t bfrag[2][NT][2];
+  int a_off[2][4];  // smem offset of the 4 k-values this lane contributes per k-step (-1 = zero padding)
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const TIN* plane = in + (static_cast<size_t>(n) * 3 + c) * H * W;
+  for (int ks = 0; ks < 2; ++ks) {
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int hh = h + kh - 1;
-      const bool row_ok = hh >= 0 && hh < H;
+    for (int j = 0; j < 4; ++j) {
+      const int k = ks * 16 + t * 2 + (j & 1) + (j >> 1) * 8;
+      a_off[ks][j] = k < 27 ? ((k / 9) * 3 + (k % 9) / 3) * (TW + 2) + k % 3 : -1;
+    }
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int ww = w + kw - 1;
-        x[(c * 3 + kh) * 3 + kw] = (row_ok && ww >= 0 && ww < W) ? load_px<TIN>(plane + static_cast<size_t>(hh) * W + ww, in_div) : 0.f;
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        const int k = ks * 16 + t * 2 + hlf * 8, co = nt * 8 + g;
+        const float lo = k < 27 ? __ldg(wgt + k * COUT + co) : 0.f;
+        const float hi = k + 1 < 27 ? __ldg(wgt + (k + 1) * COUT + co) : 0.f;
+        bfrag[ks][nt][hlf] = pack_bf16x2(lo, hi);
       }
     }
   }
-  float acc[COUT];
+  float bia[NT][2];
 #pragma unroll
-  for (int co = 0; co < COUT; ++co) acc[co] = sb[co];
-#pragma unroll
-  for (int k = 0; k < 27; ++k) {
-#pragma unroll
-    for (int co = 0; co < COUT; co += 4) {
-      const float4 wv = *reinterpret_cast<const float4*>(&sw[k * COUT + co]);
-      acc[co + 0] = fmaf(x[k], wv.x, acc[co + 0]);
-      acc[co + 1] = fmaf(x[k], wv.y, acc[co + 1]);
-      acc[co + 2] = fmaf(x[k], wv.z, acc[co + 2]);
-      acc[co + 3] = fmaf(x[k], wv.w, acc[co + 3]);
-    }
+  for (int nt = 0; nt < NT; ++nt) {
+    bia[nt][0] = __ldg(bias + nt * 8 + t * 2);
+    bia[nt][1] = __ldg(bias + nt * 8 + t * 2 + 1);
   }
-  const size_t row = (static_cast<size_t>(n) * (H + 2) + h + 1) * (W + 2) + w + 1;
-  uint4* dst = reinterpret_cast<uint4*>(out + row * out_ld + out_coff);
+  __syncthreads();
+  const float* sbase = &s_in[0][0][0];
 #pragma unroll
-  for (int q = 0; q < COUT / 8; ++q) {
-    uint4 o;
-    o.x = pack_bf16x2(silu_f(acc[q * 8 + 0]), silu_f(acc[q * 8 + 1]));
-    o.y = pack_bf16x2(silu_f(acc[q * 8 + 2]), silu_f(acc[q * 8 + 3]));
-    o.z = pack_bf16x2(silu_f(acc[q * 8 + 4]), silu_f(acc[q * 8 + 5]));
-    o.w = pack_bf16x2(silu_f(acc[q * 8 + 6]), silu_f(acc[q * 8 + 7]));
-    dst[q] = o;
+  for (int mt = 0; mt < 2; ++mt) {
+    const int px = warp * 32 + mt * 16;  // first pixel (tile-relative) of this 16-row MMA tile
+    float acc[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      // A fragment: a0 = (row g, k 2t..2t+1), a1 = (row g+8, same), a2 = (row g, k+8..), a3 = (row g+8, k+8..)
+      float v[2][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int o = a_off[ks][j];
+        v[0][j] = o >= 0 ? sbase[o + px + g] : 0.f;
+        v[1][j] = o >= 0 ? sbase[o + px + g + 8] : 0.f;
+      }
+      const uint32_t a[4] = {pack_bf16x2(v[0][0], v[0][1]), pack_bf16x2(v[1][0], v[1][1]), pack_bf16x2(v[0][2], v[0][3]),
+                             pack_bf16x2(v[1][2], v[1][3])};
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) mma_bf16_16816(acc[nt], a, bfrag[ks][nt]);
+    }
+    // C fragment: c0,c1 = (row g, cols 2t,2t+1), c2,c3 = (row g+8, same cols)
+#pragma unroll
+    for (int hlf = 0; hlf < 2; ++hlf) {
+      const int w = w0 + px + g + hlf * 8;
+      if (w >= W) continue;
+      const size_t row = (static_cast<size_t>(n) * (H + 2) + h + 1) * (W + 2) + w + 1;
+      uint32_t* dst = reinterpret_cast<uint32_t*>(out + row * out_ld + out_coff);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+        dst[nt * 4 + t] = pack_bf16x2(silu_fast(acc[nt][hlf * 2 + 0] + bia[nt][0]), silu_fast(acc[nt][hlf * 2 + 1] + bia[nt][1]));
+    }
   }
 }
 

@@ -10,9 +10,11 @@
 //   * a stride-2 conv reads the same buffer through a 5-D view (2*ld, (w+2)/2, 2, (h+2)/2, n) that splits rows and
 //     columns by parity; the A tile of tap (r,s) for a TH x TW patch of output pixels is one 5-D TMA box ("patch").
 //   * weights are bf16 [cout_pad, taps*cin] (K-major); B tile = [BLOCK_N x BLOCK_K] box.
-// Warp roles (192 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread
-// MMA issuer, warps 2-5 = epilogue (TMEM -> registers -> global).  smem ring of STAGES {A,B} tiles; two accumulator
-// buffers in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
+// Warp roles (320 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread
+// MMA issuer, warps 2-9 = epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter, each taking half of
+// the tile's columns).  smem ring of STAGES {A,B} tiles; two accumulator buffers in TMEM so the epilogue of tile i
+// overlaps the main loop of tile i+1.  Measured on B200 (profiles/r01_*): with 4 epilogue warps the 1x1 and small-K
+// layers were epilogue-bound (MUFU + issue), hence 8 warps, a one-MUFU SiLU and register-prefetched residuals.
 #include <cuda_bf16.h>
 
 #include "y3_common.cuh"
@@ -23,7 +25,8 @@ namespace y3 {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kThreads = 192;
+constexpr int kEpilogueWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpilogueWarps;
 constexpr int kSmemBudget = 200 * 1024;  // ring buffers; barriers + alignment slack come on top (227 KB max per CTA)
 
 template <int BLOCK_N, int BLOCK_K>
@@ -72,7 +75,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], 32 * kEpilogueWarps);
     }
     fence_mbar_init();
   }
@@ -158,8 +161,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5 = 128 threads)
-    const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    // ------------------------------------------------------------------ epilogue (warps 2..9 = 256 threads)
+    const int quarter = warp & 3;             // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int half = (warp - 2) >> 2;         // which half of the tile's columns this warp converts
+    constexpr int kColsPerWarp = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;
+    const int c_begin = BLOCK_N >= 64 ? half * kColsPerWarp : 0;
+    const bool active = BLOCK_N >= 64 || half == 0;
     const int m = quarter * 32 + lane;
     int iter = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
@@ -188,83 +195,98 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         ox = (t % p.tiles_w) * p.tw + tx;
         valid = ty < p.th && oy < p.ho && ox < p.wo;
       }
+      valid = valid && active;
       const int oh = p.mode == 0 ? p.hp - 2 : p.ho;  // conv-output height/width (unpadded)
       const int ow = p.mode == 0 ? p.wp - 2 : p.wo;
       const long long conv_row = (static_cast<long long>(img) * (oh + 2) + oy + 1) * (ow + 2) + ox + 1;
-      const __nv_bfloat16* res_ptr = p.res ? p.res + conv_row * p.res_ld + p.res_coff + n0 : nullptr;
+      const __nv_bfloat16* res_ptr = (p.res && valid) ? p.res + conv_row * p.res_ld + p.res_coff + n0 : nullptr;
       __nv_bfloat16* out_ptr = nullptr;
+      float* f32_ptr = nullptr;
       long long up_row_stride = 0;
-      if (p.out) {
-        if (p.upsample) {
-          const int w2 = 2 * ow + 2;
-          const long long r00 = (static_cast<long long>(img) * (2 * oh + 2) + 2 * oy + 1) * w2 + 2 * ox + 1;
-          out_ptr = p.out + r00 * p.out_ld + p.out_coff + n0;
-          up_row_stride = static_cast<long long>(w2) * p.out_ld;
-        } else {
-          out_ptr = p.out + conv_row * p.out_ld + p.out_coff + n0;
-        }
+      if (p.out_f32) {
+        f32_ptr = p.out_f32 + ((static_cast<long long>(img) * oh + oy) * ow + ox) * p.out_f32_ld + n0;
+      } else if (p.upsample) {
+        const int w2 = 2 * ow + 2;
+        const long long r00 = (static_cast<long long>(img) * (2 * oh + 2) + 2 * oy + 1) * w2 + 2 * ox + 1;
+        out_ptr = p.out + r00 * p.out_ld + p.out_coff + n0;
+        up_row_stride = static_cast<long long>(w2) * p.out_ld;
+      } else {
+        out_ptr = p.out + conv_row * p.out_ld + p.out_coff + n0;
+      }
+      // residual of the first chunk is requested before waiting for the accumulator: its latency hides behind the MMAs
+      uint4 rcur[4];
+      if (res_ptr) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rcur[q] = __ldg(reinterpret_cast<const uint4*>(res_ptr + c_begin) + q);
       }
 
       mbar_wait(&tfull_bar[as], aphase, p.err, 4);  // accumulator complete
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
+      if (active) {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(t_addr + c, v);
-        tmem_ld_wait();
-        if (!valid) continue;
-        float x[32];
+        for (int c = c_begin; c < c_begin + kColsPerWarp; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(t_addr + c, v);
+          uint4 rnext[4];
+          const bool more = c + 32 < c_begin + kColsPerWarp;
+          if (res_ptr && more) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
-          x[j + 0] = __uint_as_float(v[j + 0]) + b.x;
-          x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
-          x[j + 2] = __uint_as_float(v[j + 2]) + b.z;
-          x[j + 3] = __uint_as_float(v[j + 3]) + b.w;
-        }
-        if (p.act == Y3_ACT_SILU) {
+            for (int q = 0; q < 4; ++q) rnext[q] = __ldg(reinterpret_cast<const uint4*>(res_ptr + c + 32) + q);
+          }
+          tmem_ld_wait();
+          if (valid) {
+            float x[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) x[j] = silu_f(x[j]);
-        }
-        if (p.raw) {
-          // Detect head: fp32 logits in the reference's [n, na, ny, nx, no] layout (models/yolo.py:98)
-#pragma unroll 1
-          for (int j = 0; j < 32; ++j) {
-            const int co = n0 + c + j;
-            if (co < p.cout) {
-              const int a = co / p.no, k = co - a * p.no;
-              p.raw[(((static_cast<long long>(img) * p.na + a) * oh + oy) * ow + ox) * p.no + k] = x[j];
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
+              x[j + 0] = __uint_as_float(v[j + 0]) + b.x;
+              x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
+              x[j + 2] = __uint_as_float(v[j + 2]) + b.z;
+              x[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+            }
+            if (p.act == Y3_ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = silu_fast(x[j]);
+            }
+            if (f32_ptr) {
+              // fp32 pixel-major store (Detect heads): 128 contiguous bytes per thread and chunk
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                reinterpret_cast<float4*>(f32_ptr + c)[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
+            } else {
+              if (res_ptr) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint32_t rr[4] = {rcur[q].x, rcur[q].y, rcur[q].z, rcur[q].w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = unpack_bf16x2(rr[e]);
+                    x[q * 8 + e * 2 + 0] += f.x;
+                    x[q * 8 + e * 2 + 1] += f.y;
+                  }
+                }
+              }
+              uint4 o[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                o[q].x = pack_bf16x2(x[q * 8 + 0], x[q * 8 + 1]);
+                o[q].y = pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]);
+                o[q].z = pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]);
+                o[q].w = pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]);
+              }
+              const int reps = p.upsample ? 4 : 1;
+              for (int rep = 0; rep < reps; ++rep) {
+                uint4* dst = reinterpret_cast<uint4*>(out_ptr + (rep >> 1) * up_row_stride + (rep & 1) * p.out_ld + c);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dst[q] = o[q];
+              }
             }
           }
-          continue;
-        }
-        if (res_ptr) {
+          if (res_ptr && more) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint4 r = __ldg(reinterpret_cast<const uint4*>(res_ptr + c) + q);
-            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = unpack_bf16x2(rr[e]);
-              x[q * 8 + e * 2 + 0] += f.x;
-              x[q * 8 + e * 2 + 1] += f.y;
-            }
+            for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
           }
-        }
-        uint4 o[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          o[q].x = pack_bf16x2(x[q * 8 + 0], x[q * 8 + 1]);
-          o[q].y = pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]);
-          o[q].z = pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]);
-          o[q].w = pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]);
-        }
-        const int reps = p.upsample ? 4 : 1;
-        for (int rep = 0; rep < reps; ++rep) {
-          uint4* dst = reinterpret_cast<uint4*>(out_ptr + (rep >> 1) * up_row_stride + (rep & 1) * p.out_ld + c);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q] = o[q];
         }
       }
       tc_fence_before();
@@ -327,9 +349,10 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
   Y3_REQUIRE((reinterpret_cast<uintptr_t>(d.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.weight) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(d.bias) & 15) == 0,
              "conv: pointers must be 16-byte aligned");
-  const bool head = d.raw != nullptr;
+  const bool head = d.out_f32 != nullptr;
   if (head) {
-    Y3_REQUIRE(d.na * d.no == d.c_out && d.stride == 1 && !d.upsample && !d.res, "conv: bad Detect-head description");
+    Y3_REQUIRE(d.stride == 1 && !d.upsample && !d.res, "conv: fp32 output supports plain stride-1 convs only");
+    Y3_REQUIRE(d.out_f32_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(d.out_f32) & 15) == 0, "conv: bad fp32 output");
   } else {
     Y3_REQUIRE(d.out != nullptr, "conv: null output");
     Y3_REQUIRE(d.c_out % 32 == 0, "conv: c_out=%d must be a multiple of 32", d.c_out);
@@ -367,11 +390,14 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
   a.res = static_cast<const __nv_bfloat16*>(d.res);
   a.res_ld = d.res_ld;
   a.res_coff = d.res_coff;
-  a.raw = d.raw;
-  a.na = d.na;
-  a.no = d.no > 0 ? d.no : 1;
+  a.out_f32 = d.out_f32;
+  a.out_f32_ld = d.out_f32_ld;
   a.err = d.err;
-  if (head) a.out = nullptr;
+  if (head) {
+    a.out = nullptr;
+    Y3_REQUIRE(d.out_f32_ld >= (d.c_out + pick_block_n(d.c_out) - 1) / pick_block_n(d.c_out) * pick_block_n(d.c_out),
+               "conv: out_f32_ld must cover the padded c_out");
+  }
 
   int rc;
   if (d.stride == 1) {

@@ -52,8 +52,97 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeArgs p) {
   }
 }
 
+// ---- fused variant used by the graph executor: reads the head convs' fp32 pixel-major output [bs*ny*nx, ld]
+// (column a*no + k), writes z AND (optionally) the reference-layout logits raw_l[bs, na, ny, nx, no].
+// One warp per (image, cell, anchor): 340-byte contiguous reads and writes.
+struct HeadDecodeArgs {
+  const float* head[Y3_MAX_LEVELS];
+  float* raw[Y3_MAX_LEVELS];
+  int head_ld[Y3_MAX_LEVELS];
+  int ny[Y3_MAX_LEVELS], nx[Y3_MAX_LEVELS];
+  int row_off[Y3_MAX_LEVELS + 1];
+  float stride[Y3_MAX_LEVELS];
+  float anchor_w[Y3_MAX_LEVELS][Y3_MAX_ANCHORS], anchor_h[Y3_MAX_LEVELS][Y3_MAX_ANCHORS];
+  int nl, bs, na, no;
+  float* z;
+};
+
+__global__ void __launch_bounds__(256) head_decode_kernel(const HeadDecodeArgs p) {
+  const int lane = threadIdx.x & 31;
+  const long long rows_per_img = p.row_off[p.nl];
+  const long long total = rows_per_img * p.bs;
+  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long w = warp0; w < total; w += nwarps) {
+    const int b = static_cast<int>(w / rows_per_img);
+    const int row = static_cast<int>(w - b * rows_per_img);
+    int l = 0;
+    while (l + 1 < p.nl && row >= p.row_off[l + 1]) ++l;
+    const int r = row - p.row_off[l];
+    const int plane = p.ny[l] * p.nx[l];
+    const int a = r / plane, cell = r - a * plane;
+    const int y = cell / p.nx[l], x = cell - y * p.nx[l];
+    const float* src = p.head[l] + (static_cast<long long>(b) * plane + cell) * p.head_ld[l] + a * p.no;
+    float* zd = p.z ? p.z + (static_cast<long long>(b) * rows_per_img + row) * p.no : nullptr;
+    float* rd = p.raw[l] ? p.raw[l] + ((static_cast<long long>(b) * p.na + a) * plane + cell) * p.no : nullptr;
+    for (int k = lane; k < p.no; k += 32) {
+      const float v = __ldg(src + k);
+      if (rd) rd[k] = v;
+      if (zd) {
+        const float s = 1.0f / (1.0f + expf(-v));
+        float o = s;
+        if (k == 0)
+          o = (s * 2.0f + (static_cast<float>(x) - 0.5f)) * p.stride[l];
+        else if (k == 1)
+          o = (s * 2.0f + (static_cast<float>(y) - 0.5f)) * p.stride[l];
+        else if (k < 4) {
+          const float t = s * 2.0f;
+          o = (t * t) * (k == 2 ? p.anchor_w[l][a] : p.anchor_h[l][a]);
+        }
+        zd[k] = o;
+      }
+    }
+  }
+}
+
 }  // namespace
 }  // namespace y3
+
+extern "C" int y3_detect_head_decode_fwd(const y3_decode_desc* d, y3_stream_t stream) {
+  Y3_REQUIRE(d && d->nl >= 1 && d->nl <= Y3_MAX_LEVELS && d->na >= 1 && d->na <= Y3_MAX_ANCHORS && d->bs > 0 && d->no >= 5,
+             "head_decode: bad arguments");
+  y3::HeadDecodeArgs a{};
+  a.nl = d->nl;
+  a.bs = d->bs;
+  a.na = d->na;
+  a.no = d->no;
+  a.z = d->z;
+  int off = 0;
+  for (int l = 0; l < d->nl; ++l) {
+    const y3_detect_level& lv = d->levels[l];
+    Y3_REQUIRE(lv.head && lv.ny > 0 && lv.nx > 0 && lv.head_ld >= d->na * d->no, "head_decode: bad level %d", l);
+    a.head[l] = lv.head;
+    a.head_ld[l] = lv.head_ld;
+    a.raw[l] = lv.raw_out;
+    a.ny[l] = lv.ny;
+    a.nx[l] = lv.nx;
+    a.stride[l] = lv.stride;
+    a.row_off[l] = off;
+    off += d->na * lv.ny * lv.nx;
+    for (int j = 0; j < d->na; ++j) {
+      a.anchor_w[l][j] = lv.anchor_w[j];
+      a.anchor_h[l][j] = lv.anchor_h[j];
+    }
+  }
+  a.row_off[d->nl] = off;
+  const long long warps = static_cast<long long>(off) * d->bs;
+  long long blocks = (warps + 7) / 8;
+  const long long cap = static_cast<long long>(y3::num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  y3::head_decode_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
 
 extern "C" int y3_detect_decode_fwd(const y3_detect_level* levels, int32_t nl, int32_t bs, int32_t na, int32_t no,
                                     float* z, y3_stream_t stream) {

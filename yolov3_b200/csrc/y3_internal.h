@@ -50,8 +50,8 @@ struct ConvTcArgs {
   int out_ld, out_coff, upsample;
   const __nv_bfloat16* res;
   int res_ld, res_coff;
-  float* raw;
-  int na, no;
+  float* out_f32;   // fp32 pixel-major output [n*ho*wo, out_f32_ld] (Detect heads) instead of `out`
+  int out_f32_ld;
   int* err;
 };
 

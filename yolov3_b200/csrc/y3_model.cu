@@ -54,35 +54,6 @@ extern "C" int y3_model_create(const y3_op* ops, int32_t n_ops, y3_model** out) 
   return Y3_OK;
 }
 
-extern "C" int y3_model_forward(const y3_model* m, const void* input, y3_stream_t stream_) {
-  Y3_REQUIRE(m, "model_forward: null model");
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  for (size_t i = 0; i < m->steps.size(); ++i) {
-    const y3_model::Step& s = m->steps[i];
-    int rc = Y3_OK;
-    switch (s.kind) {
-      case Y3_OP_CONV:
-        rc = y3::conv_tc_launch(s.conv, stream);
-        break;
-      case Y3_OP_CONV_FIRST: {
-        y3_first_desc f = s.first;
-        if (input) f.in = input;
-        rc = y3_conv_first_fwd(&f, stream_);
-        break;
-      }
-      case Y3_OP_MAXPOOL:
-        rc = y3::pool_launch(s.pool, stream);
-        break;
-      case Y3_OP_DECODE:
-        rc = y3_detect_decode_fwd(s.decode.levels, s.decode.nl, s.decode.bs, s.decode.na, s.decode.no, s.decode.z,
-                                  stream_);
-        break;
-    }
-    if (rc) return rc;
-  }
-  return Y3_OK;
-}
-
 static int launch_step(const y3_model::Step& s, const void* input, y3_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   switch (s.kind) {
@@ -96,7 +67,7 @@ static int launch_step(const y3_model::Step& s, const void* input, y3_stream_t s
     case Y3_OP_MAXPOOL:
       return y3::pool_launch(s.pool, stream);
     case Y3_OP_DECODE:
-      return y3_detect_decode_fwd(s.decode.levels, s.decode.nl, s.decode.bs, s.decode.na, s.decode.no, s.decode.z, stream_);
+      return y3_detect_head_decode_fwd(&s.decode, stream_);
   }
   return Y3_OK;
 }
@@ -126,6 +97,15 @@ extern "C" int y3_model_forward_timed(const y3_model* m, const void* input, y3_s
   }
   for (auto& e : ev) cudaEventDestroy(e);
   return rc;
+}
+
+extern "C" int y3_model_forward(const y3_model* m, const void* input, y3_stream_t stream_) {
+  Y3_REQUIRE(m, "model_forward: null model");
+  for (size_t i = 0; i < m->steps.size(); ++i) {
+    const int rc = launch_step(m->steps[i], input, stream_);
+    if (rc) return rc;
+  }
+  return Y3_OK;
 }
 
 extern "C" int32_t y3_model_num_launches(const y3_model* m) { return m ? static_cast<int32_t>(m->steps.size()) : 0; }

@@ -315,11 +315,11 @@ class Engine:
         op_list: list[_lib.Op] = []
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
 
-        def emit_conv(x, prefix, c_out, k, s, act, out=None, res=None, upsample=False, raw=None):
+        def emit_conv(x, prefix, c_out, k, s, act, out=None, res=None, upsample=False, out_f32=None):
             wt, bs_ = W[prefix]
             o = _lib.Op()
             o.kind = _lib.OP_CONV
-            o.conv = ops.conv_desc(x, wt, bs_, c_out, k, s, act, out, res, upsample, raw, det.na, det.no, self.err)
+            o.conv = ops.conv_desc(x, wt, bs_, c_out, k, s, act, out, res, upsample, out_f32, self.err)
             op_list.append(o)
 
         tens: dict[int, object] = {}  # node -> PaddedNHWC (or ("zeropad", tensor))
@@ -410,19 +410,25 @@ class Engine:
             elif nd.type == "Concat":
                 tens[nd.i] = bufs[nd.i]
 
-        # ---- Detect: 1x1 head convs with fp32 [bs,na,ny,nx,no] stores, then one decode launch
+        # ---- Detect: 1x1 head convs storing fp32 pixel-major [bs*ny*nx, ld], then ONE launch that transposes them
+        #      into the reference's [bs,na,ny,nx,no] logits and decodes z
         dnode = nodes[-1]
         self.raw = []
+        self.head_out = []
+        head_ld = ops.cout_pad(det.na * det.no)
         dec = _lib.DecodeDesc()
         anchors_px = det.anchors * det.stride.view(-1, 1, 1)
         rows = 0
         for j, s in enumerate(dnode.srcs):
             x = tens[s]
             raw = torch.zeros(n, det.na, x.h, x.w, det.no, dtype=torch.float32, device=dev)
+            head = torch.zeros(n * x.h * x.w, head_ld, dtype=torch.float32, device=dev)
             self.raw.append(raw)
-            emit_conv(x, f"model.{det.i}.m.{j}", det.na * det.no, 1, 1, ops.ACT_NONE, raw=raw)
+            self.head_out.append(head)
+            emit_conv(x, f"model.{det.i}.m.{j}", det.na * det.no, 1, 1, ops.ACT_NONE, out_f32=head)
             lv = dec.levels[j]
-            lv.raw, lv.ny, lv.nx, lv.stride = raw.data_ptr(), x.h, x.w, float(det.stride[j])
+            lv.head, lv.head_ld, lv.raw_out = head.data_ptr(), head_ld, raw.data_ptr()
+            lv.ny, lv.nx, lv.stride = x.h, x.w, float(det.stride[j])
             for a in range(det.na):
                 lv.anchor_w[a], lv.anchor_h[a] = float(anchors_px[j, a, 0]), float(anchors_px[j, a, 1])
             rows += det.na * x.h * x.w

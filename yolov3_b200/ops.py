@@ -35,7 +35,7 @@ def pack_first_weight(w: torch.Tensor, b: torch.Tensor, device="cuda"):
 
 
 def conv_desc(x: PaddedNHWC, weight, bias, c_out, k, s, act, out: PaddedNHWC | None, res: PaddedNHWC | None = None,
-              upsample=False, raw: torch.Tensor | None = None, na=0, no=0, err: torch.Tensor | None = None):
+              upsample=False, out_f32: torch.Tensor | None = None, err: torch.Tensor | None = None):
     d = _lib.ConvDesc()
     d.n, d.h, d.w, d.c_in, d.c_out, d.ksize, d.stride, d.act = x.n, x.h, x.w, x.c, c_out, k, s, act
     d.in_, d.in_ld, d.in_coff = x.ptr, x.ld, x.coff
@@ -45,23 +45,24 @@ def conv_desc(x: PaddedNHWC, weight, bias, c_out, k, s, act, out: PaddedNHWC | N
     if res is not None:
         d.res, d.res_ld, d.res_coff = res.ptr, res.ld, res.coff
     d.upsample = int(bool(upsample))
-    if raw is not None:
-        d.raw, d.na, d.no = raw.data_ptr(), na, no
+    if out_f32 is not None:  # fp32 pixel-major [n*ho*wo, ld]
+        assert out_f32.dtype == torch.float32 and out_f32.dim() == 2 and out_f32.is_contiguous()
+        d.out_f32, d.out_f32_ld = out_f32.data_ptr(), out_f32.shape[1]
     if err is not None:
         d.err = err.data_ptr()
     return d
 
 
 def conv_bn_act(x: PaddedNHWC, weight, bias, c_out, k=1, s=1, act=ACT_SILU, out=None, res=None, upsample=False,
-                raw=None, na=0, no=0, err=None):
+                out_f32=None, err=None):
     """y3_conv_bn_act_fwd.  Allocates ``out`` when not given (tests); the model executor always passes buffers."""
     ho, wo = x.h // s, x.w // s
-    if out is None and raw is None:
+    if out is None and out_f32 is None:
         u = 2 if upsample else 1
         out = PaddedNHWC.zeros(x.n, ho * u, wo * u, c_out, device=x.buf.device)
-    d = conv_desc(x, weight, bias, c_out, k, s, act, out, res, upsample, raw, na, no, err)
+    d = conv_desc(x, weight, bias, c_out, k, s, act, out, res, upsample, out_f32, err)
     _lib.check(_lib.lib().y3_conv_bn_act_fwd(C.byref(d), _stream()), "y3_conv_bn_act_fwd")
-    return out if raw is None else raw
+    return out if out_f32 is None else out_f32
 
 
 def first_desc(x: torch.Tensor, weight27, bias, c_out, out: PaddedNHWC, in_div=0.0):

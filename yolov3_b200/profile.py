@@ -15,10 +15,10 @@ def describe_ops(engine):
             d = o.conv
             ho, wo = d.h // d.stride, d.w // d.stride
             flops = 2.0 * d.n * ho * wo * d.c_out * d.c_in * d.ksize * d.ksize
-            out_b = d.n * ho * wo * d.c_out * (4 if d.raw else 2) * (4 if d.upsample else 1)
+            out_b = d.n * ho * wo * d.c_out * (4 if d.out_f32 else 2) * (4 if d.upsample else 1)
             byts = d.n * d.h * d.w * d.c_in * 2 + out_b + d.c_out * d.c_in * d.ksize**2 * 2 + (out_b if d.res else 0)
             out.append(dict(kind="conv_tc", shape=f"{d.c_in}->{d.c_out} k{d.ksize} s{d.stride} @{d.h}x{d.w} n{d.n}"
-                            + (" +res" if d.res else "") + (" +up2x" if d.upsample else "") + (" head" if d.raw else ""),
+                            + (" +res" if d.res else "") + (" +up2x" if d.upsample else "") + (" head" if d.out_f32 else ""),
                             flops=flops, bytes=byts))
         elif o.kind == _lib.OP_CONV_FIRST:
             d = o.first
@@ -32,7 +32,7 @@ def describe_ops(engine):
         elif o.kind == _lib.OP_DECODE:
             d = o.decode
             rows = sum(d.na * d.levels[i].ny * d.levels[i].nx for i in range(d.nl))
-            out.append(dict(kind="decode", shape=f"rows {rows} no {d.no} n{d.bs}", flops=0.0, bytes=d.bs * rows * d.no * 8))
+            out.append(dict(kind="decode", shape=f"rows {rows} no {d.no} n{d.bs}", flops=0.0, bytes=d.bs * rows * d.no * 12))
     return out
 
 
