@@ -116,16 +116,43 @@ def build_model(device):
     return m
 
 
+_BEST_THREADS = None
+
+
+def best_threads(om):
+    """The reference leaves torch's intra-op thread count at its default; on many-core hosts that default can be far
+    from the fastest setting for this conv stack, so the baseline uses the fastest of a few candidates (stated in the
+    output)."""
+    global _BEST_THREADS
+    import torch
+
+    if _BEST_THREADS is None:
+        cores = os.cpu_count() or 1
+        x = torch.rand(1, 3, IMG, IMG)
+        best = (None, 1e30)
+        with torch.inference_mode():
+            for t in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 16)}, reverse=True):
+                torch.set_num_threads(t)
+                om(x)
+                t0 = time.perf_counter()
+                om(x)
+                dt = time.perf_counter() - t0
+                if dt < best[1]:
+                    best = (t, dt)
+        _BEST_THREADS = best[0]
+    torch.set_num_threads(_BEST_THREADS)
+    return _BEST_THREADS
+
+
 def cpu_forward_rate(n_img, iters, warmup=1):
-    """Oracle port of the reference forward on the host cores; returns (images/s, cores)."""
+    """Oracle port of the reference forward on the host cores; returns (images/s, threads used)."""
     import torch
 
     sys.path.insert(0, str(ROOT / "oracle"))
     import yolo_oracle as O
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     om = O.OracleModel(ROOT / "yolov3_b200" / "cfg" / CFG, seed=0, fused=True)
+    cores = best_threads(om)
     x = torch.rand(n_img, 3, IMG, IMG, generator=torch.Generator().manual_seed(1))
     with torch.inference_mode():
         for _ in range(warmup):
@@ -150,8 +177,8 @@ def run_reference(args, rank):
     sys.path.insert(0, str(ROOT / "oracle"))
     import yolo_oracle as O
 
-    torch.set_num_threads(cores)
     om = O.OracleModel(ROOT / "yolov3_b200" / "cfg" / CFG, seed=0, fused=True)
+    cores = best_threads(om)
     x = torch.rand(per_step, 3, IMG, IMG, generator=torch.Generator().manual_seed(1))
     with torch.inference_mode():
         for _ in range(args.warmup):
@@ -161,7 +188,8 @@ def run_reference(args, rank):
             om(x)
         dt = time.perf_counter() - t0
     v = per_step * args.steps / dt
-    sample = f"{per_step} of the {BS} images of each step (fp32, fused BN, torch CPU ops, {cores} threads)"
+    sample = (f"{per_step} of the {BS} images of each step (fp32, fused BN, torch CPU ops, {cores} threads of "
+              f"{os.cpu_count()} host cores: fastest of 4 thread counts tried)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",

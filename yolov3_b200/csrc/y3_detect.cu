@@ -67,39 +67,71 @@ struct HeadDecodeArgs {
   float* z;
 };
 
+constexpr int kDecodeRows = 4;  // z rows per warp iteration: 12 independent 128-byte loads in flight per warp
+
 __global__ void __launch_bounds__(256) head_decode_kernel(const HeadDecodeArgs p) {
   const int lane = threadIdx.x & 31;
   const long long rows_per_img = p.row_off[p.nl];
   const long long total = rows_per_img * p.bs;
+  const long long groups = (total + kDecodeRows - 1) / kDecodeRows;
   const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  for (long long w = warp0; w < total; w += nwarps) {
-    const int b = static_cast<int>(w / rows_per_img);
-    const int row = static_cast<int>(w - b * rows_per_img);
-    int l = 0;
-    while (l + 1 < p.nl && row >= p.row_off[l + 1]) ++l;
-    const int r = row - p.row_off[l];
-    const int plane = p.ny[l] * p.nx[l];
-    const int a = r / plane, cell = r - a * plane;
-    const int y = cell / p.nx[l], x = cell - y * p.nx[l];
-    const float* src = p.head[l] + (static_cast<long long>(b) * plane + cell) * p.head_ld[l] + a * p.no;
-    float* zd = p.z ? p.z + (static_cast<long long>(b) * rows_per_img + row) * p.no : nullptr;
-    float* rd = p.raw[l] ? p.raw[l] + ((static_cast<long long>(b) * p.na + a) * plane + cell) * p.no : nullptr;
-    for (int k = lane; k < p.no; k += 32) {
-      const float v = __ldg(src + k);
-      if (rd) rd[k] = v;
-      if (zd) {
-        const float s = 1.0f / (1.0f + expf(-v));
-        float o = s;
-        if (k == 0)
-          o = (s * 2.0f + (static_cast<float>(x) - 0.5f)) * p.stride[l];
-        else if (k == 1)
-          o = (s * 2.0f + (static_cast<float>(y) - 0.5f)) * p.stride[l];
-        else if (k < 4) {
-          const float t = s * 2.0f;
-          o = (t * t) * (k == 2 ? p.anchor_w[l][a] : p.anchor_h[l][a]);
+  for (long long gidx = warp0; gidx < groups; gidx += nwarps) {
+    const float* src[kDecodeRows];
+    float* zd[kDecodeRows];
+    float* rd[kDecodeRows];
+    int lx[kDecodeRows], ly[kDecodeRows], ll[kDecodeRows], la[kDecodeRows];
+    float v[kDecodeRows][3];
+#pragma unroll
+    for (int q = 0; q < kDecodeRows; ++q) {
+      const long long w = gidx * kDecodeRows + q;
+      src[q] = nullptr;
+      if (w >= total) continue;
+      const int b = static_cast<int>(w / rows_per_img);
+      const int row = static_cast<int>(w - b * rows_per_img);
+      int l = 0;
+      while (l + 1 < p.nl && row >= p.row_off[l + 1]) ++l;
+      const int r = row - p.row_off[l];
+      const int plane = p.ny[l] * p.nx[l];
+      const int a = r / plane, cell = r - a * plane;
+      ly[q] = cell / p.nx[l];
+      lx[q] = cell - ly[q] * p.nx[l];
+      ll[q] = l;
+      la[q] = a;
+      src[q] = p.head[l] + (static_cast<long long>(b) * plane + cell) * p.head_ld[l] + a * p.no;
+      zd[q] = p.z ? p.z + (static_cast<long long>(b) * rows_per_img + row) * p.no : nullptr;
+      rd[q] = p.raw[l] ? p.raw[l] + ((static_cast<long long>(b) * p.na + a) * plane + cell) * p.no : nullptr;
+    }
+#pragma unroll
+    for (int q = 0; q < kDecodeRows; ++q) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int k = lane + 32 * j;
+        v[q][j] = (src[q] && k < p.no) ? __ldg(src[q] + k) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < kDecodeRows; ++q) {
+      if (!src[q]) continue;
+      const int l = ll[q];
+      for (int j = 0; j < 3; ++j) {
+        const int k = lane + 32 * j;
+        if (k >= p.no) break;
+        const float x = v[q][j];
+        if (rd[q]) rd[q][k] = x;
+        if (zd[q]) {
+          const float s = 1.0f / (1.0f + expf(-x));
+          float o = s;
+          if (k == 0)
+            o = (s * 2.0f + (static_cast<float>(lx[q]) - 0.5f)) * p.stride[l];
+          else if (k == 1)
+            o = (s * 2.0f + (static_cast<float>(ly[q]) - 0.5f)) * p.stride[l];
+          else if (k < 4) {
+            const float t = s * 2.0f;
+            o = (t * t) * (k == 2 ? p.anchor_w[l][la[q]] : p.anchor_h[l][la[q]]);
+          }
+          zd[q][k] = o;
         }
-        zd[k] = o;
       }
     }
   }
@@ -135,7 +167,8 @@ extern "C" int y3_detect_head_decode_fwd(const y3_decode_desc* d, y3_stream_t st
     }
   }
   a.row_off[d->nl] = off;
-  const long long warps = static_cast<long long>(off) * d->bs;
+  Y3_REQUIRE(d->no <= 96, "head_decode: no=%d > 96 is not supported by this kernel", d->no);
+  const long long warps = (static_cast<long long>(off) * d->bs + y3::kDecodeRows - 1) / y3::kDecodeRows;
   long long blocks = (warps + 7) / 8;
   const long long cap = static_cast<long long>(y3::num_sms()) * 32;
   if (blocks > cap) blocks = cap;
