@@ -17,6 +17,8 @@
 // layers were epilogue-bound (MUFU + issue), hence 8 warps, a one-MUFU SiLU and register-prefetched residuals.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "y3_common.cuh"
 #include "y3_internal.h"
 
@@ -29,10 +31,11 @@ constexpr int kEpilogueWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpilogueWarps;
 constexpr int kSmemBudget = 200 * 1024;  // ring buffers; barriers + alignment slack come on top (227 KB max per CTA)
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool PAIR>
 struct Cfg {
   static constexpr uint32_t kABytes = kBlockM * BLOCK_K * 2;
-  static constexpr uint32_t kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr uint32_t kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;  // a CTA pair splits the B tile between its two CTAs
+  static constexpr uint32_t kBBytes = kBRows * BLOCK_K * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -44,13 +47,19 @@ struct Cfg {
   static_assert(kStages >= 2, "pipeline needs at least two stages");
 };
 
-template <int BLOCK_N, int BLOCK_K>
+// PAIR = true: two CTAs of a cluster (one SM pair) cooperate on a 256-row tile with tcgen05 cta_group::2: each CTA
+// stages its own 128 A rows and HALF of the B tile, the leader CTA's single MMA thread issues M=256 MMAs that read both
+// CTAs' shared memory and write both CTAs' TMEM.  Per-SM operand ingress drops from (128+N)*K to (128+N/2)*K bytes per
+// k-block — the 1-CTA kernel measured ~0.67 of the MMA rate on the big 3x3 layers because (128+256)*64*2 B per 512 MMA
+// cycles exceeds the ~64 B/clk an SM can pull from L2 (profiles/r01_per_op_v2_epilogue.json).
+template <int BLOCK_N, int BLOCK_K, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const ConvTcArgs p) {
-  using C = Cfg<BLOCK_N, BLOCK_K>;
+  using C = Cfg<BLOCK_N, BLOCK_K, PAIR>;
   constexpr int STAGES = C::kStages;
-  constexpr uint32_t IDESC = umma_idesc_bf16_m128(BLOCK_N);
+  constexpr uint32_t IDESC = umma_idesc_bf16(PAIR ? 256 : 128, BLOCK_N);
+  constexpr uint32_t kEpiThreads = 32 * kEpilogueWarps;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -65,39 +74,50 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;  // 0 = leader
+  const int n_workers = PAIR ? gridDim.x / 2 : gridDim.x;
+  const int worker = PAIR ? blockIdx.x / 2 : blockIdx.x;
 
+  if (PAIR) cluster_sync_all();  // both CTAs are resident before the pair-wide TMEM allocation
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], 1);
+      mbar_init(&full_bar[i], PAIR ? 2 : 1);  // pair: leader's expect_tx arrive + peer's remote arrive
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 32 * kEpilogueWarps);
+      mbar_init(&tempty_bar[i], PAIR ? 2 * kEpiThreads : kEpiThreads);  // pair: both CTAs' epilogues release the buffer
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, C::kTmemCols);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_slot, C::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int m_units = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles;  // a pair owns two consecutive M tiles
+  const int total_tiles = m_units * p.n_tiles;
   const int k_iters = p.taps * p.kblocks;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one thread)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
-        const int n0 = nt * BLOCK_N;
+      for (int tile = worker; tile < total_tiles; tile += n_workers) {
+        const int nt = tile % p.n_tiles;
+        const int mt = PAIR ? (tile / p.n_tiles) * 2 + static_cast<int>(rank) : tile / p.n_tiles;
+        const int n0 = nt * BLOCK_N + static_cast<int>(rank) * C::kBRows;  // this CTA's slice of the weight tile
         int row0 = 0, img = 0, oh0 = 0, ow0 = 0;
         if (p.mode == 0) {
           row0 = mt * kBlockM;
@@ -111,18 +131,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int it = 0; it < k_iters; ++it) {
           const int kb = it / p.taps, tap = it - kb * p.taps;
           mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 1);
-          mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + C::kBBytes);
           uint8_t* a_dst = smem_a + stage * C::kABytes;
           uint8_t* b_dst = smem_b + stage * C::kBBytes;
-          if (p.mode == 0) {
-            const int shift = (p.taps == 9) ? ((tap / 3 - 1) * p.wp + (tap % 3 - 1)) : 0;
-            tma_load_2d(a_dst, &map_a, &full_bar[stage], p.a_coff + kb * BLOCK_K, row0 + shift);
+          const int shift = (p.taps == 9) ? ((tap / 3 - 1) * p.wp + (tap % 3 - 1)) : 0;
+          const int r = tap / 3, s = tap - r * 3;
+          if (PAIR) {
+            // all bytes of both CTAs are credited to the LEADER's full barrier; the peer only contributes an arrival
+            const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (rank == 0)
+              mbar_expect_tx(&full_bar[stage], 2 * (p.a_tx_bytes + C::kBBytes));
+            else
+              mbar_arrive_cluster(lead_bar);
+            if (p.mode == 0)
+              tma_load_2d_pair(a_dst, &map_a, lead_bar, p.a_coff + kb * BLOCK_K, row0 + shift);
+            else
+              tma_load_5d_pair(a_dst, &map_a, lead_bar, (s & 1) * p.a_ld + p.a_coff + kb * BLOCK_K, ow0 + (s >> 1), r & 1,
+                               oh0 + (r >> 1), img);
+            tma_load_2d_pair(b_dst, &map_b, lead_bar, tap * p.cin + kb * BLOCK_K, n0);
           } else {
-            const int r = tap / 3, s = tap - r * 3;
-            tma_load_5d(a_dst, &map_a, &full_bar[stage], (s & 1) * p.a_ld + p.a_coff + kb * BLOCK_K, ow0 + (s >> 1),
-                        r & 1, oh0 + (r >> 1), img);
+            mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + C::kBBytes);
+            if (p.mode == 0)
+              tma_load_2d(a_dst, &map_a, &full_bar[stage], p.a_coff + kb * BLOCK_K, row0 + shift);
+            else
+              tma_load_5d(a_dst, &map_a, &full_bar[stage], (s & 1) * p.a_ld + p.a_coff + kb * BLOCK_K, ow0 + (s >> 1),
+                          r & 1, oh0 + (r >> 1), img);
+            tma_load_2d(b_dst, &map_b, &full_bar[stage], tap * p.cin + kb * BLOCK_K, n0);
           }
-          tma_load_2d(b_dst, &map_b, &full_bar[stage], tap * p.cin + kb * BLOCK_K, n0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -131,11 +165,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (one thread; leader CTA only)
+    if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0;
       int iter = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers, ++iter) {
         const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1u, p.err, 2);  // epilogue has drained this accumulator buffer
         tc_fence_after();
@@ -149,10 +183,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             const uint64_t adesc = umma_smem_desc(a_addr + k * 32, C::kSbo, C::kLayout);
             const uint64_t bdesc = umma_smem_desc(b_addr + k * 32, C::kSbo, C::kLayout);
-            umma_bf16_ss(d_tmem, adesc, bdesc, IDESC, (it | k) != 0 ? 1u : 0u);
+            if (PAIR)
+              umma_bf16_ss_pair(d_tmem, adesc, bdesc, IDESC, (it | k) != 0 ? 1u : 0u);
+            else
+              umma_bf16_ss(d_tmem, adesc, bdesc, IDESC, (it | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs have read it
-          if (it == k_iters - 1) umma_commit(&tfull_bar[as]);
+          // the smem slot (in BOTH CTAs of a pair) is free once these MMAs have read it
+          if (PAIR) {
+            umma_commit_pair(&empty_bar[stage], 0x3);
+            if (it == k_iters - 1) umma_commit_pair(&tfull_bar[as], 0x3);
+          } else {
+            umma_commit(&empty_bar[stage]);
+            if (it == k_iters - 1) umma_commit(&tfull_bar[as]);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -168,10 +211,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int c_begin = BLOCK_N >= 64 ? half * kColsPerWarp : 0;
     const bool active = BLOCK_N >= 64 || half == 0;
     const int m = quarter * 32 + lane;
+    const uint32_t lead_tempty[2] = {PAIR ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u,
+                                     PAIR ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u};
     int iter = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++iter) {
+    for (int tile = worker; tile < total_tiles; tile += n_workers, ++iter) {
       const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
-      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int nt = tile % p.n_tiles;
+      const int mt = PAIR ? (tile / p.n_tiles) * 2 + static_cast<int>(rank) : tile / p.n_tiles;
       const int n0 = nt * BLOCK_N;
 
       // ---- which output pixel does accumulator row m belong to?
@@ -195,7 +241,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         ox = (t % p.tiles_w) * p.tw + tx;
         valid = ty < p.th && oy < p.ho && ox < p.wo;
       }
-      valid = valid && active;
+      valid = valid && active && mt < p.m_tiles;  // a pair's second CTA may own a tile past the end
       const int oh = p.mode == 0 ? p.hp - 2 : p.ho;  // conv-output height/width (unpadded)
       const int ow = p.mode == 0 ? p.wp - 2 : p.wo;
       const long long conv_row = (static_cast<long long>(img) * (oh + 2) + oy + 1) * (ow + 2) + ox + 1;
@@ -290,30 +336,46 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      if (PAIR)
+        mbar_arrive_cluster(lead_tempty[as]);  // the leader's MMA thread waits for BOTH CTAs' epilogues
+      else
+        mbar_arrive(&tempty_bar[as]);
     }
   }
 
   __syncwarp();
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();  // pair: nobody leaves while the peer may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, C::kTmemCols); else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
-template <int BLOCK_N, int BLOCK_K>
+template <int BLOCK_N, int BLOCK_K, bool PAIR>
 int launch_cfg(const ConvTcPlan& plan, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, BLOCK_K>;
-  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K>;
+  using C = Cfg<BLOCK_N, BLOCK_K, PAIR>;
+  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, PAIR>;
   static bool attr_set = false;  // benign race: idempotent attribute
   if (!attr_set) {
     Y3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::kSmemBytes)));
     attr_set = true;
   }
-  kern<<<plan.grid, kThreads, C::kSmemBytes, stream>>>(plan.map_a, plan.map_b, plan.args);
-  Y3_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(plan.grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (PAIR) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  Y3_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, plan.map_a, plan.map_b, plan.args));
   return Y3_OK;
 }
 
@@ -322,21 +384,38 @@ int pick_block_n(int cout) { return cout <= 32 ? 32 : (cout <= 64 ? 64 : (cout <
 }  // namespace
 
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream) {
-#define Y3_DISPATCH_K(BN)                                        \
-  switch (plan.block_k) {                                        \
-    case 64: return launch_cfg<BN, 64>(plan, stream);            \
-    case 32: return launch_cfg<BN, 32>(plan, stream);            \
-    case 16: return launch_cfg<BN, 16>(plan, stream);            \
-  }                                                              \
+#define Y3_DISPATCH_K(BN, PR)                                      \
+  switch (plan.block_k) {                                          \
+    case 64: return launch_cfg<BN, 64, PR>(plan, stream);          \
+    case 32: return launch_cfg<BN, 32, PR>(plan, stream);          \
+    case 16: return launch_cfg<BN, 16, PR>(plan, stream);          \
+  }                                                                \
   break;
-  switch (plan.block_n) {
-    case 32: Y3_DISPATCH_K(32)
-    case 64: Y3_DISPATCH_K(64)
-    case 128: Y3_DISPATCH_K(128)
-    case 256: Y3_DISPATCH_K(256)
+  if (plan.pair) {
+    switch (plan.block_n) {
+      case 128: Y3_DISPATCH_K(128, true)
+      case 256: Y3_DISPATCH_K(256, true)
+    }
+  } else {
+    switch (plan.block_n) {
+      case 32: Y3_DISPATCH_K(32, false)
+      case 64: Y3_DISPATCH_K(64, false)
+      case 128: Y3_DISPATCH_K(128, false)
+      case 256: Y3_DISPATCH_K(256, false)
+    }
   }
 #undef Y3_DISPATCH_K
-  return set_error(Y3_ERR_BAD_ARG, "conv_tc: no kernel for tile N=%d K=%d", plan.block_n, plan.block_k);
+  return set_error(Y3_ERR_BAD_ARG, "conv_tc: no kernel for tile N=%d K=%d pair=%d", plan.block_n, plan.block_k, plan.pair);
+}
+
+// Y3_CONV_PAIR=0 forces the 1-CTA kernel everywhere (A/B measurements); default: CTA pairs for tile N >= 128.
+static bool pair_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("Y3_CONV_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
 }
 
 int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
@@ -451,13 +530,20 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     const uint64_t ktot = static_cast<uint64_t>(taps) * d.c_in;
     const uint64_t dims[2] = {ktot, static_cast<uint64_t>(cout_pad)};
     const uint64_t strides[2] = {0, ktot * 2};
-    const uint32_t box[2] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(bn)};
+    plan->pair = (bn >= 128 && pair_enabled() && a.m_tiles >= 2) ? 1 : 0;
+    const uint32_t box[2] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(plan->pair ? bn / 2 : bn)};
     rc = encode_tensor_map_bf16(&plan->map_b, d.weight, 2, dims, strides, box, bk * 2);
     if (rc) return rc;
   }
-  const long long total = static_cast<long long>(a.m_tiles) * a.n_tiles;
   const int sms = num_sms();
-  plan->grid = static_cast<int>(total < sms ? total : sms);
+  if (plan->pair) {
+    const long long total = static_cast<long long>((a.m_tiles + 1) / 2) * a.n_tiles;  // 256-row pair tiles
+    const long long clusters = total < sms / 2 ? total : sms / 2;
+    plan->grid = static_cast<int>(clusters * 2);
+  } else {
+    const long long total = static_cast<long long>(a.m_tiles) * a.n_tiles;
+    plan->grid = static_cast<int>(total < sms ? total : sms);
+  }
   plan->smem_bytes = 0;
   return Y3_OK;
 }

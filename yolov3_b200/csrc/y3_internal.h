@@ -59,6 +59,7 @@ struct ConvTcPlan {
   CUtensorMap map_a, map_b;
   ConvTcArgs args;
   int block_n, block_k;
+  int pair;  // 1: CTA-pair (cta_group::2) kernel, launched as clusters of 2
   int grid;
   size_t smem_bytes;
 };
