@@ -284,6 +284,28 @@ def main():
     ms_e2e = aggregate(ms_e2e, dev)
     e2e = world * BS * args.steps / (ms_e2e / 1e3)
 
+    # ---- NMS sweep (BASELINE config 5): synthetic [bs,25200,85] fp32 resident in HBM, device pipeline only (no D2H)
+    from yolov3_b200.nms import nms_batched
+
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import yolo_oracle as O
+
+    pred = O.synth_predictions(BS, n_rows=25200, nc=80, seed=3).to(dev)
+    nms_res = {}
+    for conf, iou, ml in ((0.25, 0.45, False), (0.001, 0.6, False), (0.001, 0.6, True)):
+        for _ in range(3):
+            nms_batched(pred, conf, iou, multi_label=ml, max_det=300)
+        torch.cuda.synchronize()
+        e0.record()
+        reps = 10
+        for _ in range(reps):
+            nms_batched(pred, conf, iou, multi_label=ml, max_det=300)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = aggregate(e0.elapsed_time(e1) / reps, dev)
+        nms_res[f"conf{conf}_iou{iou}_{'multi' if ml else 'single'}"] = {
+            "input_boxes_per_s": world * BS * 25200 / (ms / 1e3), "ms_per_batch": ms}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -328,6 +350,8 @@ def main():
                 "ms_per_step": ms_e2e / args.steps, "path": "Pipeline: uint8 H2D -> forward -> decode -> NMS(0.25/0.45/300) -> D2H"},
         "gpu_launches": n_launch * args.steps,
         "clocks": clocks,
+        "nms": {"workload": f"synthetic [bs {BS}/GPU, 25200, 85] fp32 (SURVEY §8d config 5), max_det 300, device-resident, "
+                            "sync-free y3_nms_batched", "unit": "input boxes/s", **nms_res},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

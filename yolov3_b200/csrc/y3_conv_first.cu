@@ -34,24 +34,27 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+constexpr int kFirstRows = 8;   // output rows per block (weight fragments and the input patch are reused across them)
+constexpr int kFirstTW = 128;   // output columns per block
+
 template <int COUT, typename TIN>
 __global__ void __launch_bounds__(128) conv_first_kernel(const TIN* __restrict__ in, float in_div, int H, int W,
                                                          const float* __restrict__ wgt, const float* __restrict__ bias,
                                                          __nv_bfloat16* __restrict__ out, int out_ld, int out_coff) {
-  constexpr int TW = 128, NT = COUT / 8;
-  __shared__ float s_in[3][3][TW + 2];
-  const int w0 = blockIdx.x * TW, h = blockIdx.y, n = blockIdx.z;
+  constexpr int TW = kFirstTW, R = kFirstRows, NT = COUT / 8, PITCH = TW + 2;
+  __shared__ float s_in[3][R + 2][PITCH];
+  const int w0 = blockIdx.x * TW, h0 = blockIdx.y * R, n = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  // ---- stage the input patch (zero outside the image = the conv's padding)
-  for (int i = threadIdx.x; i < 9 * (TW + 2); i += blockDim.x) {
-    const int col = i % (TW + 2), rc = i / (TW + 2);
-    const int c = rc / 3, kh = rc - c * 3;
-    const int hh = h + kh - 1, ww = w0 + col - 1;
+  // ---- stage the (R+2) x (TW+2) x 3 input patch (zero outside the image = the conv's padding)
+  for (int i = threadIdx.x; i < 3 * (R + 2) * PITCH; i += blockDim.x) {
+    const int col = i % PITCH, rc = i / PITCH;
+    const int c = rc / (R + 2), rr = rc - c * (R + 2);
+    const int hh = h0 + rr - 1, ww = w0 + col - 1;
     float v = 0.f;
     if (hh >= 0 && hh < H && ww >= 0 && ww < W)
       v = load_px<TIN>(in + ((static_cast<size_t>(n) * 3 + c) * H + hh) * W + ww, in_div);
-    s_in[c][kh][col] = v;
+    (&s_in[0][0][0])[i] = v;
   }
   // ---- weight fragments: B[k][n], k = (c*3+kh)*3+kw (27 real rows, zero padded to 32)
   uint32_t bfrag[2][NT][2];
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const TIN* __restrict__
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int k = ks * 16 + t * 2 + (j & 1) + (j >> 1) * 8;
-      a_off[ks][j] = k < 27 ? ((k / 9) * 3 + (k % 9) / 3) * (TW + 2) + k % 3 : -1;
+      a_off[ks][j] = k < 27 ? ((k / 9) * (R + 2) + (k % 9) / 3) * PITCH + k % 3 : -1;
     }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -82,37 +85,61 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const TIN* __restrict__
   }
   __syncthreads();
   const float* sbase = &s_in[0][0][0];
+#pragma unroll 1
+  for (int rr = 0; rr < R; ++rr) {
+    const int h = h0 + rr;
+    if (h >= H) break;
 #pragma unroll
-  for (int mt = 0; mt < 2; ++mt) {
-    const int px = warp * 32 + mt * 16;  // first pixel (tile-relative) of this 16-row MMA tile
-    float acc[NT][4];
+    for (int mt = 0; mt < 2; ++mt) {
+      const int px = warp * 32 + mt * 16;  // first pixel (tile-relative) of this 16-row MMA tile
+      float acc[NT][4];
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+      for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      // A fragment: a0 = (row g, k 2t..2t+1), a1 = (row g+8, same), a2 = (row g, k+8..), a3 = (row g+8, k+8..)
-      float v[2][4];
+      for (int ks = 0; ks < 2; ++ks) {
+        // A fragment: a0 = (row g, k 2t..2t+1), a1 = (row g+8, same), a2 = (row g, k+8..), a3 = (row g+8, k+8..)
+        float v[2][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int o = a_off[ks][j];
-        v[0][j] = o >= 0 ? sbase[o + px + g] : 0.f;
-        v[1][j] = o >= 0 ? sbase[o + px + g + 8] : 0.f;
+        for (int j = 0; j < 4; ++j) {
+          const int o = a_off[ks][j] + rr * PITCH + px + g;
+          v[0][j] = a_off[ks][j] >= 0 ? sbase[o] : 0.f;
+          v[1][j] = a_off[ks][j] >= 0 ? sbase[o + 8] : 0.f;
+        }
+        const uint32_t a[4] = {pack_bf16x2(v[0][0], v[0][1]), pack_bf16x2(v[1][0], v[1][1]), pack_bf16x2(v[0][2], v[0][3]),
+                               pack_bf16x2(v[1][2], v[1][3])};
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_bf16_16816(acc[nt], a, bfrag[ks][nt]);
       }
-      const uint32_t a[4] = {pack_bf16x2(v[0][0], v[0][1]), pack_bf16x2(v[1][0], v[1][1]), pack_bf16x2(v[0][2], v[0][3]),
-                             pack_bf16x2(v[1][2], v[1][3])};
+      // C fragment: c0,c1 = (row g, cols 2t,2t+1), c2,c3 = (row g+8, same cols)
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt) mma_bf16_16816(acc[nt], a, bfrag[ks][nt]);
-    }
-    // C fragment: c0,c1 = (row g, cols 2t,2t+1), c2,c3 = (row g+8, same cols)
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t wv[NT];
 #pragma unroll
-    for (int hlf = 0; hlf < 2; ++hlf) {
-      const int w = w0 + px + g + hlf * 8;
-      if (w >= W) continue;
-      const size_t row = (static_cast<size_t>(n) * (H + 2) + h + 1) * (W + 2) + w + 1;
-      uint32_t* dst = reinterpret_cast<uint32_t*>(out + row * out_ld + out_coff);
+        for (int nt = 0; nt < NT; ++nt)
+          wv[nt] = pack_bf16x2(silu_fast(acc[nt][hlf * 2 + 0] + bia[nt][0]), silu_fast(acc[nt][hlf * 2 + 1] + bia[nt][1]));
+        const int w = w0 + px + g + hlf * 8;
+        const size_t row = (static_cast<size_t>(n) * (H + 2) + h + 1) * (W + 2) + w + 1;
+        if (NT == 4) {
+          // 4x4 transpose inside each lane quad: afterwards lane t owns the 16 contiguous bytes of n-tile t
 #pragma unroll
-      for (int nt = 0; nt < NT; ++nt)
-        dst[nt * 4 + t] = pack_bf16x2(silu_fast(acc[nt][hlf * 2 + 0] + bia[nt][0]), silu_fast(acc[nt][hlf * 2 + 1] + bia[nt][1]));
+          for (int sft = 1; sft <= 2; sft <<= 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (i & sft) continue;
+              const bool up = (t & sft) != 0;
+              const uint32_t send = up ? wv[i] : wv[i | sft];
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, send, sft);
+              if (up) wv[i] = recv; else wv[i | sft] = recv;
+            }
+          }
+          if (w < W)
+            *reinterpret_cast<uint4*>(out + row * out_ld + out_coff + t * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        } else if (w < W) {
+          uint32_t* dst = reinterpret_cast<uint32_t*>(out + row * out_ld + out_coff);
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) dst[nt * 4 + t] = wv[nt];
+        }
+      }
     }
   }
 }
@@ -150,7 +177,7 @@ extern "C" int y3_conv_first_fwd(const y3_first_desc* d, y3_stream_t stream) {
              "conv_first: bad output slice");
   Y3_REQUIRE(d->c_out == 16 || d->c_out == 32, "conv_first: c_out=%d unsupported (16 or 32)", d->c_out);
   Y3_REQUIRE(d->in_dtype == Y3_IN_F32 || d->in_dtype == Y3_IN_U8, "conv_first: bad input dtype %d", d->in_dtype);
-  const dim3 grid((d->w + 127) / 128, d->h, d->n), block(128);
+  const dim3 grid((d->w + y3::kFirstTW - 1) / y3::kFirstTW, (d->h + y3::kFirstRows - 1) / y3::kFirstRows, d->n), block(128);
   auto* o = static_cast<__nv_bfloat16*>(d->out);
   auto s = static_cast<cudaStream_t>(stream);
 #define Y3_FIRST(CO, T)                                                                                            \

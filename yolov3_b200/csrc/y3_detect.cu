@@ -71,12 +71,12 @@ constexpr int kDecodeRows = 4;  // z rows per warp iteration: 12 independent 128
 
 __global__ void __launch_bounds__(256) head_decode_kernel(const HeadDecodeArgs p) {
   const int lane = threadIdx.x & 31;
-  const long long rows_per_img = p.row_off[p.nl];
-  const long long total = rows_per_img * p.bs;
-  const long long groups = (total + kDecodeRows - 1) / kDecodeRows;
-  const long long warp0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  for (long long gidx = warp0; gidx < groups; gidx += nwarps) {
+  const int rows_per_img = p.row_off[p.nl];
+  const int total = rows_per_img * p.bs;  // < 2^31 (checked by the launcher); 64-bit divisions here cost more than the math
+  const int groups = (total + kDecodeRows - 1) / kDecodeRows;
+  const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int gidx = warp0; gidx < groups; gidx += nwarps) {
     const float* src[kDecodeRows];
     float* zd[kDecodeRows];
     float* rd[kDecodeRows];
@@ -84,11 +84,11 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const HeadDecodeArgs p
     float v[kDecodeRows][3];
 #pragma unroll
     for (int q = 0; q < kDecodeRows; ++q) {
-      const long long w = gidx * kDecodeRows + q;
+      const int w = gidx * kDecodeRows + q;
       src[q] = nullptr;
       if (w >= total) continue;
-      const int b = static_cast<int>(w / rows_per_img);
-      const int row = static_cast<int>(w - b * rows_per_img);
+      const int b = w / rows_per_img;
+      const int row = w - b * rows_per_img;
       int l = 0;
       while (l + 1 < p.nl && row >= p.row_off[l + 1]) ++l;
       const int r = row - p.row_off[l];
@@ -168,6 +168,7 @@ extern "C" int y3_detect_head_decode_fwd(const y3_decode_desc* d, y3_stream_t st
   }
   a.row_off[d->nl] = off;
   Y3_REQUIRE(d->no <= 96, "head_decode: no=%d > 96 is not supported by this kernel", d->no);
+  Y3_REQUIRE(static_cast<long long>(off) * d->bs < (1ll << 31), "head_decode: too many rows");
   const long long warps = (static_cast<long long>(off) * d->bs + y3::kDecodeRows - 1) / y3::kDecodeRows;
   long long blocks = (warps + 7) / 8;
   const long long cap = static_cast<long long>(y3::num_sms()) * 32;
