@@ -161,8 +161,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// Remote arrive with the DEFAULT (.release.cta) semantics.  A .release.cluster arrive compiles to MEMBAR.ALL.GPU +
+// CGAERRBAR in front of the arrive, which made the peer's producer thread wait for its in-flight TMA loads on every
+// k-iteration and halved the pair kernel's throughput (profiles/r01_ncu_pair_membar.txt).  Nothing needs publishing
+// here: TMA data is ordered by complete_tx, TMEM reads by tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
