@@ -29,21 +29,29 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kEpilogueWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpilogueWarps;
-constexpr int kSmemBudget = 200 * 1024;  // ring buffers; barriers + alignment slack come on top (227 KB max per CTA)
+constexpr int kSmemBudget = 224 * 1024;  // ring + epilogue staging; barriers + alignment slack come on top (227 KB max)
 
-template <int BLOCK_N, int BLOCK_K, bool PAIR>
+// STAGED = true: the epilogue converts into a swizzled shared-memory staging tile and ONE thread stores it with TMA
+// (and pre-loads the residual tile into the same buffer with TMA), instead of every thread issuing 16-byte global
+// stores to 32 different cache lines per instruction — the thin layers were bound by exactly that (profiles/r01_*).
+template <int BLOCK_N, int BLOCK_K, bool PAIR, bool STAGED>
 struct Cfg {
   static constexpr uint32_t kABytes = kBlockM * BLOCK_K * 2;
   static constexpr uint32_t kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;  // a CTA pair splits the B tile between its two CTAs
   static constexpr uint32_t kBBytes = kBRows * BLOCK_K * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+  static constexpr uint32_t kSlabCols = BLOCK_N >= 64 ? 64 : 32;          // staging slab = [128 rows][kSlabCols bf16]
+  static constexpr uint32_t kSlabRowBytes = kSlabCols * 2;                // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+  static constexpr uint32_t kSlabBytes = kBlockM * kSlabRowBytes;
+  static constexpr uint32_t kSlabs = BLOCK_N / kSlabCols;
+  static constexpr uint32_t kStagingBytes = STAGED ? kBlockM * BLOCK_N * 2 : 0;
+  static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // power of two for N in {32,64,128,256}
   static constexpr uint32_t kSwizzleBytes = BLOCK_K * 2;                       // 32 / 64 / 128
   static constexpr uint32_t kLayout = BLOCK_K == 64 ? 2u : (BLOCK_K == 32 ? 4u : 6u);
   static constexpr uint32_t kSbo = 8 * kSwizzleBytes;
-  static constexpr size_t kSmemBytes = size_t(kStages) * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr size_t kSmemBytes = size_t(kStages) * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
 };
 
@@ -52,11 +60,12 @@ struct Cfg {
 // CTAs' shared memory and write both CTAs' TMEM.  Per-SM operand ingress drops from (128+N)*K to (128+N/2)*K bytes per
 // k-block — the 1-CTA kernel measured ~0.67 of the MMA rate on the big 3x3 layers because (128+256)*64*2 B per 512 MMA
 // cycles exceeds the ~64 B/clk an SM can pull from L2 (profiles/r01_per_op_v2_epilogue.json).
-template <int BLOCK_N, int BLOCK_K, bool PAIR>
+template <int BLOCK_N, int BLOCK_K, bool PAIR, bool STAGED>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                const ConvTcArgs p) {
-  using C = Cfg<BLOCK_N, BLOCK_K, PAIR>;
+  using C = Cfg<BLOCK_N, BLOCK_K, PAIR, STAGED>;
   constexpr int STAGES = C::kStages;
   constexpr uint32_t IDESC = umma_idesc_bf16(PAIR ? 256 : 128, BLOCK_N);
   constexpr uint32_t kEpiThreads = 32 * kEpilogueWarps;
@@ -66,11 +75,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // swizzled TMA/UMMA tiles need 1 KB alignment
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * C::kABytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::kStageBytes);
+  uint8_t* smem_stg = smem + STAGES * C::kStageBytes;  // 1 KB aligned: every stage size is a multiple of 1 KB
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stg + C::kStagingBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,6 +100,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], PAIR ? 2 * kEpiThreads : kEpiThreads);  // pair: both CTAs' epilogues release the buffer
+    }
+    mbar_init(res_bar, 1);
+    if (STAGED) {
+      tma_prefetch_desc(&map_out);
+      if (p.res) tma_prefetch_desc(&map_res);
     }
     fence_mbar_init();
   }
@@ -242,6 +258,85 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         valid = ty < p.th && oy < p.ho && ox < p.wo;
       }
       valid = valid && active && mt < p.m_tiles;  // a pair's second CTA may own a tile past the end
+      if constexpr (STAGED) {
+        // ---------------- staged epilogue (flat mode, bf16 output): TMEM -> registers -> swizzled smem tile -> TMA store
+        const bool elected = threadIdx.x == 64;  // first epilogue thread
+        const int row0 = mt * kBlockM;
+        if (elected) {
+          bulk_wait_read_all();  // the previous tile's store has finished reading the staging buffer
+          if (p.res) {
+            mbar_expect_tx(res_bar, kBlockM * BLOCK_N * 2);
+#pragma unroll
+            for (uint32_t sl = 0; sl < C::kSlabs; ++sl)
+              tma_load_2d(smem_stg + sl * C::kSlabBytes, &map_res, res_bar, p.res_coff + n0 + sl * C::kSlabCols, row0);
+          }
+        }
+        if (!p.res) named_bar_sync(1, kEpiThreads);  // staging buffer is free for everybody
+        mbar_wait(&tfull_bar[as], aphase, p.err, 4);
+        tc_fence_after();
+        if (p.res) mbar_wait(res_bar, iter & 1, p.err, 5);  // residual tile landed (implies the buffer was free)
+        const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
+        const uint32_t swz = C::kSlabRowBytes == 128 ? (m & 7) : ((m >> 1) & 3);
+        if (active) {
+#pragma unroll 1
+          for (int c = c_begin; c < c_begin + kColsPerWarp; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(t_addr + c, v);
+            tmem_ld_wait();
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
+              x[j + 0] = __uint_as_float(v[j + 0]) + b.x;
+              x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
+              x[j + 2] = __uint_as_float(v[j + 2]) + b.z;
+              x[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+            }
+            if (p.act == Y3_ACT_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = silu_fast(x[j]);
+            }
+            const uint32_t slab = c / C::kSlabCols, j0 = (c % C::kSlabCols) / 8;
+            const uint32_t row_addr = smem_u32(smem_stg) + slab * C::kSlabBytes + m * C::kSlabRowBytes;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint32_t addr = row_addr + (((j0 + q) ^ swz) << 4);
+              uint4 o = make_uint4(0u, 0u, 0u, 0u);  // halo / out-of-range rows store zeros (keeps the halo invariant)
+              if (valid) {
+                if (p.res) {
+                  const uint4 r = lds128(addr);
+                  const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = unpack_bf16x2(rr[e]);
+                    x[q * 8 + e * 2 + 0] += f.x;
+                    x[q * 8 + e * 2 + 1] += f.y;
+                  }
+                }
+                o.x = pack_bf16x2(x[q * 8 + 0], x[q * 8 + 1]);
+                o.y = pack_bf16x2(x[q * 8 + 2], x[q * 8 + 3]);
+                o.z = pack_bf16x2(x[q * 8 + 4], x[q * 8 + 5]);
+                o.w = pack_bf16x2(x[q * 8 + 6], x[q * 8 + 7]);
+              }
+              sts128(addr, o);
+            }
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        tc_fence_before();
+        if (PAIR)
+          mbar_arrive_cluster(lead_tempty[as]);
+        else
+          mbar_arrive(&tempty_bar[as]);
+        named_bar_sync(2, kEpiThreads);
+        if (elected) {
+#pragma unroll
+          for (uint32_t sl = 0; sl < C::kSlabs; ++sl)
+            tma_store_2d(&map_out, smem_stg + sl * C::kSlabBytes, p.out_coff + n0 + sl * C::kSlabCols, row0);
+          bulk_commit_group();
+        }
+        continue;
+      }
       const int oh = p.mode == 0 ? p.hp - 2 : p.ho;  // conv-output height/width (unpadded)
       const int ow = p.mode == 0 ? p.wp - 2 : p.wo;
       const long long conv_row = (static_cast<long long>(img) * (oh + 2) + oy + 1) * (ow + 2) + ox + 1;
@@ -281,7 +376,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int q = 0; q < 4; ++q) rnext[q] = __ldg(reinterpret_cast<const uint4*>(res_ptr + c + 32) + q);
           }
           tmem_ld_wait();
-          if (valid) {
+          if (valid && (f32_ptr || n0 + c < p.cout)) {
             float x[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -343,6 +438,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   }
 
+  if (STAGED && threadIdx.x == 64) bulk_wait_all();  // the last tile's TMA store has completed
   __syncwarp();
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();  // pair: nobody leaves while the peer may still signal its barriers
@@ -352,10 +448,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
-template <int BLOCK_N, int BLOCK_K, bool PAIR>
+template <int BLOCK_N, int BLOCK_K, bool PAIR, bool STAGED>
 int launch_cfg(const ConvTcPlan& plan, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, BLOCK_K, PAIR>;
-  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, PAIR>;
+  using C = Cfg<BLOCK_N, BLOCK_K, PAIR, STAGED>;
+  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, PAIR, STAGED>;
   static bool attr_set = false;  // benign race: idempotent attribute
   if (!attr_set) {
     Y3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::kSmemBytes)));
@@ -375,7 +471,7 @@ int launch_cfg(const ConvTcPlan& plan, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   }
-  Y3_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, plan.map_a, plan.map_b, plan.args));
+  Y3_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, plan.map_a, plan.map_b, plan.map_out, plan.map_res, plan.args));
   return Y3_OK;
 }
 
@@ -384,12 +480,12 @@ int pick_block_n(int cout) { return cout <= 32 ? 32 : (cout <= 64 ? 64 : (cout <
 }  // namespace
 
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream) {
-#define Y3_DISPATCH_K(BN, PR)                                      \
-  switch (plan.block_k) {                                          \
-    case 64: return launch_cfg<BN, 64, PR>(plan, stream);          \
-    case 32: return launch_cfg<BN, 32, PR>(plan, stream);          \
-    case 16: return launch_cfg<BN, 16, PR>(plan, stream);          \
-  }                                                                \
+#define Y3_DISPATCH_K(BN, PR)                                                                                   \
+  switch (plan.block_k) {                                                                                       \
+    case 64: return plan.staged ? launch_cfg<BN, 64, PR, true>(plan, stream) : launch_cfg<BN, 64, PR, false>(plan, stream); \
+    case 32: return plan.staged ? launch_cfg<BN, 32, PR, true>(plan, stream) : launch_cfg<BN, 32, PR, false>(plan, stream); \
+    case 16: return plan.staged ? launch_cfg<BN, 16, PR, true>(plan, stream) : launch_cfg<BN, 16, PR, false>(plan, stream); \
+  }                                                                                                             \
   break;
   if (plan.pair) {
     switch (plan.block_n) {
@@ -409,6 +505,16 @@ int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream) {
 }
 
 // Y3_CONV_PAIR=0 forces the 1-CTA kernel everywhere (A/B measurements); default: CTA pairs for tile N >= 128.
+// Y3_CONV_STAGED=0 forces the direct-store epilogue everywhere (A/B measurements).
+static bool staged_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("Y3_CONV_STAGED");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 static bool pair_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -534,6 +640,25 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     const uint32_t box[2] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(plan->pair ? bn / 2 : bn)};
     rc = encode_tensor_map_bf16(&plan->map_b, d.weight, 2, dims, strides, box, bk * 2);
     if (rc) return rc;
+  }
+  // staged (TMA-store) epilogue: flat mode, bf16 output, no upsample
+  plan->staged = (a.mode == 0 && !head && !d.upsample && staged_enabled()) ? 1 : 0;
+  plan->map_out = plan->map_a;
+  plan->map_res = plan->map_a;
+  if (plan->staged) {
+    const uint32_t slab_cols = bn >= 64 ? 64 : 32;
+    // dim0 ends at the last channel this conv owns, so a partial last N tile is clipped by the TMA unit
+    const uint64_t dims[2] = {static_cast<uint64_t>(d.out_coff + d.c_out), static_cast<uint64_t>(a.rows_total)};
+    const uint64_t strides[2] = {0, static_cast<uint64_t>(d.out_ld) * 2};
+    const uint32_t box[2] = {slab_cols, kBlockM};
+    rc = encode_tensor_map_bf16(&plan->map_out, d.out, 2, dims, strides, box, slab_cols * 2);
+    if (rc) return rc;
+    if (d.res) {
+      const uint64_t rdims[2] = {static_cast<uint64_t>(d.res_ld), static_cast<uint64_t>(a.rows_total)};
+      const uint64_t rstrides[2] = {0, static_cast<uint64_t>(d.res_ld) * 2};
+      rc = encode_tensor_map_bf16(&plan->map_res, d.res, 2, rdims, rstrides, box, slab_cols * 2);
+      if (rc) return rc;
+    }
   }
   const int sms = num_sms();
   if (plan->pair) {

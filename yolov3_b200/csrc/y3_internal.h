@@ -56,7 +56,8 @@ struct ConvTcArgs {
 };
 
 struct ConvTcPlan {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_out, map_res;
+  int staged;  // 1: epilogue stages the tile in shared memory and stores it with TMA
   ConvTcArgs args;
   int block_n, block_k;
   int pair;  // 1: CTA-pair (cta_group::2) kernel, launched as clusters of 2
