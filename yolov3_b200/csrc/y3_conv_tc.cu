@@ -51,7 +51,8 @@ struct Cfg {
   static constexpr uint32_t kSwizzleBytes = BLOCK_K * 2;                       // 32 / 64 / 128
   static constexpr uint32_t kLayout = BLOCK_K == 64 ? 2u : (BLOCK_K == 32 ? 4u : 6u);
   static constexpr uint32_t kSbo = 8 * kSwizzleBytes;
-  static constexpr size_t kSmemBytes = size_t(kStages) * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr size_t kSmemBytes =
+      size_t(kStages) * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/ + BLOCK_N * 4 /*bias tile*/;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
 };
 
@@ -82,6 +83,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* res_bar = tempty_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+  // bias of the current N tile.  Read through __ldg it missed the (almost entirely shared-memory) L1 and exposed an L2
+  // round trip per 32-column chunk: 29 % of all warp stall samples of the epilogue (profiles/r01_ncu_conv_tc_full_summary.txt).
+  float* s_bias = reinterpret_cast<float*>(smem_stg + C::kStagingBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -271,10 +275,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tma_load_2d(smem_stg + sl * C::kSlabBytes, &map_res, res_bar, p.res_coff + n0 + sl * C::kSlabCols, row0);
           }
         }
-        if (!p.res) named_bar_sync(1, kEpiThreads);  // staging buffer is free for everybody
+        // (the end-of-tile barrier 2 of the previous tile guarantees nobody still reads the old bias values)
+        if (int(threadIdx.x) - 64 < BLOCK_N) s_bias[threadIdx.x - 64] = __ldg(p.bias + n0 + threadIdx.x - 64);
         mbar_wait(&tfull_bar[as], aphase, p.err, 4);
         tc_fence_after();
-        if (p.res) mbar_wait(res_bar, iter & 1, p.err, 5);  // residual tile landed (implies the buffer was free)
+        named_bar_sync(1, kEpiThreads);  // bias tile visible; staging buffer is free for everybody
+        if (p.res) mbar_wait(res_bar, iter & 1, p.err, 5);  // residual tile landed
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
         const uint32_t swz = C::kSlabRowBytes == 128 ? (m & 7) : ((m >> 1) & 3);
         if (active) {
@@ -286,7 +292,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float x[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
+              const float4 b = *reinterpret_cast<const float4*>(s_bias + c + j);
               x[j + 0] = __uint_as_float(v[j + 0]) + b.x;
               x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
               x[j + 2] = __uint_as_float(v[j + 2]) + b.z;
@@ -361,8 +367,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int q = 0; q < 4; ++q) rcur[q] = __ldg(reinterpret_cast<const uint4*>(res_ptr + c_begin) + q);
       }
 
+      if (int(threadIdx.x) - 64 < BLOCK_N) s_bias[threadIdx.x - 64] = __ldg(p.bias + n0 + threadIdx.x - 64);
       mbar_wait(&tfull_bar[as], aphase, p.err, 4);  // accumulator complete
       tc_fence_after();
+      named_bar_sync(1, kEpiThreads);  // bias tile visible
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
       if (active) {
 #pragma unroll 1
@@ -380,7 +388,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float x[32];
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
+              const float4 b = *reinterpret_cast<const float4*>(s_bias + c + j);
               x[j + 0] = __uint_as_float(v[j + 0]) + b.x;
               x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
               x[j + 2] = __uint_as_float(v[j + 2]) + b.z;
@@ -435,6 +443,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_arrive_cluster(lead_tempty[as]);  // the leader's MMA thread waits for BOTH CTAs' epilogues
       else
         mbar_arrive(&tempty_bar[as]);
+      named_bar_sync(2, kEpiThreads);  // everybody is done with this tile's bias values
     }
   }
 

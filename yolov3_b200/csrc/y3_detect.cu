@@ -67,26 +67,26 @@ struct HeadDecodeArgs {
   float* z;
 };
 
-constexpr int kDecodeRows = 4;  // z rows per warp iteration: 12 independent 128-byte loads in flight per warp
+constexpr int kDecodeRows = 4;  // consecutive z rows per warp iteration (they are contiguous in z and in the logits)
+
+// sigmoid through the fast exp/divide units: relative error ~1e-6, far inside the 1e-5 decode tolerance (the bit-exact
+// requirement applies to NMS on a given z, not to z itself); the IEEE expf/division sequence cost ~1/3 of this kernel.
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 __global__ void __launch_bounds__(256) head_decode_kernel(const HeadDecodeArgs p) {
   const int lane = threadIdx.x & 31;
   const int rows_per_img = p.row_off[p.nl];
-  const int total = rows_per_img * p.bs;  // < 2^31 (checked by the launcher); 64-bit divisions here cost more than the math
+  const int total = rows_per_img * p.bs;  // < 2^31 (checked by the launcher)
   const int groups = (total + kDecodeRows - 1) / kDecodeRows;
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int no = p.no;
   for (int gidx = warp0; gidx < groups; gidx += nwarps) {
-    const float* src[kDecodeRows];
-    float* zd[kDecodeRows];
-    float* rd[kDecodeRows];
-    int lx[kDecodeRows], ly[kDecodeRows], ll[kDecodeRows], la[kDecodeRows];
-    float v[kDecodeRows][3];
-#pragma unroll
-    for (int q = 0; q < kDecodeRows; ++q) {
-      const int w = gidx * kDecodeRows + q;
-      src[q] = nullptr;
-      if (w >= total) continue;
+    // per-row descriptors, computed by lanes 0..3 and broadcast (saves every lane redoing the integer divisions)
+    const int w = gidx * kDecodeRows + (lane & 3);
+    long long src_off = -1, raw_off = 0;
+    int lxy = 0, lla = 0;
+    if (lane < kDecodeRows && w < total) {
       const int b = w / rows_per_img;
       const int row = w - b * rows_per_img;
       int l = 0;
@@ -94,43 +94,52 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const HeadDecodeArgs p
       const int r = row - p.row_off[l];
       const int plane = p.ny[l] * p.nx[l];
       const int a = r / plane, cell = r - a * plane;
-      ly[q] = cell / p.nx[l];
-      lx[q] = cell - ly[q] * p.nx[l];
-      ll[q] = l;
-      la[q] = a;
-      src[q] = p.head[l] + (static_cast<long long>(b) * plane + cell) * p.head_ld[l] + a * p.no;
-      zd[q] = p.z ? p.z + (static_cast<long long>(b) * rows_per_img + row) * p.no : nullptr;
-      rd[q] = p.raw[l] ? p.raw[l] + ((static_cast<long long>(b) * p.na + a) * plane + cell) * p.no : nullptr;
+      const int y = cell / p.nx[l], x = cell - y * p.nx[l];
+      src_off = (static_cast<long long>(b) * plane + cell) * p.head_ld[l] + a * no;
+      raw_off = ((static_cast<long long>(b) * p.na + a) * plane + cell) * no;
+      lxy = (y << 16) | x;
+      lla = (l << 8) | a;
     }
+    const long long z_base = static_cast<long long>(gidx) * kDecodeRows * no;  // rows of a group are contiguous in z
+    const int n_el = min(kDecodeRows, total - gidx * kDecodeRows) * no;
+    // the group's kDecodeRows*no outputs form one contiguous range of z: lanes stride over it -> fully coalesced stores
+#pragma unroll 1
+    for (int e0 = 0; e0 < n_el; e0 += 128) {
+      float v[4];
+      int qq[4], kk[4];
 #pragma unroll
-    for (int q = 0; q < kDecodeRows; ++q) {
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const int k = lane + 32 * j;
-        v[q][j] = (src[q] && k < p.no) ? __ldg(src[q] + k) : 0.f;
+      for (int j = 0; j < 4; ++j) {
+        const int e = e0 + j * 32 + lane;
+        const int q = e / no;
+        qq[j] = q;
+        kk[j] = e - q * no;
+        const long long so = __shfl_sync(0xffffffffu, src_off, q & 3);
+        const int l = __shfl_sync(0xffffffffu, lla, q & 3) >> 8;
+        v[j] = (e < n_el) ? __ldg(p.head[l] + so + kk[j]) : 0.f;
       }
-    }
 #pragma unroll
-    for (int q = 0; q < kDecodeRows; ++q) {
-      if (!src[q]) continue;
-      const int l = ll[q];
-      for (int j = 0; j < 3; ++j) {
-        const int k = lane + 32 * j;
-        if (k >= p.no) break;
-        const float x = v[q][j];
-        if (rd[q]) rd[q][k] = x;
-        if (zd[q]) {
-          const float s = 1.0f / (1.0f + expf(-x));
+      for (int j = 0; j < 4; ++j) {
+        const int e = e0 + j * 32 + lane;
+        const int q = qq[j], k = kk[j];
+        const long long ro = __shfl_sync(0xffffffffu, raw_off, q & 3);
+        const int la = __shfl_sync(0xffffffffu, lla, q & 3);
+        const int xy = __shfl_sync(0xffffffffu, lxy, q & 3);
+        if (e >= n_el) continue;
+        const int l = la >> 8, a = la & 255;
+        const float x = v[j];
+        if (p.raw[l]) p.raw[l][ro + k] = x;
+        if (p.z) {
+          const float s = sigmoid_fast(x);
           float o = s;
           if (k == 0)
-            o = (s * 2.0f + (static_cast<float>(lx[q]) - 0.5f)) * p.stride[l];
+            o = (s * 2.0f + (static_cast<float>(xy & 0xFFFF) - 0.5f)) * p.stride[l];
           else if (k == 1)
-            o = (s * 2.0f + (static_cast<float>(ly[q]) - 0.5f)) * p.stride[l];
+            o = (s * 2.0f + (static_cast<float>(xy >> 16) - 0.5f)) * p.stride[l];
           else if (k < 4) {
             const float t = s * 2.0f;
-            o = (t * t) * (k == 2 ? p.anchor_w[l][la[q]] : p.anchor_h[l][la[q]]);
+            o = (t * t) * (k == 2 ? p.anchor_w[l][a] : p.anchor_h[l][a]);
           }
-          zd[q][k] = o;
+          p.z[z_base + e] = o;
         }
       }
     }
