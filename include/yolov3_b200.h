@@ -197,6 +197,63 @@ int64_t y3_loss_workspace_bytes(const y3_loss_desc* d);
 int y3_loss_fwd_bwd(const y3_loss_desc* d, void* workspace, int64_t workspace_bytes, float* out, y3_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Training-mode Conv block (models/common.py:71-75 with BatchNorm2d in train mode) and its backward.  The convolution
+ * (forward; dgrad = convolution with the transposed, tap-flipped weights) is y3_conv_bn_act_fwd with zero bias and
+ * Y3_ACT_NONE; these entry points are the bandwidth-bound parts around it.  All activations: padded NHWC bf16 slices.
+ */
+/* per-channel sum and sum of squares of y over all `rows` = n*(h+2)*(w+2) padded pixels (halo = 0); sum/sumsq must be
+ * zeroed by the caller */
+int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, int64_t rows, float* sum, float* sumsq,
+                y3_stream_t stream);
+/* batch statistics -> scale = gamma*rstd, shift = beta - mean*scale, saved mean/rstd; running stats updated in place
+ * with the unbiased variance when non-NULL (nn.BatchNorm2d semantics).  count = n*h*w. */
+int y3_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, int32_t c, float count,
+                   float eps, float momentum, float* scale, float* shift, float* mean, float* rstd, float* running_mean,
+                   float* running_var, y3_stream_t stream);
+typedef struct y3_bn_act_desc {
+  const void* y;   int32_t y_ld, y_coff;       /* conv output (pre-BN) */
+  const void* res; int32_t res_ld, res_coff;   /* optional residual added after the activation (Bottleneck shortcut) */
+  void* out;       int32_t out_ld, out_coff;   /* a = SiLU(y*scale+shift) (+res); [n, h*u+2, w*u+2, out_ld], u = 1+upsample */
+  const float* scale; const float* shift;
+  int32_t n, h, w, c, upsample;
+} y3_bn_act_desc;
+int y3_bn_act_fwd(const y3_bn_act_desc* d, y3_stream_t stream);
+typedef struct y3_bn_bwd_desc {
+  const void* y;  int32_t y_ld, y_coff;        /* saved conv output */
+  const void* da; int32_t da_ld, da_coff;      /* gradient w.r.t. the block output (2x geometry when upsample) */
+  void* dy;       int32_t dy_ld, dy_coff;      /* gradient w.r.t. the conv output (input of dgrad / wgrad) */
+  const float* scale; const float* shift; const float* mean; const float* rstd;
+  float* sum_dz;   /* [c] out: dbeta  */
+  float* sum_dzy;  /* [c] out: dgamma */
+  int32_t n, h, w, c, upsample;
+} y3_bn_bwd_desc;
+int y3_bn_act_bwd(const y3_bn_bwd_desc* d, y3_stream_t stream);
+/* fp32 master weights [co, ci, k, k] -> bf16 forward pack [co_pad, k*k*ci] and/or dgrad pack [ci_pad, k*k*co] (taps
+ * flipped, channels swapped); pad rows must already be zero */
+int y3_pack_weights(const float* w, int32_t co, int32_t ci, int32_t k, void* fwd, void* dgrad, y3_stream_t stream);
+/* dy of a stride-2 conv scattered onto the even positions of a zeroed [n, 2ho+2, 2wo+2, dst_ld] buffer */
+int y3_zero_stuff(const void* src, int32_t src_ld, int32_t src_coff, void* dst, int32_t dst_ld, int32_t dst_coff, int32_t n,
+                  int32_t ho, int32_t wo, int32_t c, y3_stream_t stream);
+/* dW[co, ci, kh, kw] += sum_p dy[p, co] * x[p + shift(kh,kw), ci] on the stride-1 padded grid [n, h+2, w+2]; dw is fp32 in
+ * PyTorch's [co, ci, k, k] layout, zeroed by the caller; co, ci multiples of 8 */
+typedef struct y3_wgrad_desc {
+  const void* dy; int32_t dy_ld, dy_coff;
+  const void* x;  int32_t x_ld, x_coff;
+  float* dw;
+  int32_t co, ci, ksize, n, h, w;
+} y3_wgrad_desc;
+int y3_conv_wgrad(const y3_wgrad_desc* d, y3_stream_t stream);
+/* dst (+)= src over the interior pixels of two padded NHWC bf16 slices of equal [n,h,w,c] (gradient fan-in) */
+int y3_add_nhwc(const void* src, int32_t src_ld, int32_t src_coff, void* dst, int32_t dst_ld, int32_t dst_coff, int32_t n,
+                int32_t h, int32_t w, int32_t c, int32_t accumulate, y3_stream_t stream);
+/* 3x3 pad-1 im2col of the [n,3,h,w] image (Y3_IN_F32 | Y3_IN_U8, optional /in_div) into 32 bf16 channels of a padded
+ * NHWC buffer, column (c*3+kh)*3+kw; lets training run layer 0 as a 1x1 conv with the generic kernels */
+int y3_im2col_first(const void* in, int32_t in_dtype, float in_div, int32_t n, int32_t h, int32_t w, void* out,
+                    int32_t out_ld, int32_t out_coff, y3_stream_t stream);
+/* out[c] += sum over rows of g[row, c] (fp32 pixel-major; Detect-head bias gradients) */
+int y3_colsum_f32(const float* g, int32_t ld, int32_t c, int64_t rows, float* out, y3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Whole-graph executor.  Replaces BaseModel._forward_once (models/yolo.py:135-147): the Python loop over nn.Modules
  * becomes an immutable list of prepared launches (TMA descriptors encoded once at create) replayed on one stream.
  * All buffers belong to the caller; y3_model_forward is CUDA-graph capturable.

@@ -187,13 +187,14 @@ def fold_bn(w, gamma, beta, mean, var, eps=BN_EPS):
 # Forward (models/yolo.py:135-147 executor semantics; models/common.py blocks; Detect models/yolo.py:89-123)
 # ----------------------------------------------------------------------------------------------------------------------
 class OracleModel:
-    def __init__(self, cfg, params=None, seed=0, ch=3, fused=True, act_dtype=None, weight_dtype=None):
+    def __init__(self, cfg, params=None, seed=0, ch=3, fused=True, act_dtype=None, weight_dtype=None, train=False):
         """act_dtype/weight_dtype = torch.bfloat16 emulates the CUDA path's storage rounding (activations rounded to
         bf16 after every conv block, folded weights rounded to bf16, fp32 accumulation) for tight per-layer checks."""
         self.cfg = load_cfg(cfg)
         self.nodes, self.save = parse_graph(self.cfg, ch)
         self.params = params if params is not None else init_params(self.cfg, seed, ch=ch)
-        self.fused = fused
+        self.fused = fused and not train
+        self.train = train  # BatchNorm with batch statistics (train.py:403 runs the model in train mode)
         self.act_dtype, self.weight_dtype = act_dtype, weight_dtype
         det = self.nodes[-1]
         self.nc, anchors, _ = det["args"]
@@ -215,6 +216,9 @@ class OracleModel:
             if self.weight_dtype is not None:
                 w = w.to(self.weight_dtype).float()
             y = F.conv2d(x, w, b, stride=s, padding=k // 2)
+        elif self.train:
+            y = F.conv2d(x, w, None, stride=s, padding=k // 2)
+            y = F.batch_norm(y, None, None, bn[0], bn[1], True, 0.03, BN_EPS)
         else:
             y = F.conv2d(x, w, None, stride=s, padding=k // 2)
             y = F.batch_norm(y, bn[2], bn[3], bn[0], bn[1], False, 0.0, BN_EPS)

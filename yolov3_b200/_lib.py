@@ -104,6 +104,36 @@ class LossDesc(C.Structure):
                 ("balance", C.c_float * MAX_LEVELS), ("grad_scale", C.c_float)]
 
 
+class BnActDesc(C.Structure):
+    """struct y3_bn_act_desc."""
+
+    _fields_ = [("y", C.c_void_p), ("y_ld", C.c_int32), ("y_coff", C.c_int32),
+                ("res", C.c_void_p), ("res_ld", C.c_int32), ("res_coff", C.c_int32),
+                ("out", C.c_void_p), ("out_ld", C.c_int32), ("out_coff", C.c_int32),
+                ("scale", C.c_void_p), ("shift", C.c_void_p),
+                ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("upsample", C.c_int32)]
+
+
+class BnBwdDesc(C.Structure):
+    """struct y3_bn_bwd_desc."""
+
+    _fields_ = [("y", C.c_void_p), ("y_ld", C.c_int32), ("y_coff", C.c_int32),
+                ("da", C.c_void_p), ("da_ld", C.c_int32), ("da_coff", C.c_int32),
+                ("dy", C.c_void_p), ("dy_ld", C.c_int32), ("dy_coff", C.c_int32),
+                ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
+                ("sum_dz", C.c_void_p), ("sum_dzy", C.c_void_p),
+                ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("upsample", C.c_int32)]
+
+
+class WgradDesc(C.Structure):
+    """struct y3_wgrad_desc."""
+
+    _fields_ = [("dy", C.c_void_p), ("dy_ld", C.c_int32), ("dy_coff", C.c_int32),
+                ("x", C.c_void_p), ("x_ld", C.c_int32), ("x_coff", C.c_int32),
+                ("dw", C.c_void_p),
+                ("co", C.c_int32), ("ci", C.c_int32), ("ksize", C.c_int32), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32)]
+
+
 def _declare(lib):
     i32, vp, sz = C.c_int32, C.c_void_p, C.c_size_t
     sigs = {
@@ -115,6 +145,16 @@ def _declare(lib):
         "y3_abi_sizeof": ([i32], C.c_int64),
         "y3_conv_first_fwd": ([C.POINTER(FirstDesc), vp], C.c_int),
         "y3_maxpool_fwd": ([C.POINTER(PoolDesc), vp], C.c_int),
+        "y3_bn_stats": ([vp, i32, i32, i32, C.c_int64, vp, vp, vp], C.c_int),
+        "y3_bn_finalize": ([vp, vp, vp, vp, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp], C.c_int),
+        "y3_bn_act_fwd": ([C.POINTER(BnActDesc), vp], C.c_int),
+        "y3_bn_act_bwd": ([C.POINTER(BnBwdDesc), vp], C.c_int),
+        "y3_pack_weights": ([vp, i32, i32, i32, vp, vp, vp], C.c_int),
+        "y3_zero_stuff": ([vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, vp], C.c_int),
+        "y3_conv_wgrad": ([C.POINTER(WgradDesc), vp], C.c_int),
+        "y3_add_nhwc": ([vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp], C.c_int),
+        "y3_im2col_first": ([vp, i32, C.c_float, i32, i32, i32, vp, i32, i32, vp], C.c_int),
+        "y3_colsum_f32": ([vp, i32, i32, C.c_int64, vp, vp], C.c_int),
         "y3_box_iou": ([vp, i32, vp, i32, C.c_float, vp, vp], C.c_int),
         "y3_loss_workspace_bytes": ([C.POINTER(LossDesc)], C.c_int64),
         "y3_loss_fwd_bwd": ([C.POINTER(LossDesc), vp, C.c_int64, vp, vp], C.c_int),

@@ -1,0 +1,684 @@
+// yolov3_b200 — training-mode pieces of the Conv block (reference models/common.py:71-75 `act(bn(conv(x)))` with
+// BatchNorm2d in training mode, eps 1e-3 / momentum 0.03 set by initialize_weights, models/yolo.py:229) and their
+// backward.  The convolution itself (forward, and dgrad as a convolution with transposed/flipped weights) runs in
+// conv_tc_kernel with an identity epilogue; this file holds the bandwidth-bound parts around it:
+//   bn_stats        per-channel sum / sum of squares of the conv output y (padded NHWC bf16; the zero halo adds nothing)
+//   bn_finalize     batch mean/var -> (scale, shift), saved (mean, rstd), running-stat update (unbiased var, momentum)
+//   bn_act_fwd      a = SiLU(y*scale + shift) (+ residual), optional nearest-2x store / concat-offset store
+//   bn_act_bwd_red  dz = da * SiLU'(z);  per-channel sum(dz), sum(dz * yhat)          (dgamma, dbeta)
+//   bn_act_bwd      dy = scale * (dz - mean(dz) - yhat * mean(dz*yhat))               (input of dgrad / wgrad)
+//   pack_weights    fp32 master weights [co,ci,k,k] -> bf16 forward pack [co_pad, tap*ci+c] and dgrad pack
+//                   [ci_pad, tap'*co+o] (taps flipped), every optimizer step
+//   zero_stuff      dy of a stride-2 conv scattered onto the even positions of a zero 2x grid (its dgrad is then a
+//                   stride-1 conv with flipped weights)
+//   wgrad           dW[co, tap, ci] = sum_p dy[p, co] * x[p + shift(tap), ci]  (warp-level bf16 MMA, split over pixels)
+//   bias_grad       Detect heads: db[co] = sum_p dy[p, co]
+#include "y3_common.cuh"
+#include "y3_internal.h"
+
+namespace y3 {
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = unpack_bf16x2(w[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// geometry of a padded NHWC slice
+struct Slice {
+  const __nv_bfloat16* p;
+  int ld, coff;
+};
+struct SliceW {
+  __nv_bfloat16* p;
+  int ld, coff;
+};
+
+// ---------------------------------------------------------------------------------------------- bn_stats
+// grid: (row blocks); block = 256 threads = (C/8 channel groups) x (256/(C/8) row lanes); rows = all padded pixels
+__global__ void __launch_bounds__(256) bn_stats_kernel(Slice y, int c8, long long rows, int rows_per_block, float* sum,
+                                                       float* sumsq) {
+  extern __shared__ float sh[];  // [2][256][8]
+  const int cg = threadIdx.x % c8, rl = threadIdx.x / c8, nrl = blockDim.x / c8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  if (rl < nrl) {
+    for (long long r = r0 + rl; r < r1; r += nrl) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(y.p + r * y.ld + y.coff + cg * 8));
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        q[i] += f[i] * f[i];
+      }
+    }
+  }
+  float* ss = sh + threadIdx.x * 8;
+  float* qq = sh + 256 * 8 + threadIdx.x * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    ss[i] = s[i];
+    qq[i] = q[i];
+  }
+  __syncthreads();
+  if (rl == 0) {
+    for (int k = 1; k < nrl; ++k) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += sh[(k * c8 + cg) * 8 + i];
+        q[i] += sh[256 * 8 + (k * c8 + cg) * 8 + i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(sum + cg * 8 + i, s[i]);
+      atomicAdd(sumsq + cg * 8 + i, q[i]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- bn_finalize
+__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, const float* gamma, const float* beta, int c,
+                                   float count, float eps, float momentum, float* scale, float* shift, float* mean_out,
+                                   float* rstd_out, float* running_mean, float* running_var) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const float mean = sum[i] / count;
+  float var = sumsq[i] / count - mean * mean;
+  var = var > 0.f ? var : 0.f;
+  const float rstd = rsqrtf(var + eps);
+  const float sc = gamma[i] * rstd;
+  scale[i] = sc;
+  shift[i] = beta[i] - mean * sc;
+  mean_out[i] = mean;
+  rstd_out[i] = rstd;
+  if (running_mean) {
+    const float unbiased = count > 1.f ? var * count / (count - 1.f) : var;
+    running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * mean;
+    running_var[i] = (1.f - momentum) * running_var[i] + momentum * unbiased;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- bn_act_fwd
+// one thread = one interior pixel x 8 channels
+struct BnActArgs {
+  Slice y;        // conv output (pre-BN)
+  Slice res;      // optional residual (p == nullptr: none), geometry of y
+  SliceW out;     // activation; padded (h*u+2, w*u+2) when upsample
+  const float* scale;
+  const float* shift;
+  int n, h, w, c8, upsample;
+};
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const BnActArgs p) {
+  const long long total = static_cast<long long>(p.n) * p.h * p.w * p.c8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % p.c8);
+    long long t = i / p.c8;
+    const int x = static_cast<int>(t % p.w);
+    t /= p.w;
+    const int yy = static_cast<int>(t % p.h);
+    const int n = static_cast<int>(t / p.h);
+    const long long row = (static_cast<long long>(n) * (p.h + 2) + yy + 1) * (p.w + 2) + x + 1;
+    float f[8], r[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p.y.p + row * p.y.ld + p.y.coff + cg * 8)), f);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + cg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + cg * 8 + 4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift + cg * 8)), h1 = __ldg(reinterpret_cast<const float4*>(p.shift + cg * 8 + 4));
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = silu_f(fmaf(f[k], sc[k], sh[k]));
+    if (p.res.p) {
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.res.p + row * p.res.ld + p.res.coff + cg * 8)), r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += r[k];
+    }
+    const uint4 o = pack8(f);
+    if (p.upsample) {
+      const int w2 = 2 * p.w + 2;
+      const long long r00 = (static_cast<long long>(n) * (2 * p.h + 2) + 2 * yy + 1) * w2 + 2 * x + 1;
+#pragma unroll
+      for (int rep = 0; rep < 4; ++rep)
+        *reinterpret_cast<uint4*>(p.out.p + (r00 + (rep >> 1) * w2 + (rep & 1)) * p.out.ld + p.out.coff + cg * 8) = o;
+    } else {
+      *reinterpret_cast<uint4*>(p.out.p + row * p.out.ld + p.out.coff + cg * 8) = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- bn_act_bwd
+// da: gradient w.r.t. the block output a (geometry of `out` in the forward, i.e. 2x when upsample: the 4 replicas are
+// summed).  Pass 1 (reduce) accumulates sum(dz), sum(dz*yhat); pass 2 (apply) writes dy.
+struct BnBwdArgs {
+  Slice y;
+  Slice da;
+  SliceW dy;
+  const float* scale;  // gamma * rstd
+  const float* shift;  // beta - mean*scale
+  const float* mean;
+  const float* rstd;
+  float* sum_dz;       // [c] (= dbeta)
+  float* sum_dzy;      // [c] (= dgamma)
+  int n, h, w, c8, upsample;
+  float inv_count;
+};
+__device__ __forceinline__ void load_da(const BnBwdArgs& p, int n, int yy, int x, int cg, float (&d)[8]) {
+  if (p.upsample) {
+    const int w2 = 2 * p.w + 2;
+    const long long r00 = (static_cast<long long>(n) * (2 * p.h + 2) + 2 * yy + 1) * w2 + 2 * x + 1;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] = 0.f;
+#pragma unroll
+    for (int rep = 0; rep < 4; ++rep) {
+      float t[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.da.p + (r00 + (rep >> 1) * w2 + (rep & 1)) * p.da.ld + p.da.coff + cg * 8)), t);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] += t[k];
+    }
+  } else {
+    const long long row = (static_cast<long long>(n) * (p.h + 2) + yy + 1) * (p.w + 2) + x + 1;
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p.da.p + row * p.da.ld + p.da.coff + cg * 8)), d);
+  }
+}
+// dz = da * d/dz[z*sigmoid(z)] = da * s*(1 + z*(1-s))
+__device__ __forceinline__ float silu_grad(float z) {
+  const float s = __fdividef(1.0f, 1.0f + __expf(-z));
+  return s * fmaf(z, 1.0f - s, 1.0f);
+}
+
+template <bool APPLY>
+__global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BnBwdArgs p) {
+  // block = 256 threads = c8 channel groups x (256/c8) pixel lanes (c8 <= 256); grid-stride over pixels
+  extern __shared__ float sh[];
+  const int cg = threadIdx.x % p.c8, pl = threadIdx.x / p.c8, npl = blockDim.x / p.c8;
+  const long long pixels = static_cast<long long>(p.n) * p.h * p.w;
+  float a_dz[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a_dzy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float sc[8], shf[8], mu[8], rs[8], m_dz[8], m_dzy[8];
+  if (pl < npl) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      sc[k] = p.scale[cg * 8 + k];
+      shf[k] = p.shift[cg * 8 + k];
+      mu[k] = p.mean[cg * 8 + k];
+      rs[k] = p.rstd[cg * 8 + k];
+      if (APPLY) {
+        m_dz[k] = p.sum_dz[cg * 8 + k] * p.inv_count;
+        m_dzy[k] = p.sum_dzy[cg * 8 + k] * p.inv_count;
+      }
+    }
+    for (long long px = static_cast<long long>(blockIdx.x) * npl + pl; px < pixels; px += static_cast<long long>(gridDim.x) * npl) {
+      const int x = static_cast<int>(px % p.w);
+      const long long t = px / p.w;
+      const int yy = static_cast<int>(t % p.h);
+      const int n = static_cast<int>(t / p.h);
+      const long long row = (static_cast<long long>(n) * (p.h + 2) + yy + 1) * (p.w + 2) + x + 1;
+      float yv[8], d[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.y.p + row * p.y.ld + p.y.coff + cg * 8)), yv);
+      load_da(p, n, yy, x, cg, d);
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float z = fmaf(yv[k], sc[k], shf[k]);
+        const float dz = d[k] * silu_grad(z);
+        const float yh = (yv[k] - mu[k]) * rs[k];
+        if (APPLY) {
+          o[k] = sc[k] * (dz - m_dz[k] - yh * m_dzy[k]);
+        } else {
+          a_dz[k] += dz;
+          a_dzy[k] += dz * yh;
+        }
+      }
+      if (APPLY) *reinterpret_cast<uint4*>(p.dy.p + row * p.dy.ld + p.dy.coff + cg * 8) = pack8(o);
+    }
+  }
+  if (!APPLY) {
+    float* s0 = sh + threadIdx.x * 8;
+    float* s1 = sh + 256 * 8 + threadIdx.x * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s0[k] = a_dz[k];
+      s1[k] = a_dzy[k];
+    }
+    __syncthreads();
+    if (pl == 0) {
+      for (int j = 1; j < npl; ++j) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          a_dz[k] += sh[(j * p.c8 + cg) * 8 + k];
+          a_dzy[k] += sh[256 * 8 + (j * p.c8 + cg) * 8 + k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        atomicAdd(p.sum_dz + cg * 8 + k, a_dz[k]);
+        atomicAdd(p.sum_dzy + cg * 8 + k, a_dzy[k]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- pack_weights
+// w: fp32 [co, ci, k, k] (PyTorch layout).  fwd: bf16 [co_pad, (kh*k+kw)*ci + c];  dgrad: bf16 [ci_pad, (kh'*k+kw')*co + o]
+// with (kh', kw') = (k-1-kh, k-1-kw).  Rows beyond co / ci stay zero (buffers are zero-initialised once).
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, int co, int ci, int k,
+                                                           __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgr) {
+  const long long total = static_cast<long long>(co) * ci * k * k;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kw = static_cast<int>(i % k);
+    long long t = i / k;
+    const int kh = static_cast<int>(t % k);
+    t /= k;
+    const int c = static_cast<int>(t % ci);
+    const int o = static_cast<int>(t / ci);
+    const __nv_bfloat16 v = __float2bfloat16(w[i]);
+    if (fwd) fwd[static_cast<long long>(o) * k * k * ci + (kh * k + kw) * ci + c] = v;
+    if (dgr) dgr[static_cast<long long>(c) * k * k * co + ((k - 1 - kh) * k + (k - 1 - kw)) * co + o] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- zero_stuff
+// src: dy of a stride-2 conv, padded NHWC [n, ho+2, wo+2, ld]; dst: zero-initialised padded [n, 2ho+2, 2wo+2, c]:
+// dst(2*oy, 2*ox) = src(oy, ox)  (unpadded coordinates).  Only the even positions are ever written.
+__global__ void __launch_bounds__(256) zero_stuff_kernel(Slice src, SliceW dst, int n, int ho, int wo, int c8) {
+  const long long total = static_cast<long long>(n) * ho * wo * c8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % c8);
+    long long t = i / c8;
+    const int x = static_cast<int>(t % wo);
+    t /= wo;
+    const int y = static_cast<int>(t % ho);
+    const int b = static_cast<int>(t / ho);
+    const long long rs = (static_cast<long long>(b) * (ho + 2) + y + 1) * (wo + 2) + x + 1;
+    const long long rd = (static_cast<long long>(b) * (2 * ho + 2) + 2 * y + 1) * (2 * wo + 2) + 2 * x + 1;
+    *reinterpret_cast<uint4*>(dst.p + rd * dst.ld + dst.coff + cg * 8) =
+        __ldg(reinterpret_cast<const uint4*>(src.p + rs * src.ld + src.coff + cg * 8));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- wgrad
+// dW[co, tap, ci] += sum over a chunk of padded pixels p of dy[p, co] * x[p + shift(tap), ci]   (stride-1 geometry;
+// for a stride-2 conv the caller passes the zero-stuffed dy so that the same relation holds on the input grid).
+// CTA tile: 64 (co) x 64 (ci) for one tap; K = pixels, consumed 32 at a time.  Both operands are "K-rows" in memory
+// (pixel-major, channels contiguous), i.e. exactly the col-major A / row... fragments of mma.m16n8k16 after a transposed
+// shared-memory read (ldmatrix.trans).  fp32 partial sums are reduced with atomics into the fp32 gradient.
+constexpr int kWgPix = 32;    // pixels per smem stage
+constexpr int kWgTile = 64;   // channels per tile side
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(saddr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct WgradArgs {
+  Slice dy;   // [rows, ld] padded pixel list, channels [coff, coff+co)
+  Slice x;    // input activation, same padded geometry
+  float* dw;  // fp32 [co, ci, taps] == PyTorch's [co, ci, k, k]
+  int co, ci, taps, wp;
+  long long rows;
+  int rows_per_cta;
+};
+
+// grid: (pixel chunks, co/64 * ci/64, taps); block 128 threads (4 warps: 2x2 over the 64x64 tile, 32x32 each)
+__global__ void __launch_bounds__(128) wgrad_kernel(const WgradArgs p) {
+  __shared__ __align__(16) __nv_bfloat16 s_a[kWgPix][kWgTile + 8];  // dy chunk  [pixel][co]   (+8: conflict-free ldmatrix)
+  __shared__ __align__(16) __nv_bfloat16 s_b[kWgPix][kWgTile + 8];  // x chunk   [pixel][ci]
+  const int tiles_ci = (p.ci + kWgTile - 1) / kWgTile;
+  const int co0 = (blockIdx.y / tiles_ci) * kWgTile, ci0 = (blockIdx.y % tiles_ci) * kWgTile;
+  const int tap = blockIdx.z;
+  const int shift = p.taps == 9 ? (tap / 3 - 1) * p.wp + (tap % 3 - 1) : 0;
+  const long long r0 = static_cast<long long>(blockIdx.x) * p.rows_per_cta;
+  const long long r1 = r0 + p.rows_per_cta < p.rows ? r0 + p.rows_per_cta : p.rows;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;  // warp's 32x32 sub-tile (co, ci)
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
+
+  for (long long r = r0; r < r1; r += kWgPix) {
+    // stage 32 pixels x 64 channels of dy and of (shifted) x: 128 threads x 2 x 16 B each
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int idx = threadIdx.x + it * 128;  // 0..255 = 32 pixels x 8 chunks
+      const int px = idx >> 3, ch = (idx & 7) * 8;
+      const long long ra = r + px, rb = r + px + shift;
+      uint4 va = make_uint4(0, 0, 0, 0), vb = make_uint4(0, 0, 0, 0);
+      if (ra < r1 && co0 + ch < p.co) va = __ldg(reinterpret_cast<const uint4*>(p.dy.p + ra * p.dy.ld + p.dy.coff + co0 + ch));
+      if (ra < r1 && rb >= 0 && rb < p.rows && ci0 + ch < p.ci)
+        vb = __ldg(reinterpret_cast<const uint4*>(p.x.p + rb * p.x.ld + p.x.coff + ci0 + ch));
+      *reinterpret_cast<uint4*>(&s_a[px][ch]) = va;
+      *reinterpret_cast<uint4*>(&s_b[px][ch]) = vb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < kWgPix / 16; ++ks) {
+      // A fragments (16 co x 16 pixels, row-major A[m][k] = dy[pixel k][co m]): transposed 8x8 loads from [pixel][co]
+      uint32_t af[2][4];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        // matrices: (m0-7,k0-7) (m8-15,k0-7) (m0-7,k8-15) (m8-15,k8-15); smem rows are pixels (k), 8 consecutive co per row
+        const int mat = lane >> 3, rr = lane & 7;
+        const int kk = ks * 16 + (mat >> 1) * 8 + rr;
+        const int mm = wm + mi * 16 + (mat & 1) * 8;
+        ldmatrix_x4_trans(af[mi], smem_u32(&s_a[kk][mm]));
+      }
+      // B fragments (16 pixels x 8 ci, "col" operand B[k][n] = x[pixel k][ci n]): b0 = (k 2t..2t+1, n g), b1 = k+8
+      uint32_t bf[4][2];
+#pragma unroll
+      for (int nj = 0; nj < 2; ++nj) {
+        // one x4.trans covers two n8 tiles: matrices (k0-7,n0-7) (k8-15,n0-7) (k0-7,n8-15) (k8-15,n8-15)
+        uint32_t t4[4];
+        const int mat = lane >> 3, rr = lane & 7;
+        const int kk = ks * 16 + (mat & 1) * 8 + rr;
+        const int nn = wn + nj * 16 + (mat >> 1) * 8;
+        ldmatrix_x4_trans(t4, smem_u32(&s_b[kk][nn]));
+        bf[nj * 2 + 0][0] = t4[0];
+        bf[nj * 2 + 0][1] = t4[1];
+        bf[nj * 2 + 1][0] = t4[2];
+        bf[nj * 2 + 1][1] = t4[3];
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int nj = 0; nj < 4; ++nj) mma16816(acc[mi][nj], af[mi], bf[nj][0], bf[nj][1]);
+    }
+    __syncthreads();
+  }
+  // C fragment: c0,c1 = (row g, cols 2t,2t+1), c2,c3 = (row g+8, same cols)
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int nj = 0; nj < 4; ++nj) {
+      const int co = co0 + wm + mi * 16 + g, ci = ci0 + wn + nj * 8 + t * 2;
+      if (ci >= p.ci) continue;  // ci is a multiple of 8, so ci+1 is in range with ci
+      if (co < p.co) {
+        float* d0 = p.dw + (static_cast<long long>(co) * p.ci + ci) * p.taps + tap;
+        atomicAdd(d0, acc[mi][nj][0]);
+        atomicAdd(d0 + p.taps, acc[mi][nj][1]);
+      }
+      if (co + 8 < p.co) {
+        float* d1 = p.dw + (static_cast<long long>(co + 8) * p.ci + ci) * p.taps + tap;
+        atomicAdd(d1, acc[mi][nj][2]);
+        atomicAdd(d1 + p.taps, acc[mi][nj][3]);
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- bias_grad (fp32 head grads)
+// g: fp32 pixel-major [rows, ld]; db[c] += sum_rows g[row, c]
+__global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict__ g, int ld, int c, long long rows,
+                                                         int rows_per_block, float* __restrict__ db) {
+  const int col = threadIdx.x % c, rl = threadIdx.x / c, nrl = blockDim.x / c;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
+  float s = 0.f;
+  if (rl < nrl)
+    for (long long r = r0 + rl; r < r1; r += nrl) s += g[r * ld + col];
+  if (rl < nrl) atomicAdd(db + col, s);
+}
+
+// ---------------------------------------------------------------------------------------------- add / copy
+// dst (+)= src over the interior pixels of two padded NHWC slices with the same [n,h,w,c] (gradient fan-in:
+// Bottleneck shortcut, tensors with several consumers)
+__global__ void __launch_bounds__(256) add_nhwc_kernel(Slice src, SliceW dst, int n, int h, int w, int c8, int accumulate) {
+  const long long total = static_cast<long long>(n) * h * w * c8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % c8);
+    long long t = i / c8;
+    const int x = static_cast<int>(t % w);
+    t /= w;
+    const int y = static_cast<int>(t % h);
+    const int b = static_cast<int>(t / h);
+    const long long row = (static_cast<long long>(b) * (h + 2) + y + 1) * (w + 2) + x + 1;
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(src.p + row * src.ld + src.coff + cg * 8));
+    uint4* d = reinterpret_cast<uint4*>(dst.p + row * dst.ld + dst.coff + cg * 8);
+    if (accumulate) {
+      float a[8], bq[8];
+      unpack8(v, a);
+      unpack8(*d, bq);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += bq[k];
+      v = pack8(a);
+    }
+    *d = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- im2col of the image
+// Training treats layer 0 (3x3, c_in = 3) as a 1x1 convolution over this buffer so that forward, dgrad-free backward
+// and wgrad reuse the generic kernels: out[pixel][(c*3+kh)*3+kw] = image[c][y+kh-1][x+kw-1] (zero outside), 27 -> 32.
+template <typename TIN>
+__global__ void __launch_bounds__(256) im2col_first_kernel(const TIN* __restrict__ in, float div, int n, int h, int w,
+                                                           SliceW out) {
+  const long long total = static_cast<long long>(n) * h * w;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % w);
+    const long long t = i / w;
+    const int y = static_cast<int>(t % h);
+    const int b = static_cast<int>(t / h);
+    float v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int yy = y + kh - 1, xx = x + kw - 1;
+          if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+            const float px = static_cast<float>(in[((static_cast<long long>(b) * 3 + c) * h + yy) * w + xx]);
+            v[(c * 3 + kh) * 3 + kw] = div > 0.f ? px / div : px;
+          }
+        }
+    const long long row = (static_cast<long long>(b) * (h + 2) + y + 1) * (w + 2) + x + 1;
+    uint4* d = reinterpret_cast<uint4*>(out.p + row * out.ld + out.coff);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float f[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = v[q * 8 + k];
+      d[q] = pack8(f);
+    }
+  }
+}
+
+int grid_for(long long total, int per_block = 256, int cap_mult = 32) {
+  long long b = (total + per_block - 1) / per_block;
+  const long long cap = static_cast<long long>(num_sms()) * cap_mult;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+}  // namespace y3
+
+// =============================================================================================== C ABI
+using y3::Slice;
+using y3::SliceW;
+
+extern "C" int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, int64_t rows, float* sum, float* sumsq,
+                           y3_stream_t stream) {
+  Y3_REQUIRE(y && sum && sumsq && c > 0 && c % 8 == 0 && c / 8 <= 256 && rows > 0 && ld % 8 == 0 && coff % 8 == 0,
+             "bn_stats: bad arguments");
+  const int rows_per_block = 512;
+  const long long blocks = (rows + rows_per_block - 1) / rows_per_block;
+  y3::bn_stats_kernel<<<static_cast<unsigned>(blocks), 256, 2 * 256 * 8 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      Slice{static_cast<const __nv_bfloat16*>(y), ld, coff}, c / 8, rows, rows_per_block, sum, sumsq);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+extern "C" int y3_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, int32_t c,
+                              float count, float eps, float momentum, float* scale, float* shift, float* mean, float* rstd,
+                              float* running_mean, float* running_var, y3_stream_t stream) {
+  Y3_REQUIRE(sum && sumsq && gamma && beta && scale && shift && mean && rstd && c > 0 && count > 0, "bn_finalize: bad arguments");
+  y3::bn_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      sum, sumsq, gamma, beta, c, count, eps, momentum, scale, shift, mean, rstd, running_mean, running_var);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+extern "C" int y3_bn_act_fwd(const y3_bn_act_desc* d, y3_stream_t stream) {
+  Y3_REQUIRE(d && d->y && d->out && d->scale && d->shift && d->c % 8 == 0 && d->n > 0 && d->h > 0 && d->w > 0,
+             "bn_act_fwd: bad arguments");
+  y3::BnActArgs a;
+  a.y = Slice{static_cast<const __nv_bfloat16*>(d->y), d->y_ld, d->y_coff};
+  a.res = Slice{static_cast<const __nv_bfloat16*>(d->res), d->res_ld, d->res_coff};
+  a.out = SliceW{static_cast<__nv_bfloat16*>(d->out), d->out_ld, d->out_coff};
+  a.scale = d->scale;
+  a.shift = d->shift;
+  a.n = d->n;
+  a.h = d->h;
+  a.w = d->w;
+  a.c8 = d->c / 8;
+  a.upsample = d->upsample;
+  const long long total = static_cast<long long>(d->n) * d->h * d->w * a.c8;
+  y3::bn_act_fwd_kernel<<<y3::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+extern "C" int y3_bn_act_bwd(const y3_bn_bwd_desc* d, y3_stream_t stream_) {
+  Y3_REQUIRE(d && d->y && d->da && d->dy && d->scale && d->shift && d->mean && d->rstd && d->sum_dz && d->sum_dzy,
+             "bn_act_bwd: null pointer");
+  Y3_REQUIRE(d->c % 8 == 0 && d->c / 8 <= 256 && d->n > 0 && d->h > 0 && d->w > 0, "bn_act_bwd: bad shape");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  y3::BnBwdArgs a;
+  a.y = Slice{static_cast<const __nv_bfloat16*>(d->y), d->y_ld, d->y_coff};
+  a.da = Slice{static_cast<const __nv_bfloat16*>(d->da), d->da_ld, d->da_coff};
+  a.dy = SliceW{static_cast<__nv_bfloat16*>(d->dy), d->dy_ld, d->dy_coff};
+  a.scale = d->scale;
+  a.shift = d->shift;
+  a.mean = d->mean;
+  a.rstd = d->rstd;
+  a.sum_dz = d->sum_dz;
+  a.sum_dzy = d->sum_dzy;
+  a.n = d->n;
+  a.h = d->h;
+  a.w = d->w;
+  a.c8 = d->c / 8;
+  a.upsample = d->upsample;
+  const long long pixels = static_cast<long long>(d->n) * d->h * d->w;
+  a.inv_count = 1.0f / static_cast<float>(pixels);
+  const int npl = 256 / a.c8;
+  const int grid = y3::grid_for((pixels + npl - 1) / npl, 8, 8);
+  Y3_CHECK_CUDA(cudaMemsetAsync(d->sum_dz, 0, sizeof(float) * d->c, stream));
+  Y3_CHECK_CUDA(cudaMemsetAsync(d->sum_dzy, 0, sizeof(float) * d->c, stream));
+  y3::bn_act_bwd_kernel<false><<<grid, 256, 2 * 256 * 8 * sizeof(float), stream>>>(a);
+  y3::bn_act_bwd_kernel<true><<<grid, 256, 2 * 256 * 8 * sizeof(float), stream>>>(a);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+extern "C" int y3_pack_weights(const float* w, int32_t co, int32_t ci, int32_t k, void* fwd, void* dgrad,
+                               y3_stream_t stream) {
+  Y3_REQUIRE(w && (fwd || dgrad) && co > 0 && ci > 0 && (k == 1 || k == 3), "pack_weights: bad arguments");
+  const long long total = static_cast<long long>(co) * ci * k * k;
+  y3::pack_weights_kernel<<<y3::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, co, ci, k, static_cast<__nv_bfloat16*>(fwd), static_cast<__nv_bfloat16*>(dgrad));
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+extern "C" int y3_zero_stuff(const void* src, int32_t src_ld, int32_t src_coff, void* dst, int32_t dst_ld, int32_t dst_coff,
+                             int32_t n, int32_t ho, int32_t wo, int32_t c, y3_stream_t stream) {
+  Y3_REQUIRE(src && dst && c % 8 == 0 && n > 0 && ho > 0 && wo > 0, "zero_stuff: bad arguments");
+  const long long total = static_cast<long long>(n) * ho * wo * (c / 8);
+  y3::zero_stuff_kernel<<<y3::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      Slice{static_cast<const __nv_bfloat16*>(src), src_ld, src_coff}, SliceW{static_cast<__nv_bfloat16*>(dst), dst_ld, dst_coff}, n,
+      ho, wo, c / 8);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+extern "C" int y3_conv_wgrad(const y3_wgrad_desc* d, y3_stream_t stream) {
+  Y3_REQUIRE(d && d->dy && d->x && d->dw, "wgrad: null pointer");
+  Y3_REQUIRE(d->co % 8 == 0 && d->ci % 8 == 0 && (d->ksize == 1 || d->ksize == 3) && d->n > 0 && d->h > 0 && d->w > 0,
+             "wgrad: c_out/c_in must be multiples of 8 (got %d/%d), ksize 1|3", d->co, d->ci);
+  Y3_REQUIRE(d->dy_ld % 8 == 0 && d->dy_coff % 8 == 0 && d->x_ld % 8 == 0 && d->x_coff % 8 == 0, "wgrad: bad slices");
+  y3::WgradArgs a;
+  a.dy = Slice{static_cast<const __nv_bfloat16*>(d->dy), d->dy_ld, d->dy_coff};
+  a.x = Slice{static_cast<const __nv_bfloat16*>(d->x), d->x_ld, d->x_coff};
+  a.dw = d->dw;
+  a.co = d->co;
+  a.ci = d->ci;
+  a.taps = d->ksize * d->ksize;
+  a.wp = d->w + 2;
+  a.rows = static_cast<long long>(d->n) * (d->h + 2) * (d->w + 2);
+  // split the pixel dimension so that the grid fills the machine ~4x
+  const int t_co = (d->co + 63) / 64, t_ci = (d->ci + 63) / 64;
+  const long long tiles = static_cast<long long>(t_co) * t_ci * a.taps;
+  long long chunks = (4ll * y3::num_sms() + tiles - 1) / tiles;
+  const long long max_chunks = (a.rows + 1023) / 1024;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  long long rpc = (a.rows + chunks - 1) / chunks;
+  rpc = (rpc + y3::kWgPix - 1) / y3::kWgPix * y3::kWgPix;
+  chunks = (a.rows + rpc - 1) / rpc;
+  a.rows_per_cta = static_cast<int>(rpc);
+  const dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(t_co * t_ci), a.taps);
+  y3::wgrad_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+extern "C" int y3_colsum_f32(const float* g, int32_t ld, int32_t c, int64_t rows, float* out, y3_stream_t stream) {
+  Y3_REQUIRE(g && out && c > 0 && c <= 256 && rows > 0, "colsum: bad arguments");
+  const int rows_per_block = 1024;
+  const long long blocks = (rows + rows_per_block - 1) / rows_per_block;
+  y3::colsum_f32_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, ld, c, rows, rows_per_block, out);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+extern "C" int y3_add_nhwc(const void* src, int32_t src_ld, int32_t src_coff, void* dst, int32_t dst_ld, int32_t dst_coff,
+                           int32_t n, int32_t h, int32_t w, int32_t c, int32_t accumulate, y3_stream_t stream) {
+  Y3_REQUIRE(src && dst && c % 8 == 0 && n > 0 && h > 0 && w > 0, "add_nhwc: bad arguments");
+  const long long total = static_cast<long long>(n) * h * w * (c / 8);
+  y3::add_nhwc_kernel<<<y3::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      Slice{static_cast<const __nv_bfloat16*>(src), src_ld, src_coff}, SliceW{static_cast<__nv_bfloat16*>(dst), dst_ld, dst_coff}, n, h,
+      w, c / 8, accumulate);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+extern "C" int y3_im2col_first(const void* in, int32_t in_dtype, float in_div, int32_t n, int32_t h, int32_t w, void* out,
+                               int32_t out_ld, int32_t out_coff, y3_stream_t stream) {
+  Y3_REQUIRE(in && out && n > 0 && h > 0 && w > 0 && out_ld % 8 == 0 && out_coff % 8 == 0 && out_coff + 32 <= out_ld,
+             "im2col_first: bad arguments");
+  const long long total = static_cast<long long>(n) * h * w;
+  const SliceW o{static_cast<__nv_bfloat16*>(out), out_ld, out_coff};
+  if (in_dtype == Y3_IN_U8)
+    y3::im2col_first_kernel<uint8_t><<<y3::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint8_t*>(in), in_div, n, h, w, o);
+  else
+    y3::im2col_first_kernel<float><<<y3::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float*>(in), in_div, n, h, w, o);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}

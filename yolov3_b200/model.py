@@ -81,6 +81,8 @@ class Model:
         self.params = self._init_params()
         self._packed = None
         self._engines: dict = {}
+        self._dev = None
+        self._train_engines: dict = {}
 
     # ------------------------------------------------------------------------------------------------ parameters
     def _init_params(self):
@@ -109,6 +111,8 @@ class Model:
         return OrderedDict((k, v.clone()) for k, v in self.params.items())
 
     def load_state_dict(self, sd, strict=True):
+        self._dev = None
+        self._train_engines.clear()
         missing = [k for k in self.params if k not in sd]
         unexpected = [k for k in sd if k not in self.params and not k.endswith("num_batches_tracked")]
         if strict and (missing or unexpected):
@@ -124,13 +128,38 @@ class Model:
         return missing, unexpected
 
     def parameters(self):
+        """Trainable parameters.  Before training starts these are the host fp32 tensors; after ``train()`` +
+        ``device_params()`` they are the device-resident fp32 master tensors an optimizer updates."""
+        if self._dev is not None:
+            return iter([v for v in self._dev.values() if v.requires_grad])
         return iter(self.params.values())
+
+    def device_params(self):
+        """fp32 master copy of every parameter/buffer on the device (leaf tensors, requires_grad for the trainable
+        ones): what ``TrainEngine`` reads each step and what ``optimizer.step()`` writes."""
+        if self._dev is None:
+            self._dev = OrderedDict()
+            for k, v in self.params.items():
+                t = v.detach().to(self.device, torch.float32).contiguous()
+                trainable = not (k.endswith("running_mean") or k.endswith("running_var") or k.endswith("anchors"))
+                self._dev[k] = t.requires_grad_(trainable)
+        return self._dev
+
+    def sync_from_device(self):
+        """Copy the trained master parameters back into ``self.params`` (invalidates packed weights and engines)."""
+        if self._dev is not None:
+            for k, v in self._dev.items():
+                self.params[k] = v.detach().float().cpu().clone()
+            self._packed = None
+            self._engines.clear()
 
     # reference-surface no-ops / bookkeeping
     def fuse(self):
         return self  # BN is always folded when an engine is built (models/yolo.py:163-172)
 
     def eval(self):
+        if self.training and self._dev is not None:
+            self.sync_from_device()
         self.training = False
         return self
 
@@ -190,8 +219,6 @@ class Model:
         """Eval-mode Model.forward (models/yolo.py:233-237): returns (z[bs, rows, no], [p_i[bs,na,ny,nx,no]])."""
         if augment or profile or visualize:
             raise NotImplementedError("augment/profile/visualize are outside the accelerated path (SURVEY §8a)")
-        if self.training:
-            raise NotImplementedError("training-mode forward (conv backward) is not built yet; use .eval()")
         if not x.is_cuda:
             raise RuntimeError("yolov3_b200 has no CPU path: move the input to the B200 (x.cuda())")
         if x.dtype not in (torch.float32, torch.uint8):
@@ -199,6 +226,16 @@ class Model:
         x = x.contiguous()
         n, c, h, w = x.shape
         assert c == self.ch, f"expected {self.ch} input channels"
+        if self.training:
+            # train mode (models/yolo.py:110 returns the raw maps): BatchNorm batch statistics, autograd-connected
+            from .train import TrainEngine, TrainFn
+
+            te = self._train_engines.get((n, h, w))
+            if te is None:
+                self._train_engines.clear()
+                te = self._train_engines[(n, h, w)] = TrainEngine(self, n, h, w)
+            P = self.device_params()
+            return list(TrainFn.apply(te, x, 255.0 if x.dtype == torch.uint8 else 0.0, *[P[k] for k in te.param_names]))
         e = self.engine(n, h, w, x.dtype, 255.0 if x.dtype == torch.uint8 else 0.0)  # uint8 images: im/255
         e.run(x)
         z = e.z.clone()

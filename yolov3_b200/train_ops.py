@@ -1,0 +1,102 @@
+"""Adapters for the training-mode entry points of the C ABI (csrc/y3_train.cu): BatchNorm statistics / apply / backward,
+weight packing, zero-stuffing, wgrad.  Like ops.py they only marshal pointers; all arithmetic is in the library."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .tensors import PaddedNHWC, _stream
+
+BN_EPS, BN_MOMENTUM = 1e-3, 0.03  # ultralytics initialize_weights (models/yolo.py:229)
+
+
+def bn_stats(y: PaddedNHWC, sum_: torch.Tensor, sumsq: torch.Tensor):
+    """sum/sumsq (fp32 [c], zeroed here) of the conv output over all padded pixels (the halo is zero)."""
+    sum_.zero_()
+    sumsq.zero_()
+    rows = y.n * (y.h + 2) * (y.w + 2)
+    _lib.check(_lib.lib().y3_bn_stats(y.ptr, y.ld, y.coff, y.c, rows, sum_.data_ptr(), sumsq.data_ptr(), _stream()), "y3_bn_stats")
+
+
+def bn_finalize(sum_, sumsq, gamma, beta, count, scale, shift, mean, rstd, running_mean=None, running_var=None,
+                eps=BN_EPS, momentum=BN_MOMENTUM):
+    c = gamma.numel()
+    _lib.check(_lib.lib().y3_bn_finalize(sum_.data_ptr(), sumsq.data_ptr(), gamma.data_ptr(), beta.data_ptr(), c, float(count),
+                                         eps, momentum, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                         running_mean.data_ptr() if running_mean is not None else None,
+                                         running_var.data_ptr() if running_var is not None else None, _stream()),
+               "y3_bn_finalize")
+
+
+def bn_act_fwd(y: PaddedNHWC, scale, shift, out: PaddedNHWC, res: PaddedNHWC | None = None, upsample=False):
+    d = _lib.BnActDesc()
+    d.y, d.y_ld, d.y_coff = y.ptr, y.ld, y.coff
+    if res is not None:
+        d.res, d.res_ld, d.res_coff = res.ptr, res.ld, res.coff
+    d.out, d.out_ld, d.out_coff = out.ptr, out.ld, out.coff
+    d.scale, d.shift = scale.data_ptr(), shift.data_ptr()
+    d.n, d.h, d.w, d.c, d.upsample = y.n, y.h, y.w, y.c, int(bool(upsample))
+    _lib.check(_lib.lib().y3_bn_act_fwd(C.byref(d), _stream()), "y3_bn_act_fwd")
+    return out
+
+
+def bn_act_bwd(y: PaddedNHWC, da: PaddedNHWC, dy: PaddedNHWC, scale, shift, mean, rstd, dbeta, dgamma, upsample=False):
+    d = _lib.BnBwdDesc()
+    d.y, d.y_ld, d.y_coff = y.ptr, y.ld, y.coff
+    d.da, d.da_ld, d.da_coff = da.ptr, da.ld, da.coff
+    d.dy, d.dy_ld, d.dy_coff = dy.ptr, dy.ld, dy.coff
+    d.scale, d.shift, d.mean, d.rstd = scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr()
+    d.sum_dz, d.sum_dzy = dbeta.data_ptr(), dgamma.data_ptr()
+    d.n, d.h, d.w, d.c, d.upsample = y.n, y.h, y.w, y.c, int(bool(upsample))
+    _lib.check(_lib.lib().y3_bn_act_bwd(C.byref(d), _stream()), "y3_bn_act_bwd")
+    return dy
+
+
+def pack_weights(w: torch.Tensor, fwd: torch.Tensor | None, dgrad: torch.Tensor | None):
+    """w fp32 [co,ci,k,k] (device) -> bf16 forward pack [co_pad, k*k*ci] / dgrad pack [ci_pad, k*k*co] (pad rows pre-zeroed)."""
+    co, ci, k, _ = w.shape
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous()
+    _lib.check(_lib.lib().y3_pack_weights(w.data_ptr(), co, ci, k, fwd.data_ptr() if fwd is not None else None,
+                                          dgrad.data_ptr() if dgrad is not None else None, _stream()), "y3_pack_weights")
+
+
+def zero_stuff(src: PaddedNHWC, dst: PaddedNHWC):
+    assert dst.h == 2 * src.h and dst.w == 2 * src.w and dst.c == src.c
+    _lib.check(_lib.lib().y3_zero_stuff(src.ptr, src.ld, src.coff, dst.ptr, dst.ld, dst.coff, src.n, src.h, src.w, src.c,
+                                        _stream()), "y3_zero_stuff")
+    return dst
+
+
+def conv_wgrad(dy: PaddedNHWC, x: PaddedNHWC, dw: torch.Tensor, ksize: int):
+    """dw (fp32 [co,ci,k,k], accumulated into) from dy and x on the same stride-1 padded grid."""
+    assert dy.n == x.n and dy.h == x.h and dy.w == x.w and dw.dtype == torch.float32 and dw.is_contiguous()
+    d = _lib.WgradDesc()
+    d.dy, d.dy_ld, d.dy_coff = dy.ptr, dy.ld, dy.coff
+    d.x, d.x_ld, d.x_coff = x.ptr, x.ld, x.coff
+    d.dw, d.co, d.ci, d.ksize = dw.data_ptr(), dy.c, x.c, ksize
+    d.n, d.h, d.w = x.n, x.h, x.w
+    _lib.check(_lib.lib().y3_conv_wgrad(C.byref(d), _stream()), "y3_conv_wgrad")
+    return dw
+
+
+def colsum_f32(g: torch.Tensor, c: int, out: torch.Tensor):
+    assert g.dtype == torch.float32 and g.dim() == 2 and g.is_contiguous()
+    _lib.check(_lib.lib().y3_colsum_f32(g.data_ptr(), g.shape[1], c, g.shape[0], out.data_ptr(), _stream()), "y3_colsum_f32")
+    return out
+
+
+def add_nhwc(src: PaddedNHWC, dst: PaddedNHWC, accumulate: bool):
+    assert (src.n, src.h, src.w, src.c) == (dst.n, dst.h, dst.w, dst.c)
+    _lib.check(_lib.lib().y3_add_nhwc(src.ptr, src.ld, src.coff, dst.ptr, dst.ld, dst.coff, src.n, src.h, src.w, src.c,
+                                      int(bool(accumulate)), _stream()), "y3_add_nhwc")
+    return dst
+
+
+def im2col_first(x: torch.Tensor, out: PaddedNHWC, in_div=0.0):
+    assert x.is_cuda and x.is_contiguous() and x.shape[1] == 3 and x.dtype in (torch.float32, torch.uint8) and out.c == 32
+    n, _, h, w = x.shape
+    _lib.check(_lib.lib().y3_im2col_first(x.data_ptr(), _lib.IN_U8 if x.dtype == torch.uint8 else _lib.IN_F32, float(in_div),
+                                          n, h, w, out.ptr, out.ld, out.coff, _stream()), "y3_im2col_first")
+    return out
