@@ -132,3 +132,40 @@ def test_multi_rank_aggregation_gloo(tmp_path):
     assert p.returncode == 0, p.stderr[-2000:]
     line = [l for l in p.stdout.splitlines() if l.startswith("AGG")][0].split()
     assert float(line[1]) == 150.0 and abs(float(line[2]) - 2 * 32 * 10 / 0.15) < 1e-6
+
+
+DDP_WORKER = r'''
+import sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/oracle")
+from yolov3_b200.parallel import allreduce_gradients, broadcast_parameters, scale_loss, world_size
+import torch.nn.functional as F
+dist.init_process_group("gloo")
+r, W = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(100 + r)                      # ranks start different: the broadcast must make them equal
+w = torch.randn(8, 4, 3, 3, requires_grad=True); b = torch.randn(8, requires_grad=True)
+broadcast_parameters([w, b], 0)
+g = torch.Generator().manual_seed(7)
+x = torch.randn(6, 4, 10, 10, generator=g); t = torch.randn(6, 8, 10, 10, generator=g)
+def shard_loss(xs, ts):                          # reference convention: per-shard mean loss times the shard batch size
+    return F.mse_loss(F.conv2d(xs, w, b, padding=1), ts) * xs.shape[0]
+lo, hi = r * 3, (r + 1) * 3
+scale_loss(shard_loss(x[lo:hi], t[lo:hi])).backward()      # loss *= WORLD_SIZE (train.py:405-406)
+allreduce_gradients([w, b])                                  # DDP mean all-reduce
+got_w, got_b = w.grad.clone(), b.grad.clone()
+w.grad = None; b.grad = None
+sum(shard_loss(x[i * 3:(i + 1) * 3], t[i * 3:(i + 1) * 3]) for i in range(W)).backward()   # single-process equivalent
+assert torch.allclose(got_w, w.grad, rtol=1e-5, atol=1e-6) and torch.allclose(got_b, b.grad, rtol=1e-5, atol=1e-6)
+if r == 0: print("DDP_OK", world_size())
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def test_ddp_gradient_exchange_semantics_gloo(tmp_path):
+    """SURVEY App. D last row: `loss * WORLD_SIZE` + mean all-reduce == sum of the per-rank (loss * bs_rank) gradients."""
+    script = tmp_path / "ddp.py"
+    script.write_text(DDP_WORKER)
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29654", str(script), str(ROOT)], capture_output=True, text=True,
+                       timeout=240, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
+    assert p.returncode == 0, p.stderr[-2000:]
+    assert "DDP_OK 2" in p.stdout
