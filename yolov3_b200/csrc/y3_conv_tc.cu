@@ -34,12 +34,19 @@ constexpr int kSmemBudget = 224 * 1024;  // ring + epilogue staging; barriers + 
 // STAGED = true: the epilogue converts into a swizzled shared-memory staging tile and ONE thread stores it with TMA
 // (and pre-loads the residual tile into the same buffer with TMA), instead of every thread issuing 16-byte global
 // stores to 32 different cache lines per instruction — the thin layers were bound by exactly that (profiles/r01_*).
-template <int BLOCK_N, int BLOCK_K, bool PAIR, bool STAGED>
+// HALO = true (stride-1 3x3, BLOCK_K = 64): one pipeline stage covers a whole filter ROW (3 taps): the A operand is ONE
+// TMA box of 128+2 consecutive pixels and the three taps read it at row offsets 0/1/2 through UMMA descriptors whose
+// start address is not aligned to the 1 KB swizzle pattern (descriptor base_offset = (addr >> 7) & 7).  A rows fetched per
+// k-block drop from 9*128 to 3*130; the TMA unit's row rate (~1 row / 2.5 clk / SM), not its byte rate, was the limit.
+template <int BLOCK_N, int BLOCK_K, bool PAIR, bool STAGED, bool HALO>
 struct Cfg {
-  static constexpr uint32_t kABytes = kBlockM * BLOCK_K * 2;
+  static constexpr uint32_t kARows = HALO ? kBlockM + 2 : kBlockM;
+  static constexpr uint32_t kATxBytes = kARows * BLOCK_K * 2;                         // bytes one A box delivers (flat mode)
+  static constexpr uint32_t kABytes = (kATxBytes + 1023u) / 1024u * 1024u;            // slot size, 1 KB aligned
+  static constexpr uint32_t kTaps = HALO ? 3 : 1;                                     // filter taps per stage
   static constexpr uint32_t kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;  // a CTA pair splits the B tile between its two CTAs
   static constexpr uint32_t kBBytes = kBRows * BLOCK_K * 2;
-  static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+  static constexpr uint32_t kStageBytes = kABytes + kTaps * kBBytes;
   static constexpr uint32_t kSlabCols = BLOCK_N >= 64 ? 64 : 32;          // staging slab = [128 rows][kSlabCols bf16]
   static constexpr uint32_t kSlabRowBytes = kSlabCols * 2;                // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
   static constexpr uint32_t kSlabBytes = kBlockM * kSlabRowBytes;
@@ -54,6 +61,7 @@ struct Cfg {
   static constexpr size_t kSmemBytes =
       size_t(kStages) * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/ + BLOCK_N * 4 /*bias tile*/;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
+  static_assert(!HALO || BLOCK_K == 64, "halo reuse is built for 128-byte rows only");
 };
 
 // PAIR = true: two CTAs of a cluster (one SM pair) cooperate on a 256-row tile with tcgen05 cta_group::2: each CTA
@@ -61,13 +69,14 @@ struct Cfg {
 // CTAs' shared memory and write both CTAs' TMEM.  Per-SM operand ingress drops from (128+N)*K to (128+N/2)*K bytes per
 // k-block — the 1-CTA kernel measured ~0.67 of the MMA rate on the big 3x3 layers because (128+256)*64*2 B per 512 MMA
 // cycles exceeds the ~64 B/clk an SM can pull from L2 (profiles/r01_per_op_v2_epilogue.json).
-template <int BLOCK_N, int BLOCK_K, bool PAIR, bool STAGED>
+template <int BLOCK_N, int BLOCK_K, bool PAIR, bool STAGED, bool HALO>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                const ConvTcArgs p) {
-  using C = Cfg<BLOCK_N, BLOCK_K, PAIR, STAGED>;
+  using C = Cfg<BLOCK_N, BLOCK_K, PAIR, STAGED, HALO>;
   constexpr int STAGES = C::kStages;
+  constexpr uint32_t kBStage = C::kTaps * C::kBBytes;  // B bytes per stage
   constexpr uint32_t IDESC = umma_idesc_bf16(PAIR ? 256 : 128, BLOCK_N);
   constexpr uint32_t kEpiThreads = 32 * kEpilogueWarps;
 
@@ -128,7 +137,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int m_units = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles;  // a pair owns two consecutive M tiles
   const int total_tiles = m_units * p.n_tiles;
-  const int k_iters = p.taps * p.kblocks;
+  const int k_iters = HALO ? 3 * p.kblocks : p.taps * p.kblocks;  // HALO: one iteration = one filter row of one k-block
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (one thread)
@@ -149,33 +158,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           ow0 = (t % p.tiles_w) * p.tw;
         }
         for (int it = 0; it < k_iters; ++it) {
-          const int kb = it / p.taps, tap = it - kb * p.taps;
+          const int taps_it = HALO ? 3 : p.taps;
+          const int kb = it / taps_it, tap = it - kb * taps_it;  // HALO: tap = filter row r
           mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 1);
           uint8_t* a_dst = smem_a + stage * C::kABytes;
-          uint8_t* b_dst = smem_b + stage * C::kBBytes;
-          const int shift = (p.taps == 9) ? ((tap / 3 - 1) * p.wp + (tap % 3 - 1)) : 0;
+          uint8_t* b_dst = smem_b + stage * kBStage;
+          const int shift = HALO ? (tap - 1) * p.wp - 1 : ((p.taps == 9) ? ((tap / 3 - 1) * p.wp + (tap % 3 - 1)) : 0);
           const int r = tap / 3, s = tap - r * 3;
+          const uint32_t stage_tx = p.a_tx_bytes + kBStage;
+          uint32_t bar_addr;
           if (PAIR) {
             // all bytes of both CTAs are credited to the LEADER's full barrier; the peer only contributes an arrival
-            const uint32_t lead_bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            bar_addr = mapa_u32(smem_u32(&full_bar[stage]), 0);
             if (rank == 0)
-              mbar_expect_tx(&full_bar[stage], 2 * (p.a_tx_bytes + C::kBBytes));
+              mbar_expect_tx(&full_bar[stage], 2 * stage_tx);
             else
-              mbar_arrive_cluster(lead_bar);
+              mbar_arrive_cluster(bar_addr);
             if (p.mode == 0)
-              tma_load_2d_pair(a_dst, &map_a, lead_bar, p.a_coff + kb * BLOCK_K, row0 + shift);
+              tma_load_2d_pair(a_dst, &map_a, bar_addr, p.a_coff + kb * BLOCK_K, row0 + shift);
             else
-              tma_load_5d_pair(a_dst, &map_a, lead_bar, (s & 1) * p.a_ld + p.a_coff + kb * BLOCK_K, ow0 + (s >> 1), r & 1,
+              tma_load_5d_pair(a_dst, &map_a, bar_addr, (s & 1) * p.a_ld + p.a_coff + kb * BLOCK_K, ow0 + (s >> 1), r & 1,
                                oh0 + (r >> 1), img);
-            tma_load_2d_pair(b_dst, &map_b, lead_bar, tap * p.cin + kb * BLOCK_K, n0);
+#pragma unroll
+            for (uint32_t t = 0; t < C::kTaps; ++t)
+              tma_load_2d_pair(b_dst + t * C::kBBytes, &map_b, bar_addr, (HALO ? tap * 3 + int(t) : tap) * p.cin + kb * BLOCK_K, n0);
           } else {
-            mbar_expect_tx(&full_bar[stage], p.a_tx_bytes + C::kBBytes);
+            mbar_expect_tx(&full_bar[stage], stage_tx);
             if (p.mode == 0)
               tma_load_2d(a_dst, &map_a, &full_bar[stage], p.a_coff + kb * BLOCK_K, row0 + shift);
             else
               tma_load_5d(a_dst, &map_a, &full_bar[stage], (s & 1) * p.a_ld + p.a_coff + kb * BLOCK_K, ow0 + (s >> 1),
                           r & 1, oh0 + (r >> 1), img);
-            tma_load_2d(b_dst, &map_b, &full_bar[stage], tap * p.cin + kb * BLOCK_K, n0);
+#pragma unroll
+            for (uint32_t t = 0; t < C::kTaps; ++t)
+              tma_load_2d(b_dst + t * C::kBBytes, &map_b, &full_bar[stage], (HALO ? tap * 3 + int(t) : tap) * p.cin + kb * BLOCK_K, n0);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -198,15 +214,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&full_bar[stage], phase, p.err, 3);  // TMA bytes have landed
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * C::kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * C::kBBytes);
+          const uint32_t b_addr = smem_u32(smem_b + stage * kBStage);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t adesc = umma_smem_desc(a_addr + k * 32, C::kSbo, C::kLayout);
-            const uint64_t bdesc = umma_smem_desc(b_addr + k * 32, C::kSbo, C::kLayout);
-            if (PAIR)
-              umma_bf16_ss_pair(d_tmem, adesc, bdesc, IDESC, (it | k) != 0 ? 1u : 0u);
-            else
-              umma_bf16_ss(d_tmem, adesc, bdesc, IDESC, (it | k) != 0 ? 1u : 0u);
+          for (uint32_t t = 0; t < C::kTaps; ++t) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              // HALO: tap t reads the A box shifted by t pixel rows (128 B each): start address off the 1 KB swizzle
+              // pattern, described to the tensor core through the descriptor's base_offset field
+              const uint64_t adesc = umma_smem_desc(a_addr + t * (BLOCK_K * 2) + k * 32, C::kSbo, C::kLayout, p.desc_mode);
+              const uint64_t bdesc = umma_smem_desc(b_addr + t * C::kBBytes + k * 32, C::kSbo, C::kLayout, p.desc_mode);
+              const uint32_t acc = (it | int(t) | k) != 0 ? 1u : 0u;
+              if (PAIR)
+                umma_bf16_ss_pair(d_tmem, adesc, bdesc, IDESC, acc);
+              else
+                umma_bf16_ss(d_tmem, adesc, bdesc, IDESC, acc);
+            }
           }
           // the smem slot (in BOTH CTAs of a pair) is free once these MMAs have read it
           if (PAIR) {
@@ -457,10 +479,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
-template <int BLOCK_N, int BLOCK_K, bool PAIR, bool STAGED>
+template <int BLOCK_N, int BLOCK_K, bool PAIR, bool STAGED, bool HALO = false>
 int launch_cfg(const ConvTcPlan& plan, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N, BLOCK_K, PAIR, STAGED>;
-  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, PAIR, STAGED>;
+  using C = Cfg<BLOCK_N, BLOCK_K, PAIR, STAGED, HALO>;
+  auto kern = conv_tc_kernel<BLOCK_N, BLOCK_K, PAIR, STAGED, HALO>;
   static bool attr_set = false;  // benign race: idempotent attribute
   if (!attr_set) {
     Y3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::kSmemBytes)));
@@ -496,6 +518,21 @@ int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream) {
     case 16: return plan.staged ? launch_cfg<BN, 16, PR, true>(plan, stream) : launch_cfg<BN, 16, PR, false>(plan, stream); \
   }                                                                                                             \
   break;
+  if (plan.halo) {  // block_k == 64, stride-1 3x3; N = 256 only as a CTA pair and never staged (smem)
+    if (plan.pair) {
+      if (plan.block_n == 256) return launch_cfg<256, 64, true, false, true>(plan, stream);
+      if (plan.block_n == 128)
+        return plan.staged ? launch_cfg<128, 64, true, true, true>(plan, stream) : launch_cfg<128, 64, true, false, true>(plan, stream);
+    } else {
+      if (plan.block_n == 128)
+        return plan.staged ? launch_cfg<128, 64, false, true, true>(plan, stream) : launch_cfg<128, 64, false, false, true>(plan, stream);
+      if (plan.block_n == 64)
+        return plan.staged ? launch_cfg<64, 64, false, true, true>(plan, stream) : launch_cfg<64, 64, false, false, true>(plan, stream);
+      if (plan.block_n == 32)
+        return plan.staged ? launch_cfg<32, 64, false, true, true>(plan, stream) : launch_cfg<32, 64, false, false, true>(plan, stream);
+    }
+    return set_error(Y3_ERR_BAD_ARG, "conv_tc: no halo kernel for tile N=%d pair=%d", plan.block_n, plan.pair);
+  }
   if (plan.pair) {
     switch (plan.block_n) {
       case 128: Y3_DISPATCH_K(128, true)
@@ -522,6 +559,18 @@ static bool staged_enabled() {
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v != 0;
+}
+
+// Y3_CONV_HALO=0 disables the halo-reuse A path; Y3_CONV_HALO=2 keeps it but writes base_offset = 0 in the descriptors
+// (hardware-semantics probe: which of the two makes the unaligned-start operand read correctly).
+static int halo_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("Y3_CONV_HALO");
+    v = e ? (e[0] - '0') : 1;
+    if (v < 0 || v > 2) v = 1;
+  }
+  return v;
 }
 
 static bool pair_enabled() {
@@ -602,13 +651,20 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     Y3_REQUIRE(rows < (1ll << 31) - 4096, "conv: too many pixels");
     a.rows_total = static_cast<int>(rows);
     a.m_tiles = static_cast<int>((rows + kBlockM - 1) / kBlockM);
-    a.a_tx_bytes = kBlockM * bk * 2;
+    // halo reuse needs >= 2 stages of (17 KB + 3 B tiles): any N <= 128, N = 256 only as a CTA pair
+    const bool pair_ok = bn >= 128 && pair_enabled() && a.m_tiles >= 2;
+    plan->halo = (taps == 9 && bk == 64 && halo_mode() != 0 && (bn <= 128 || pair_ok)) ? 1 : 0;
+    a.desc_mode = halo_mode() == 2 ? 0 : 1;
+    const uint32_t a_rows = plan->halo ? kBlockM + 2 : kBlockM;
+    a.a_tx_bytes = a_rows * bk * 2;
     const uint64_t dims[2] = {static_cast<uint64_t>(d.in_ld), static_cast<uint64_t>(rows)};
     const uint64_t strides[2] = {0, static_cast<uint64_t>(d.in_ld) * 2};
-    const uint32_t box[2] = {static_cast<uint32_t>(bk), kBlockM};
+    const uint32_t box[2] = {static_cast<uint32_t>(bk), a_rows};
     rc = encode_tensor_map_bf16(&plan->map_a, d.in, 2, dims, strides, box, bk * 2);
     if (rc) return rc;
   } else {
+    plan->halo = 0;
+    a.desc_mode = 1;
     a.mode = 1;
     a.ho = d.h / 2;
     a.wo = d.w / 2;
@@ -651,7 +707,7 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     if (rc) return rc;
   }
   // staged (TMA-store) epilogue: flat mode, bf16 output, no upsample
-  plan->staged = (a.mode == 0 && !head && !d.upsample && staged_enabled()) ? 1 : 0;
+  plan->staged = (a.mode == 0 && !head && !d.upsample && staged_enabled() && !(plan->halo && bn == 256)) ? 1 : 0;
   plan->map_out = plan->map_a;
   plan->map_res = plan->map_a;
   if (plan->staged) {

@@ -38,6 +38,7 @@ struct ConvTcArgs {
   int taps, kblocks, cin;
   int a_coff, a_ld;
   uint32_t a_tx_bytes;   // bytes one A box delivers
+  int desc_mode;         // 1: UMMA descriptors carry base_offset = (addr>>7)&7; 0: base_offset = 0 (probe)
   int m_tiles, n_tiles;
   // flat geometry (input and conv-output share it)
   int hp, wp, rows_total;
@@ -58,6 +59,7 @@ struct ConvTcArgs {
 struct ConvTcPlan {
   CUtensorMap map_a, map_b, map_out, map_res;
   int staged;  // 1: epilogue stages the tile in shared memory and stores it with TMA
+  int halo;    // 1: stride-1 3x3 with one A box per filter row (halo reuse)
   ConvTcArgs args;
   int block_n, block_k;
   int pair;  // 1: CTA-pair (cta_group::2) kernel, launched as clusters of 2
