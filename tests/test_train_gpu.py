@@ -200,6 +200,17 @@ def test_train_step_vs_oracle_autograd():
     assert med <= 0.30 and med <= 2.5 * med_amp + 0.02, (med, med_amp)
     # running statistics were updated with momentum 0.03
     assert not torch.equal(P["model.0.bn.running_mean"].cpu(), params["model.0.bn.running_mean"])
+    # steps 2 and 3 run through the captured CUDA graphs (forward + backward): same inputs -> same gradients
+    first = {k: P[k].grad.clone() for k in g_o}
+    for _ in range(2):
+        for k in g_o:
+            P[k].grad = None
+        loss2, _ = ComputeLoss(m)(m(x.cuda()), targets.cuda())
+        loss2.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss2.detach()) - float(loss.detach())) < 1e-3 * abs(float(loss.detach()))
+    worst = max(rel_l2(P[k].grad, first[k]) for k in g_o)
+    assert worst < 2e-2, worst  # fp32 atomics reorder + bf16 rounding of re-accumulated sums
     # an SGD step on the master parameters, then eval-mode inference with the updated weights
     opt = torch.optim.SGD(list(m.parameters()), lr=0.01, momentum=0.9)
     opt.step()

@@ -154,12 +154,13 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [49,52) base offset | [61,64) layout
 // layout: 0 none, 2 SWIZZLE_128B, 4 SWIZZLE_64B, 6 SWIZZLE_32B.  SBO = byte distance between 8-row groups.
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout,
-                                                   int base_off_mode = 1) {
+                                                   int base_off_mode = 0) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  // base offset: non-zero only for operands whose start is not aligned to the 1 KB swizzle pattern (halo-reuse A operand)
+  // base offset stays 0 even for operands that start off the 1 KB pattern: the swizzle XOR uses absolute address bits
+  // (measured, y3_conv_tc.cu halo_mode()); base_off_mode = 1 is only kept as a probe of the other reading of the ISA text
   if (base_off_mode) d |= static_cast<uint64_t>((saddr >> 7) & 0x7u) << 49;
   d |= static_cast<uint64_t>(layout) << 61;
   return d;

@@ -36,7 +36,8 @@ constexpr int kSmemBudget = 224 * 1024;  // ring + epilogue staging; barriers + 
 // stores to 32 different cache lines per instruction — the thin layers were bound by exactly that (profiles/r01_*).
 // HALO = true (stride-1 3x3, BLOCK_K = 64): one pipeline stage covers a whole filter ROW (3 taps): the A operand is ONE
 // TMA box of 128+2 consecutive pixels and the three taps read it at row offsets 0/1/2 through UMMA descriptors whose
-// start address is not aligned to the 1 KB swizzle pattern (descriptor base_offset = (addr >> 7) & 7).  A rows fetched per
+// start address is not aligned to the 1 KB swizzle pattern (the swizzle is a function of the absolute address, so the
+// descriptor's base_offset stays 0 — verified on hardware, see halo_mode()).  A rows fetched per
 // k-block drop from 9*128 to 3*130; the TMA unit's row rate (~1 row / 2.5 clk / SM), not its byte rate, was the limit.
 template <int BLOCK_N, int BLOCK_K, bool PAIR, bool STAGED, bool HALO>
 struct Cfg {
@@ -220,7 +221,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int k = 0; k < BLOCK_K / 16; ++k) {
               // HALO: tap t reads the A box shifted by t pixel rows (128 B each): start address off the 1 KB swizzle
-              // pattern, described to the tensor core through the descriptor's base_offset field
+              // pattern (legal: the XOR pattern is taken from the absolute address)
               const uint64_t adesc = umma_smem_desc(a_addr + t * (BLOCK_K * 2) + k * 32, C::kSbo, C::kLayout, p.desc_mode);
               const uint64_t bdesc = umma_smem_desc(b_addr + t * C::kBBytes + k * 32, C::kSbo, C::kLayout, p.desc_mode);
               const uint32_t acc = (it | int(t) | k) != 0 ? 1u : 0u;
@@ -561,8 +562,10 @@ static bool staged_enabled() {
   return v != 0;
 }
 
-// Y3_CONV_HALO=0 disables the halo-reuse A path; Y3_CONV_HALO=2 keeps it but writes base_offset = 0 in the descriptors
-// (hardware-semantics probe: which of the two makes the unaligned-start operand read correctly).
+// Y3_CONV_HALO=0 disables the halo-reuse A path.  Default (1): descriptors of the row-shifted taps carry base_offset = 0.
+// Measured on B200 (tools/probe_conv.py, round 1): with base_offset = 0 all 27 conv cases are exact, i.e. the tensor core
+// applies the 128B-swizzle XOR to the ABSOLUTE shared-memory address bits [7,10) exactly as the TMA unit did when it
+// wrote the box; with base_offset = (addr >> 7) & 7 (Y3_CONV_HALO=2) the shifted taps read wrong rows.
 static int halo_mode() {
   static int v = -1;
   if (v < 0) {
@@ -654,7 +657,7 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     // halo reuse needs >= 2 stages of (17 KB + 3 B tiles): any N <= 128, N = 256 only as a CTA pair
     const bool pair_ok = bn >= 128 && pair_enabled() && a.m_tiles >= 2;
     plan->halo = (taps == 9 && bk == 64 && halo_mode() != 0 && (bn <= 128 || pair_ok)) ? 1 : 0;
-    a.desc_mode = halo_mode() == 2 ? 0 : 1;
+    a.desc_mode = halo_mode() == 2 ? 1 : 0;
     const uint32_t a_rows = plan->halo ? kBlockM + 2 : kBlockM;
     a.a_tx_bytes = a_rows * bk * 2;
     const uint64_t dims[2] = {static_cast<uint64_t>(d.in_ld), static_cast<uint64_t>(rows)};
@@ -664,7 +667,7 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     if (rc) return rc;
   } else {
     plan->halo = 0;
-    a.desc_mode = 1;
+    a.desc_mode = 0;
     a.mode = 1;
     a.ho = d.h / 2;
     a.wo = d.w / 2;
