@@ -62,7 +62,7 @@ struct Cfg {
   static constexpr size_t kSmemBytes =
       size_t(kStages) * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/ + BLOCK_N * 4 /*bias tile*/;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
-  static_assert(!HALO || BLOCK_K == 64, "halo reuse is built for 128-byte rows only");
+  static_assert(!HALO || BLOCK_K >= 32, "halo reuse: rows of 64 or 128 bytes");
 };
 
 // PAIR = true: two CTAs of a cluster (one SM pair) cooperate on a 256-row tile with tcgen05 cta_group::2: each CTA
@@ -519,6 +519,13 @@ int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream) {
     case 16: return plan.staged ? launch_cfg<BN, 16, PR, true>(plan, stream) : launch_cfg<BN, 16, PR, false>(plan, stream); \
   }                                                                                                             \
   break;
+  if (plan.halo && plan.block_k == 32) {  // c_in = 32 layers (64-byte rows, SWIZZLE_64B)
+    if (plan.block_n == 64)
+      return plan.staged ? launch_cfg<64, 32, false, true, true>(plan, stream) : launch_cfg<64, 32, false, false, true>(plan, stream);
+    if (plan.block_n == 32)
+      return plan.staged ? launch_cfg<32, 32, false, true, true>(plan, stream) : launch_cfg<32, 32, false, false, true>(plan, stream);
+    return set_error(Y3_ERR_BAD_ARG, "conv_tc: no K=32 halo kernel for tile N=%d", plan.block_n);
+  }
   if (plan.halo) {  // block_k == 64, stride-1 3x3; N = 256 only as a CTA pair and never staged (smem)
     if (plan.pair) {
       if (plan.block_n == 256) return launch_cfg<256, 64, true, false, true>(plan, stream);
@@ -656,7 +663,7 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     a.m_tiles = static_cast<int>((rows + kBlockM - 1) / kBlockM);
     // halo reuse needs >= 2 stages of (17 KB + 3 B tiles): any N <= 128, N = 256 only as a CTA pair
     const bool pair_ok = bn >= 128 && pair_enabled() && a.m_tiles >= 2;
-    plan->halo = (taps == 9 && bk == 64 && halo_mode() != 0 && (bn <= 128 || pair_ok)) ? 1 : 0;
+    plan->halo = (taps == 9 && (bk == 64 || (bk == 32 && bn <= 64)) && halo_mode() != 0 && (bn <= 128 || pair_ok)) ? 1 : 0;
     a.desc_mode = halo_mode() == 2 ? 1 : 0;
     const uint32_t a_rows = plan->halo ? kBlockM + 2 : kBlockM;
     a.a_tx_bytes = a_rows * bk * 2;
