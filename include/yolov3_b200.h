@@ -67,8 +67,18 @@ typedef struct y3_conv_desc {
                             columns [0, c_out_pad) of every row are written (pad columns = 0) */
   int32_t out_f32_ld;    /* >= c_out_pad, multiple of 4 */
   int32_t* err;          /* optional device int32 error word written by the in-kernel watchdog */
+  int32_t weight_layout; /* Y3_W_*: how `weight` is packed (0 = tap-major as documented above) */
 } y3_conv_desc;
 int y3_conv_bn_act_fwd(const y3_conv_desc* d, y3_stream_t stream);
+/* Weight layouts.  Y3_W_XPAIR (stride-2 3x3 with c_in in {16,32}, in_ld == c_in, in_coff == 0): bf16
+ * [c_out_pad, 3, 2, 2, c_in] with element (kh, sp, par, c) = W[kh][2*sp+par][c] and zeros for the phantom column
+ * 2*sp+par == 3 — two horizontally adjacent taps form one 2*c_in-channel GEMM k-block, which turns the 64-byte rows of
+ * the thin first stride-2 layer (models/yolov3.yaml:19) into full 128-byte TMA rows.  y3_conv_weight_layout returns the
+ * layout the kernel prefers for a descriptor's geometry (weight/bias/out pointers are not inspected); packing the
+ * weights that way and setting weight_layout is optional — Y3_W_TAPS always works. */
+#define Y3_W_TAPS 0
+#define Y3_W_XPAIR 1
+int y3_conv_weight_layout(const y3_conv_desc* d);
 /* Tile N the kernel will use for c_out (weights/bias must be padded to a multiple of it). */
 int y3_conv_cout_pad(int32_t c_out);
 

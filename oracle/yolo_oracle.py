@@ -357,7 +357,7 @@ def greedy_nms(boxes, scores, iou_thres):
     return order[np.asarray(keep, dtype=np.int64)]
 
 
-def nms_image(x, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False, max_det=300):
+def nms_image(x, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False, max_det=300, lb=None):
     """One image of non_max_suppression (utils/general.py:683-743).  x: [n, 5+nc] float32.
 
     Returns (det[k,6] float32 = xyxy,conf,cls sorted by conf desc; src[k,2] int64 = (row, cls) of each kept detection).
@@ -367,10 +367,19 @@ def nms_image(x, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, 
     """
     x = np.asarray(x, dtype=np.float32)
     nc = x.shape[1] - 5
+    n_pred = x.shape[0]
     multi_label = multi_label and nc > 1
     thr = np.float32(conf_thres)
     rows = np.nonzero(x[:, 4] > thr)[0]  # :669,686
     x = x[rows]
+    if lb is not None and len(lb):  # autolabel priors appended AFTER the confidence filter (:689-695); src row = n + i
+        lb = np.asarray(lb, dtype=np.float32).reshape(-1, 5)
+        v = np.zeros((len(lb), nc + 5), np.float32)
+        v[:, :4] = lb[:, 1:5]
+        v[:, 4] = 1.0
+        v[np.arange(len(lb)), lb[:, 0].astype(np.int64) + 5] = 1.0
+        rows = np.concatenate((rows, np.arange(len(lb)) + n_pred))
+        x = np.concatenate((x, v), 0)
     empty = (np.zeros((0, 6), np.float32), np.zeros((0, 2), np.int64))
     if x.shape[0] == 0:
         return empty
@@ -401,7 +410,7 @@ def nms_image(x, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, 
 
 
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
-                        max_det=300):
+                        max_det=300, labels=()):
     """Batch wrapper; the reference's wall-clock ``time_limit`` break (utils/general.py:675,746-748) is NOT restated:
     it is a hazard, not a result."""
     assert 0 <= conf_thres <= 1 and 0 <= iou_thres <= 1
@@ -410,7 +419,8 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     pred = prediction.detach().cpu().float().numpy() if isinstance(prediction, torch.Tensor) else np.asarray(prediction)
     outs, srcs = [], []
     for xi in range(pred.shape[0]):
-        d, s = nms_image(pred[xi], conf_thres, iou_thres, classes, agnostic, multi_label, max_det)
+        d, s = nms_image(pred[xi], conf_thres, iou_thres, classes, agnostic, multi_label, max_det,
+                         lb=labels[xi] if labels else None)
         outs.append(d)
         srcs.append(s)
     return outs, srcs

@@ -105,6 +105,11 @@ def nms_case_list():
     cases.append(("maxdet1", base, dict(conf_thres=0.05, iou_thres=0.45, max_det=1)))
     cases.append(("maxdet1000", base, dict(conf_thres=0.001, iou_thres=0.6, max_det=1000, multi_label=True)))
     cases.append(("empty", base, dict(conf_thres=1.0, iou_thres=0.45)))
+    # autolabel priors (general.py:689-695), (cls, x, y, w, h) rows in pixels.  Every prior has conf exactly 1.0 and the
+    # reference's argsort is unstable, so the goldens carry at most one prior per image (tie-free)
+    cases.append(("labels", base, dict(conf_thres=0.25, iou_thres=0.45, labels=[[[3.0, 320.0, 320.0, 120.0, 90.0]], []])))
+    cases.append(("labels_ml", base, dict(conf_thres=0.05, iou_thres=0.45, multi_label=True,
+                                          labels=[[[3.0, 320.0, 320.0, 120.0, 90.0]], [[17.0, 100.5, 200.25, 50.0, 60.0]]])))
     # adversarial: zero-area boxes, identical boxes, class 0 and 79 with IoU near the threshold, fp16-rounded values
     g = torch.Generator().manual_seed(7)
     adv = torch.zeros(1, 64, 85)
@@ -135,7 +140,10 @@ def gen_nms():
         real_time = G.time.time
         G.time.time = lambda: 0.0  # disable the wall-clock time_limit break (utils/general.py:675,746-748)
         try:
-            ref = G.non_max_suppression(pred.clone(), **kw)
+            kw_ref = dict(kw)
+            if "labels" in kw:  # the reference indexes label tensors
+                kw_ref["labels"] = [torch.tensor(l, dtype=torch.float32).reshape(-1, 5) for l in kw["labels"]]
+            ref = G.non_max_suppression(pred.clone(), **kw_ref)
         finally:
             G.time.time = real_time
         ora, src = O.non_max_suppression(pred.clone(), **kw)

@@ -39,6 +39,11 @@ CASES = [
     dict(name="head_255", n=2, h=10, w=10, cin=256, cout=255, k=1, s=1, head=True, act=0),
     dict(name="head_255_k1024", n=1, h=6, w=6, cin=1024, cout=255, k=1, s=1, head=True, act=0),
     dict(name="big_flat", n=8, h=80, w=80, cin=128, cout=256, k=3, s=1),
+    dict(name="s2_k32_xpair", n=2, h=32, w=48, cin=32, cout=64, k=3, s=2, xpair=True),
+    dict(name="s2_k16_xpair", n=1, h=16, w=16, cin=16, cout=32, k=3, s=2, xpair=True),
+    dict(name="s2_k32_xpair_many_tiles", n=4, h=160, w=160, cin=32, cout=64, k=3, s=2, xpair=True),
+    dict(name="3x3_k32_res_many_tiles", n=4, h=80, w=80, cin=32, cout=64, k=3, s=1, res=True),
+    dict(name="1x1_res_many_tiles", n=4, h=80, w=80, cin=128, cout=128, k=1, s=1, res=True),
 ]
 
 
@@ -64,7 +69,8 @@ def run_case(c):
         xin.buf[:, 1:-1, 1:-1, :] = 7.0
     xin = xin.slice(c.get("in_coff", 0), cin) if c.get("in_ld") else xin
     xin.load_nchw(x.to(dev))
-    wp, bp = ops.pack_conv_weight(wt, b)
+    wp, bp = ops.pack_conv_weight_xpair(wt, b) if c.get("xpair") else ops.pack_conv_weight(wt, b)
+    layout = 1 if c.get("xpair") else 0
     ho, wo = h // s, w // s
     u = 2 if c.get("upsample") else 1
     res = None
@@ -88,7 +94,8 @@ def run_case(c):
     else:
         out = PaddedNHWC.zeros(n, ho * u, wo * u, cout, ld=c.get("out_ld", cout))
         out = out.slice(c.get("out_coff", 0), cout) if c.get("out_ld") else out
-        ops.conv_bn_act(xin, wp, bp, cout, k, s, act, out=out, res=res, upsample=bool(c.get("upsample")), err=err)
+        ops.conv_bn_act(xin, wp, bp, cout, k, s, act, out=out, res=res, upsample=bool(c.get("upsample")), err=err,
+                        weight_layout=layout)
         torch.cuda.synchronize()
         got = out.to_nchw()
         if u == 2:

@@ -29,9 +29,11 @@ class ConvDesc(C.Structure):
         ("upsample", C.c_int32),
         ("out_f32", C.c_void_p), ("out_f32_ld", C.c_int32),
         ("err", C.c_void_p),
+        ("weight_layout", C.c_int32),
     ]
 
 
+W_TAPS, W_XPAIR = 0, 1
 MAX_LEVELS, MAX_ANCHORS = 5, 6
 
 
@@ -142,6 +144,7 @@ def _declare(lib):
         "y3_device_check": ([], C.c_int),
         "y3_conv_bn_act_fwd": ([C.POINTER(ConvDesc), vp], C.c_int),
         "y3_conv_cout_pad": ([i32], C.c_int),
+        "y3_conv_weight_layout": ([C.POINTER(ConvDesc)], C.c_int),
         "y3_abi_sizeof": ([i32], C.c_int64),
         "y3_conv_first_fwd": ([C.POINTER(FirstDesc), vp], C.c_int),
         "y3_maxpool_fwd": ([C.POINTER(PoolDesc), vp], C.c_int),

@@ -52,15 +52,25 @@ struct Cfg {
   static constexpr uint32_t kSlabRowBytes = kSlabCols * 2;                // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
   static constexpr uint32_t kSlabBytes = kBlockM * kSlabRowBytes;
   static constexpr uint32_t kSlabs = BLOCK_N / kSlabCols;
-  static constexpr uint32_t kStagingBytes = STAGED ? kBlockM * BLOCK_N * 2 : 0;
+  // two staging tiles for N <= 128: the residual of tile i+1 is TMA-loaded while tile i is converted and stored, so the
+  // epilogue of the thin layers no longer exposes one L2/HBM round trip per tile (their k-loop is only ~600 clk long)
+  static constexpr uint32_t kStgTile = kBlockM * BLOCK_N * 2;
+  static constexpr uint32_t kStgBufs = BLOCK_N <= 128 ? 2 : 1;
+  static constexpr uint32_t kStagingBytes = STAGED ? kStgBufs * kStgTile : 0;
+  static constexpr int kMaxStages = 8;
   static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
+  // B-resident mode: `steps` weight boxes of kBBytes stay in shared memory for the whole kernel; the ring carries A only
+  __host__ __device__ static constexpr uint32_t bres_bytes(int steps) { return (uint32_t(steps) * kBBytes + 1023u) / 1024u * 1024u; }
+  __host__ __device__ static constexpr int bres_stages(int steps) {
+    const int s = (int(kSmemBudget) - int(kStagingBytes) - int(bres_bytes(steps))) / int(kABytes);
+    return s > kMaxStages ? kMaxStages : s;
+  }
   static constexpr uint32_t kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // power of two for N in {32,64,128,256}
   static constexpr uint32_t kSwizzleBytes = BLOCK_K * 2;                       // 32 / 64 / 128
   static constexpr uint32_t kLayout = BLOCK_K == 64 ? 2u : (BLOCK_K == 32 ? 4u : 6u);
   static constexpr uint32_t kSbo = 8 * kSwizzleBytes;
-  static constexpr size_t kSmemBytes =
-      size_t(kStages) * kStageBytes + kStagingBytes + 1024 /*align*/ + 256 /*barriers*/ + BLOCK_N * 4 /*bias tile*/;
+  static constexpr size_t kSmemBytes = size_t(kSmemBudget) + 1024 /*align*/ + 256 /*barriers*/ + BLOCK_N * 4 /*bias tile*/;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(!HALO || BLOCK_K >= 32, "halo reuse: rows of 64 or 128 bytes");
 };
@@ -76,8 +86,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                const ConvTcArgs p) {
   using C = Cfg<BLOCK_N, BLOCK_K, PAIR, STAGED, HALO>;
-  constexpr int STAGES = C::kStages;
-  constexpr uint32_t kBStage = C::kTaps * C::kBBytes;  // B bytes per stage
+  const int STAGES = p.stages;
+  const bool bres = p.bres != 0;
+  constexpr uint32_t kBStage = C::kTaps * C::kBBytes;  // B bytes per stage (ring mode)
+  const int b_steps = p.taps * p.kblocks;             // weight boxes of one N tile (resident mode keeps them all)
   constexpr uint32_t IDESC = umma_idesc_bf16(PAIR ? 256 : 128, BLOCK_N);
   constexpr uint32_t kEpiThreads = 32 * kEpilogueWarps;
 
@@ -85,14 +97,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // swizzled TMA/UMMA tiles need 1 KB alignment
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * C::kABytes;
-  uint8_t* smem_stg = smem + STAGES * C::kStageBytes;  // 1 KB aligned: every stage size is a multiple of 1 KB
+  uint8_t* smem_b = smem + STAGES * C::kABytes;  // ring of B stages, or the resident weight tile
+  uint8_t* smem_stg = smem_b + (bres ? C::bres_bytes(b_steps) : uint32_t(STAGES) * kBStage);  // 1 KB aligned
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stg + C::kStagingBytes);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + C::kMaxStages;
+  uint64_t* tfull_bar = empty_bar + C::kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* res_bar = tempty_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
+  uint64_t* res_bar = tempty_bar + 2;  // [2]: one per staging buffer
+  uint64_t* bres_bar = res_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
   // bias of the current N tile.  Read through __ldg it missed the (almost entirely shared-memory) L1 and exposed an L2
   // round trip per 32-column chunk: 29 % of all warp stall samples of the epilogue (profiles/r01_ncu_conv_tc_full_summary.txt).
   float* s_bias = reinterpret_cast<float*>(smem_stg + C::kStagingBytes + 256);
@@ -115,7 +128,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], PAIR ? 2 * kEpiThreads : kEpiThreads);  // pair: both CTAs' epilogues release the buffer
     }
-    mbar_init(res_bar, 1);
+    mbar_init(&res_bar[0], 1);
+    mbar_init(&res_bar[1], 1);
+    mbar_init(bres_bar, PAIR ? 2 : 1);
     if (STAGED) {
       tma_prefetch_desc(&map_out);
       if (p.res) tma_prefetch_desc(&map_res);
@@ -144,6 +159,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer (one thread)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
+      if (bres && worker < total_tiles) {
+        // resident weights (single N tile): every (k-block, tap) box once, all credited to one barrier
+        const int n0 = static_cast<int>(rank) * C::kBRows;
+        const uint32_t bytes = uint32_t(b_steps) * C::kBBytes;
+        if (PAIR) {
+          const uint32_t bar_addr = mapa_u32(smem_u32(bres_bar), 0);
+          if (rank == 0)
+            mbar_expect_tx(bres_bar, 2 * bytes);
+          else
+            mbar_arrive_cluster(bar_addr);
+          for (int st = 0; st < b_steps; ++st) {
+            const int kb = st / p.taps, tap = st - kb * p.taps;
+            tma_load_2d_pair(smem_b + st * C::kBBytes, &map_b, bar_addr, tap * p.cin + kb * BLOCK_K, n0);
+          }
+        } else {
+          mbar_expect_tx(bres_bar, bytes);
+          for (int st = 0; st < b_steps; ++st) {
+            const int kb = st / p.taps, tap = st - kb * p.taps;
+            tma_load_2d(smem_b + st * C::kBBytes, &map_b, bres_bar, tap * p.cin + kb * BLOCK_K, n0);
+          }
+        }
+      }
       for (int tile = worker; tile < total_tiles; tile += n_workers) {
         const int nt = tile % p.n_tiles;
         const int mt = PAIR ? (tile / p.n_tiles) * 2 + static_cast<int>(rank) : tile / p.n_tiles;
@@ -165,8 +202,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* a_dst = smem_a + stage * C::kABytes;
           uint8_t* b_dst = smem_b + stage * kBStage;
           const int shift = HALO ? (tap - 1) * p.wp - 1 : ((p.taps == 9) ? ((tap / 3 - 1) * p.wp + (tap % 3 - 1)) : 0);
-          const int r = tap / 3, s = tap - r * 3;
-          const uint32_t stage_tx = p.a_tx_bytes + kBStage;
+          // patch mode: filter row r, column s.  x-paired weights (stride 2, in_ld == c_in): one box covers the two
+          // horizontally adjacent taps (r, 2s) and (r, 2s+1), which are contiguous channels of the parity view
+          const int r = p.xpair ? tap >> 1 : tap / 3, s = p.xpair ? tap & 1 : tap - r * 3;
+          const int c0 = p.xpair ? p.a_coff : (s & 1) * p.a_ld + p.a_coff + kb * BLOCK_K;
+          const int c1 = p.xpair ? s : (s >> 1);
+          const uint32_t stage_tx = p.a_tx_bytes + (bres ? 0u : kBStage);
           uint32_t bar_addr;
           if (PAIR) {
             // all bytes of both CTAs are credited to the LEADER's full barrier; the peer only contributes an arrival
@@ -178,21 +219,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             if (p.mode == 0)
               tma_load_2d_pair(a_dst, &map_a, bar_addr, p.a_coff + kb * BLOCK_K, row0 + shift);
             else
-              tma_load_5d_pair(a_dst, &map_a, bar_addr, (s & 1) * p.a_ld + p.a_coff + kb * BLOCK_K, ow0 + (s >> 1), r & 1,
-                               oh0 + (r >> 1), img);
+              tma_load_5d_pair(a_dst, &map_a, bar_addr, c0, ow0 + c1, r & 1, oh0 + (r >> 1), img);
+            if (!bres) {
 #pragma unroll
-            for (uint32_t t = 0; t < C::kTaps; ++t)
-              tma_load_2d_pair(b_dst + t * C::kBBytes, &map_b, bar_addr, (HALO ? tap * 3 + int(t) : tap) * p.cin + kb * BLOCK_K, n0);
+              for (uint32_t t = 0; t < C::kTaps; ++t)
+                tma_load_2d_pair(b_dst + t * C::kBBytes, &map_b, bar_addr, (HALO ? tap * 3 + int(t) : tap) * p.cin + kb * BLOCK_K, n0);
+            }
           } else {
             mbar_expect_tx(&full_bar[stage], stage_tx);
             if (p.mode == 0)
               tma_load_2d(a_dst, &map_a, &full_bar[stage], p.a_coff + kb * BLOCK_K, row0 + shift);
             else
-              tma_load_5d(a_dst, &map_a, &full_bar[stage], (s & 1) * p.a_ld + p.a_coff + kb * BLOCK_K, ow0 + (s >> 1),
-                          r & 1, oh0 + (r >> 1), img);
+              tma_load_5d(a_dst, &map_a, &full_bar[stage], c0, ow0 + c1, r & 1, oh0 + (r >> 1), img);
+            if (!bres) {
 #pragma unroll
-            for (uint32_t t = 0; t < C::kTaps; ++t)
-              tma_load_2d(b_dst + t * C::kBBytes, &map_b, &full_bar[stage], (HALO ? tap * 3 + int(t) : tap) * p.cin + kb * BLOCK_K, n0);
+              for (uint32_t t = 0; t < C::kTaps; ++t)
+                tma_load_2d(b_dst + t * C::kBBytes, &map_b, &full_bar[stage], (HALO ? tap * 3 + int(t) : tap) * p.cin + kb * BLOCK_K, n0);
+            }
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -206,6 +249,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0;
       int iter = 0;
+      if (bres && worker < total_tiles) mbar_wait(bres_bar, 0, p.err, 6);  // resident weights have landed
       for (int tile = worker; tile < total_tiles; tile += n_workers, ++iter) {
         const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
         mbar_wait(&tempty_bar[as], aphase ^ 1u, p.err, 2);  // epilogue has drained this accumulator buffer
@@ -215,7 +259,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&full_bar[stage], phase, p.err, 3);  // TMA bytes have landed
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * C::kABytes);
-          const uint32_t b_addr = smem_u32(smem_b + stage * kBStage);
+          const uint32_t b_addr = smem_u32(smem_b) + (bres ? uint32_t(it) * kBStage : stage * kBStage);
 #pragma unroll
           for (uint32_t t = 0; t < C::kTaps; ++t) {
 #pragma unroll
@@ -257,6 +301,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const uint32_t lead_tempty[2] = {PAIR ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u,
                                      PAIR ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u};
     int iter = 0;
+    int bias_nt = -1;  // N tile whose bias currently sits in s_bias
     for (int tile = worker; tile < total_tiles; tile += n_workers, ++iter) {
       const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
       const int nt = tile % p.n_tiles;
@@ -289,21 +334,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ---------------- staged epilogue (flat mode, bf16 output): TMEM -> registers -> swizzled smem tile -> TMA store
         const bool elected = threadIdx.x == 64;  // first epilogue thread
         const int row0 = mt * kBlockM;
+        constexpr bool kTwo = C::kStgBufs == 2;
+        const uint32_t sb = kTwo ? uint32_t(iter & 1) : 0u;            // staging buffer of this tile
+        const uint32_t rphase = kTwo ? uint32_t(iter >> 1) & 1u : uint32_t(iter) & 1u;
+        uint8_t* stg = smem_stg + sb * C::kStgTile;
         if (elected) {
-          bulk_wait_read_all();  // the previous tile's store has finished reading the staging buffer
-          if (p.res) {
-            mbar_expect_tx(res_bar, kBlockM * BLOCK_N * 2);
+          if (kTwo) {
+            // residual prefetch distance 1: tile i+1's residual goes into the OTHER buffer, which the store of tile i-1
+            // must have finished reading; without a residual only the store of tile i-2 (this buffer) has to be done
+            if (p.res) bulk_wait_read_all(); else bulk_wait_read_1();
+            if (p.res) {
+              if (iter == 0) {
+                mbar_expect_tx(&res_bar[0], C::kStgTile);
 #pragma unroll
-            for (uint32_t sl = 0; sl < C::kSlabs; ++sl)
-              tma_load_2d(smem_stg + sl * C::kSlabBytes, &map_res, res_bar, p.res_coff + n0 + sl * C::kSlabCols, row0);
+                for (uint32_t sl = 0; sl < C::kSlabs; ++sl)
+                  tma_load_2d(stg + sl * C::kSlabBytes, &map_res, &res_bar[0], p.res_coff + n0 + sl * C::kSlabCols, row0);
+              }
+              const int tnext = tile + n_workers;
+              if (tnext < total_tiles) {
+                const int nt2 = tnext % p.n_tiles;
+                const int mt2 = PAIR ? (tnext / p.n_tiles) * 2 + static_cast<int>(rank) : tnext / p.n_tiles;
+                uint8_t* stg2 = smem_stg + (sb ^ 1u) * C::kStgTile;
+                mbar_expect_tx(&res_bar[sb ^ 1u], C::kStgTile);
+#pragma unroll
+                for (uint32_t sl = 0; sl < C::kSlabs; ++sl)
+                  tma_load_2d(stg2 + sl * C::kSlabBytes, &map_res, &res_bar[sb ^ 1u],
+                              p.res_coff + nt2 * BLOCK_N + sl * C::kSlabCols, mt2 * kBlockM);
+              }
+            }
+          } else {
+            bulk_wait_read_all();  // the previous tile's store has finished reading the staging buffer
+            if (p.res) {
+              mbar_expect_tx(&res_bar[0], C::kStgTile);
+#pragma unroll
+              for (uint32_t sl = 0; sl < C::kSlabs; ++sl)
+                tma_load_2d(stg + sl * C::kSlabBytes, &map_res, &res_bar[0], p.res_coff + n0 + sl * C::kSlabCols, row0);
+            }
           }
         }
-        // (the end-of-tile barrier 2 of the previous tile guarantees nobody still reads the old bias values)
-        if (int(threadIdx.x) - 64 < BLOCK_N) s_bias[threadIdx.x - 64] = __ldg(p.bias + n0 + threadIdx.x - 64);
+        // (the end-of-tile barrier 2 of the previous tile guarantees nobody still reads the old bias values); a layer
+        // with a single N tile loads its bias once — the L2 round trip per tile was exposed on the thin layers
+        if (nt != bias_nt && int(threadIdx.x) - 64 < BLOCK_N) s_bias[threadIdx.x - 64] = __ldg(p.bias + n0 + threadIdx.x - 64);
+        bias_nt = nt;
         mbar_wait(&tfull_bar[as], aphase, p.err, 4);
         tc_fence_after();
         named_bar_sync(1, kEpiThreads);  // bias tile visible; staging buffer is free for everybody
-        if (p.res) mbar_wait(res_bar, iter & 1, p.err, 5);  // residual tile landed
+        if (p.res) mbar_wait(&res_bar[sb], rphase, p.err, 5);  // residual tile landed
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
         const uint32_t swz = C::kSlabRowBytes == 128 ? (m & 7) : ((m >> 1) & 3);
         if (active) {
@@ -326,7 +402,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               for (int j = 0; j < 32; ++j) x[j] = silu_fast(x[j]);
             }
             const uint32_t slab = c / C::kSlabCols, j0 = (c % C::kSlabCols) / 8;
-            const uint32_t row_addr = smem_u32(smem_stg) + slab * C::kSlabBytes + m * C::kSlabRowBytes;
+            const uint32_t row_addr = smem_u32(stg) + slab * C::kSlabBytes + m * C::kSlabRowBytes;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint32_t addr = row_addr + (((j0 + q) ^ swz) << 4);
@@ -361,7 +437,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (elected) {
 #pragma unroll
           for (uint32_t sl = 0; sl < C::kSlabs; ++sl)
-            tma_store_2d(&map_out, smem_stg + sl * C::kSlabBytes, p.out_coff + n0 + sl * C::kSlabCols, row0);
+            tma_store_2d(&map_out, stg + sl * C::kSlabBytes, p.out_coff + n0 + sl * C::kSlabCols, row0);
           bulk_commit_group();
         }
         continue;
@@ -390,7 +466,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int q = 0; q < 4; ++q) rcur[q] = __ldg(reinterpret_cast<const uint4*>(res_ptr + c_begin) + q);
       }
 
-      if (int(threadIdx.x) - 64 < BLOCK_N) s_bias[threadIdx.x - 64] = __ldg(p.bias + n0 + threadIdx.x - 64);
+      if (nt != bias_nt && int(threadIdx.x) - 64 < BLOCK_N) s_bias[threadIdx.x - 64] = __ldg(p.bias + n0 + threadIdx.x - 64);
+      bias_nt = nt;
       mbar_wait(&tfull_bar[as], aphase, p.err, 4);  // accumulator complete
       tc_fence_after();
       named_bar_sync(1, kEpiThreads);  // bias tile visible
@@ -503,7 +580,14 @@ int launch_cfg(const ConvTcPlan& plan, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   }
-  Y3_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, plan.map_a, plan.map_b, plan.map_out, plan.map_res, plan.args));
+  ConvTcArgs args = plan.args;
+  args.bres = plan.bres;
+  args.stages = plan.bres ? C::bres_stages(args.taps * args.kblocks) : C::kStages;
+  if (args.stages < 3) {  // not enough ring left beside the resident weights: fall back to streaming them
+    args.bres = 0;
+    args.stages = C::kStages;
+  }
+  Y3_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, plan.map_a, plan.map_b, plan.map_out, plan.map_res, args));
   return Y3_OK;
 }
 
@@ -583,6 +667,16 @@ static int halo_mode() {
   return v;
 }
 
+// Y3_CONV_BRES=0 streams the weights through the ring everywhere (A/B measurements).
+static bool bres_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("Y3_CONV_BRES");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 static bool pair_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -590,6 +684,12 @@ static bool pair_enabled() {
     v = (e && e[0] == '0') ? 0 : 1;
   }
   return v != 0;
+}
+
+// Layer 1 of yolov3 (32 -> 64, stride 2 at 640x640) moved 64-byte rows through 9 five-dimensional TMA boxes per tile
+// and ran at 0.2 PFLOP/s; paired, the same tile is 6 boxes of full 128-byte rows and one K = 64 MMA group per box.
+static bool conv_prefers_xpair(const y3_conv_desc& d) {
+  return d.ksize == 3 && d.stride == 2 && (d.c_in == 32 || d.c_in == 16) && d.in_ld == d.c_in && d.in_coff == 0;
 }
 
 int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
@@ -617,10 +717,15 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
   }
   if (d.stride == 2) Y3_REQUIRE(d.h % 2 == 0 && d.w % 2 == 0, "conv: stride-2 needs even h, w");
 
+  const bool xpair = d.weight_layout == Y3_W_XPAIR;
+  if (xpair) Y3_REQUIRE(conv_prefers_xpair(d), "conv: x-paired weights need ksize 3, stride 2, c_in 16|32 == in_ld, in_coff 0");
+  else Y3_REQUIRE(d.weight_layout == Y3_W_TAPS, "conv: unknown weight_layout %d", d.weight_layout);
   const int bn = pick_block_n(d.c_out);
-  const int bk = d.c_in % 64 == 0 ? 64 : (d.c_in % 32 == 0 ? 32 : 16);
+  // x-paired: the GEMM sees 3 x 2 taps of 2*c_in channels (the phantom 4th column carries zero weights)
+  const int gemm_cin = xpair ? 2 * d.c_in : d.c_in;
+  const int bk = gemm_cin % 64 == 0 ? 64 : (gemm_cin % 32 == 0 ? 32 : 16);
   const int cout_pad = (d.c_out + bn - 1) / bn * bn;
-  const int taps = d.ksize * d.ksize;
+  const int taps = xpair ? 6 : d.ksize * d.ksize;
   const int hp = d.h + 2, wp = d.w + 2;
 
   ConvTcArgs& a = plan->args;
@@ -628,8 +733,9 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
   plan->block_n = bn;
   plan->block_k = bk;
   a.taps = taps;
-  a.kblocks = d.c_in / bk;
-  a.cin = d.c_in;
+  a.kblocks = gemm_cin / bk;
+  a.cin = gemm_cin;
+  a.xpair = xpair ? 1 : 0;
   a.a_coff = d.in_coff;
   a.a_ld = d.in_ld;
   a.n_tiles = cout_pad / bn;
@@ -708,13 +814,19 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     if (rc) return rc;
   }
   {
-    const uint64_t ktot = static_cast<uint64_t>(taps) * d.c_in;
+    const uint64_t ktot = static_cast<uint64_t>(taps) * gemm_cin;
     const uint64_t dims[2] = {ktot, static_cast<uint64_t>(cout_pad)};
     const uint64_t strides[2] = {0, ktot * 2};
     plan->pair = (bn >= 128 && pair_enabled() && a.m_tiles >= 2) ? 1 : 0;
     const uint32_t box[2] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(plan->pair ? bn / 2 : bn)};
     rc = encode_tensor_map_bf16(&plan->map_b, d.weight, 2, dims, strides, box, bk * 2);
     if (rc) return rc;
+  }
+  {
+    // resident weights: one N tile whose (taps x k-blocks) boxes fit beside a useful A ring.  The TMA unit's row rate
+    // (not bytes) bounds the thin layers, and re-fetching the same <= 96 KB of weights for every M tile was most of it.
+    const long long b_bytes = static_cast<long long>(taps) * a.kblocks * (plan->pair ? bn / 2 : bn) * bk * 2;
+    plan->bres = (a.n_tiles == 1 && b_bytes <= 96 * 1024 && bres_enabled()) ? 1 : 0;
   }
   // staged (TMA-store) epilogue: flat mode, bf16 output, no upsample
   plan->staged = (a.mode == 0 && !head && !d.upsample && staged_enabled() && !(plan->halo && bn == 256)) ? 1 : 0;
@@ -749,6 +861,16 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
 }
 
 }  // namespace y3
+
+extern "C" int y3_conv_weight_layout(const y3_conv_desc* d) {
+  if (!d) return y3::set_error(Y3_ERR_BAD_ARG, "conv: null descriptor");
+  static int enabled = -1;  // Y3_CONV_XPAIR=0 keeps the plain tap-major layout everywhere (A/B measurements)
+  if (enabled < 0) {
+    const char* e = getenv("Y3_CONV_XPAIR");
+    enabled = (e && e[0] == '0') ? 0 : 1;
+  }
+  return (enabled && y3::conv_prefers_xpair(*d)) ? Y3_W_XPAIR : Y3_W_TAPS;
+}
 
 extern "C" int y3_conv_cout_pad(int32_t c_out) {
   const int bn = y3::pick_block_n(c_out);

@@ -176,7 +176,6 @@ extern "C" int y3_detect_head_decode_fwd(const y3_decode_desc* d, y3_stream_t st
     }
   }
   a.row_off[d->nl] = off;
-  Y3_REQUIRE(d->no <= 96, "head_decode: no=%d > 96 is not supported by this kernel", d->no);
   Y3_REQUIRE(static_cast<long long>(off) * d->bs < (1ll << 31), "head_decode: too many rows");
   const long long warps = (static_cast<long long>(off) * d->bs + y3::kDecodeRows - 1) / y3::kDecodeRows;
   long long blocks = (warps + 7) / 8;

@@ -39,6 +39,9 @@ struct ConvTcArgs {
   int a_coff, a_ld;
   uint32_t a_tx_bytes;   // bytes one A box delivers
   int desc_mode;         // 1: UMMA descriptors carry base_offset = (addr>>7)&7; 0: base_offset = 0 (probe)
+  int xpair;             // patch mode with x-paired weights: 6 taps of 2*c_in channels
+  int stages;            // depth of the shared-memory ring (set by the launcher from the tile configuration)
+  int bres;              // 1: the whole weight tile stays resident in shared memory (loaded once per CTA)
   int m_tiles, n_tiles;
   // flat geometry (input and conv-output share it)
   int hp, wp, rows_total;
@@ -60,6 +63,7 @@ struct ConvTcPlan {
   CUtensorMap map_a, map_b, map_out, map_res;
   int staged;  // 1: epilogue stages the tile in shared memory and stores it with TMA
   int halo;    // 1: stride-1 3x3 with one A box per filter row (halo reuse)
+  int bres;    // 1: weights resident in shared memory (single N tile, small K)
   ConvTcArgs args;
   int block_n, block_k;
   int pair;  // 1: CTA-pair (cta_group::2) kernel, launched as clusters of 2

@@ -207,6 +207,18 @@ class Model:
             self._packed = out
         return self._packed
 
+    def packed_xpair(self, prefix):
+        """The x-paired pack of one stride-2 conv (``y3_conv_weight_layout`` asked for it); cached inside ``packed()``'s dict
+        so that every invalidation of the packed weights drops it too."""
+        W = self.packed()
+        key = prefix + "#xpair"
+        if key not in W:
+            P = self.params
+            w, b = self.fold_bn(P[prefix + ".conv.weight"], P[prefix + ".bn.weight"], P[prefix + ".bn.bias"],
+                                P[prefix + ".bn.running_mean"], P[prefix + ".bn.running_var"])
+            W[key] = ops.pack_conv_weight_xpair(w, b, self.device)
+        return W[key]
+
     # ------------------------------------------------------------------------------------------------ forward
     def engine(self, n, h, w, in_dtype=torch.float32, in_div=0.0) -> "Engine":
         key = (n, h, w, in_dtype, float(in_div))
@@ -239,7 +251,7 @@ class Model:
         e = self.engine(n, h, w, x.dtype, 255.0 if x.dtype == torch.uint8 else 0.0)  # uint8 images: im/255
         e.run(x)
         z = e.z.clone()
-        raw = [r.clone() for r in e.raw]
+        raw = [r.contiguous() for r in e.raw]  # strided views of the head buffers -> the reference's contiguous maps
         return (z,) if self.detect.export else (z, raw)
 
     __call__ = forward
@@ -357,6 +369,9 @@ class Engine:
             o = _lib.Op()
             o.kind = _lib.OP_CONV
             o.conv = ops.conv_desc(x, wt, bs_, c_out, k, s, act, out, res, upsample, out_f32, self.err)
+            if L.y3_conv_weight_layout(C.byref(o.conv)) == _lib.W_XPAIR and prefix + ".bn.weight" in model.params:
+                wx, _ = model.packed_xpair(prefix)
+                o.conv.weight, o.conv.weight_layout = wx.data_ptr(), _lib.W_XPAIR
             op_list.append(o)
 
         tens: dict[int, object] = {}  # node -> PaddedNHWC (or ("zeropad", tensor))
@@ -458,13 +473,16 @@ class Engine:
         rows = 0
         for j, s in enumerate(dnode.srcs):
             x = tens[s]
-            raw = torch.zeros(n, det.na, x.h, x.w, det.no, dtype=torch.float32, device=dev)
             head = torch.zeros(n * x.h * x.w, head_ld, dtype=torch.float32, device=dev)
+            # the reference's raw map x[i] = conv(x).view(bs,na,no,ny,nx).permute(0,1,3,4,2) (models/yolo.py:96-98) IS this
+            # buffer seen through strides: no second copy of 8.6 MB/image is written.  Model.forward() clones it into the
+            # reference's contiguous format; Engine users get the zero-copy view.
+            raw = head.view(n, x.h, x.w, head_ld)[..., : det.na * det.no].unflatten(-1, (det.na, det.no)).permute(0, 3, 1, 2, 4)
             self.raw.append(raw)
             self.head_out.append(head)
             emit_conv(x, f"model.{det.i}.m.{j}", det.na * det.no, 1, 1, ops.ACT_NONE, out_f32=head)
             lv = dec.levels[j]
-            lv.head, lv.head_ld, lv.raw_out = head.data_ptr(), head_ld, raw.data_ptr()
+            lv.head, lv.head_ld, lv.raw_out = head.data_ptr(), head_ld, None
             lv.ny, lv.nx, lv.stride = x.h, x.w, float(det.stride[j])
             for a in range(det.na):
                 lv.anchor_w[a], lv.anchor_h[a] = float(anchors_px[j, a, 0]), float(anchors_px[j, a, 1])

@@ -59,6 +59,24 @@ def nms_batched(prediction: torch.Tensor, conf_thres=0.25, iou_thres=0.45, class
     return out, counts, overflow, src
 
 
+def _append_labels(pred: torch.Tensor, labels):
+    """Autolabel priors (utils/general.py:689-695): each image's (cls, x, y, w, h) rows become extra candidates with
+    obj = 1 and a one-hot class, placed after that image's predictions (the reference concatenates them after its
+    confidence filter, so candidate order is identical).  Images with fewer labels get obj = 0 filler rows, which the
+    confidence filter drops."""
+    bs, _, no = pred.shape
+    lmax = max(len(l) for l in labels)
+    v = torch.zeros(bs, lmax, no, dtype=pred.dtype, device=pred.device)
+    for xi, lb in enumerate(labels):
+        if len(lb):
+            lb = torch.as_tensor(lb, dtype=torch.float32, device=pred.device).reshape(-1, 5)
+            m = lb.shape[0]
+            v[xi, :m, :4] = lb[:, 1:5].to(pred.dtype)
+            v[xi, :m, 4] = 1.0
+            v[xi, torch.arange(m, device=pred.device), lb[:, 0].long() + 5] = 1.0
+    return torch.cat((pred, v), 1)
+
+
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
                         labels=(), max_det=300, nm=0, return_src=False):
     """Drop-in for utils/general.py:630.  Returns list[Tensor[n,6]] (xyxy, conf, cls), rows sorted by conf desc."""
@@ -69,7 +87,7 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     if nm:
         raise NotImplementedError("mask coefficients (nm>0) are not part of the YOLOv3 detection path")
     if labels and any(len(l) for l in labels):
-        raise NotImplementedError("autolabel priors (labels=...) are not supported by the device NMS")
+        prediction = _append_labels(prediction, labels)
     cap = None
     while True:
         out, counts, overflow, src = nms_batched(prediction, conf_thres, iou_thres, classes, agnostic, multi_label,

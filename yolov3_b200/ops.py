@@ -27,6 +27,19 @@ def pack_conv_weight(w: torch.Tensor, b: torch.Tensor, device="cuda"):
     return wp.to(device=device, dtype=torch.bfloat16).contiguous(), bp.to(device).contiguous()
 
 
+def pack_conv_weight_xpair(w: torch.Tensor, b: torch.Tensor, device="cuda"):
+    """Y3_W_XPAIR pack of a stride-2 3x3 conv: bf16 [c_out_pad, 3, 2, 2, c_in], (kh, sp, par, c) = W[kh][2*sp+par][c] with a
+    zero phantom column (include/yolov3_b200.h)."""
+    c_out, c_in, k, _ = w.shape
+    assert k == 3
+    cp = cout_pad(c_out)
+    wp = torch.zeros(cp, 3, 4, c_in, dtype=torch.float32)
+    wp[:c_out, :, :3] = w.detach().float().cpu().permute(0, 2, 3, 1)
+    bp = torch.zeros(cp, dtype=torch.float32)
+    bp[:c_out] = b.detach().float().cpu()
+    return wp.reshape(cp, 12 * c_in).to(device=device, dtype=torch.bfloat16).contiguous(), bp.to(device).contiguous()
+
+
 def pack_first_weight(w: torch.Tensor, b: torch.Tensor, device="cuda"):
     """[c_out, 3, 3, 3] fp32 -> fp32 [27, c_out] with k = (c*3+kh)*3+kw."""
     c_out = w.shape[0]
@@ -35,7 +48,7 @@ def pack_first_weight(w: torch.Tensor, b: torch.Tensor, device="cuda"):
 
 
 def conv_desc(x: PaddedNHWC, weight, bias, c_out, k, s, act, out: PaddedNHWC | None, res: PaddedNHWC | None = None,
-              upsample=False, out_f32: torch.Tensor | None = None, err: torch.Tensor | None = None):
+              upsample=False, out_f32: torch.Tensor | None = None, err: torch.Tensor | None = None, weight_layout=0):
     d = _lib.ConvDesc()
     d.n, d.h, d.w, d.c_in, d.c_out, d.ksize, d.stride, d.act = x.n, x.h, x.w, x.c, c_out, k, s, act
     d.in_, d.in_ld, d.in_coff = x.ptr, x.ld, x.coff
@@ -50,17 +63,18 @@ def conv_desc(x: PaddedNHWC, weight, bias, c_out, k, s, act, out: PaddedNHWC | N
         d.out_f32, d.out_f32_ld = out_f32.data_ptr(), out_f32.shape[1]
     if err is not None:
         d.err = err.data_ptr()
+    d.weight_layout = int(weight_layout)
     return d
 
 
 def conv_bn_act(x: PaddedNHWC, weight, bias, c_out, k=1, s=1, act=ACT_SILU, out=None, res=None, upsample=False,
-                out_f32=None, err=None):
+                out_f32=None, err=None, weight_layout=0):
     """y3_conv_bn_act_fwd.  Allocates ``out`` when not given (tests); the model executor always passes buffers."""
     ho, wo = x.h // s, x.w // s
     if out is None and out_f32 is None:
         u = 2 if upsample else 1
         out = PaddedNHWC.zeros(x.n, ho * u, wo * u, c_out, device=x.buf.device)
-    d = conv_desc(x, weight, bias, c_out, k, s, act, out, res, upsample, out_f32, err)
+    d = conv_desc(x, weight, bias, c_out, k, s, act, out, res, upsample, out_f32, err, weight_layout)
     _lib.check(_lib.lib().y3_conv_bn_act_fwd(C.byref(d), _stream()), "y3_conv_bn_act_fwd")
     return out if out_f32 is None else out_f32
 

@@ -32,7 +32,8 @@ def describe_ops(engine):
         elif o.kind == _lib.OP_DECODE:
             d = o.decode
             rows = sum(d.na * d.levels[i].ny * d.levels[i].nx for i in range(d.nl))
-            out.append(dict(kind="decode", shape=f"rows {rows} no {d.no} n{d.bs}", flops=0.0, bytes=d.bs * rows * d.no * 12))
+            out.append(dict(kind="decode", shape=f"rows {rows} no {d.no} n{d.bs}", flops=0.0,
+                            bytes=d.bs * rows * d.no * (12 if any(d.levels[l].raw_out for l in range(d.nl)) else 8)))
     return out
 
 
