@@ -114,6 +114,12 @@ typedef struct y3_pool_desc {
   int32_t k, stride, off, oob_zero;
 } y3_pool_desc;
 int y3_maxpool_fwd(const y3_pool_desc* d, y3_stream_t stream);
+/* Training mode (SPP, models/common.py:281-290, under autograd): the forward also records idx[n, ho, wo, c] (uint8) =
+ * dy*k + dx of the first maximum in row-major window order — the element torch.nn.MaxPool2d back-propagates to — and the
+ * backward gathers dIn[p] (+)= sum of dOut over the windows whose argmax is p (no atomics).  For y3_maxpool_bwd the
+ * descriptor's `in` is dOut (geometry ho x wo), `out` is dIn (geometry h x w); oob_zero windows are not supported. */
+int y3_maxpool_train_fwd(const y3_pool_desc* d, uint8_t* idx, y3_stream_t stream);
+int y3_maxpool_bwd(const y3_pool_desc* d, const uint8_t* idx, int32_t accumulate, y3_stream_t stream);
 
 /* Layout helpers (tests / feeding intermediate tensors): NCHW fp32 <-> padded NHWC bf16 channel slice. */
 int y3_nchw_to_padded_nhwc(const float* src, int32_t n, int32_t c, int32_t h, int32_t w, void* dst, int32_t dst_ld,

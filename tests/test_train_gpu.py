@@ -124,6 +124,35 @@ def test_dgrad_and_wgrad_stride2(ci, co):
     assert rel_l2(dw, wtt.grad) < 3e-3
 
 
+@pytest.mark.parametrize("k", [5, 9, 13])
+def test_maxpool_train_fwd_bwd(k):
+    """SPP pools under autograd (models/common.py:281-290): values and argmax routing equal torch.nn.MaxPool2d on the same
+    bf16-rounded input — including ties, which bf16 makes frequent (coarse values below): exact equality."""
+    from yolov3_b200 import train_ops as T
+    from yolov3_b200.tensors import PaddedNHWC
+
+    g = torch.Generator().manual_seed(k)
+    n, c, h, w = 2, 16, 20, 20
+    x = (torch.randn(n, c, h, w, generator=g) * 2).round().div(2).bfloat16().float()  # many exact ties
+    dout = torch.randn(n, c, h, w, generator=g).bfloat16().float()
+    xt = x.clone().requires_grad_(True)
+    yt = F.max_pool2d(xt, k, 1, k // 2)
+    yt.backward(dout)
+    xin = _padded(x, ld=32, coff=8)
+    out = PaddedNHWC.zeros(n, h, w, c)
+    idx = torch.zeros(n * h * w * c, dtype=torch.uint8, device="cuda")
+    T.maxpool_train_fwd(xin, out, k, idx)
+    assert torch.equal(out.to_nchw().cpu(), yt.detach())
+    gd = _padded(dout)
+    gin = _padded(torch.ones(n, c, h, w).bfloat16().float())  # accumulate on top of ones
+    T.maxpool_bwd(gd, gin, k, idx, accumulate=True)
+    ref = (xt.grad + 1).bfloat16().float()
+    assert rel_l2(gin.to_nchw(), ref) < 4e-3  # one bf16 rounding of the accumulated sum
+    T.maxpool_bwd(gd, gin, k, idx, accumulate=False)
+    assert rel_l2(gin.to_nchw(), xt.grad) < 4e-3
+    assert torch.equal(gin.to_nchw().cpu() != 0, xt.grad.bfloat16().float() != 0)  # identical routing
+
+
 def test_colsum():
     from yolov3_b200 import train_ops as T
 
@@ -133,8 +162,9 @@ def test_colsum():
     assert torch.allclose(out, g[:, :255].sum(0), rtol=1e-4, atol=1e-3)
 
 
-def test_train_step_vs_oracle_autograd():
-    """One full training step (train-mode forward -> ComputeLoss -> backward) on yolov3.yaml against the CPU oracle
+@pytest.mark.parametrize("cfg_name", ["yolov3.yaml", "yolov3-spp.yaml"])
+def test_train_step_vs_oracle_autograd(cfg_name):
+    """One full training step (train-mode forward -> ComputeLoss -> backward) on yolov3(-spp).yaml against the CPU oracle
     (torch autograd, fp32) AND against the same oracle run on the GPU under torch.autocast(bfloat16) — the precision the
     reference trains at (train.py:345,402 AMP; bf16 per BASELINE.json).
 
@@ -150,7 +180,7 @@ def test_train_step_vs_oracle_autograd():
     from yolov3_b200.loss import ComputeLoss
     from yolov3_b200.model import Model
 
-    cfg = Path(__file__).resolve().parents[1] / "yolov3_b200" / "cfg" / "yolov3.yaml"
+    cfg = Path(__file__).resolve().parents[1] / "yolov3_b200" / "cfg" / cfg_name
     params = O.init_params(cfg, seed=0)
     hyp = O.scaled_hyp()
     x = torch.rand(4, 3, 96, 96, generator=torch.Generator().manual_seed(3))

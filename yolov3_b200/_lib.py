@@ -148,6 +148,8 @@ def _declare(lib):
         "y3_abi_sizeof": ([i32], C.c_int64),
         "y3_conv_first_fwd": ([C.POINTER(FirstDesc), vp], C.c_int),
         "y3_maxpool_fwd": ([C.POINTER(PoolDesc), vp], C.c_int),
+        "y3_maxpool_train_fwd": ([C.POINTER(PoolDesc), vp, vp], C.c_int),
+        "y3_maxpool_bwd": ([C.POINTER(PoolDesc), vp, i32, vp], C.c_int),
         "y3_bn_stats": ([vp, i32, i32, i32, C.c_int64, vp, vp, vp], C.c_int),
         "y3_bn_finalize": ([vp, vp, vp, vp, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp], C.c_int),
         "y3_bn_act_fwd": ([C.POINTER(BnActDesc), vp], C.c_int),

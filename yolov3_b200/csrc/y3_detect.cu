@@ -73,7 +73,12 @@ constexpr int kDecodeRows = 4;  // consecutive z rows per warp iteration (they a
 // requirement applies to NMS on a given z, not to z itself); the IEEE expf/division sequence cost ~1/3 of this kernel.
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
-__global__ void __launch_bounds__(256) head_decode_kernel(const HeadDecodeArgs p) {
+// NITER = ceil(kDecodeRows * no / 128) unrolled iterations of 4 x 32 elements.  The split of a group-local element index
+// e into (row q, field k) depends only on e, so every lane computes its NITER*4 pairs ONCE; per group only the four
+// row descriptors change (two 32-bit words each, broadcast by shuffle).  The first version redid the division and moved
+// seven shuffle words per element: ~60 instructions per 4-byte output, i.e. issue-bound at 1.8 TB/s.
+template <int NITER>
+__global__ void __launch_bounds__(256, NITER <= 3 ? 3 : 1) head_decode_kernel(const HeadDecodeArgs p) {
   const int lane = threadIdx.x & 31;
   const int rows_per_img = p.row_off[p.nl];
   const int total = rows_per_img * p.bs;  // < 2^31 (checked by the launcher)
@@ -81,11 +86,18 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const HeadDecodeArgs p
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int no = p.no;
+  uint32_t qk[NITER * 4];  // (q << 16) | k of this lane's elements
+#pragma unroll
+  for (int t = 0; t < NITER * 4; ++t) {
+    const int e = (t >> 2) * 128 + (t & 3) * 32 + lane;
+    const int q = e / no;
+    qk[t] = (static_cast<uint32_t>(q) << 16) | static_cast<uint32_t>(e - q * no);
+  }
   for (int gidx = warp0; gidx < groups; gidx += nwarps) {
-    // per-row descriptors, computed by lanes 0..3 and broadcast (saves every lane redoing the integer divisions)
+    // row descriptors, computed by lanes 0..3: element offset inside the level's head buffer (< 2^31, checked by the
+    // launcher) and x | y << 13 | a << 26 | l << 29
     const int w = gidx * kDecodeRows + (lane & 3);
-    long long src_off = -1, raw_off = 0;
-    int lxy = 0, lla = 0;
+    uint32_t d_off = 0, d_pos = 0;
     if (lane < kDecodeRows && w < total) {
       const int b = w / rows_per_img;
       const int row = w - b * rows_per_img;
@@ -95,52 +107,49 @@ __global__ void __launch_bounds__(256) head_decode_kernel(const HeadDecodeArgs p
       const int plane = p.ny[l] * p.nx[l];
       const int a = r / plane, cell = r - a * plane;
       const int y = cell / p.nx[l], x = cell - y * p.nx[l];
-      src_off = (static_cast<long long>(b) * plane + cell) * p.head_ld[l] + a * no;
-      raw_off = ((static_cast<long long>(b) * p.na + a) * plane + cell) * no;
-      lxy = (y << 16) | x;
-      lla = (l << 8) | a;
+      d_off = static_cast<uint32_t>((b * plane + cell) * p.head_ld[l] + a * no);
+      d_pos = static_cast<uint32_t>(x) | (static_cast<uint32_t>(y) << 13) | (static_cast<uint32_t>(a) << 26) |
+              (static_cast<uint32_t>(l) << 29);
     }
     const long long z_base = static_cast<long long>(gidx) * kDecodeRows * no;  // rows of a group are contiguous in z
     const int n_el = min(kDecodeRows, total - gidx * kDecodeRows) * no;
-    // the group's kDecodeRows*no outputs form one contiguous range of z: lanes stride over it -> fully coalesced stores
-#pragma unroll 1
-    for (int e0 = 0; e0 < n_el; e0 += 128) {
-      float v[4];
-      int qq[4], kk[4];
+    float v[NITER * 4];
+    uint32_t pos[NITER * 4];
+    // all loads of the group first (NITER*4 independent 128-byte warp requests in flight), then the arithmetic
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int e = e0 + j * 32 + lane;
-        const int q = e / no;
-        qq[j] = q;
-        kk[j] = e - q * no;
-        const long long so = __shfl_sync(0xffffffffu, src_off, q & 3);
-        const int l = __shfl_sync(0xffffffffu, lla, q & 3) >> 8;
-        v[j] = (e < n_el) ? __ldg(p.head[l] + so + kk[j]) : 0.f;
+    for (int t = 0; t < NITER * 4; ++t) {
+      const int e = (t >> 2) * 128 + (t & 3) * 32 + lane;
+      const int q = qk[t] >> 16, k = qk[t] & 0xFFFF;
+      const uint32_t so = __shfl_sync(0xffffffffu, d_off, q & 3);
+      pos[t] = __shfl_sync(0xffffffffu, d_pos, q & 3);
+      v[t] = (e < n_el) ? __ldg(p.head[pos[t] >> 29] + so + k) : 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < NITER * 4; ++t) {
+      const int e = (t >> 2) * 128 + (t & 3) * 32 + lane;
+      if (e >= n_el) continue;
+      const int k = qk[t] & 0xFFFF;
+      const int l = pos[t] >> 29, a = (pos[t] >> 26) & 7;
+      const float x = v[t];
+      if (p.raw[l]) {
+        // reference-layout logits [bs, na, ny, nx, no]: row (b*na + a)*plane + cell
+        const int wrow = gidx * kDecodeRows + (qk[t] >> 16);
+        const int b = wrow / rows_per_img;
+        const int plane = p.ny[l] * p.nx[l];
+        const int cell = ((pos[t] >> 13) & 0x1FFF) * p.nx[l] + (pos[t] & 0x1FFF);
+        p.raw[l][((static_cast<long long>(b) * p.na + a) * plane + cell) * no + k] = x;
       }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int e = e0 + j * 32 + lane;
-        const int q = qq[j], k = kk[j];
-        const long long ro = __shfl_sync(0xffffffffu, raw_off, q & 3);
-        const int la = __shfl_sync(0xffffffffu, lla, q & 3);
-        const int xy = __shfl_sync(0xffffffffu, lxy, q & 3);
-        if (e >= n_el) continue;
-        const int l = la >> 8, a = la & 255;
-        const float x = v[j];
-        if (p.raw[l]) p.raw[l][ro + k] = x;
-        if (p.z) {
-          const float s = sigmoid_fast(x);
-          float o = s;
-          if (k == 0)
-            o = (s * 2.0f + (static_cast<float>(xy & 0xFFFF) - 0.5f)) * p.stride[l];
-          else if (k == 1)
-            o = (s * 2.0f + (static_cast<float>(xy >> 16) - 0.5f)) * p.stride[l];
-          else if (k < 4) {
-            const float t = s * 2.0f;
-            o = (t * t) * (k == 2 ? p.anchor_w[l][a] : p.anchor_h[l][a]);
-          }
-          p.z[z_base + e] = o;
+      if (p.z) {
+        const float s = sigmoid_fast(x);
+        float o = s;
+        if (k < 4) {
+          const float t2 = s * 2.0f;
+          if (k < 2)
+            o = (t2 + (static_cast<float>(k == 0 ? (pos[t] & 0x1FFF) : ((pos[t] >> 13) & 0x1FFF)) - 0.5f)) * p.stride[l];
+          else
+            o = (t2 * t2) * (k == 2 ? p.anchor_w[l][a] : p.anchor_h[l][a]);
         }
+        p.z[z_base + e] = o;
       }
     }
   }
@@ -181,7 +190,23 @@ extern "C" int y3_detect_head_decode_fwd(const y3_decode_desc* d, y3_stream_t st
   long long blocks = (warps + 7) / 8;
   const long long cap = static_cast<long long>(y3::num_sms()) * 32;
   if (blocks > cap) blocks = cap;
-  y3::head_decode_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  for (int l = 0; l < d->nl; ++l) {
+    Y3_REQUIRE(static_cast<long long>(d->bs) * d->levels[l].ny * d->levels[l].nx * d->levels[l].head_ld < (1ll << 31) &&
+                   d->levels[l].ny < 8192 && d->levels[l].nx < 8192,
+               "head_decode: level %d too large", l);
+  }
+  Y3_REQUIRE(d->na <= 8 && d->nl <= 8, "head_decode: na/nl > 8");
+  const int niter = (y3::kDecodeRows * d->no + 127) / 128;
+  Y3_REQUIRE(niter <= 8, "head_decode: no=%d > 256 is not supported", d->no);
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned g = static_cast<unsigned>(blocks);
+  switch (niter) {
+    case 1: y3::head_decode_kernel<1><<<g, 256, 0, st>>>(a); break;
+    case 2: y3::head_decode_kernel<2><<<g, 256, 0, st>>>(a); break;
+    case 3: y3::head_decode_kernel<3><<<g, 256, 0, st>>>(a); break;
+    case 4: y3::head_decode_kernel<4><<<g, 256, 0, st>>>(a); break;
+    default: y3::head_decode_kernel<8><<<g, 256, 0, st>>>(a); break;
+  }
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }

@@ -73,5 +73,7 @@ struct ConvTcPlan {
 int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan);
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);
 int pool_launch(const y3_pool_desc& d, cudaStream_t stream);
+int pool_train_fwd(const y3_pool_desc& d, uint8_t* idx, cudaStream_t stream);
+int pool_bwd(const y3_pool_desc& d, const uint8_t* idx, int accumulate, cudaStream_t stream);
 
 }  // namespace y3

@@ -49,36 +49,54 @@ struct NmsArgs {
 __device__ __forceinline__ int next_pow2(int v) { return v <= 1 ? 1 : 1 << (32 - __clz(v - 1)); }
 
 // ------------------------------------------------------------------------------------------------ K1 candidates
-// one warp per prediction row, 32 rows per block; one global atomic per block
-__global__ void __launch_bounds__(1024) nms_candidates_kernel(const NmsArgs p) {
-  __shared__ int s_cnt[32];
-  __shared__ int s_base;
+// One warp per 32 consecutive prediction rows: the lanes test obj of 32 rows with one strided load, then the warp visits
+// only the rows that passed (85 contiguous floats each), and one atomic per warp reserves the key slots.  The first
+// version spent a warp, two block barriers and a share of a block atomic on EVERY row and was bound by those serial
+// latencies (64 rows in flight per SM): 282 us for 806 k rows at conf 0.25 (profiles/r01_nms_launches_*.txt).
+constexpr int kCandWarps = 8;
+
+__global__ void __launch_bounds__(32 * kCandWarps) nms_candidates_kernel(const NmsArgs p) {
+  const unsigned full = 0xffffffffu;
   const int img = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 32 + warp;
-  const float* x = p.pred + (static_cast<size_t>(img) * p.n_rows + (row < p.n_rows ? row : 0)) * p.no;
-  float obj = 0.f;
-  bool row_ok = false;
-  if (row < p.n_rows) {
-    obj = __ldg(x + 4);
-    row_ok = obj > p.conf_thres;
+  const int row0 = (blockIdx.x * kCandWarps + warp) * 32;
+  if (row0 >= p.n_rows) return;
+  const float* base = p.pred + static_cast<size_t>(img) * p.n_rows * p.no;
+  const int my_row = row0 + lane;
+  float my_obj = 0.f;
+  bool pass = false;
+  if (my_row < p.n_rows) {
+    my_obj = __ldg(base + static_cast<size_t>(my_row) * p.no + 4);
+    pass = my_obj > p.conf_thres;
   }
-  int my_cnt = 0;          // candidates this LANE contributes
-  float best = 0.f;        // single-label: best conf / class (valid in all lanes after the reduce)
-  int best_c = 0;
-  if (row_ok) {
+  const unsigned todo = __ballot_sync(full, pass);
+  if (todo == 0u) return;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int my_cnt = 0;      // candidates of row `lane`
+  float my_best = 0.f; // single-label: best conf / class of row `lane`
+  int my_c = 0;
+  for (unsigned rem = todo; rem; rem &= rem - 1u) {
+    const int r = __ffs(rem) - 1;
+    const float obj = __shfl_sync(full, my_obj, r);
+    const float* x = base + static_cast<size_t>(row0 + r) * p.no + 5;
     if (p.multi_label) {
-      for (int c = lane; c < p.nc; c += 32) {
-        const float conf = __fmul_rn(__ldg(x + 5 + c), obj);
-        const bool in_set = !p.use_mask || ((p.cls_mask[c >> 5] >> (c & 31)) & 1u);
-        my_cnt += (conf > p.conf_thres) && in_set;
+      int cnt = 0;
+      for (int c0 = 0; c0 < p.nc; c0 += 32) {
+        const int c = c0 + lane;
+        bool ok = false;
+        if (c < p.nc) {
+          const float conf = __fmul_rn(__ldg(x + c), obj);
+          ok = (conf > p.conf_thres) && (!p.use_mask || ((p.cls_mask[c >> 5] >> (c & 31)) & 1u));
+        }
+        cnt += __popc(__ballot_sync(full, ok));
       }
+      if (lane == r) my_cnt = cnt;
     } else {
       float bv = -INFINITY;
       int bc = 0x7fffffff;
       bool any_nan = false;
       for (int c = lane; c < p.nc; c += 32) {
-        const float conf = __fmul_rn(__ldg(x + 5 + c), obj);
+        const float conf = __fmul_rn(__ldg(x + c), obj);
         any_nan |= (conf != conf);
         if (conf > bv) {  // first maximum wins inside a lane (ascending c)
           bv = conf;
@@ -87,59 +105,64 @@ __global__ void __launch_bounds__(1024) nms_candidates_kernel(const NmsArgs p) {
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+        const float ov = __shfl_xor_sync(full, bv, o);
+        const int oc = __shfl_xor_sync(full, bc, o);
         if (ov > bv || (ov == bv && oc < bc)) {
           bv = ov;
           bc = oc;
         }
       }
-      best = __any_sync(0xffffffffu, any_nan) ? __int_as_float(0x7fc00000) : bv;  // torch.max propagates NaN
-      best_c = bc;
-      const bool in_set = !p.use_mask || ((p.cls_mask[(best_c & 1023) >> 5] >> (best_c & 31)) & 1u);
-      my_cnt = (lane == 0 && best > p.conf_thres && in_set) ? 1 : 0;
+      const float best = __any_sync(full, any_nan) ? __int_as_float(0x7fc00000) : bv;  // torch.max propagates NaN
+      const bool in_set = !p.use_mask || ((p.cls_mask[(bc & 1023) >> 5] >> (bc & 31)) & 1u);
+      if (lane == r) {
+        my_best = best;
+        my_c = bc;
+        my_cnt = (best > p.conf_thres && in_set) ? 1 : 0;
+      }
     }
   }
-  // warp total + exclusive prefix over lanes
+  // exclusive prefix of my_cnt over the lanes, one atomic for the warp
   int incl = my_cnt;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    const int t = __shfl_up_sync(full, incl, o);
     if (lane >= o) incl += t;
   }
-  const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
-  if (lane == 0) s_cnt[warp] = warp_total;
-  __syncthreads();
-  if (warp == 0) {
-    int v = s_cnt[lane];
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    s_cnt[lane] = inc - v;  // exclusive offset of each warp
-    if (lane == 31) s_base = inc > 0 ? atomicAdd(&p.count[img], inc) : 0;
-  }
-  __syncthreads();
-  if (my_cnt == 0) return;
-  int slot = s_base + s_cnt[warp] + (incl - my_cnt);
+  const int warp_total = __shfl_sync(full, incl, 31);
+  if (warp_total == 0) return;
+  int slot0 = 0;
+  if (lane == 0) slot0 = atomicAdd(&p.count[img], warp_total);
+  slot0 = __shfl_sync(full, slot0, 0);
+  const int my_slot = slot0 + incl - my_cnt;
   unsigned long long* keys = p.keys + static_cast<size_t>(img) * p.cap;
-  if (p.multi_label) {
-    for (int c = lane; c < p.nc; c += 32) {
-      const float conf = __fmul_rn(__ldg(x + 5 + c), obj);
-      const bool in_set = !p.use_mask || ((p.cls_mask[c >> 5] >> (c & 31)) & 1u);
-      if ((conf > p.conf_thres) && in_set) {
-        if (slot < p.cap) {
-          const uint32_t id = static_cast<uint32_t>(row) * p.nc + c;
-          keys[slot] = (static_cast<unsigned long long>(__float_as_uint(conf)) << 32) | (0xFFFFFFFFu - id);
-        }
-        ++slot;
-      }
+  if (!p.multi_label) {
+    if (my_cnt && my_slot < p.cap) {
+      const uint32_t id = static_cast<uint32_t>(my_row) * p.nc + my_c;
+      keys[my_slot] = (static_cast<unsigned long long>(__float_as_uint(my_best)) << 32) | (0xFFFFFFFFu - id);
     }
-  } else if (slot < p.cap) {
-    const uint32_t id = static_cast<uint32_t>(row) * p.nc + best_c;
-    keys[slot] = (static_cast<unsigned long long>(__float_as_uint(best)) << 32) | (0xFFFFFFFFu - id);
+    return;
+  }
+  for (unsigned rem = __ballot_sync(full, my_cnt > 0); rem; rem &= rem - 1u) {
+    const int r = __ffs(rem) - 1;
+    const float obj = __shfl_sync(full, my_obj, r);
+    int slot = __shfl_sync(full, my_slot, r);
+    const float* x = base + static_cast<size_t>(row0 + r) * p.no + 5;
+    for (int c0 = 0; c0 < p.nc; c0 += 32) {
+      const int c = c0 + lane;
+      bool ok = false;
+      float conf = 0.f;
+      if (c < p.nc) {
+        conf = __fmul_rn(__ldg(x + c), obj);
+        ok = (conf > p.conf_thres) && (!p.use_mask || ((p.cls_mask[c >> 5] >> (c & 31)) & 1u));
+      }
+      const unsigned b = __ballot_sync(full, ok);
+      const int at = slot + __popc(b & lt_mask);
+      if (ok && at < p.cap) {
+        const uint32_t id = static_cast<uint32_t>(row0 + r) * p.nc + c;
+        keys[at] = (static_cast<unsigned long long>(__float_as_uint(conf)) << 32) | (0xFFFFFFFFu - id);
+      }
+      slot += __popc(b);
+    }
   }
 }
 
@@ -286,19 +309,29 @@ __global__ void __launch_bounds__(256) nms_gather_kernel(const NmsArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------ K5 segments
-__device__ __forceinline__ int lower_bound_u32(const uint32_t* a, int n, uint32_t v) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (a[mid] < v) lo = mid + 1; else hi = mid;
+// 32-ary search by one warp: 3 probes of 32 positions instead of 15 dependent global loads
+__device__ __forceinline__ int lower_bound_warp(const uint32_t* a, int n, uint32_t v, int lane) {
+  int lo = 0, hi = n;  // invariant: a[lo-1] < v <= a[hi]
+  while (hi - lo > 0) {
+    const int span = hi - lo;
+    const int step = (span + 32) / 33;  // 32 probes split the span into 33 pieces
+    const int pos = lo + (lane + 1) * step - 1;
+    const bool less = pos < hi && a[pos] < v;
+    const unsigned b = __ballot_sync(0xffffffffu, less);
+    const int k = __popc(b);  // probes 0..k-1 are < v (monotone)
+    const int new_lo = k ? lo + k * step : lo;
+    const int new_hi = k < 32 ? min(hi, lo + (k + 1) * step - 1) : hi;
+    lo = min(new_lo, hi);
+    hi = new_hi;
   }
   return lo;
 }
 
 __global__ void __launch_bounds__(256) nms_segments_kernel(const NmsArgs p) {
   __shared__ float4 s_box[kSegSmemBoxes];
-  __shared__ float s_area[kSegSmemBoxes];
+  __shared__ uint16_t s_rank[kSegSmemBoxes];
   __shared__ uint32_t s_supp[(kRankCap + 31) / 32];
+  __shared__ int s_bounds[2];
   const int img = blockIdx.y, seg = blockIdx.x;
   int c = p.count[img];
   c = c < p.cap ? c : p.cap;
@@ -307,19 +340,23 @@ __global__ void __launch_bounds__(256) nms_segments_kernel(const NmsArgs p) {
   const bool single = p.agnostic || (p.flags[img] & 1);
   if (single && seg != 0) return;
   const uint32_t* sk = p.seg_keys + static_cast<size_t>(img) * kRankCap;
-  int lo = 0, hi = n;
   if (!single) {
-    lo = lower_bound_u32(sk, n, static_cast<uint32_t>(seg) << 15);
-    hi = lower_bound_u32(sk, n, static_cast<uint32_t>(seg + 1) << 15);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < 2) {
+      const int b = lower_bound_warp(sk, n, static_cast<uint32_t>(seg + warp) << 15, lane);
+      if (lane == 0) s_bounds[warp] = b;
+    }
+    __syncthreads();
   }
+  const int lo = single ? 0 : s_bounds[0], hi = single ? n : s_bounds[1];
   const int m = hi - lo;
   if (m <= 0) return;
   const float* det = p.det + static_cast<size_t>(img) * kRankCap * 6;
   uint8_t* keep = p.keep + static_cast<size_t>(img) * kRankCap;
   // member j of the segment (confidence order) -> rank
   auto rank_of = [&](int j) -> int { return single ? j : static_cast<int>(sk[lo + j] & 0x7FFFu); };
-  auto load_box = [&](int j) -> float4 {
-    const float* d = det + static_cast<size_t>(rank_of(j)) * 6;
+  auto load_box = [&](int rank) -> float4 {
+    const float* d = det + static_cast<size_t>(rank) * 6;
     const float off = p.agnostic ? 0.0f : __fmul_rn(d[5], p.max_wh);
     return make_float4(__fadd_rn(d[0], off), __fadd_rn(d[1], off), __fadd_rn(d[2], off), __fadd_rn(d[3], off));
   };
@@ -327,35 +364,27 @@ __global__ void __launch_bounds__(256) nms_segments_kernel(const NmsArgs p) {
   for (int j = threadIdx.x; j < (m + 31) / 32; j += blockDim.x) s_supp[j] = 0;
   if (in_smem) {
     for (int j = threadIdx.x; j < m; j += blockDim.x) {
-      const float4 b = load_box(j);
+      const int rk = rank_of(j);
+      const float4 b = load_box(rk);
+      s_rank[j] = static_cast<uint16_t>(rk);
       s_box[j] = b;
-      s_area[j] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
     }
   }
   __syncthreads();
+  // greedy pass: nothing inside the serial loop touches global memory when the segment fits in shared memory
   for (int i = 0; i < m; ++i) {
     if ((s_supp[i >> 5] >> (i & 31)) & 1u) continue;  // uniform: every thread reads the same word
-    if (threadIdx.x == 0) keep[rank_of(i)] = 1;
     float4 bi;
     float ai;
-    if (in_smem) {
-      bi = s_box[i];
-      ai = s_area[i];
-    } else {
-      bi = load_box(i);
-      ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
-    }
+    bi = in_smem ? s_box[i] : load_box(rank_of(i));
+    ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+    if (i + 1 >= m) break;
     for (int j = i + 1 + threadIdx.x; j < m; j += blockDim.x) {
       if ((s_supp[j >> 5] >> (j & 31)) & 1u) continue;
       float4 bj;
       float aj;
-      if (in_smem) {
-        bj = s_box[j];
-        aj = s_area[j];
-      } else {
-        bj = load_box(j);
-        aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
-      }
+      bj = in_smem ? s_box[j] : load_box(rank_of(j));
+      aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
       const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
       const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
       const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
@@ -365,6 +394,10 @@ __global__ void __launch_bounds__(256) nms_segments_kernel(const NmsArgs p) {
     }
     __syncthreads();
   }
+  __syncthreads();
+  // a member that was never suppressed was kept (gather zeroed the keep flags)
+  for (int j = threadIdx.x; j < m; j += blockDim.x)
+    if (!((s_supp[j >> 5] >> (j & 31)) & 1u)) keep[in_smem ? static_cast<int>(s_rank[j]) : rank_of(j)] = 1;
 }
 
 // ------------------------------------------------------------------------------------------------ K6 compact
@@ -497,7 +530,7 @@ extern "C" int y3_nms_batched(const float* pred, const y3_nms_params* q, void* w
 
   Y3_CHECK_CUDA(cudaMemsetAsync(a.count, 0, sizeof(int) * size_t(a.bs) * 2, stream));
   // K1
-  nms_candidates_kernel<<<dim3((a.n_rows + 31) / 32, a.bs), 1024, 0, stream>>>(a);
+  nms_candidates_kernel<<<dim3((a.n_rows + 32 * kCandWarps - 1) / (32 * kCandWarps), a.bs), 32 * kCandWarps, 0, stream>>>(a);
   pad_keys_kernel<<<dim3(8, a.bs), 256, 0, stream>>>(a);
   // K2: sort candidates by confidence (descending)
   {

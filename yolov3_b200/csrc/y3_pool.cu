@@ -65,7 +65,165 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const PoolArgs p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------- training mode
+// Forward with argmax: idx[n, ho, wo, c] (uint8) = dy*k + dx of the FIRST maximum in row-major window order, which is the
+// element torch.nn.MaxPool2d routes the gradient to (ATen max_pool2d_with_indices: `val > maxval || isnan(val)`).
+__global__ void __launch_bounds__(256) maxpool_idx_kernel(const PoolArgs p, uint8_t* __restrict__ idx) {
+  const long long total = static_cast<long long>(p.n) * p.ho * p.wo * p.c8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % p.c8);
+    long long t = i / p.c8;
+    const int x = static_cast<int>(t % p.wo);
+    t /= p.wo;
+    const int y = static_cast<int>(t % p.ho);
+    const int n = static_cast<int>(t / p.ho);
+    float m[8];
+    uint32_t am[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      m[e] = -INFINITY;
+      am[e] = 255u;  // no in-image element seen (cannot happen for pad <= k/2)
+    }
+    for (int dy = 0; dy < p.k; ++dy) {
+      const int yy = y * p.stride + p.off + dy;
+      if (yy < 0 || yy >= p.h) continue;
+      for (int dx = 0; dx < p.k; ++dx) {
+        const int xx = x * p.stride + p.off + dx;
+        if (xx < 0 || xx >= p.w) continue;
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+            p.in + ((static_cast<long long>(n) * (p.h + 2) + yy + 1) * (p.w + 2) + xx + 1) * p.in_ld + p.in_coff + cg * 8));
+        float f[8];
+        unpack8(v, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          if (f[e] > m[e] || f[e] != f[e] || am[e] == 255u) {  // ATen: (val > maxval) || isnan(val); first element seeds
+            m[e] = f[e];
+            am[e] = static_cast<uint32_t>(dy * p.k + dx);
+          }
+        }
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(m[0], m[1]);
+    o.y = pack_bf16x2(m[2], m[3]);
+    o.z = pack_bf16x2(m[4], m[5]);
+    o.w = pack_bf16x2(m[6], m[7]);
+    *reinterpret_cast<uint4*>(p.out + ((static_cast<long long>(n) * (p.ho + 2) + y + 1) * (p.wo + 2) + x + 1) * p.out_ld +
+                              p.out_coff + cg * 8) = o;
+    uint2 ii;
+    ii.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+    ii.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+    *reinterpret_cast<uint2*>(idx + ((static_cast<long long>(n) * p.ho + y) * p.wo + x) * (p.c8 * 8) + cg * 8) = ii;
+  }
+}
+
+// Backward as a gather (no atomics, deterministic): input pixel (yy, xx) collects dy of every window whose recorded argmax
+// is this pixel.  `in`/`out` of PoolArgs are reused as dOut (read) / dIn (written or accumulated).
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const PoolArgs p, const uint8_t* __restrict__ idx, int accumulate) {
+  const long long total = static_cast<long long>(p.n) * p.h * p.w * p.c8;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % p.c8);
+    long long t = i / p.c8;
+    const int xx = static_cast<int>(t % p.w);
+    t /= p.w;
+    const int yy = static_cast<int>(t % p.h);
+    const int n = static_cast<int>(t / p.h);
+    float g[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // windows (y, x) with y*stride + off <= yy < y*stride + off + k
+    for (int dy = 0; dy < p.k; ++dy) {
+      const int ys = yy - p.off - dy;
+      if (ys < 0 || ys % p.stride) continue;
+      const int y = ys / p.stride;
+      if (y >= p.ho) continue;
+      for (int dx = 0; dx < p.k; ++dx) {
+        const int xs = xx - p.off - dx;
+        if (xs < 0 || xs % p.stride) continue;
+        const int x = xs / p.stride;
+        if (x >= p.wo) continue;
+        const uint2 ii = __ldg(reinterpret_cast<const uint2*>(idx + ((static_cast<long long>(n) * p.ho + y) * p.wo + x) * (p.c8 * 8) + cg * 8));
+        const uint32_t want = static_cast<uint32_t>(dy * p.k + dx);
+        const uint32_t w4 = want * 0x01010101u;
+        if (__vcmpeq4(ii.x, w4) | __vcmpeq4(ii.y, w4)) {
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(
+              p.in + ((static_cast<long long>(n) * (p.ho + 2) + y + 1) * (p.wo + 2) + x + 1) * p.in_ld + p.in_coff + cg * 8));
+          float f[8];
+          unpack8(v, f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const uint32_t a = ((e < 4 ? ii.x : ii.y) >> (8 * (e & 3))) & 255u;
+            if (a == want) g[e] += f[e];
+          }
+        }
+      }
+    }
+    __nv_bfloat16* dst = p.out + ((static_cast<long long>(n) * (p.h + 2) + yy + 1) * (p.w + 2) + xx + 1) * p.out_ld + p.out_coff + cg * 8;
+    if (accumulate) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(dst), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] += f[e];
+    }
+    uint4 o;
+    o.x = pack_bf16x2(g[0], g[1]);
+    o.y = pack_bf16x2(g[2], g[3]);
+    o.z = pack_bf16x2(g[4], g[5]);
+    o.w = pack_bf16x2(g[6], g[7]);
+    *reinterpret_cast<uint4*>(dst) = o;
+  }
+}
+
 }  // namespace
+
+static int pool_args(const y3_pool_desc& d, PoolArgs* a) {
+  Y3_REQUIRE(d.in && d.out && d.n > 0 && d.h > 0 && d.w > 0 && d.c > 0 && d.c % 8 == 0, "pool: bad shape");
+  Y3_REQUIRE(d.in_ld % 8 == 0 && d.in_coff % 8 == 0 && d.out_ld % 8 == 0 && d.out_coff % 8 == 0 &&
+                 d.in_coff + d.c <= d.in_ld && d.out_coff + d.c <= d.out_ld,
+             "pool: bad channel slice");
+  Y3_REQUIRE(d.k >= 1 && d.k <= 13 && d.stride >= 1 && d.ho > 0 && d.wo > 0, "pool: bad window");
+  a->in = static_cast<const __nv_bfloat16*>(d.in);
+  a->out = static_cast<__nv_bfloat16*>(d.out);
+  a->in_ld = d.in_ld;
+  a->in_coff = d.in_coff;
+  a->out_ld = d.out_ld;
+  a->out_coff = d.out_coff;
+  a->n = d.n;
+  a->h = d.h;
+  a->w = d.w;
+  a->c8 = d.c / 8;
+  a->ho = d.ho;
+  a->wo = d.wo;
+  a->k = d.k;
+  a->stride = d.stride;
+  a->off = d.off;
+  a->oob_zero = d.oob_zero;
+  return Y3_OK;
+}
+
+static unsigned pool_grid(long long total) {
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms()) * 32;
+  return static_cast<unsigned>(blocks > cap ? cap : blocks);
+}
+
+int pool_train_fwd(const y3_pool_desc& d, uint8_t* idx, cudaStream_t stream) {
+  PoolArgs a;
+  if (int rc = pool_args(d, &a)) return rc;
+  Y3_REQUIRE(idx && !d.oob_zero, "pool (train): idx is required; zero-padded windows are not differentiated here");
+  maxpool_idx_kernel<<<pool_grid(static_cast<long long>(a.n) * a.ho * a.wo * a.c8), 256, 0, stream>>>(a, idx);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+int pool_bwd(const y3_pool_desc& d, const uint8_t* idx, int accumulate, cudaStream_t stream) {
+  PoolArgs a;
+  if (int rc = pool_args(d, &a)) return rc;
+  Y3_REQUIRE(idx, "pool_bwd: null idx");
+  maxpool_bwd_kernel<<<pool_grid(static_cast<long long>(a.n) * a.h * a.w * a.c8), 256, 0, stream>>>(a, idx, accumulate);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
 
 int pool_launch(const y3_pool_desc& d, cudaStream_t stream) {
   Y3_REQUIRE(d.in && d.out && d.n > 0 && d.h > 0 && d.w > 0 && d.c > 0 && d.c % 8 == 0, "pool: bad shape");
@@ -100,6 +258,16 @@ int pool_launch(const y3_pool_desc& d, cudaStream_t stream) {
 }
 
 }  // namespace y3
+
+extern "C" int y3_maxpool_train_fwd(const y3_pool_desc* d, uint8_t* idx, y3_stream_t stream) {
+  if (!d) return y3::set_error(Y3_ERR_BAD_ARG, "pool: null descriptor");
+  return y3::pool_train_fwd(*d, idx, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int y3_maxpool_bwd(const y3_pool_desc* d, const uint8_t* idx, int32_t accumulate, y3_stream_t stream) {
+  if (!d) return y3::set_error(Y3_ERR_BAD_ARG, "pool: null descriptor");
+  return y3::pool_bwd(*d, idx, accumulate, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int y3_maxpool_fwd(const y3_pool_desc* d, y3_stream_t stream) {
   if (!d) return y3::set_error(Y3_ERR_BAD_ARG, "pool: null descriptor");

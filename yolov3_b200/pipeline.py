@@ -1,7 +1,11 @@
 """``Pipeline`` — the detect.py inner loop as one call (reference detect.py:185-200): host uint8 images ->
 device (``im.to(device)``) -> ``im.float()/255`` + Model.forward (fused into layer 0) -> Detect decode ->
 non_max_suppression -> detections back on the host.  Everything between the H2D copy of the images and the D2H copy
-of the kept boxes stays on the device with no host synchronisation."""
+of the kept boxes stays on the device with no host synchronisation.
+
+``Pipeline(images)`` is the synchronous per-batch call of the reference loop.  ``Pipeline.stream(batches)`` runs the same
+steps software-pipelined over two buffers: the H2D copy of batch i+1 (copy stream) and the host-side read-out of batch
+i-1 overlap the forward + NMS of batch i, results come back in order."""
 from __future__ import annotations
 
 import torch
@@ -26,6 +30,7 @@ class Pipeline:
         if use_graph:
             self.engine.capture()
         self.dev = dev
+        self._stream_state = None
 
     def __call__(self, images_u8: torch.Tensor):
         """images_u8: HOST uint8 [n,3,h,w] (pinned for an async copy).  Returns list of host tensors [k,6]."""
@@ -43,3 +48,55 @@ class Pipeline:
         if int(self.host_cnt[1].max()):
             raise RuntimeError("NMS candidate capacity exceeded; rerun through non_max_suppression() for the exact retry")
         return [self.host_out[i, : int(self.host_cnt[0, i])] for i in range(self.host_out.shape[0])]
+
+    # ------------------------------------------------------------------------------------------------ streaming
+    def _slots(self):
+        if self._stream_state is None:
+            e = self.engine
+            n, max_det = self.host_out.shape[0], self.host_out.shape[1]
+            self._stream_state = dict(
+                copy=torch.cuda.Stream(device=self.dev),
+                slots=[dict(dev_in=torch.empty_like(e.static_in),
+                            host_out=torch.empty(n, max_det, 6, dtype=torch.float32).pin_memory(),
+                            host_cnt=torch.empty(2, n, dtype=torch.int32).pin_memory(),
+                            h2d=torch.cuda.Event(), free=torch.cuda.Event(), done=torch.cuda.Event()) for _ in range(2)])
+            for sl in self._stream_state["slots"]:
+                sl["free"].record()
+        return self._stream_state
+
+    def _collect(self, sl):
+        sl["done"].synchronize()
+        if int(sl["host_cnt"][1].max()):
+            raise RuntimeError("NMS candidate capacity exceeded; rerun through non_max_suppression() for the exact retry")
+        return [sl["host_out"][i, : int(sl["host_cnt"][0, i])].clone() for i in range(sl["host_out"].shape[0])]
+
+    def stream(self, batches):
+        """Generator over per-batch detections (same values as ``self(batch)``) for an iterable of HOST uint8 batches
+        (pinned for a truly asynchronous copy)."""
+        st = self._slots()
+        e, cs = self.engine, st["copy"]
+        main = torch.cuda.current_stream()
+        pending = None
+        for i, images_u8 in enumerate(batches):
+            sl = st["slots"][i & 1]
+            with torch.cuda.stream(cs):
+                cs.wait_event(sl["free"])  # the forward that read this slot's device buffer two steps ago has consumed it
+                sl["dev_in"].copy_(images_u8, non_blocking=True)
+                sl["h2d"].record(cs)
+            main.wait_event(sl["h2d"])
+            e.static_in.copy_(sl["dev_in"], non_blocking=True)  # device-to-device, 39 MB at bs 32: ~15 us
+            sl["free"].record(main)
+            if self.use_graph:
+                e.replay()
+            else:
+                e.run(None)
+            out, counts, overflow, _ = nms_batched(e.z, **self.kw)
+            sl["host_out"].copy_(out, non_blocking=True)
+            sl["host_cnt"][0].copy_(counts, non_blocking=True)
+            sl["host_cnt"][1].copy_(overflow, non_blocking=True)
+            sl["done"].record(main)
+            if pending is not None:
+                yield self._collect(pending)
+            pending = sl
+        if pending is not None:
+            yield self._collect(pending)

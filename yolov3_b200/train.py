@@ -38,9 +38,9 @@ class TrainEngine:
         det = model.detect
         nodes = model.nodes
         for nd in nodes[:-1]:
-            if nd.type not in ("Conv", "Bottleneck", "Upsample", "Concat"):
-                raise NotImplementedError(f"training-mode {nd.type} is not built (yolov3.yaml only needs Conv/Bottleneck/"
-                                          "Upsample/Concat)")
+            if nd.type not in ("Conv", "Bottleneck", "Upsample", "Concat", "SPP"):
+                raise NotImplementedError(f"training-mode {nd.type} is not built (yolov3.yaml / yolov3-spp.yaml need "
+                                          "Conv/Bottleneck/Upsample/Concat/SPP)")
         P = model.device_params()
         self.P = P
         self.blocks: list[_Block] = []
@@ -73,6 +73,7 @@ class TrainEngine:
             b.dw = torch.zeros(c2, ci, kk, kk, dtype=torch.float32, device=dev)
             b.dy = self._scratch(c2, ho, wo, dev)
             b.dy_up = self._scratch(c2, x.h, x.w, dev, tag="up") if s == 2 else None
+            b.post_fwd, b.pre_bwd = [], []  # extra launches after this block's forward / before its backward (SPP pools)
             self.blocks.append(b)
             return b
 
@@ -84,7 +85,7 @@ class TrainEngine:
             if nd.type == "Conv":
                 s_ = nd.args[3] if len(nd.args) > 3 else 1
                 shp[nd.i] = (nd.c_out, h0 // s_, w0 // s_)
-            elif nd.type == "Bottleneck":
+            elif nd.type in ("Bottleneck", "SPP"):
                 shp[nd.i] = (nd.c_out, h0, w0)
             elif nd.type == "Upsample":
                 shp[nd.i] = (c0, h0 * 2, w0 * 2)
@@ -157,6 +158,24 @@ class TrainEngine:
                     new_block(r + ".cv2", c_, c2, 3, 1, t, yb, res=x if (shortcut and c1 == c2) else None)
                     x, c1 = yb, c2
                 tens[nd.i] = x
+            elif nd.type == "SPP":
+                # models/common.py:281-290: cv2(cat[x, mp5(x), mp9(x), mp13(x)]) with x = cv1(input); each pool reads x
+                c1, c2, *rest = nd.args
+                ks = tuple(rest[0]) if rest else (5, 9, 13)
+                x = srcs[0]
+                c_ = c1 // 2
+                cat = buf((len(ks) + 1) * c_, x.h, x.w)
+                b1 = new_block(base + ".cv1", c1, c_, 1, 1, x, cat.slice(0, c_))
+                for q, k in enumerate(ks):
+                    idx = torch.zeros(n * x.h * x.w * c_, dtype=torch.uint8, device=dev)
+                    self.keep.append(idx)
+                    src, dst = cat.slice(0, c_), cat.slice((q + 1) * c_, c_)
+                    b1.post_fwd.append(lambda src=src, dst=dst, k=k, idx=idx: T.maxpool_train_fwd(src, dst, k, idx))
+                    b1.pre_bwd.append(lambda src=src, dst=dst, k=k, idx=idx: T.maxpool_bwd(self.grad_of(dst), self.grad_of(src),
+                                                                                        k, idx, accumulate=True))
+                y = out_of(nd.i)
+                new_block(base + ".cv2", (len(ks) + 1) * c_, c2, 1, 1, cat, y)
+                tens[nd.i] = y
             elif nd.type == "Upsample":
                 tens[nd.i] = None
             elif nd.type == "Concat":
@@ -270,6 +289,8 @@ class TrainEngine:
                           self.n * b.y.h * b.y.w, st["scale"], st["shift"], st["mean"], st["rstd"],
                           P[b.prefix + ".bn.running_mean"], P[b.prefix + ".bn.running_var"])
             T.bn_act_fwd(b.y, st["scale"], st["shift"], b.a, b.res, b.upsample)
+            for fn in b.post_fwd:
+                fn()
         for hd in self.heads:
             w = P[f"model.{det.i}.m.{hd['j']}.weight"].detach()
             co = det.na * det.no
@@ -315,6 +336,8 @@ class TrainEngine:
         grads = {}
         for b in reversed(self.blocks):
             st = b.st
+            for fn in b.pre_bwd:
+                fn()
             da = self.grad_of(b.a)
             T.bn_act_bwd(b.y, da, b.dy, st["scale"], st["shift"], st["mean"], st["rstd"], st["dbeta"], st["dgamma"], b.upsample)
             b.dw.zero_()

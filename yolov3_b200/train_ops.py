@@ -100,3 +100,25 @@ def im2col_first(x: torch.Tensor, out: PaddedNHWC, in_div=0.0):
     _lib.check(_lib.lib().y3_im2col_first(x.data_ptr(), _lib.IN_U8 if x.dtype == torch.uint8 else _lib.IN_F32, float(in_div),
                                           n, h, w, out.ptr, out.ld, out.coff, _stream()), "y3_im2col_first")
     return out
+
+
+def maxpool_train_fwd(x: PaddedNHWC, out: PaddedNHWC, k: int, idx: torch.Tensor):
+    """Stride-1 'same' max-pool (SPP) that also records the argmax idx[n,h,w,c] uint8 for the backward."""
+    from . import ops
+
+    assert idx.dtype == torch.uint8 and idx.numel() == x.n * x.h * x.w * x.c
+    d = ops.pool_desc(x, out, k, 1, -(k // 2), False)
+    _lib.check(_lib.lib().y3_maxpool_train_fwd(C.byref(d), idx.data_ptr(), _stream()), "y3_maxpool_train_fwd")
+    return out
+
+
+def maxpool_bwd(dout: PaddedNHWC, din: PaddedNHWC, k: int, idx: torch.Tensor, accumulate: bool):
+    """din (+)= gather of dout through the recorded argmax (deterministic, no atomics)."""
+    d = _lib.PoolDesc()
+    d.in_, d.in_ld, d.in_coff = dout.ptr, dout.ld, dout.coff
+    d.out, d.out_ld, d.out_coff = din.ptr, din.ld, din.coff
+    d.n, d.h, d.w, d.c = din.n, din.h, din.w, din.c
+    d.ho, d.wo = dout.h, dout.w
+    d.k, d.stride, d.off, d.oob_zero = k, 1, -(k // 2), 0
+    _lib.check(_lib.lib().y3_maxpool_bwd(C.byref(d), idx.data_ptr(), int(bool(accumulate)), _stream()), "y3_maxpool_bwd")
+    return din
