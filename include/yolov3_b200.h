@@ -239,9 +239,12 @@ typedef struct y3_bn_bwd_desc {
   const void* da; int32_t da_ld, da_coff;      /* gradient w.r.t. the block output (2x geometry when upsample) */
   void* dy;       int32_t dy_ld, dy_coff;      /* gradient w.r.t. the conv output (input of dgrad / wgrad) */
   const float* scale; const float* shift; const float* mean; const float* rstd;
-  float* sum_dz;   /* [c] out: dbeta  */
-  float* sum_dzy;  /* [c] out: dgamma */
+  float* sum_dz;   /* [c] phase 0/1: out, dbeta = sum dz;  phase 2: in, the (all-reduced) sum */
+  float* sum_dzy;  /* [c] phase 0/1: out, dgamma = sum dz*xhat;  phase 2: in */
   int32_t n, h, w, c, upsample;
+  int32_t phase;   /* 0: sums then apply (single GPU); 1: sums only; 2: apply only — SyncBatchNorm (train.py:270-272) puts
+                      an all-reduce of the two sums between 1 and 2 */
+  float count;     /* pixels behind the sums used by the apply phase (all ranks); 0 = this rank's n*h*w */
 } y3_bn_bwd_desc;
 int y3_bn_act_bwd(const y3_bn_bwd_desc* d, y3_stream_t stream);
 /* fp32 master weights [co, ci, k, k] -> bf16 forward pack [co_pad, k*k*ci] and/or dgrad pack [ci_pad, k*k*co] (taps

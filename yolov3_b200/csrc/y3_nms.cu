@@ -14,6 +14,9 @@
 // class*max_wh cannot intersect across classes while all coordinates lie inside (-max_wh/2, max_wh/2); images that
 // violate that bound (or agnostic=True) take the single-segment path over all candidates.
 // The reference's wall-clock time_limit break (general.py:675,746-748) is deliberately not reproduced.
+#include <cmath>
+#include <cstring>
+
 #include "y3_common.cuh"
 #include "y3_internal.h"
 
@@ -28,6 +31,8 @@ struct NmsArgs {
   const float* pred;  // [bs, n_rows, no]
   int bs, n_rows, nc, no;
   float conf_thres, iou_thres, max_wh;
+  double iou_mid;  // midpoint between iou_thres and the next float above it (division-free exact IoU test)
+  int iou_odd;     // mantissa LSB of iou_thres: where a quotient exactly at the midpoint rounds to
   int multi_label, agnostic, max_det, max_nms;
   int cap;  // candidate capacity per image (power of two >= kSortTile)
   uint32_t cls_mask[32];
@@ -35,7 +40,7 @@ struct NmsArgs {
   // workspace
   unsigned long long* keys;  // [bs, cap]
   int* count;                // [bs] candidates found (may exceed cap)
-  int* flags;                // [bs] bit0: needs single-segment path
+  int* flags;                // [bs] bit0: needs single-segment path; bit1: has a class segment too long for one warp
   float* det;                // [bs, kRankCap, 6]
   uint32_t* seg_keys;        // [bs, kRankCap]
   uint8_t* keep;             // [bs, kRankCap]
@@ -327,6 +332,99 @@ __device__ __forceinline__ int lower_bound_warp(const uint32_t* a, int n, uint32
   return lo;
 }
 
+// fdiv_rn(inter, uni) > thr  without the division: the correctly rounded quotient exceeds thr iff the exact quotient lies
+// above the midpoint `mid` of thr and its successor (or exactly on it when round-to-nearest-even picks the successor).
+// uni has 24 and mid at most 25 significant bits, so uni * mid is exact in double.  Degenerate operands (uni <= 0, NaN,
+// infinities) take the IEEE division, which is what torchvision's kernel evaluates.
+__device__ __forceinline__ bool iou_exceeds(float inter, float uni, const NmsArgs& p) {
+  if (uni > 0.0f && uni < INFINITY && inter < INFINITY) {
+    const double a = static_cast<double>(inter), d = __dmul_rn(static_cast<double>(uni), p.iou_mid);
+    return a > d || (a == d && p.iou_odd);
+  }
+  return __fdiv_rn(inter, uni) > p.iou_thres;
+}
+
+__device__ __forceinline__ bool box_suppresses(const float4& bi, float ai, const float4& bj, const NmsArgs& p) {
+  const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
+  const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+  const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+  const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  return iou_exceeds(inter, __fsub_rn(__fadd_rn(ai, aj), inter), p);
+}
+
+// One WARP per (image, class) segment of up to 512 members: boxes live in registers (member j -> lane j % 32, slot j / 32),
+// the box of the current keeper is broadcast by shuffle, no block barrier in the greedy loop.  The block-per-segment
+// kernel below spent 8 warps and a __syncthreads per keeper and was issue-bound (5 blocks per SM in lock-step):
+// 138 us / 1.07 ms for 65 / 375 members per class (profiles/r01_nms_launches_summary.txt).
+constexpr int kWarpSlots = 16;
+constexpr int kWarpSegMax = 32 * kWarpSlots;
+
+__global__ void __launch_bounds__(256) nms_segments_warp_kernel(const NmsArgs p) {
+  const unsigned full = 0xffffffffu;
+  const int img = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seg = blockIdx.x * 8 + warp;
+  if (seg >= p.nc) return;
+  int c = p.count[img];
+  c = c < p.cap ? c : p.cap;
+  const int n = c < p.max_nms ? c : p.max_nms;
+  if (n == 0 || p.agnostic || (p.flags[img] & 1)) return;  // single-segment images go to the block kernel
+  const uint32_t* sk = p.seg_keys + static_cast<size_t>(img) * kRankCap;
+  const int lo = lower_bound_warp(sk, n, static_cast<uint32_t>(seg) << 15, lane);
+  const int hi = lower_bound_warp(sk, n, static_cast<uint32_t>(seg + 1) << 15, lane);
+  const int m = hi - lo;
+  if (m <= 0) return;
+  if (m > kWarpSegMax) {
+    if (lane == 0) atomicOr(&p.flags[img], 2);
+    return;
+  }
+  const float* det = p.det + static_cast<size_t>(img) * kRankCap * 6;
+  float4 b[kWarpSlots];
+  uint32_t supp = 0;  // bit s: my member of slot s is suppressed (or does not exist)
+#pragma unroll
+  for (int s = 0; s < kWarpSlots; ++s) {
+    const int j = s * 32 + lane;
+    b[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < m) {
+      const float* d = det + static_cast<size_t>(sk[lo + j] & 0x7FFFu) * 6;
+      const float off = __fmul_rn(d[5], p.max_wh);
+      b[s] = make_float4(__fadd_rn(d[0], off), __fadd_rn(d[1], off), __fadd_rn(d[2], off), __fadd_rn(d[3], off));
+    } else {
+      supp |= 1u << s;
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < kWarpSlots; ++s) {
+    if (s * 32 >= m) break;
+    unsigned dead = __ballot_sync(full, (supp >> s) & 1u);  // warp-uniform view of slot s
+    const int cnt = min(32, m - s * 32);
+    for (int l = 0; l < cnt; ++l) {
+      if ((dead >> l) & 1u) continue;
+      float4 bi;
+      bi.x = __shfl_sync(full, b[s].x, l);
+      bi.y = __shfl_sync(full, b[s].y, l);
+      bi.z = __shfl_sync(full, b[s].z, l);
+      bi.w = __shfl_sync(full, b[s].w, l);
+      const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+      const bool hit = lane > l && !((supp >> s) & 1u) && box_suppresses(bi, ai, b[s], p);
+      if (hit) supp |= 1u << s;
+      dead |= __ballot_sync(full, hit);
+#pragma unroll
+      for (int s2 = s + 1; s2 < kWarpSlots; ++s2) {
+        if (s2 * 32 >= m) break;
+        if (!((supp >> s2) & 1u) && box_suppresses(bi, ai, b[s2], p)) supp |= 1u << s2;
+      }
+    }
+  }
+  uint8_t* keep = p.keep + static_cast<size_t>(img) * kRankCap;
+#pragma unroll
+  for (int s = 0; s < kWarpSlots; ++s) {
+    const int j = s * 32 + lane;
+    if (j < m && !((supp >> s) & 1u)) keep[sk[lo + j] & 0x7FFFu] = 1;
+  }
+}
+
 __global__ void __launch_bounds__(256) nms_segments_kernel(const NmsArgs p) {
   __shared__ float4 s_box[kSegSmemBoxes];
   __shared__ uint16_t s_rank[kSegSmemBoxes];
@@ -337,8 +435,10 @@ __global__ void __launch_bounds__(256) nms_segments_kernel(const NmsArgs p) {
   c = c < p.cap ? c : p.cap;
   const int n = c < p.max_nms ? c : p.max_nms;
   if (n == 0) return;
-  const bool single = p.agnostic || (p.flags[img] & 1);
+  const int fl = p.flags[img];
+  const bool single = p.agnostic || (fl & 1);
   if (single && seg != 0) return;
+  if (!single && !(fl & 2)) return;  // every class segment of this image fitted the warp kernel
   const uint32_t* sk = p.seg_keys + static_cast<size_t>(img) * kRankCap;
   if (!single) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -351,6 +451,7 @@ __global__ void __launch_bounds__(256) nms_segments_kernel(const NmsArgs p) {
   const int lo = single ? 0 : s_bounds[0], hi = single ? n : s_bounds[1];
   const int m = hi - lo;
   if (m <= 0) return;
+  if (!single && m <= kWarpSegMax) return;  // done by nms_segments_warp_kernel
   const float* det = p.det + static_cast<size_t>(img) * kRankCap * 6;
   uint8_t* keep = p.keep + static_cast<size_t>(img) * kRankCap;
   // member j of the segment (confidence order) -> rank
@@ -381,16 +482,8 @@ __global__ void __launch_bounds__(256) nms_segments_kernel(const NmsArgs p) {
     if (i + 1 >= m) break;
     for (int j = i + 1 + threadIdx.x; j < m; j += blockDim.x) {
       if ((s_supp[j >> 5] >> (j & 31)) & 1u) continue;
-      float4 bj;
-      float aj;
-      bj = in_smem ? s_box[j] : load_box(rank_of(j));
-      aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
-      const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
-      const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
-      const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
-      const float inter = __fmul_rn(w, h);
-      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, aj), inter));
-      if (ovr > p.iou_thres) atomicOr(&s_supp[j >> 5], 1u << (j & 31));
+      const float4 bj = in_smem ? s_box[j] : load_box(rank_of(j));
+      if (box_suppresses(bi, ai, bj, p)) atomicOr(&s_supp[j >> 5], 1u << (j & 31));
     }
     __syncthreads();
   }
@@ -501,6 +594,13 @@ extern "C" int y3_nms_batched(const float* pred, const y3_nms_params* q, void* w
   a.no = q->nc + 5;
   a.conf_thres = q->conf_thres;
   a.iou_thres = q->iou_thres;
+  {
+    const float t = q->iou_thres, up = nextafterf(t, INFINITY);
+    a.iou_mid = 0.5 * (static_cast<double>(t) + static_cast<double>(up));
+    uint32_t bits;
+    memcpy(&bits, &t, sizeof(bits));
+    a.iou_odd = static_cast<int>(bits & 1u);
+  }
   a.max_wh = q->max_wh > 0 ? q->max_wh : 7680.f;
   a.multi_label = (q->multi_label && q->nc > 1) ? 1 : 0;  // general.py:677
   a.agnostic = q->agnostic ? 1 : 0;
@@ -557,6 +657,7 @@ extern "C" int y3_nms_batched(const float* pred, const y3_nms_params* q, void* w
     }
   }
   // K5, K6
+  nms_segments_warp_kernel<<<dim3((a.nc + 7) / 8, a.bs), 256, 0, stream>>>(a);
   nms_segments_kernel<<<dim3(a.nc, a.bs), 256, 0, stream>>>(a);
   nms_compact_kernel<<<a.bs, 1024, 0, stream>>>(a);
   Y3_CHECK_CUDA(cudaGetLastError());

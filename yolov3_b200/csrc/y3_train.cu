@@ -571,13 +571,16 @@ extern "C" int y3_bn_act_bwd(const y3_bn_bwd_desc* d, y3_stream_t stream_) {
   a.c8 = d->c / 8;
   a.upsample = d->upsample;
   const long long pixels = static_cast<long long>(d->n) * d->h * d->w;
-  a.inv_count = 1.0f / static_cast<float>(pixels);
+  Y3_REQUIRE(d->phase >= 0 && d->phase <= 2 && d->count >= 0.f, "bn_act_bwd: bad phase/count");
+  a.inv_count = 1.0f / (d->count > 0.f ? d->count : static_cast<float>(pixels));
   const int npl = 256 / a.c8;
   const int grid = y3::grid_for((pixels + npl - 1) / npl, 8, 8);
-  Y3_CHECK_CUDA(cudaMemsetAsync(d->sum_dz, 0, sizeof(float) * d->c, stream));
-  Y3_CHECK_CUDA(cudaMemsetAsync(d->sum_dzy, 0, sizeof(float) * d->c, stream));
-  y3::bn_act_bwd_kernel<false><<<grid, 256, 2 * 256 * 8 * sizeof(float), stream>>>(a);
-  y3::bn_act_bwd_kernel<true><<<grid, 256, 2 * 256 * 8 * sizeof(float), stream>>>(a);
+  if (d->phase != 2) {
+    Y3_CHECK_CUDA(cudaMemsetAsync(d->sum_dz, 0, sizeof(float) * d->c, stream));
+    Y3_CHECK_CUDA(cudaMemsetAsync(d->sum_dzy, 0, sizeof(float) * d->c, stream));
+    y3::bn_act_bwd_kernel<false><<<grid, 256, 2 * 256 * 8 * sizeof(float), stream>>>(a);
+  }
+  if (d->phase != 1) y3::bn_act_bwd_kernel<true><<<grid, 256, 2 * 256 * 8 * sizeof(float), stream>>>(a);
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }

@@ -77,6 +77,7 @@ class Model:
         self.conv_specs = graph.conv_specs(self.nodes)
         self.device = torch.device(device)
         self.training = False
+        self.sync_bn = False  # parallel.convert_sync_batchnorm(): train-mode BN statistics over all ranks
         self.hyp = None
         self.params = self._init_params()
         self._packed = None

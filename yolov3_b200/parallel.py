@@ -53,3 +53,13 @@ def broadcast_parameters(params, src: int = 0):
         return
     for p in params:
         dist.broadcast(p.data, src)
+
+
+def convert_sync_batchnorm(model):
+    """``torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)`` of the reference's ``--sync-bn`` switch (train.py:270-272):
+    the training engine all-reduces every BatchNorm's (sum, sum of squares) in the forward and (sum dz, sum dz*xhat) in the
+    backward, so batch statistics cover all ranks' images.  gamma/beta gradients stay rank-local sums (the gradient
+    all-reduce averages them like every other parameter), exactly as torch's SyncBatchNorm does under DDP."""
+    model.sync_bn = True
+    model._train_engines.clear()
+    return model

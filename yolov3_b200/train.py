@@ -18,6 +18,7 @@ from __future__ import annotations
 import ctypes as C
 
 import torch
+import torch.distributed as dist
 
 from . import _lib, ops
 from . import train_ops as T
@@ -28,7 +29,7 @@ class _Block:
     """One Conv+BN+SiLU block (models/common.py:57-81) with everything its forward and backward need."""
 
     __slots__ = ("prefix", "c1", "c2", "k", "s", "x", "y", "a", "res", "upsample", "wf", "wd", "zero_b", "zero_bi", "st",
-                 "dw", "first", "dy", "dy_up")
+                 "dw", "first", "dy", "dy_up", "post_fwd", "pre_bwd")
 
 
 class TrainEngine:
@@ -43,6 +44,10 @@ class TrainEngine:
                                           "Conv/Bottleneck/Upsample/Concat/SPP)")
         P = model.device_params()
         self.P = P
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.sync_bn = bool(getattr(model, "sync_bn", False)) and self.world > 1
+        if self.sync_bn:
+            self.use_graphs = False  # the per-layer collectives stay eager launches
         self.blocks: list[_Block] = []
         self.keep = []
         self.grad_bufs: dict[int, PaddedNHWC] = {}
@@ -69,7 +74,9 @@ class TrainEngine:
             b.wd = None if first else torch.zeros(ops.cout_pad(c1), k * k * c2, dtype=torch.bfloat16, device=dev)
             b.zero_b = f32(ops.cout_pad(c2))
             b.zero_bi = None if first else f32(ops.cout_pad(c1))
-            b.st = {name: f32(c2) for name in ("sum", "sumsq", "scale", "shift", "mean", "rstd", "dgamma", "dbeta")}
+            b.st = {name: f32(c2) for name in ("scale", "shift", "mean", "rstd")}
+            sums, dsums, gsums = f32(2 * c2).view(2, c2), f32(2 * c2).view(2, c2), f32(2 * c2).view(2, c2)
+            b.st.update(sums=sums, sum=sums[0], sumsq=sums[1], dsums=dsums, dbeta=dsums[0], dgamma=dsums[1], gsums=gsums)
             b.dw = torch.zeros(c2, ci, kk, kk, dtype=torch.float32, device=dev)
             b.dy = self._scratch(c2, ho, wo, dev)
             b.dy_up = self._scratch(c2, x.h, x.w, dev, tag="up") if s == 2 else None
@@ -285,8 +292,12 @@ class TrainEngine:
                 ops.conv_bn_act(b.x, b.wf, b.zero_b, b.c2, b.k, b.s, ops.ACT_NONE, out=b.y, err=self.err)
             st = b.st
             T.bn_stats(b.y, st["sum"], st["sumsq"])
+            count = self.n * b.y.h * b.y.w
+            if self.sync_bn:  # nn.SyncBatchNorm (train.py:270-272): batch statistics over every rank's pixels
+                dist.all_reduce(st["sums"])  # [sum | sumsq] share one buffer: one collective per layer
+                count *= self.world
             T.bn_finalize(st["sum"], st["sumsq"], P[b.prefix + ".bn.weight"].detach(), P[b.prefix + ".bn.bias"].detach(),
-                          self.n * b.y.h * b.y.w, st["scale"], st["shift"], st["mean"], st["rstd"],
+                          count, st["scale"], st["shift"], st["mean"], st["rstd"],
                           P[b.prefix + ".bn.running_mean"], P[b.prefix + ".bn.running_var"])
             T.bn_act_fwd(b.y, st["scale"], st["shift"], b.a, b.res, b.upsample)
             for fn in b.post_fwd:
@@ -339,7 +350,17 @@ class TrainEngine:
             for fn in b.pre_bwd:
                 fn()
             da = self.grad_of(b.a)
-            T.bn_act_bwd(b.y, da, b.dy, st["scale"], st["shift"], st["mean"], st["rstd"], st["dbeta"], st["dgamma"], b.upsample)
+            if self.sync_bn:
+                # local sums are the (rank-local) gamma/beta gradients; dy needs the sums over all ranks
+                T.bn_act_bwd(b.y, da, b.dy, st["scale"], st["shift"], st["mean"], st["rstd"], st["dbeta"], st["dgamma"],
+                             b.upsample, phase=1)
+                st["gsums"].copy_(st["dsums"])
+                dist.all_reduce(st["gsums"])
+                T.bn_act_bwd(b.y, da, b.dy, st["scale"], st["shift"], st["mean"], st["rstd"], st["gsums"][0], st["gsums"][1],
+                             b.upsample, phase=2, count=self.n * b.y.h * b.y.w * self.world)
+            else:
+                T.bn_act_bwd(b.y, da, b.dy, st["scale"], st["shift"], st["mean"], st["rstd"], st["dbeta"], st["dgamma"],
+                             b.upsample)
             b.dw.zero_()
             src = b.dy
             if b.s == 2:

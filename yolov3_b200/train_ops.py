@@ -42,8 +42,12 @@ def bn_act_fwd(y: PaddedNHWC, scale, shift, out: PaddedNHWC, res: PaddedNHWC | N
     return out
 
 
-def bn_act_bwd(y: PaddedNHWC, da: PaddedNHWC, dy: PaddedNHWC, scale, shift, mean, rstd, dbeta, dgamma, upsample=False):
+def bn_act_bwd(y: PaddedNHWC, da: PaddedNHWC, dy: PaddedNHWC, scale, shift, mean, rstd, dbeta, dgamma, upsample=False,
+               phase=0, count=0.0):
+    """phase 0: sums (-> dbeta, dgamma) then dy.  SyncBatchNorm: phase 1 (local sums), all-reduce, phase 2 (dy from the
+    global sums passed as dbeta/dgamma, ``count`` = pixels over all ranks)."""
     d = _lib.BnBwdDesc()
+    d.phase, d.count = int(phase), float(count)
     d.y, d.y_ld, d.y_coff = y.ptr, y.ld, y.coff
     d.da, d.da_ld, d.da_coff = da.ptr, da.ld, da.coff
     d.dy, d.dy_ld, d.dy_coff = dy.ptr, dy.ld, dy.coff
