@@ -21,14 +21,16 @@ def test_conv_tc(case):
     assert r["ok"], r
 
 
-@pytest.mark.parametrize("c_out,dtype", [(32, torch.float32), (16, torch.float32), (32, torch.uint8)])
-def test_conv_first(c_out, dtype):
+@pytest.mark.parametrize("c_out,dtype,hw", [(32, torch.float32, (40, 56)), (16, torch.float32, (40, 56)), (32, torch.uint8, (40, 56)),
+                                            (32, torch.float32, (21, 300)), (32, torch.uint8, (24, 260)),  # > 1 column tile
+                                            (32, torch.float32, (18, 54)), (16, torch.uint8, (18, 131))])  # W % 4 != 0: scalar staging
+def test_conv_first(c_out, dtype, hw):
     import torch.nn.functional as F
 
     from yolov3_b200 import ops
 
     g = torch.Generator().manual_seed(3)
-    n, h, w = 2, 40, 56
+    n, (h, w) = 2, hw
     if dtype == torch.uint8:
         xi = torch.randint(0, 256, (n, 3, h, w), generator=g, dtype=torch.uint8)
         x = xi.float() / 255

@@ -44,6 +44,10 @@ CASES = [
     dict(name="s2_k32_xpair_many_tiles", n=4, h=160, w=160, cin=32, cout=64, k=3, s=2, xpair=True),
     dict(name="3x3_k32_res_many_tiles", n=4, h=80, w=80, cin=32, cout=64, k=3, s=1, res=True),
     dict(name="1x1_res_many_tiles", n=4, h=80, w=80, cin=128, cout=128, k=1, s=1, res=True),
+    dict(name="3x3_k64_n32_res", n=2, h=40, w=40, cin=64, cout=32, k=3, s=1, res=True, act=0),   # dgrad of a 32->64 conv
+    dict(name="1x1_n32_res_many_tiles", n=4, h=80, w=80, cin=64, cout=32, k=1, s=1, res=True),
+    dict(name="1x1_k512_n256_res", n=2, h=40, w=40, cin=512, cout=256, k=1, s=1, res=True),      # staged, one buffer
+    dict(name="3x3_k64_n64_res_many_tiles", n=4, h=80, w=80, cin=64, cout=64, k=3, s=1, res=True),
 ]
 
 

@@ -23,6 +23,23 @@ __device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p, float div) {
   return div > 0.f ? __fdiv_rn(v, div) : v;
 }
 
+// four consecutive pixels of one row (16-byte / 4-byte vector load)
+template <typename TIN>
+__device__ __forceinline__ float4 load_px4(const TIN* p, float div);
+template <>
+__device__ __forceinline__ float4 load_px4<float>(const float* p, float div) {
+  float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  if (div > 0.f) v = make_float4(__fdiv_rn(v.x, div), __fdiv_rn(v.y, div), __fdiv_rn(v.z, div), __fdiv_rn(v.w, div));
+  return v;
+}
+template <>
+__device__ __forceinline__ float4 load_px4<uint8_t>(const uint8_t* p, float div) {
+  const uchar4 u = __ldg(reinterpret_cast<const uchar4*>(p));
+  float4 v = make_float4(u.x, u.y, u.z, u.w);
+  if (div > 0.f) v = make_float4(__fdiv_rn(v.x, div), __fdiv_rn(v.y, div), __fdiv_rn(v.z, div), __fdiv_rn(v.w, div));
+  return v;
+}
+
 // Tensor-core version (legacy warp-level mma.sync m16n8k16: K = 27 padded to 32 is far too thin for a tcgen05 tile and
 // the layer is bandwidth-bound anyway).  One block = 128 consecutive pixels of one image row; the 3x3x(128+2) input
 // patch is staged in shared memory with coalesced loads, each warp then builds the im2col A fragments for its 32 pixels
@@ -37,24 +54,57 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 constexpr int kFirstRows = 8;   // output rows per block (weight fragments and the input patch are reused across them)
 constexpr int kFirstTW = 128;   // output columns per block
 
-template <int COUT, typename TIN>
+// VEC: W % 4 == 0 and the image base is 16-byte (fp32) / 4-byte (uint8) aligned: the patch rows are staged with one
+// vector load per lane, all 8 rows a warp owns in flight at once.  The scalar staging loop kept ~5 dependent 4-byte loads
+// per thread in flight and 46 % of the kernel's stall samples sat on its STS (profiles/r01_ncu_conv_first_summary.txt).
+template <int COUT, typename TIN, bool VEC>
 __global__ void __launch_bounds__(128) conv_first_kernel(const TIN* __restrict__ in, float in_div, int H, int W,
                                                          const float* __restrict__ wgt, const float* __restrict__ bias,
                                                          __nv_bfloat16* __restrict__ out, int out_ld, int out_coff) {
-  constexpr int TW = kFirstTW, R = kFirstRows, NT = COUT / 8, PITCH = TW + 2;
-  __shared__ float s_in[3][R + 2][PITCH];
+  // patch column of image column ww is (ww - w0) + 4: the 128 interior columns start 16-byte aligned, halos at 3 and 132
+  constexpr int TW = kFirstTW, R = kFirstRows, NT = COUT / 8, PITCH = TW + 8, C0 = 3;
+  __shared__ __align__(16) float s_in[3][R + 2][PITCH];
   const int w0 = blockIdx.x * TW, h0 = blockIdx.y * R, n = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   // ---- stage the (R+2) x (TW+2) x 3 input patch (zero outside the image = the conv's padding)
-  for (int i = threadIdx.x; i < 3 * (R + 2) * PITCH; i += blockDim.x) {
-    const int col = i % PITCH, rc = i / PITCH;
-    const int c = rc / (R + 2), rr = rc - c * (R + 2);
-    const int hh = h0 + rr - 1, ww = w0 + col - 1;
-    float v = 0.f;
-    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-      v = load_px<TIN>(in + ((static_cast<size_t>(n) * 3 + c) * H + hh) * W + ww, in_div);
-    (&s_in[0][0][0])[i] = v;
+  if (VEC) {
+    constexpr int ROWS = 3 * (R + 2), PER_WARP = (ROWS + 3) / 4;
+    float4 v[PER_WARP];
+    float hv[PER_WARP];
+#pragma unroll
+    for (int i = 0; i < PER_WARP; ++i) {
+      const int rc = warp + i * 4;  // patch row = (channel, rr)
+      const int c = rc / (R + 2), rr = rc - c * (R + 2);
+      const int hh = h0 + rr - 1, ww = w0 + lane * 4;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      hv[i] = 0.f;
+      if (rc < ROWS && hh >= 0 && hh < H) {
+        const TIN* row = in + ((static_cast<size_t>(n) * 3 + c) * H + hh) * W;
+        if (ww < W) v[i] = load_px4<TIN>(row + ww, in_div);
+        const int hw = lane == 0 ? w0 - 1 : w0 + TW;  // lanes 0 / 1: left / right halo column
+        if (lane < 2 && hw >= 0 && hw < W) hv[i] = load_px<TIN>(row + hw, in_div);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PER_WARP; ++i) {
+      const int rc = warp + i * 4;
+      if (rc < ROWS) {
+        float* dst = &s_in[0][0][0] + rc * PITCH;
+        *reinterpret_cast<float4*>(dst + 4 + lane * 4) = v[i];
+        if (lane < 2) dst[lane == 0 ? C0 : C0 + TW + 1] = hv[i];
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < 3 * (R + 2) * (TW + 2); i += blockDim.x) {
+      const int col = i % (TW + 2), rc = i / (TW + 2);
+      const int c = rc / (R + 2), rr = rc - c * (R + 2);
+      const int hh = h0 + rr - 1, ww = w0 + col - 1;
+      float v = 0.f;
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+        v = load_px<TIN>(in + ((static_cast<size_t>(n) * 3 + c) * H + hh) * W + ww, in_div);
+      (&s_in[0][0][0])[rc * PITCH + C0 + col] = v;
+    }
   }
   // ---- weight fragments: B[k][n], k = (c*3+kh)*3+kw (27 real rows, zero padded to 32)
   uint32_t bfrag[2][NT][2];
@@ -64,7 +114,7 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const TIN* __restrict__
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int k = ks * 16 + t * 2 + (j & 1) + (j >> 1) * 8;
-      a_off[ks][j] = k < 27 ? ((k / 9) * (R + 2) + (k % 9) / 3) * PITCH + k % 3 : -1;
+      a_off[ks][j] = k < 27 ? ((k / 9) * (R + 2) + (k % 9) / 3) * PITCH + k % 3 + C0 : -1;
     }
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
@@ -180,9 +230,16 @@ extern "C" int y3_conv_first_fwd(const y3_first_desc* d, y3_stream_t stream) {
   const dim3 grid((d->w + y3::kFirstTW - 1) / y3::kFirstTW, (d->h + y3::kFirstRows - 1) / y3::kFirstRows, d->n), block(128);
   auto* o = static_cast<__nv_bfloat16*>(d->out);
   auto s = static_cast<cudaStream_t>(stream);
-#define Y3_FIRST(CO, T)                                                                                            \
-  y3::conv_first_kernel<CO, T><<<grid, block, 0, s>>>(static_cast<const T*>(d->in), d->in_div, d->h, d->w, d->weight, \
-                                                      d->bias, o, d->out_ld, d->out_coff)
+  const bool vec = d->w % 4 == 0 && (reinterpret_cast<uintptr_t>(d->in) & (d->in_dtype == Y3_IN_F32 ? 15 : 3)) == 0;
+#define Y3_FIRST(CO, T)                                                                                                 \
+  do {                                                                                                                  \
+    if (vec)                                                                                                            \
+      y3::conv_first_kernel<CO, T, true><<<grid, block, 0, s>>>(static_cast<const T*>(d->in), d->in_div, d->h, d->w,    \
+                                                                d->weight, d->bias, o, d->out_ld, d->out_coff);         \
+    else                                                                                                                \
+      y3::conv_first_kernel<CO, T, false><<<grid, block, 0, s>>>(static_cast<const T*>(d->in), d->in_div, d->h, d->w,   \
+                                                                 d->weight, d->bias, o, d->out_ld, d->out_coff);        \
+  } while (0)
   if (d->c_out == 32) {
     if (d->in_dtype == Y3_IN_F32) Y3_FIRST(32, float); else Y3_FIRST(32, uint8_t);
   } else {

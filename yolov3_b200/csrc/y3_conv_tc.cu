@@ -29,7 +29,7 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kEpilogueWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpilogueWarps;
-constexpr int kSmemBudget = 224 * 1024;  // ring + epilogue staging; barriers + alignment slack come on top (227 KB max)
+constexpr int kSmemBudget = 221 * 1024;  // ring + epilogue staging; alignment slack, barriers and bias slices come on top (227 KB max)
 
 // STAGED = true: the epilogue converts into a swizzled shared-memory staging tile and ONE thread stores it with TMA
 // (and pre-loads the residual tile into the same buffer with TMA), instead of every thread issuing 16-byte global
@@ -70,10 +70,42 @@ struct Cfg {
   static constexpr uint32_t kSwizzleBytes = BLOCK_K * 2;                       // 32 / 64 / 128
   static constexpr uint32_t kLayout = BLOCK_K == 64 ? 2u : (BLOCK_K == 32 ? 4u : 6u);
   static constexpr uint32_t kSbo = 8 * kSwizzleBytes;
-  static constexpr size_t kSmemBytes = size_t(kSmemBudget) + 1024 /*align*/ + 256 /*barriers*/ + BLOCK_N * 4 /*bias tile*/;
+  static constexpr uint32_t kColsPerWarp = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;  // columns one epilogue warp converts
+  static constexpr uint32_t kBarBytes = 512;                                       // mbarriers + TMEM slot
+  static constexpr uint32_t kBiasBytes = kEpilogueWarps * kColsPerWarp * 4;        // one private bias slice per warp
+  static constexpr size_t kSmemBytes = size_t(kSmemBudget) + 1024 /*align*/ + kBarBytes + kBiasBytes;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(!HALO || BLOCK_K >= 32, "halo reuse: rows of 64 or 128 bytes");
 };
+
+// accumulator chunk + bias (+ SiLU).  SiLU(x) = h + h*tanh(h) with h = x/2 = fma(acc, 0.5, b/2): the bias slice holds
+// b/2 for SiLU layers, so bias add and halving are one FFMA (bit-identical: scaling by 0.5 is exact) — 3 instructions
+// per element; the thin layers' epilogue is issue-bound (profiles/r01_ncu_issue_loop.txt).
+__device__ __forceinline__ void bias_act(const uint32_t (&v)[32], const float* __restrict__ sb, float (&x)[32], bool silu) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b = *reinterpret_cast<const float4*>(sb + j);
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = __uint_as_float(v[j + e]);
+      if (silu) {
+        const float h = fmaf(a, 0.5f, bb[e]);
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+        x[j + e] = fmaf(h, t, h);
+      } else {
+        x[j + e] = a + bb[e];
+      }
+    }
+  }
+}
+
+// exact n / d for any 32-bit n with a precomputed (multiplier, shift) pair (host: fast_div_for)
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t shr) {
+  const uint32_t t = __umulhi(n, mul);
+  return (t + ((n - t) >> (shr ? 1 : 0))) >> (shr ? shr - 1 : 0);
+}
 
 // PAIR = true: two CTAs of a cluster (one SM pair) cooperate on a 256-row tile with tcgen05 cta_group::2: each CTA
 // stages its own 128 A rows and HALF of the B tile, the leader CTA's single MMA thread issues M=256 MMAs that read both
@@ -103,12 +135,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* empty_bar = full_bar + C::kMaxStages;
   uint64_t* tfull_bar = empty_bar + C::kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* res_bar = tempty_bar + 2;  // [2]: one per staging buffer
-  uint64_t* bres_bar = res_bar + 2;
+  uint64_t* res_bar = tempty_bar + 2;  // [8 row-group owners][2 staging buffers]
+  uint64_t* bres_bar = res_bar + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
   // bias of the current N tile.  Read through __ldg it missed the (almost entirely shared-memory) L1 and exposed an L2
   // round trip per 32-column chunk: 29 % of all warp stall samples of the epilogue (profiles/r01_ncu_conv_tc_full_summary.txt).
-  float* s_bias = reinterpret_cast<float*>(smem_stg + C::kStagingBytes + 256);
+  float* s_bias = reinterpret_cast<float*>(smem_stg + C::kStagingBytes + C::kBarBytes);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,8 +160,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], PAIR ? 2 * kEpiThreads : kEpiThreads);  // pair: both CTAs' epilogues release the buffer
     }
-    mbar_init(&res_bar[0], 1);
-    mbar_init(&res_bar[1], 1);
+    for (int i = 0; i < 16; ++i) mbar_init(&res_bar[i], 1);
     mbar_init(bres_bar, PAIR ? 2 : 1);
     if (STAGED) {
       tma_prefetch_desc(&map_out);
@@ -199,17 +230,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           oh0 = (t / p.tiles_w) * p.th;
           ow0 = (t % p.tiles_w) * p.tw;
         }
+        // (k-block kb, tap) advance incrementally: this loop runs on one lane's issue slots, a runtime division per
+        // stage was a quarter of its ~150 instructions and the loop paced layer 1 (profiles/r01_ncu_issue_loop.txt)
+        const int taps_it = HALO ? 3 : p.taps;  // HALO: tap = filter row r
+        const int taps_w = p.xpair ? 2 : 3;     // taps per filter row
+        int kb = 0, tap = 0, r = 0, s = 0;      // tap = r * taps_w + s  (1x1: always 0)
         for (int it = 0; it < k_iters; ++it) {
-          const int taps_it = HALO ? 3 : p.taps;
-          const int kb = it / taps_it, tap = it - kb * taps_it;  // HALO: tap = filter row r
           mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 1);
           if (elect_one()) {
           uint8_t* a_dst = smem_a + stage * C::kABytes;
           uint8_t* b_dst = smem_b + stage * kBStage;
-          const int shift = HALO ? (tap - 1) * p.wp - 1 : ((p.taps == 9) ? ((tap / 3 - 1) * p.wp + (tap % 3 - 1)) : 0);
+          const int shift = HALO ? (tap - 1) * p.wp - 1 : ((p.taps == 9) ? ((r - 1) * p.wp + (s - 1)) : 0);
           // patch mode: filter row r, column s.  x-paired weights (stride 2, in_ld == c_in): one box covers the two
           // horizontally adjacent taps (r, 2s) and (r, 2s+1), which are contiguous channels of the parity view
-          const int r = p.xpair ? tap >> 1 : tap / 3, s = p.xpair ? tap & 1 : tap - r * 3;
           const int c0 = p.xpair ? p.a_coff : (s & 1) * p.a_ld + p.a_coff + kb * BLOCK_K;
           const int c1 = p.xpair ? s : (s >> 1);
           const uint32_t stage_tx = p.a_tx_bytes + (bres ? 0u : kBStage);
@@ -247,6 +280,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
+          }
+          if (++s == taps_w) {
+            s = 0;
+            ++r;
+          }
+          if (++tap == taps_it) {
+            tap = 0;
+            r = 0;
+            s = 0;
+            ++kb;
           }
         }
       }
@@ -305,16 +348,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9 = 256 threads)
+    // Every warp runs on its own: it owns TMEM lane quarter `quarter` (32 tile rows) and column half `half`, keeps a
+    // private copy of its bias slice, and (STAGED) loads the residual of / stores exactly its 32 rows with its own TMA
+    // boxes and mbarriers.  No block-wide barrier is left in the tile loop, so a warp that is done starts on the next tile
+    // (other TMEM buffer) while slower ones finish.  The first version walked all 8 warps through every tile in lock-step
+    // (two 256-thread named barriers, one elected TMA thread) and the thin layers were bound by that serial chain:
+    // the MMA warp waited on tmem_empty for 430 k polls per launch (profiles/r01_ncu_issue_loop.txt).
     const int quarter = warp & 3;             // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int half = (warp - 2) >> 2;         // which half of the tile's columns this warp converts
-    constexpr int kColsPerWarp = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;
+    constexpr int kColsPerWarp = C::kColsPerWarp;
     const int c_begin = BLOCK_N >= 64 ? half * kColsPerWarp : 0;
     const bool active = BLOCK_N >= 64 || half == 0;
     const int m = quarter * 32 + lane;
+    float* s_bias_w = s_bias + (warp - 2) * kColsPerWarp;
     const uint32_t lead_tempty[2] = {PAIR ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u,
                                      PAIR ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u};
+    // STAGED: N = 64 has ONE 64-column slab, shared by the two warps of a lane quarter (pair barrier 1 + quarter, 64
+    // threads; the half-0 warp issues the TMA traffic); otherwise each warp owns whole slabs
+    constexpr bool kPairSync = STAGED && BLOCK_N == 64;
+    constexpr uint32_t kMySlabs = kPairSync ? 1u : (C::kColsPerWarp + C::kSlabCols - 1) / C::kSlabCols;
+    const uint32_t slab0 = kPairSync ? 0u : uint32_t(c_begin) / C::kSlabCols;
+    const bool issuer = STAGED && active && lane == 0 && (!kPairSync || half == 0);
+    uint64_t* my_res_bar = res_bar + (kPairSync ? quarter : warp - 2) * 2;
+    constexpr uint32_t kMyResBytes = kMySlabs * 32u * C::kSlabRowBytes;
     int iter = 0;
-    int bias_nt = -1;  // N tile whose bias currently sits in s_bias
+    int bias_nt = -1;  // N tile whose bias currently sits in s_bias_w
+    const bool silu = p.act == Y3_ACT_SILU;
+    const float bscale = silu ? 0.5f : 1.0f;
     for (int tile = worker; tile < total_tiles; tile += n_workers, ++iter) {
       const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
       const int nt = tile % p.n_tiles;
@@ -327,9 +387,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (p.mode == 0) {
         const int row = mt * kBlockM + m;
         const int plane = p.hp * p.wp;
-        img = row / plane;
+        img = static_cast<int>(fast_div(static_cast<uint32_t>(row), p.plane_mul, p.plane_shr));
         const int rem = row - img * plane;
-        const int yp = rem / p.wp, xp = rem - yp * p.wp;
+        const int yp = static_cast<int>(fast_div(static_cast<uint32_t>(rem), p.wp_mul, p.wp_shr)), xp = rem - yp * p.wp;
         valid = row < p.rows_total && yp >= 1 && yp <= p.hp - 2 && xp >= 1 && xp <= p.wp - 2;
         oy = yp - 1;
         ox = xp - 1;
@@ -343,56 +403,62 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         valid = ty < p.th && oy < p.ho && ox < p.wo;
       }
       valid = valid && active && mt < p.m_tiles;  // a pair's second CTA may own a tile past the end
+      if (nt != bias_nt) {  // a layer with a single N tile loads its bias once
+        if (active)
+          for (int c = lane; c < kColsPerWarp; c += 32) s_bias_w[c] = bscale * __ldg(p.bias + n0 + c_begin + c);
+        bias_nt = nt;
+        __syncwarp();
+      }
       if constexpr (STAGED) {
         // ---------------- staged epilogue (flat mode, bf16 output): TMEM -> registers -> swizzled smem tile -> TMA store
-        const bool elected = threadIdx.x == 64;  // first epilogue thread
-        const int row0 = mt * kBlockM;
+        const int row0 = mt * kBlockM + quarter * 32;  // first tile row of this warp
         constexpr bool kTwo = C::kStgBufs == 2;
         const uint32_t sb = kTwo ? uint32_t(iter & 1) : 0u;            // staging buffer of this tile
         const uint32_t rphase = kTwo ? uint32_t(iter >> 1) & 1u : uint32_t(iter) & 1u;
-        uint8_t* stg = smem_stg + sb * C::kStgTile;
-        if (elected) {
+        // this warp's 32 rows of its first slab, in buffer sb
+        const uint32_t reg_off = slab0 * C::kSlabBytes + uint32_t(quarter) * 32u * C::kSlabRowBytes;
+        uint8_t* reg = smem_stg + sb * C::kStgTile + reg_off;
+        if (issuer) {
           if (kTwo) {
-            // residual prefetch distance 1: tile i+1's residual goes into the OTHER buffer, which the store of tile i-1
-            // must have finished reading; without a residual only the store of tile i-2 (this buffer) has to be done
+            // residual prefetch distance 1: tile i+1's residual goes into the OTHER buffer, which this thread's store of
+            // tile i-1 must have finished reading; without a residual only its store of tile i-2 (this buffer)
             if (p.res) bulk_wait_read_all(); else bulk_wait_read_1();
             if (p.res) {
               if (iter == 0) {
-                mbar_expect_tx(&res_bar[0], C::kStgTile);
+                mbar_expect_tx(&my_res_bar[0], kMyResBytes);
 #pragma unroll
-                for (uint32_t sl = 0; sl < C::kSlabs; ++sl)
-                  tma_load_2d(stg + sl * C::kSlabBytes, &map_res, &res_bar[0], p.res_coff + n0 + sl * C::kSlabCols, row0);
+                for (uint32_t sl = 0; sl < kMySlabs; ++sl)
+                  tma_load_2d(reg + sl * C::kSlabBytes, &map_res, &my_res_bar[0],
+                              p.res_coff + n0 + (slab0 + sl) * C::kSlabCols, row0);
               }
               const int tnext = tile + n_workers;
               if (tnext < total_tiles) {
                 const int nt2 = tnext % p.n_tiles;
                 const int mt2 = PAIR ? (tnext / p.n_tiles) * 2 + static_cast<int>(rank) : tnext / p.n_tiles;
-                uint8_t* stg2 = smem_stg + (sb ^ 1u) * C::kStgTile;
-                mbar_expect_tx(&res_bar[sb ^ 1u], C::kStgTile);
+                uint8_t* reg2 = smem_stg + (sb ^ 1u) * C::kStgTile + reg_off;
+                mbar_expect_tx(&my_res_bar[sb ^ 1u], kMyResBytes);
 #pragma unroll
-                for (uint32_t sl = 0; sl < C::kSlabs; ++sl)
-                  tma_load_2d(stg2 + sl * C::kSlabBytes, &map_res, &res_bar[sb ^ 1u],
-                              p.res_coff + nt2 * BLOCK_N + sl * C::kSlabCols, mt2 * kBlockM);
+                for (uint32_t sl = 0; sl < kMySlabs; ++sl)
+                  tma_load_2d(reg2 + sl * C::kSlabBytes, &map_res, &my_res_bar[sb ^ 1u],
+                              p.res_coff + nt2 * BLOCK_N + (slab0 + sl) * C::kSlabCols, mt2 * kBlockM + quarter * 32);
               }
             }
           } else {
-            bulk_wait_read_all();  // the previous tile's store has finished reading the staging buffer
+            bulk_wait_read_all();  // the previous tile's store has finished reading this warp's staging rows
             if (p.res) {
-              mbar_expect_tx(&res_bar[0], C::kStgTile);
+              mbar_expect_tx(&my_res_bar[0], kMyResBytes);
 #pragma unroll
-              for (uint32_t sl = 0; sl < C::kSlabs; ++sl)
-                tma_load_2d(stg + sl * C::kSlabBytes, &map_res, &res_bar[0], p.res_coff + n0 + sl * C::kSlabCols, row0);
+              for (uint32_t sl = 0; sl < kMySlabs; ++sl)
+                tma_load_2d(reg + sl * C::kSlabBytes, &map_res, &my_res_bar[0], p.res_coff + n0 + (slab0 + sl) * C::kSlabCols,
+                            row0);
             }
           }
         }
-        // (the end-of-tile barrier 2 of the previous tile guarantees nobody still reads the old bias values); a layer
-        // with a single N tile loads its bias once — the L2 round trip per tile was exposed on the thin layers
-        if (nt != bias_nt && int(threadIdx.x) - 64 < BLOCK_N) s_bias[threadIdx.x - 64] = __ldg(p.bias + n0 + threadIdx.x - 64);
-        bias_nt = nt;
+        // the staging rows are free (the issuer has waited for the store that last read them)
+        if (kPairSync) named_bar_sync(1 + quarter, 64); else __syncwarp();
         mbar_wait(&tfull_bar[as], aphase, p.err, 4);
         tc_fence_after();
-        named_bar_sync(1, kEpiThreads);  // bias tile visible; staging buffer is free for everybody
-        if (p.res) mbar_wait(&res_bar[sb], rphase, p.err, 5);  // residual tile landed
+        if (p.res && active) mbar_wait(&my_res_bar[sb], rphase, p.err, 5);  // residual rows landed (idle warps own none)
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
         const uint32_t swz = C::kSlabRowBytes == 128 ? (m & 7) : ((m >> 1) & 3);
         if (active) {
@@ -402,20 +468,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tmem_ld_32x32b_x32(t_addr + c, v);
             tmem_ld_wait();
             float x[32];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(s_bias + c + j);
-              x[j + 0] = __uint_as_float(v[j + 0]) + b.x;
-              x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
-              x[j + 2] = __uint_as_float(v[j + 2]) + b.z;
-              x[j + 3] = __uint_as_float(v[j + 3]) + b.w;
-            }
-            if (p.act == Y3_ACT_SILU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = silu_fast(x[j]);
-            }
+            bias_act(v, s_bias_w + (c - c_begin), x, silu);
             const uint32_t slab = c / C::kSlabCols, j0 = (c % C::kSlabCols) / 8;
-            const uint32_t row_addr = smem_u32(stg) + slab * C::kSlabBytes + m * C::kSlabRowBytes;
+            const uint32_t row_addr = smem_u32(smem_stg) + sb * C::kStgTile + slab * C::kSlabBytes + m * C::kSlabRowBytes;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint32_t addr = row_addr + (((j0 + q) ^ swz) << 4);
@@ -446,11 +501,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_arrive_cluster(lead_tempty[as]);
         else
           mbar_arrive(&tempty_bar[as]);
-        named_bar_sync(2, kEpiThreads);
-        if (elected) {
+        if (kPairSync) named_bar_sync(1 + quarter, 64); else __syncwarp();
+        if (issuer) {
 #pragma unroll
-          for (uint32_t sl = 0; sl < C::kSlabs; ++sl)
-            tma_store_2d(&map_out, stg + sl * C::kSlabBytes, p.out_coff + n0 + sl * C::kSlabCols, row0);
+          for (uint32_t sl = 0; sl < kMySlabs; ++sl)
+            tma_store_2d(&map_out, reg + sl * C::kSlabBytes, p.out_coff + n0 + (slab0 + sl) * C::kSlabCols, row0);
           bulk_commit_group();
         }
         continue;
@@ -479,11 +534,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int q = 0; q < 4; ++q) rcur[q] = __ldg(reinterpret_cast<const uint4*>(res_ptr + c_begin) + q);
       }
 
-      if (nt != bias_nt && int(threadIdx.x) - 64 < BLOCK_N) s_bias[threadIdx.x - 64] = __ldg(p.bias + n0 + threadIdx.x - 64);
-      bias_nt = nt;
       mbar_wait(&tfull_bar[as], aphase, p.err, 4);  // accumulator complete
       tc_fence_after();
-      named_bar_sync(1, kEpiThreads);  // bias tile visible
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
       if (active) {
 #pragma unroll 1
@@ -499,18 +551,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tmem_ld_wait();
           if (valid && (f32_ptr || n0 + c < p.cout)) {
             float x[32];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b = *reinterpret_cast<const float4*>(s_bias + c + j);
-              x[j + 0] = __uint_as_float(v[j + 0]) + b.x;
-              x[j + 1] = __uint_as_float(v[j + 1]) + b.y;
-              x[j + 2] = __uint_as_float(v[j + 2]) + b.z;
-              x[j + 3] = __uint_as_float(v[j + 3]) + b.w;
-            }
-            if (p.act == Y3_ACT_SILU) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = silu_fast(x[j]);
-            }
+            bias_act(v, s_bias_w + (c - c_begin), x, silu);
             if (f32_ptr) {
               // fp32 pixel-major store (Detect heads): 128 contiguous bytes per thread and chunk
 #pragma unroll
@@ -556,11 +597,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_arrive_cluster(lead_tempty[as]);  // the leader's MMA thread waits for BOTH CTAs' epilogues
       else
         mbar_arrive(&tempty_bar[as]);
-      named_bar_sync(2, kEpiThreads);  // everybody is done with this tile's bias values
     }
+    if (issuer) bulk_wait_all();  // this thread's last TMA store has completed
   }
 
-  if (STAGED && threadIdx.x == 64) bulk_wait_all();  // the last tile's TMA store has completed
   __syncwarp();
   tc_fence_before();
   if (PAIR) cluster_sync_all(); else __syncthreads();  // pair: nobody leaves while the peer may still signal its barriers
@@ -701,6 +741,20 @@ static bool pair_enabled() {
 
 // Layer 1 of yolov3 (32 -> 64, stride 2 at 640x640) moved 64-byte rows through 9 five-dimensional TMA boxes per tile
 // and ran at 0.2 PFLOP/s; paired, the same tile is 6 boxes of full 128-byte rows and one K = 64 MMA group per box.
+// (mul, shr) such that n / d == (t + ((n - t) >> 1)) >> (shr - 1), t = umulhi(n, mul), for every 32-bit n (d >= 2);
+// d == 1: mul = 0, shr = 0 (identity).  Granlund-Montgomery round-up method.
+static void fast_div_for(uint32_t d, uint32_t* mul, uint32_t* shr) {
+  if (d <= 1) {
+    *mul = 0;
+    *shr = 0;
+    return;
+  }
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  *mul = static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  *shr = l;
+}
+
 static bool conv_prefers_xpair(const y3_conv_desc& d) {
   return d.ksize == 3 && d.stride == 2 && (d.c_in == 32 || d.c_in == 16) && d.in_ld == d.c_in && d.in_coff == 0;
 }
@@ -776,6 +830,8 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     a.mode = 0;
     a.hp = hp;
     a.wp = wp;
+    fast_div_for(static_cast<uint32_t>(hp) * wp, &a.plane_mul, &a.plane_shr);
+    fast_div_for(static_cast<uint32_t>(wp), &a.wp_mul, &a.wp_shr);
     const long long rows = static_cast<long long>(d.n) * hp * wp;
     Y3_REQUIRE(rows < (1ll << 31) - 4096, "conv: too many pixels");
     a.rows_total = static_cast<int>(rows);
@@ -850,7 +906,7 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     // dim0 ends at the last channel this conv owns, so a partial last N tile is clipped by the TMA unit
     const uint64_t dims[2] = {static_cast<uint64_t>(d.out_coff + d.c_out), static_cast<uint64_t>(a.rows_total)};
     const uint64_t strides[2] = {0, static_cast<uint64_t>(d.out_ld) * 2};
-    const uint32_t box[2] = {slab_cols, kBlockM};
+    const uint32_t box[2] = {slab_cols, 32};  // one epilogue warp's rows
     rc = encode_tensor_map_bf16(&plan->map_out, d.out, 2, dims, strides, box, slab_cols * 2);
     if (rc) return rc;
     if (d.res) {

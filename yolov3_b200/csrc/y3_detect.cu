@@ -73,10 +73,13 @@ constexpr int kDecodeRows = 4;  // consecutive z rows per warp iteration (they a
 // requirement applies to NMS on a given z, not to z itself); the IEEE expf/division sequence cost ~1/3 of this kernel.
 __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
-// NITER = ceil(kDecodeRows * no / 128) unrolled iterations of 4 x 32 elements.  The split of a group-local element index
-// e into (row q, field k) depends only on e, so every lane computes its NITER*4 pairs ONCE; per group only the four
-// row descriptors change (two 32-bit words each, broadcast by shuffle).  The first version redid the division and moved
-// seven shuffle words per element: ~60 instructions per 4-byte output, i.e. issue-bound at 1.8 TB/s.
+// NITER = ceil(kDecodeRows * no / 128) unrolled iterations of 4 x 32 elements per warp and group of 4 z rows.
+// Fast path (the 4 rows share image, level and anchor — always, when ny*nx is a multiple of 4): the rows are consecutive
+// cells, so the source of group-local element e = q*no + k is base + q*head_ld + k and its destination is z_base + e:
+// both offsets are per-lane constants computed once before the loop; per element the kernel then does one load, one
+// sigmoid, one store, and only the 4 box fields of each row take the grid/anchor branch.  The first version recomputed the
+// (q, k) split and moved seven shuffle words per element: 96 warp instructions per 32 outputs, issue-bound at 1.9 TB/s
+// (profiles/r01_ncu_decode_summary.txt).
 template <int NITER>
 __global__ void __launch_bounds__(256, NITER <= 3 ? 3 : 1) head_decode_kernel(const HeadDecodeArgs p) {
   const int lane = threadIdx.x & 31;
@@ -86,17 +89,67 @@ __global__ void __launch_bounds__(256, NITER <= 3 ? 3 : 1) head_decode_kernel(co
   const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int no = p.no;
+  const int full_el = kDecodeRows * no;
   uint32_t qk[NITER * 4];  // (q << 16) | k of this lane's elements
+  int rel[NITER * 4];      // q * head_ld + k (all levels share head_ld on the fast path)
 #pragma unroll
   for (int t = 0; t < NITER * 4; ++t) {
     const int e = (t >> 2) * 128 + (t & 3) * 32 + lane;
     const int q = e / no;
     qk[t] = (static_cast<uint32_t>(q) << 16) | static_cast<uint32_t>(e - q * no);
+    rel[t] = q * p.head_ld[0] + (e - q * no);
   }
+  bool same_ld = true;
+  for (int l = 1; l < p.nl; ++l) same_ld = same_ld && p.head_ld[l] == p.head_ld[0];
   for (int gidx = warp0; gidx < groups; gidx += nwarps) {
-    // row descriptors, computed by lanes 0..3: element offset inside the level's head buffer (< 2^31, checked by the
-    // launcher) and x | y << 13 | a << 26 | l << 29
-    const int w = gidx * kDecodeRows + (lane & 3);
+    // descriptor of the group's first row (warp-uniform integer work, no shuffles)
+    const int w0 = gidx * kDecodeRows;
+    const int b0 = w0 / rows_per_img;
+    const int row0 = w0 - b0 * rows_per_img;
+    int l0 = 0;
+    while (l0 + 1 < p.nl && row0 >= p.row_off[l0 + 1]) ++l0;
+    const int r0 = row0 - p.row_off[l0];
+    const int nx0 = p.nx[l0], plane0 = p.ny[l0] * nx0;
+    const int a0 = r0 / plane0, cell0 = r0 - a0 * plane0;
+    const long long z_base = static_cast<long long>(gidx) * full_el;  // rows of a group are contiguous in z
+    if (same_ld && w0 + kDecodeRows <= total && cell0 + kDecodeRows <= plane0 && row0 + kDecodeRows <= rows_per_img &&
+        !p.raw[l0] && p.z) {
+      const float* src = p.head[l0] + (static_cast<long long>(b0) * plane0 + cell0) * p.head_ld[l0] + a0 * no;
+      float* dst = p.z + z_base;
+      const float stride = p.stride[l0], aw = p.anchor_w[l0][a0], ah = p.anchor_h[l0][a0];
+      const int y0 = cell0 / nx0, x0 = cell0 - y0 * nx0;
+      float v[NITER * 4];
+#pragma unroll
+      for (int t = 0; t < NITER * 4; ++t) {
+        const int e = (t >> 2) * 128 + (t & 3) * 32 + lane;
+        v[t] = (e < full_el) ? __ldg(src + rel[t]) : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < NITER * 4; ++t) {
+        const int e = (t >> 2) * 128 + (t & 3) * 32 + lane;
+        if (e >= full_el) continue;
+        const int k = qk[t] & 0xFFFF;
+        const float s = sigmoid_fast(v[t]);
+        float o = s;
+        if (k < 4) {
+          const float t2 = s * 2.0f;
+          if (k < 2) {
+            int x = x0 + static_cast<int>(qk[t] >> 16), y = y0;
+            if (x >= nx0) {  // the four cells wrap onto the next grid row
+              x -= nx0;
+              ++y;
+            }
+            o = (t2 + (static_cast<float>(k == 0 ? x : y) - 0.5f)) * stride;
+          } else {
+            o = (t2 * t2) * (k == 2 ? aw : ah);
+          }
+        }
+        dst[e] = o;
+      }
+      continue;
+    }
+    // ---- general path: rows of different levels / anchors / images in one group, the tail group, raw_out requested
+    const int w = w0 + (lane & 3);
     uint32_t d_off = 0, d_pos = 0;
     if (lane < kDecodeRows && w < total) {
       const int b = w / rows_per_img;
@@ -111,32 +164,21 @@ __global__ void __launch_bounds__(256, NITER <= 3 ? 3 : 1) head_decode_kernel(co
       d_pos = static_cast<uint32_t>(x) | (static_cast<uint32_t>(y) << 13) | (static_cast<uint32_t>(a) << 26) |
               (static_cast<uint32_t>(l) << 29);
     }
-    const long long z_base = static_cast<long long>(gidx) * kDecodeRows * no;  // rows of a group are contiguous in z
-    const int n_el = min(kDecodeRows, total - gidx * kDecodeRows) * no;
-    float v[NITER * 4];
-    uint32_t pos[NITER * 4];
-    // all loads of the group first (NITER*4 independent 128-byte warp requests in flight), then the arithmetic
-#pragma unroll
+    const int n_el = min(kDecodeRows, total - w0) * no;
+#pragma unroll 1
     for (int t = 0; t < NITER * 4; ++t) {
       const int e = (t >> 2) * 128 + (t & 3) * 32 + lane;
-      const int q = qk[t] >> 16, k = qk[t] & 0xFFFF;
+      const int q = e / no, k = e - q * no;
       const uint32_t so = __shfl_sync(0xffffffffu, d_off, q & 3);
-      pos[t] = __shfl_sync(0xffffffffu, d_pos, q & 3);
-      v[t] = (e < n_el) ? __ldg(p.head[pos[t] >> 29] + so + k) : 0.f;
-    }
-#pragma unroll
-    for (int t = 0; t < NITER * 4; ++t) {
-      const int e = (t >> 2) * 128 + (t & 3) * 32 + lane;
+      const uint32_t pos = __shfl_sync(0xffffffffu, d_pos, q & 3);
       if (e >= n_el) continue;
-      const int k = qk[t] & 0xFFFF;
-      const int l = pos[t] >> 29, a = (pos[t] >> 26) & 7;
-      const float x = v[t];
+      const int l = pos >> 29, a = (pos >> 26) & 7;
+      const float x = __ldg(p.head[l] + so + k);
       if (p.raw[l]) {
         // reference-layout logits [bs, na, ny, nx, no]: row (b*na + a)*plane + cell
-        const int wrow = gidx * kDecodeRows + (qk[t] >> 16);
-        const int b = wrow / rows_per_img;
+        const int b = (w0 + q) / rows_per_img;
         const int plane = p.ny[l] * p.nx[l];
-        const int cell = ((pos[t] >> 13) & 0x1FFF) * p.nx[l] + (pos[t] & 0x1FFF);
+        const int cell = ((pos >> 13) & 0x1FFF) * p.nx[l] + (pos & 0x1FFF);
         p.raw[l][((static_cast<long long>(b) * p.na + a) * plane + cell) * no + k] = x;
       }
       if (p.z) {
@@ -145,7 +187,7 @@ __global__ void __launch_bounds__(256, NITER <= 3 ? 3 : 1) head_decode_kernel(co
         if (k < 4) {
           const float t2 = s * 2.0f;
           if (k < 2)
-            o = (t2 + (static_cast<float>(k == 0 ? (pos[t] & 0x1FFF) : ((pos[t] >> 13) & 0x1FFF)) - 0.5f)) * p.stride[l];
+            o = (t2 + (static_cast<float>(k == 0 ? (pos & 0x1FFF) : ((pos >> 13) & 0x1FFF)) - 0.5f)) * p.stride[l];
           else
             o = (t2 * t2) * (k == 2 ? p.anchor_w[l][a] : p.anchor_h[l][a]);
         }

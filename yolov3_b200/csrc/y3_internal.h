@@ -45,6 +45,7 @@ struct ConvTcArgs {
   int m_tiles, n_tiles;
   // flat geometry (input and conv-output share it)
   int hp, wp, rows_total;
+  uint32_t plane_mul, plane_shr, wp_mul, wp_shr;  // exact division by hp*wp and wp (fast_div)
   // patch geometry
   int tw, th, tiles_w, tiles_h, ho, wo;
   // epilogue
