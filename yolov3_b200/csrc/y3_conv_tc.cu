@@ -55,8 +55,12 @@ struct Cfg {
   // two staging tiles for N <= 128: the residual of tile i+1 is TMA-loaded while tile i is converted and stored, so the
   // epilogue of the thin layers no longer exposes one L2/HBM round trip per tile (their k-loop is only ~600 clk long)
   static constexpr uint32_t kStgTile = kBlockM * BLOCK_N * 2;
-  static constexpr uint32_t kStgBufs = BLOCK_N <= 128 ? 2 : 1;
-  static constexpr uint32_t kStagingBytes = STAGED ? kStgBufs * kStgTile : 0;
+  static constexpr uint32_t kStgBufs = BLOCK_N <= 128 ? 2 : 1;  // per epilogue group
+  // Thin tiles (N <= 64) can run TWO epilogue groups of 8 warps, group g converting the tiles of TMEM buffer g: their
+  // epilogue is issue-latency-bound (IPC ~1.5 with 2 warps per scheduler), more resident warps fill the issue slots.
+  static constexpr int kMaxGroups = BLOCK_N <= 64 ? 2 : 1;
+  static constexpr int kMaxThreads = 64 + 32 * kEpilogueWarps * kMaxGroups;
+  static constexpr uint32_t kStagingBytes = STAGED ? kMaxGroups * kStgBufs * kStgTile : 0;
   static constexpr int kMaxStages = 8;
   static constexpr int kStagesRaw = (kSmemBudget - kStagingBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > kMaxStages ? kMaxStages : kStagesRaw;
@@ -72,7 +76,7 @@ struct Cfg {
   static constexpr uint32_t kSbo = 8 * kSwizzleBytes;
   static constexpr uint32_t kColsPerWarp = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;  // columns one epilogue warp converts
   static constexpr uint32_t kBarBytes = 512;                                       // mbarriers + TMEM slot
-  static constexpr uint32_t kBiasBytes = kEpilogueWarps * kColsPerWarp * 4;        // one private bias slice per warp
+  static constexpr uint32_t kBiasBytes = kMaxGroups * kEpilogueWarps * kColsPerWarp * 4;  // one private bias slice per warp
   static constexpr size_t kSmemBytes = size_t(kSmemBudget) + 1024 /*align*/ + kBarBytes + kBiasBytes;
   static_assert(kStages >= 2, "pipeline needs at least two stages");
   static_assert(!HALO || BLOCK_K >= 32, "halo reuse: rows of 64 or 128 bytes");
@@ -113,7 +117,7 @@ __device__ __forceinline__ uint32_t fast_div(uint32_t n, uint32_t mul, uint32_t 
 // k-block — the 1-CTA kernel measured ~0.67 of the MMA rate on the big 3x3 layers because (128+256)*64*2 B per 512 MMA
 // cycles exceeds the ~64 B/clk an SM can pull from L2 (profiles/r01_per_op_v2_epilogue.json).
 template <int BLOCK_N, int BLOCK_K, bool PAIR, bool STAGED, bool HALO>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__((Cfg<BLOCK_N, BLOCK_K, PAIR, STAGED, HALO>::kMaxThreads), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_res,
                const ConvTcArgs p) {
@@ -135,8 +139,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* empty_bar = full_bar + C::kMaxStages;
   uint64_t* tfull_bar = empty_bar + C::kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* res_bar = tempty_bar + 2;  // [8 row-group owners][2 staging buffers]
-  uint64_t* bres_bar = res_bar + 16;
+  uint64_t* res_bar = tempty_bar + 2;  // [16 epilogue warps / row-group owners][2 staging buffers]
+  uint64_t* bres_bar = res_bar + 32;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
   // bias of the current N tile.  Read through __ldg it missed the (almost entirely shared-memory) L1 and exposed an L2
   // round trip per 32-column chunk: 29 % of all warp stall samples of the epilogue (profiles/r01_ncu_conv_tc_full_summary.txt).
@@ -160,7 +164,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], PAIR ? 2 * kEpiThreads : kEpiThreads);  // pair: both CTAs' epilogues release the buffer
     }
-    for (int i = 0; i < 16; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < 32; ++i) mbar_init(&res_bar[i], 1);
     mbar_init(bres_bar, PAIR ? 2 : 1);
     if (STAGED) {
       tma_prefetch_desc(&map_out);
@@ -354,13 +358,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // (other TMEM buffer) while slower ones finish.  The first version walked all 8 warps through every tile in lock-step
     // (two 256-thread named barriers, one elected TMA thread) and the thin layers were bound by that serial chain:
     // the MMA warp waited on tmem_empty for 430 k polls per launch (profiles/r01_ncu_issue_loop.txt).
+    const int groups = (static_cast<int>(blockDim.x) - 64) >> 8;  // 1, or 2 for thin tiles (launch_cfg)
+    const int ew = warp - 2;                  // epilogue warp index
+    const int group = ew >> 3;                // group g converts the tiles whose accumulator is TMEM buffer g
     const int quarter = warp & 3;             // a warp may only touch TMEM lanes [32*(warp%4), +32)
-    const int half = (warp - 2) >> 2;         // which half of the tile's columns this warp converts
+    const int half = (ew & 7) >> 2;           // which half of the tile's columns this warp converts
     constexpr int kColsPerWarp = C::kColsPerWarp;
     const int c_begin = BLOCK_N >= 64 ? half * kColsPerWarp : 0;
     const bool active = BLOCK_N >= 64 || half == 0;
     const int m = quarter * 32 + lane;
-    float* s_bias_w = s_bias + (warp - 2) * kColsPerWarp;
+    float* s_bias_w = s_bias + ew * kColsPerWarp;
     const uint32_t lead_tempty[2] = {PAIR ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u,
                                      PAIR ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u};
     // STAGED: N = 64 has ONE 64-column slab, shared by the two warps of a lane quarter (pair barrier 1 + quarter, 64
@@ -369,14 +376,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     constexpr uint32_t kMySlabs = kPairSync ? 1u : (C::kColsPerWarp + C::kSlabCols - 1) / C::kSlabCols;
     const uint32_t slab0 = kPairSync ? 0u : uint32_t(c_begin) / C::kSlabCols;
     const bool issuer = STAGED && active && lane == 0 && (!kPairSync || half == 0);
-    uint64_t* my_res_bar = res_bar + (kPairSync ? quarter : warp - 2) * 2;
+    uint64_t* my_res_bar = res_bar + (kPairSync ? group * 4 + quarter : ew) * 2;
+    const int pair_bar = 1 + quarter + 4 * group;  // named barrier of the two warps sharing a lane quarter (N = 64)
     constexpr uint32_t kMyResBytes = kMySlabs * 32u * C::kSlabRowBytes;
     int iter = 0;
     int bias_nt = -1;  // N tile whose bias currently sits in s_bias_w
     const bool silu = p.act == Y3_ACT_SILU;
     const float bscale = silu ? 0.5f : 1.0f;
     for (int tile = worker; tile < total_tiles; tile += n_workers, ++iter) {
+      if (groups == 2 && (iter & 1) != group) continue;
       const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+      const int li = groups == 2 ? iter >> 1 : iter;  // tiles this group has converted so far
       const int nt = tile % p.n_tiles;
       const int mt = PAIR ? (tile / p.n_tiles) * 2 + static_cast<int>(rank) : tile / p.n_tiles;
       const int n0 = nt * BLOCK_N;
@@ -413,29 +423,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         // ---------------- staged epilogue (flat mode, bf16 output): TMEM -> registers -> swizzled smem tile -> TMA store
         const int row0 = mt * kBlockM + quarter * 32;  // first tile row of this warp
         constexpr bool kTwo = C::kStgBufs == 2;
-        const uint32_t sb = kTwo ? uint32_t(iter & 1) : 0u;            // staging buffer of this tile
-        const uint32_t rphase = kTwo ? uint32_t(iter >> 1) & 1u : uint32_t(iter) & 1u;
+        const uint32_t sb = kTwo ? uint32_t(li & 1) : 0u;              // this group's staging buffer for this tile
+        const uint32_t rphase = kTwo ? uint32_t(li >> 1) & 1u : uint32_t(li) & 1u;
+        uint8_t* stg_g = smem_stg + uint32_t(group) * C::kStgBufs * C::kStgTile;  // this group's buffers
         // this warp's 32 rows of its first slab, in buffer sb
         const uint32_t reg_off = slab0 * C::kSlabBytes + uint32_t(quarter) * 32u * C::kSlabRowBytes;
-        uint8_t* reg = smem_stg + sb * C::kStgTile + reg_off;
+        uint8_t* reg = stg_g + sb * C::kStgTile + reg_off;
         if (issuer) {
           if (kTwo) {
             // residual prefetch distance 1: tile i+1's residual goes into the OTHER buffer, which this thread's store of
             // tile i-1 must have finished reading; without a residual only its store of tile i-2 (this buffer)
             if (p.res) bulk_wait_read_all(); else bulk_wait_read_1();
             if (p.res) {
-              if (iter == 0) {
+              if (li == 0) {
                 mbar_expect_tx(&my_res_bar[0], kMyResBytes);
 #pragma unroll
                 for (uint32_t sl = 0; sl < kMySlabs; ++sl)
                   tma_load_2d(reg + sl * C::kSlabBytes, &map_res, &my_res_bar[0],
                               p.res_coff + n0 + (slab0 + sl) * C::kSlabCols, row0);
               }
-              const int tnext = tile + n_workers;
+              const int tnext = tile + groups * n_workers;  // this group's next tile
               if (tnext < total_tiles) {
                 const int nt2 = tnext % p.n_tiles;
                 const int mt2 = PAIR ? (tnext / p.n_tiles) * 2 + static_cast<int>(rank) : tnext / p.n_tiles;
-                uint8_t* reg2 = smem_stg + (sb ^ 1u) * C::kStgTile + reg_off;
+                uint8_t* reg2 = stg_g + (sb ^ 1u) * C::kStgTile + reg_off;
                 mbar_expect_tx(&my_res_bar[sb ^ 1u], kMyResBytes);
 #pragma unroll
                 for (uint32_t sl = 0; sl < kMySlabs; ++sl)
@@ -455,7 +466,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
         // the staging rows are free (the issuer has waited for the store that last read them)
-        if (kPairSync) named_bar_sync(1 + quarter, 64); else __syncwarp();
+        if (kPairSync) named_bar_sync(pair_bar, 64); else __syncwarp();
         mbar_wait(&tfull_bar[as], aphase, p.err, 4);
         tc_fence_after();
         if (p.res && active) mbar_wait(&my_res_bar[sb], rphase, p.err, 5);  // residual rows landed (idle warps own none)
@@ -470,7 +481,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float x[32];
             bias_act(v, s_bias_w + (c - c_begin), x, silu);
             const uint32_t slab = c / C::kSlabCols, j0 = (c % C::kSlabCols) / 8;
-            const uint32_t row_addr = smem_u32(smem_stg) + sb * C::kStgTile + slab * C::kSlabBytes + m * C::kSlabRowBytes;
+            const uint32_t row_addr = smem_u32(stg_g) + sb * C::kStgTile + slab * C::kSlabBytes + m * C::kSlabRowBytes;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const uint32_t addr = row_addr + (((j0 + q) ^ swz) << 4);
@@ -501,7 +512,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_arrive_cluster(lead_tempty[as]);
         else
           mbar_arrive(&tempty_bar[as]);
-        if (kPairSync) named_bar_sync(1 + quarter, 64); else __syncwarp();
+        if (kPairSync) named_bar_sync(pair_bar, 64); else __syncwarp();
         if (issuer) {
 #pragma unroll
           for (uint32_t sl = 0; sl < kMySlabs; ++sl)
@@ -621,7 +632,8 @@ int launch_cfg(const ConvTcPlan& plan, cudaStream_t stream) {
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(plan.grid);
-  cfg.blockDim = dim3(kThreads);
+  const int groups = plan.groups == 2 && C::kMaxGroups == 2 ? 2 : 1;
+  cfg.blockDim = dim3(64 + 32 * kEpilogueWarps * groups);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -726,6 +738,16 @@ static bool bres_enabled() {
   if (v < 0) {
     const char* e = getenv("Y3_CONV_BRES");
     v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+// Y3_CONV_GROUPS=1 keeps a single epilogue group for the thin tiles (A/B measurements).
+static bool groups_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("Y3_CONV_GROUPS");
+    v = (e && e[0] == '1') ? 0 : 1;
   }
   return v != 0;
 }
@@ -925,6 +947,7 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     const long long total = static_cast<long long>(a.m_tiles) * a.n_tiles;
     plan->grid = static_cast<int>(total < sms ? total : sms);
   }
+  plan->groups = (bn <= 64 && groups_enabled()) ? 2 : 1;
   plan->smem_bytes = 0;
   return Y3_OK;
 }

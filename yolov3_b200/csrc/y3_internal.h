@@ -65,6 +65,7 @@ struct ConvTcPlan {
   int staged;  // 1: epilogue stages the tile in shared memory and stores it with TMA
   int halo;    // 1: stride-1 3x3 with one A box per filter row (halo reuse)
   int bres;    // 1: weights resident in shared memory (single N tile, small K)
+  int groups;  // epilogue groups of 8 warps (2 for tile N <= 64)
   ConvTcArgs args;
   int block_n, block_k;
   int pair;  // 1: CTA-pair (cta_group::2) kernel, launched as clusters of 2
