@@ -24,6 +24,7 @@ ap.add_argument("--bs", type=int, default=8)
 ap.add_argument("--img", type=int, default=640)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--no-graphs", action="store_true", help="eager launches (ncu launch lists)")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -31,6 +32,10 @@ dev = torch.device("cuda", local)
 if world > 1:
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=dev)
+if a.no_graphs:
+    from yolov3_b200.train import TrainEngine
+
+    TrainEngine.use_graphs = False
 torch.manual_seed(0)
 m = Model("yolov3.yaml", device=dev)
 m.hyp = O.scaled_hyp()

@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "y3_common.cuh"
 #include "y3_internal.h"
@@ -52,13 +53,14 @@ struct Cfg {
   static constexpr uint32_t kSlabRowBytes = kSlabCols * 2;                // 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
   static constexpr uint32_t kSlabBytes = kBlockM * kSlabRowBytes;
   static constexpr uint32_t kSlabs = BLOCK_N / kSlabCols;
-  // two staging tiles for N <= 128: the residual of tile i+1 is TMA-loaded while tile i is converted and stored, so the
-  // epilogue of the thin layers no longer exposes one L2/HBM round trip per tile (their k-loop is only ~600 clk long)
+  // two staging tiles per group for N <= 64: the residual of tile i+1 is TMA-loaded while tile i is converted and stored,
+  // so the epilogue of the thin layers does not expose one L2/HBM round trip per tile (their k-loop is ~600 clk long);
+  // N = 128 has one buffer per group (shared-memory budget) and relies on the other group to cover that latency
   static constexpr uint32_t kStgTile = kBlockM * BLOCK_N * 2;
-  static constexpr uint32_t kStgBufs = BLOCK_N <= 128 ? 2 : 1;  // per epilogue group
+  static constexpr uint32_t kStgBufs = BLOCK_N <= 64 ? 2 : 1;   // per epilogue group (two: residual prefetch one tile ahead)
   // Thin tiles (N <= 64) can run TWO epilogue groups of 8 warps, group g converting the tiles of TMEM buffer g: their
   // epilogue is issue-latency-bound (IPC ~1.5 with 2 warps per scheduler), more resident warps fill the issue slots.
-  static constexpr int kMaxGroups = BLOCK_N <= 64 ? 2 : 1;
+  static constexpr int kMaxGroups = BLOCK_N <= 128 ? 2 : 1;  // N = 256 kernels need > 112 registers per thread
   static constexpr int kMaxThreads = 64 + 32 * kEpilogueWarps * kMaxGroups;
   static constexpr uint32_t kStagingBytes = STAGED ? kMaxGroups * kStgBufs * kStgTile : 0;
   static constexpr int kMaxStages = 8;
@@ -220,83 +222,95 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
-      for (int tile = worker; tile < total_tiles; tile += n_workers) {
-        const int nt = tile % p.n_tiles;
-        const int mt = PAIR ? (tile / p.n_tiles) * 2 + static_cast<int>(rank) : tile / p.n_tiles;
-        const int n0 = nt * BLOCK_N + static_cast<int>(rank) * C::kBRows;  // this CTA's slice of the weight tile
-        int row0 = 0, img = 0, oh0 = 0, ow0 = 0;
-        if (p.mode == 0) {
-          row0 = mt * kBlockM;
-        } else {
-          const int per_img = p.tiles_w * p.tiles_h;
-          img = mt / per_img;
-          const int t = mt - img * per_img;
-          oh0 = (t / p.tiles_w) * p.th;
-          ow0 = (t % p.tiles_w) * p.tw;
-        }
-        // (k-block kb, tap) advance incrementally: this loop runs on one lane's issue slots, a runtime division per
-        // stage was a quarter of its ~150 instructions and the loop paced layer 1 (profiles/r01_ncu_issue_loop.txt)
-        const int taps_it = HALO ? 3 : p.taps;  // HALO: tap = filter row r
-        const int taps_w = p.xpair ? 2 : 3;     // taps per filter row
-        int kb = 0, tap = 0, r = 0, s = 0;      // tap = r * taps_w + s  (1x1: always 0)
-        for (int it = 0; it < k_iters; ++it) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 1);
-          if (elect_one()) {
-          uint8_t* a_dst = smem_a + stage * C::kABytes;
-          uint8_t* b_dst = smem_b + stage * kBStage;
-          const int shift = HALO ? (tap - 1) * p.wp - 1 : ((p.taps == 9) ? ((r - 1) * p.wp + (s - 1)) : 0);
-          // patch mode: filter row r, column s.  x-paired weights (stride 2, in_ld == c_in): one box covers the two
-          // horizontally adjacent taps (r, 2s) and (r, 2s+1), which are contiguous channels of the parity view
-          const int c0 = p.xpair ? p.a_coff : (s & 1) * p.a_ld + p.a_coff + kb * BLOCK_K;
-          const int c1 = p.xpair ? s : (s >> 1);
-          const uint32_t stage_tx = p.a_tx_bytes + (bres ? 0u : kBStage);
-          uint32_t bar_addr;
-          if (PAIR) {
-            // all bytes of both CTAs are credited to the LEADER's full barrier; the peer only contributes an arrival
-            bar_addr = mapa_u32(smem_u32(&full_bar[stage]), 0);
-            if (rank == 0)
-              mbar_expect_tx(&full_bar[stage], 2 * stage_tx);
-            else
-              mbar_arrive_cluster(bar_addr);
-            if (p.mode == 0)
-              tma_load_2d_pair(a_dst, &map_a, bar_addr, p.a_coff + kb * BLOCK_K, row0 + shift);
-            else
-              tma_load_5d_pair(a_dst, &map_a, bar_addr, c0, ow0 + c1, r & 1, oh0 + (r >> 1), img);
-            if (!bres) {
-#pragma unroll
-              for (uint32_t t = 0; t < C::kTaps; ++t)
-                tma_load_2d_pair(b_dst + t * C::kBBytes, &map_b, bar_addr, (HALO ? tap * 3 + int(t) : tap) * p.cin + kb * BLOCK_K, n0);
-            }
+      // loop-invariant parameters in registers, and one copy of the tile loop per addressing mode: this loop runs on a
+      // single lane's issue slots (~5 clk per dependent instruction), every instruction in it is paid per pipeline stage
+      const int n_tiles = p.n_tiles, kblocks = p.kblocks, wp = p.wp, cin = p.cin, a_coff = p.a_coff, a_ld = p.a_ld;
+      const int taps_it = HALO ? 3 : p.taps;  // HALO: tap = filter row r
+      const bool xpair = p.xpair != 0, nine = p.taps == 9;
+      const int taps_w = xpair ? 2 : 3;       // taps per filter row
+      const uint32_t stage_tx = p.a_tx_bytes + (bres ? 0u : kBStage);
+      auto run = [&](auto mode_tag) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        for (int tile = worker; tile < total_tiles; tile += n_workers) {
+          const int nt = tile % n_tiles;
+          const int mt = PAIR ? (tile / n_tiles) * 2 + static_cast<int>(rank) : tile / n_tiles;
+          const int n0 = nt * BLOCK_N + static_cast<int>(rank) * C::kBRows;  // this CTA's slice of the weight tile
+          int row0 = 0, img = 0, oh0 = 0, ow0 = 0;
+          if (MODE == 0) {
+            row0 = mt * kBlockM;
           } else {
-            mbar_expect_tx(&full_bar[stage], stage_tx);
-            if (p.mode == 0)
-              tma_load_2d(a_dst, &map_a, &full_bar[stage], p.a_coff + kb * BLOCK_K, row0 + shift);
-            else
-              tma_load_5d(a_dst, &map_a, &full_bar[stage], c0, ow0 + c1, r & 1, oh0 + (r >> 1), img);
-            if (!bres) {
+            const int per_img = p.tiles_w * p.tiles_h;
+            img = mt / per_img;
+            const int t = mt - img * per_img;
+            oh0 = (t / p.tiles_w) * p.th;
+            ow0 = (t % p.tiles_w) * p.tw;
+          }
+          // (k-block kb, tap) advance incrementally: a runtime division per stage was a quarter of the loop
+          int kb = 0, tap = 0, r = 0, s = 0;  // tap = r * taps_w + s  (1x1: always 0)
+          for (int it = 0; it < k_iters; ++it) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u, p.err, 1);
+            if (elect_one()) {
+              uint8_t* a_dst = smem_a + stage * C::kABytes;
+              uint8_t* b_dst = smem_b + stage * kBStage;
+              const int kcol = kb * BLOCK_K;
+              // flat mode: the tap's A box is the tile's pixel rows shifted by (r-1)*wp + (s-1) (HALO: a whole filter row)
+              const int shift = HALO ? (tap - 1) * wp - 1 : (nine ? (r - 1) * wp + (s - 1) : 0);
+              // patch mode: filter row r, column s.  x-paired weights (stride 2, in_ld == c_in): one box covers the two
+              // horizontally adjacent taps (r, 2s) and (r, 2s+1), which are contiguous channels of the parity view
+              const int c0 = xpair ? a_coff : (s & 1) * a_ld + a_coff + kcol;
+              const int c1 = xpair ? s : (s >> 1);
+              const int bcol = (HALO ? tap * 3 : tap) * cin + kcol;
+              if (PAIR) {
+                // all bytes of both CTAs are credited to the LEADER's full barrier; the peer only contributes an arrival
+                const uint32_t bar_addr = mapa_u32(smem_u32(&full_bar[stage]), 0);
+                if (rank == 0)
+                  mbar_expect_tx(&full_bar[stage], 2 * stage_tx);
+                else
+                  mbar_arrive_cluster(bar_addr);
+                if (MODE == 0)
+                  tma_load_2d_pair(a_dst, &map_a, bar_addr, a_coff + kcol, row0 + shift);
+                else
+                  tma_load_5d_pair(a_dst, &map_a, bar_addr, c0, ow0 + c1, r & 1, oh0 + (r >> 1), img);
+                if (!bres) {
 #pragma unroll
-              for (uint32_t t = 0; t < C::kTaps; ++t)
-                tma_load_2d(b_dst + t * C::kBBytes, &map_b, &full_bar[stage], (HALO ? tap * 3 + int(t) : tap) * p.cin + kb * BLOCK_K, n0);
+                  for (uint32_t t = 0; t < C::kTaps; ++t)
+                    tma_load_2d_pair(b_dst + t * C::kBBytes, &map_b, bar_addr, bcol + int(t) * cin, n0);
+                }
+              } else {
+                mbar_expect_tx(&full_bar[stage], stage_tx);
+                if (MODE == 0)
+                  tma_load_2d(a_dst, &map_a, &full_bar[stage], a_coff + kcol, row0 + shift);
+                else
+                  tma_load_5d(a_dst, &map_a, &full_bar[stage], c0, ow0 + c1, r & 1, oh0 + (r >> 1), img);
+                if (!bres) {
+#pragma unroll
+                  for (uint32_t t = 0; t < C::kTaps; ++t)
+                    tma_load_2d(b_dst + t * C::kBBytes, &map_b, &full_bar[stage], bcol + int(t) * cin, n0);
+                }
+              }
+            }
+            __syncwarp();
+            if (++stage == uint32_t(STAGES)) {
+              stage = 0;
+              phase ^= 1u;
+            }
+            if (++s == taps_w) {
+              s = 0;
+              ++r;
+            }
+            if (++tap == taps_it) {
+              tap = 0;
+              r = 0;
+              s = 0;
+              ++kb;
             }
           }
-          }
-          __syncwarp();
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1u;
-          }
-          if (++s == taps_w) {
-            s = 0;
-            ++r;
-          }
-          if (++tap == taps_it) {
-            tap = 0;
-            r = 0;
-            s = 0;
-            ++kb;
-          }
         }
-      }
+      };
+      if (p.mode == 0)
+        run(std::integral_constant<int, 0>{});
+      else
+        run(std::integral_constant<int, 1>{});
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA; whole warp, elected lane)
@@ -947,7 +961,7 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     const long long total = static_cast<long long>(a.m_tiles) * a.n_tiles;
     plan->grid = static_cast<int>(total < sms ? total : sms);
   }
-  plan->groups = (bn <= 64 && groups_enabled()) ? 2 : 1;
+  plan->groups = (bn <= 128 && groups_enabled()) ? 2 : 1;
   plan->smem_bytes = 0;
   return Y3_OK;
 }
