@@ -47,6 +47,10 @@ def peaks():
 class ClockSampler:
     FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    # nvidia-smi needs ~0.2 s to deliver its first line and the timed region of the default run is shorter than that,
+    # so the sampler is started before the warm-up, every line is stamped with its arrival time, and stop(t0, t1) keeps
+    # the lines that arrived while the GPU ran this workload: the timed region [t0, t1] plus, when that holds fewer than
+    # three, the identical untimed replays the caller appends right after it (same graph, same inputs, same clocks)
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
@@ -55,12 +59,12 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append((time.time(), l)) for l in self.proc.stdout], daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         time.sleep(0.15)
@@ -68,7 +72,9 @@ class ClockSampler:
         self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        for ts, l in self.lines:
+            if t0 is not None and not (t0 + 0.05 <= ts <= t1 + 0.05):  # a line reports the ~100 ms before it arrived
+                continue
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7:
                 continue
@@ -243,24 +249,37 @@ def main():
         eng.static_in.copy_(xs[i & 1])   # device->device, part of the step (the graph reads static_in)
         eng.replay()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()
     eng.check_errors()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    t_load0 = time.time()
     e0.record()
     for i in range(args.steps):
         step(i)
     e1.record()
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        # the clock samples must come from this workload: keep replaying it (untimed) until >= 0.6 s of load were observed
+        i = args.steps
+        while time.time() - t_load0 < 0.6:
+            step(i)
+            i += 1
+            if i % 8 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        clocks = sampler.stop(t_load0, time.time())
+        clocks["window_s"] = round(time.time() - t_load0, 3)
+        clocks["timed_region_s"] = round(ms_total / 1e3, 3)
     ms_total = aggregate(ms_total, dev)
     if world > 1:
         dist.barrier()

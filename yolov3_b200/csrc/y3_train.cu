@@ -512,7 +512,15 @@ extern "C" int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, i
                            y3_stream_t stream) {
   Y3_REQUIRE(y && sum && sumsq && c > 0 && c % 8 == 0 && c / 8 <= 256 && rows > 0 && ld % 8 == 0 && coff % 8 == 0,
              "bn_stats: bad arguments");
-  const int rows_per_block = 512;
+  // enough blocks to fill the machine even for the deep layers (few pixels, many channels: c/8 channel groups leave
+  // only 256/(c/8) row lanes per block — with a fixed 512 rows per block a 1024-channel layer ran 8 blocks whose threads
+  // walked 256 rows serially, 14x off the HBM floor, profiles/r01_train_launches_summary.txt)
+  const int nrl = 256 / (c / 8) > 0 ? 256 / (c / 8) : 1;
+  long long rpb = (rows + 4ll * y3::num_sms() - 1) / (4ll * y3::num_sms());
+  rpb = (rpb + nrl - 1) / nrl * nrl;
+  if (rpb < 4ll * nrl) rpb = 4ll * nrl;
+  if (rpb > 512) rpb = 512;
+  const int rows_per_block = static_cast<int>(rpb);
   const long long blocks = (rows + rows_per_block - 1) / rows_per_block;
   y3::bn_stats_kernel<<<static_cast<unsigned>(blocks), 256, 2 * 256 * 8 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       Slice{static_cast<const __nv_bfloat16*>(y), ld, coff}, c / 8, rows, rows_per_block, sum, sumsq);

@@ -36,7 +36,7 @@ struct WgTcArgs {
 
 // N = ci tile width (32 .. 256); SWZ = bytes of one smem row = min(N, 64) * 2 for B, 128 for A
 template <int N>
-__global__ void __launch_bounds__(kWgThreads, 1)
+__global__ void __launch_bounds__(kWgThreads, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgTcArgs p) {
   constexpr int kBCols = N >= 64 ? 64 : N;            // channels per B box
   constexpr int kBBoxes = N / kBCols;
@@ -45,7 +45,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   constexpr uint32_t kBBox = kWgK * kBCols * 2;
   constexpr uint32_t kBBytes = kBBoxes * kBBox;
   constexpr uint32_t kStage = kABytes + kBBytes;
-  constexpr int STAGES = (200 * 1024) / kStage > 6 ? 6 : (200 * 1024) / kStage;
+  // <= ~100 KB of ring: two CTAs per SM, so one CTA's prologue / atomic epilogue overlaps the other's main loop
+  constexpr int STAGES = N >= 256 ? 3 : ((100 * 1024) / kStage > 4 ? 4 : (100 * 1024) / kStage);
   constexpr uint32_t kLayoutA = 2u, kLayoutB = kBCols == 64 ? 2u : 4u;  // SWIZZLE_128B / SWIZZLE_64B
   constexpr uint32_t IDESC = umma_idesc_bf16(kWgM, N) | (1u << 15) | (1u << 16);  // A and B MN-major
   constexpr uint32_t kTmemCols = N < 32 ? 32 : N;
@@ -166,7 +167,7 @@ template <int N>
 int wgrad_tc_launch(const CUtensorMap& mdy, const CUtensorMap& mx, const WgTcArgs& a, dim3 grid, cudaStream_t stream) {
   constexpr int kBCols = N >= 64 ? 64 : N;
   constexpr uint32_t kStage = 2 * kWgK * 128 + (N / kBCols) * kWgK * kBCols * 2;
-  constexpr int STAGES = (200 * 1024) / kStage > 6 ? 6 : (200 * 1024) / kStage;
+  constexpr int STAGES = N >= 256 ? 3 : ((100 * 1024) / kStage > 4 ? 4 : (100 * 1024) / kStage);
   constexpr size_t smem = size_t(STAGES) * kStage + 1024 + 256;
   auto kern = wgrad_tc_kernel<N>;
   static bool attr_set = false;
@@ -196,7 +197,12 @@ int wgrad_tc(const y3_wgrad_desc& d, cudaStream_t stream) {
   const int taps = d.ksize * d.ksize;
   const long long rows = static_cast<long long>(d.n) * (d.h + 2) * (d.w + 2);
   Y3_REQUIRE(rows < (1ll << 31) - 4096, "wgrad: too many pixels");
-  const int n_tile = d.ci >= 256 ? 256 : (d.ci >= 128 ? 128 : (d.ci >= 64 ? 64 : 32));
+  static int n_max = -1;  // Y3_WGRAD_NMAX=256 allows 256-wide ci tiles (one CTA per SM); default 128 (two CTAs per SM)
+  if (n_max < 0) {
+    const char* e = getenv("Y3_WGRAD_NMAX");
+    n_max = (e && atoi(e) == 256) ? 256 : 128;
+  }
+  const int n_tile = (d.ci >= 256 && n_max == 256) ? 256 : (d.ci >= 128 ? 128 : (d.ci >= 64 ? 64 : 32));
   Y3_REQUIRE(d.ci % 32 == 0 || d.ci < 32, "wgrad_tc: c_in=%d must be a multiple of 32", d.ci);
   CUtensorMap mdy, mx;
   {
