@@ -253,15 +253,23 @@ int y3_pack_weights(const float* w, int32_t co, int32_t ci, int32_t k, void* fwd
 /* dy of a stride-2 conv scattered onto the even positions of a zeroed [n, 2ho+2, 2wo+2, dst_ld] buffer */
 int y3_zero_stuff(const void* src, int32_t src_ld, int32_t src_coff, void* dst, int32_t dst_ld, int32_t dst_coff, int32_t n,
                   int32_t ho, int32_t wo, int32_t c, y3_stream_t stream);
-/* dW[co, ci, kh, kw] += sum_p dy[p, co] * x[p + shift(kh,kw), ci] on the stride-1 padded grid [n, h+2, w+2]; dw is fp32 in
- * PyTorch's [co, ci, k, k] layout, zeroed by the caller; co, ci multiples of 8 */
+/* dW[co, ci, kh, kw] += sum_p dy[p, co] * x[p + shift(kh,kw), ci] on the stride-1 padded grid [n, h+2, w+2]; dw is fp32,
+ * zeroed by the caller; co, ci multiples of 8.  dw_layout Y3_DW_OIHW: PyTorch's [co, ci, k, k].  Y3_DW_TAP_MAJOR:
+ * [k*k, co, ci] — every (tap, co) row is contiguous in ci, so the tensor-core kernel accumulates with 16-byte vector
+ * reductions instead of one 4-byte atomic per element (the scattered atomics, ~45 G/s, were all of its time); the caller
+ * permutes once when it hands the gradient to the optimizer.  Needs c_in % 32 == 0 (y3_conv_wgrad_tap_major tells). */
+#define Y3_DW_OIHW 0
+#define Y3_DW_TAP_MAJOR 1
 typedef struct y3_wgrad_desc {
   const void* dy; int32_t dy_ld, dy_coff;
   const void* x;  int32_t x_ld, x_coff;
   float* dw;
   int32_t co, ci, ksize, n, h, w;
+  int32_t dw_layout;
 } y3_wgrad_desc;
 int y3_conv_wgrad(const y3_wgrad_desc* d, y3_stream_t stream);
+/* 1 if y3_conv_wgrad accepts Y3_DW_TAP_MAJOR for this c_in (the tcgen05 kernel is in use), else 0 */
+int y3_conv_wgrad_tap_major(int32_t c_in);
 /* dst (+)= src over the interior pixels of two padded NHWC bf16 slices of equal [n,h,w,c] (gradient fan-in) */
 int y3_add_nhwc(const void* src, int32_t src_ld, int32_t src_coff, void* dst, int32_t dst_ld, int32_t dst_coff, int32_t n,
                 int32_t h, int32_t w, int32_t c, int32_t accumulate, y3_stream_t stream);

@@ -169,3 +169,37 @@ def test_ddp_gradient_exchange_semantics_gloo(tmp_path):
                        timeout=240, env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
     assert p.returncode == 0, p.stderr[-2000:]
     assert "DDP_OK 2" in p.stdout
+
+
+def test_autolabel_rows_match_the_reference_semantics():
+    """non_max_suppression(labels=...) (utils/general.py:689-695): the adapter appends the priors as obj = 1 / one-hot
+    rows; running the ORACLE on that augmented tensor must equal the oracle's own labels= path (which was pinned against
+    the reference in tests/golden/make_golden.py)."""
+    import numpy as np
+    import torch
+
+    import yolo_oracle as O
+    from yolov3_b200.nms import _append_labels
+
+    pred = O.synth_predictions(2, n_rows=300, nc=80, seed=4)
+    labels = [[[3.0, 320.0, 320.0, 120.0, 90.0]], []]
+    aug = _append_labels(pred, labels)
+    assert aug.shape == (2, 301, 85) and float(aug[1, 300, 4]) == 0.0 and float(aug[0, 300, 5 + 3]) == 1.0
+    a, sa = O.non_max_suppression(aug, 0.25, 0.45)
+    b, sb = O.non_max_suppression(pred, 0.25, 0.45, labels=labels)
+    for x, y, sx, sy in zip(a, b, sa, sb):
+        assert np.array_equal(x, y) and np.array_equal(sx, sy)
+
+
+def test_xpair_weight_pack_layout():
+    """Y3_W_XPAIR (include/yolov3_b200.h): [c_out_pad, 3, 2, 2, c_in] with a zero phantom column."""
+    import torch
+
+    from yolov3_b200 import ops
+
+    w = torch.randn(64, 32, 3, 3)
+    wp, bp = ops.pack_conv_weight_xpair(w, torch.zeros(64), device="cpu")
+    v = wp.float().view(64, 3, 2, 2, 32)
+    ref = w.bfloat16().float()
+    assert torch.equal(v[:, :, 0, 0], ref[:, :, :, 0].permute(0, 2, 1)) and torch.equal(v[:, :, 0, 1], ref[:, :, :, 1].permute(0, 2, 1))
+    assert torch.equal(v[:, :, 1, 0], ref[:, :, :, 2].permute(0, 2, 1)) and float(v[:, :, 1, 1].abs().max()) == 0.0

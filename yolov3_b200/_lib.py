@@ -134,7 +134,8 @@ class WgradDesc(C.Structure):
     _fields_ = [("dy", C.c_void_p), ("dy_ld", C.c_int32), ("dy_coff", C.c_int32),
                 ("x", C.c_void_p), ("x_ld", C.c_int32), ("x_coff", C.c_int32),
                 ("dw", C.c_void_p),
-                ("co", C.c_int32), ("ci", C.c_int32), ("ksize", C.c_int32), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32)]
+                ("co", C.c_int32), ("ci", C.c_int32), ("ksize", C.c_int32), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
+                ("dw_layout", C.c_int32)]
 
 
 def _declare(lib):
@@ -158,6 +159,7 @@ def _declare(lib):
         "y3_pack_weights": ([vp, i32, i32, i32, vp, vp, vp], C.c_int),
         "y3_zero_stuff": ([vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, vp], C.c_int),
         "y3_conv_wgrad": ([C.POINTER(WgradDesc), vp], C.c_int),
+        "y3_conv_wgrad_tap_major": ([i32], C.c_int),
         "y3_add_nhwc": ([vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp], C.c_int),
         "y3_im2col_first": ([vp, i32, C.c_float, i32, i32, i32, vp, i32, i32, vp], C.c_int),
         "y3_colsum_f32": ([vp, i32, i32, C.c_int64, vp, vp], C.c_int),

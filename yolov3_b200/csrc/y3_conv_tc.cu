@@ -10,11 +10,13 @@
 //   * a stride-2 conv reads the same buffer through a 5-D view (2*ld, (w+2)/2, 2, (h+2)/2, n) that splits rows and
 //     columns by parity; the A tile of tap (r,s) for a TH x TW patch of output pixels is one 5-D TMA box ("patch").
 //   * weights are bf16 [cout_pad, taps*cin] (K-major); B tile = [BLOCK_N x BLOCK_K] box.
-// Warp roles (320 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread
-// MMA issuer, warps 2-9 = epilogue (TMEM -> registers -> global; two warps per TMEM lane quarter, each taking half of
-// the tile's columns).  smem ring of STAGES {A,B} tiles; two accumulator buffers in TMEM so the epilogue of tile i
-// overlaps the main loop of tile i+1.  Measured on B200 (profiles/r01_*): with 4 epilogue warps the 1x1 and small-K
-// layers were epilogue-bound (MUFU + issue), hence 8 warps, a one-MUFU SiLU and register-prefetched residuals.
+// Warp roles (320 or 576 threads, 1 CTA/SM, persistent over tiles): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer
+// (both run warp-uniform loops and elect one lane per issue), warps 2.. = epilogue, 8 warps per group (TMEM -> registers ->
+// global / swizzled smem + TMA store; two warps per TMEM lane quarter, each taking half of the tile's columns); tiles with
+// N <= 128 run two groups, group g converting the tiles of TMEM accumulator buffer g.  smem ring of STAGES {A,B} tiles; two
+// accumulator buffers in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.  What bounded what, measured on
+// B200: profiles/r01_ncu_*.txt (epilogue MUFU/issue -> 8 warps + one-MUFU SiLU; SM operand ingress -> CTA pairs; TMA row
+// rate -> halo reuse; single-lane issue loops -> elect.sync; lock-step epilogue -> per-warp TMA + private bias slices).
 #include <cuda_bf16.h>
 
 #include <cstdlib>

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(Slice y, int c8, long lon
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
   if (rl < nrl) {
+#pragma unroll 4
     for (long long r = r0 + rl; r < r1; r += nrl) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(y.p + r * y.ld + y.coff + cg * 8));
       float f[8];
@@ -512,14 +513,13 @@ extern "C" int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, i
                            y3_stream_t stream) {
   Y3_REQUIRE(y && sum && sumsq && c > 0 && c % 8 == 0 && c / 8 <= 256 && rows > 0 && ld % 8 == 0 && coff % 8 == 0,
              "bn_stats: bad arguments");
-  // enough blocks to fill the machine even for the deep layers (few pixels, many channels: c/8 channel groups leave
-  // only 256/(c/8) row lanes per block — with a fixed 512 rows per block a 1024-channel layer ran 8 blocks whose threads
-  // walked 256 rows serially, 14x off the HBM floor, profiles/r01_train_launches_summary.txt)
+  // ~4 blocks per SM, each walking a long row range: with fixed 512-row blocks the 640x640 layers launched 6441 blocks whose
+  // 64 atomics each all hit the same 64 addresses (283 us for 211 MB), and the 1024-channel layers ran 8 blocks
+  // (profiles/r01_train_launches_summary.txt)
   const int nrl = 256 / (c / 8) > 0 ? 256 / (c / 8) : 1;
   long long rpb = (rows + 4ll * y3::num_sms() - 1) / (4ll * y3::num_sms());
   rpb = (rpb + nrl - 1) / nrl * nrl;
   if (rpb < 4ll * nrl) rpb = 4ll * nrl;
-  if (rpb > 512) rpb = 512;
   const int rows_per_block = static_cast<int>(rpb);
   const long long blocks = (rows + rows_per_block - 1) / rows_per_block;
   y3::bn_stats_kernel<<<static_cast<unsigned>(blocks), 256, 2 * 256 * 8 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
@@ -623,6 +623,7 @@ extern "C" int y3_conv_wgrad(const y3_wgrad_desc* d, y3_stream_t stream) {
   if (y3::wgrad_tc_enabled() && d->ci % 32 == 0 && (reinterpret_cast<uintptr_t>(d->dy) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(d->x) & 15) == 0)
     return y3::wgrad_tc(*d, static_cast<cudaStream_t>(stream));
+  Y3_REQUIRE(d->dw_layout == Y3_DW_OIHW, "wgrad: the tap-major accumulation layout needs the tensor-core kernel (c_in % 32 == 0)");
   y3::WgradArgs a;
   a.dy = Slice{static_cast<const __nv_bfloat16*>(d->dy), d->dy_ld, d->dy_coff};
   a.x = Slice{static_cast<const __nv_bfloat16*>(d->x), d->x_ld, d->x_coff};
@@ -648,6 +649,8 @@ extern "C" int y3_conv_wgrad(const y3_wgrad_desc* d, y3_stream_t stream) {
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
+
+extern "C" int y3_conv_wgrad_tap_major(int32_t c_in) { return (y3::wgrad_tc_enabled() && c_in % 32 == 0) ? 1 : 0; }
 
 extern "C" int y3_colsum_f32(const float* g, int32_t ld, int32_t c, int64_t rows, float* out, y3_stream_t stream) {
   Y3_REQUIRE(g && out && c > 0 && c <= 256 && rows > 0, "colsum: bad arguments");

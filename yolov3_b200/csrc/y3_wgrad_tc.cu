@@ -30,6 +30,8 @@ struct WgTcArgs {
   int kblocks_per_cta;  // pixel blocks one CTA accumulates (split-K)
   int dy_coff, x_coff;
   float* dw;
+  int tap_major;        // dw is [taps][co][ci] (vector reductions) instead of [co][ci][taps]
+  int single;           // 1: this CTA is the only contributor to its dW tile (plain stores)
   int* err;
   uint32_t lbo_a, lbo_b, sbo_a, sbo_b;  // descriptor strides in bytes (probe-able, see Y3_WGRAD_VARIANT)
 };
@@ -141,16 +143,33 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       const int co = co0 + quarter * 32 + lane;
       mbar_wait(done_bar, 0, p.err, 13);
       tc_fence_after();
-      float* dst = p.dw + (static_cast<long long>(co) * p.ci + ci0) * p.taps + tap;
+      const bool rows_contig = p.tap_major || p.taps == 1;  // this thread's ci run is contiguous in memory
+      float* dst = rows_contig ? p.dw + (static_cast<long long>(tap) * p.co + co) * p.ci + ci0
+                               : p.dw + (static_cast<long long>(co) * p.ci + ci0) * p.taps + tap;
 #pragma unroll 1
       for (int c = 0; c < N; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c, v);
         tmem_ld_wait();
-        if (co < p.co) {
+        if (co >= p.co) continue;
+        if (rows_contig && ci0 + c + 32 <= p.ci) {
+          // 128 contiguous bytes per thread: 16-byte vector reductions (or plain stores when nobody else adds to this tile)
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float* q = dst + c + j;
+            if (p.single)
+              *reinterpret_cast<float4*>(q) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                          __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            else
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q), "f"(__uint_as_float(v[j])),
+                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
+          }
+        } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (ci0 + c + j < p.ci) atomicAdd(dst + static_cast<long long>(c + j) * p.taps, __uint_as_float(v[j]));
+            if (ci0 + c + j < p.ci)
+              atomicAdd(dst + static_cast<long long>(c + j) * (rows_contig ? 1 : p.taps), __uint_as_float(v[j]));
         }
       }
     }
@@ -258,6 +277,8 @@ int wgrad_tc(const y3_wgrad_desc& d, cudaStream_t stream) {
   if (want < 1) want = 1;
   a.kblocks_per_cta = static_cast<int>((a.kblocks_total + want - 1) / want);
   const unsigned splits = static_cast<unsigned>((a.kblocks_total + a.kblocks_per_cta - 1) / a.kblocks_per_cta);
+  a.tap_major = d.dw_layout == Y3_DW_TAP_MAJOR ? 1 : 0;
+  a.single = splits == 1 ? 1 : 0;
   const dim3 grid(splits, static_cast<unsigned>(tiles), static_cast<unsigned>(taps));
   switch (n_tile) {
     case 256: return wgrad_tc_launch<256>(mdy, mx, a, grid, stream);

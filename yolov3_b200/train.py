@@ -29,7 +29,7 @@ class _Block:
     """One Conv+BN+SiLU block (models/common.py:57-81) with everything its forward and backward need."""
 
     __slots__ = ("prefix", "c1", "c2", "k", "s", "x", "y", "a", "res", "upsample", "wf", "wd", "zero_b", "zero_bi", "st",
-                 "dw", "first", "dy", "dy_up", "post_fwd", "pre_bwd")
+                 "dw", "dw_tm", "first", "dy", "dy_up", "post_fwd", "pre_bwd")
 
 
 class TrainEngine:
@@ -77,7 +77,9 @@ class TrainEngine:
             b.st = {name: f32(c2) for name in ("scale", "shift", "mean", "rstd")}
             sums, dsums, gsums = f32(2 * c2).view(2, c2), f32(2 * c2).view(2, c2), f32(2 * c2).view(2, c2)
             b.st.update(sums=sums, sum=sums[0], sumsq=sums[1], dsums=dsums, dbeta=dsums[0], dgamma=dsums[1], gsums=gsums)
-            b.dw = torch.zeros(c2, ci, kk, kk, dtype=torch.float32, device=dev)
+            # wgrad accumulator: [k*k, co, ci] when the tensor-core kernel is in use (vector reductions), else PyTorch's layout
+            b.dw_tm = T.wgrad_tap_major(ci)
+            b.dw = torch.zeros((kk * kk, c2, ci) if b.dw_tm else (c2, ci, kk, kk), dtype=torch.float32, device=dev)
             b.dy = self._scratch(c2, ho, wo, dev)
             b.dy_up = self._scratch(c2, x.h, x.w, dev, tag="up") if s == 2 else None
             b.post_fwd, b.pre_bwd = [], []  # extra launches after this block's forward / before its backward (SPP pools)
@@ -365,11 +367,13 @@ class TrainEngine:
             src = b.dy
             if b.s == 2:
                 src = T.zero_stuff(b.dy, b.dy_up)
-            T.conv_wgrad(src, b.x, b.dw, 1 if b.first else b.k)
+            kk = 1 if b.first else b.k
+            T.conv_wgrad(src, b.x, b.dw, kk, tap_major=b.dw_tm)
+            dw = b.dw.permute(1, 2, 0).reshape(b.c2, -1, kk, kk) if b.dw_tm else b.dw  # -> [co, ci, k, k]
             if b.first:
-                grads[b.prefix + ".conv.weight"] = b.dw[:, :27].reshape(b.c2, 3, 3, 3).clone()
+                grads[b.prefix + ".conv.weight"] = dw[:, :27].reshape(b.c2, 3, 3, 3).clone()
             else:
-                grads[b.prefix + ".conv.weight"] = b.dw.clone()
+                grads[b.prefix + ".conv.weight"] = dw.contiguous().clone() if b.dw_tm and kk > 1 else dw.clone()
                 contribute_conv(src, b.wd, b.zero_bi, b.c1, b.k, b.x)
             grads[b.prefix + ".bn.weight"] = st["dgamma"].clone()
             grads[b.prefix + ".bn.bias"] = st["dbeta"].clone()

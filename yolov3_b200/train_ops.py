@@ -73,10 +73,16 @@ def zero_stuff(src: PaddedNHWC, dst: PaddedNHWC):
     return dst
 
 
-def conv_wgrad(dy: PaddedNHWC, x: PaddedNHWC, dw: torch.Tensor, ksize: int):
-    """dw (fp32 [co,ci,k,k], accumulated into) from dy and x on the same stride-1 padded grid."""
+def wgrad_tap_major(ci: int) -> bool:
+    """True when y3_conv_wgrad takes the [k*k, co, ci] accumulation layout for this c_in (tcgen05 kernel in use)."""
+    return bool(_lib.lib().y3_conv_wgrad_tap_major(int(ci)))
+
+
+def conv_wgrad(dy: PaddedNHWC, x: PaddedNHWC, dw: torch.Tensor, ksize: int, tap_major: bool = False):
+    """dw (fp32, accumulated into; [co,ci,k,k] or, tap_major, [k*k,co,ci]) from dy and x on the same stride-1 padded grid."""
     assert dy.n == x.n and dy.h == x.h and dy.w == x.w and dw.dtype == torch.float32 and dw.is_contiguous()
     d = _lib.WgradDesc()
+    d.dw_layout = 1 if tap_major else 0
     d.dy, d.dy_ld, d.dy_coff = dy.ptr, dy.ld, dy.coff
     d.x, d.x_ld, d.x_coff = x.ptr, x.ld, x.coff
     d.dw, d.co, d.ci, d.ksize = dw.data_ptr(), dy.c, x.c, ksize
