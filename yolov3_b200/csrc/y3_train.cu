@@ -191,19 +191,25 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BnBwdArgs p) {
   const int cg = threadIdx.x % p.c8, pl = threadIdx.x / p.c8, npl = blockDim.x / p.c8;
   const long long pixels = static_cast<long long>(p.n) * p.h * p.w;
   float a_dz[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a_dzy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  float sc[8], shf[8], mu[8], rs[8], m_dz[8], m_dzy[8];
+  // per-channel constants.  APPLY: dy = sc*(dz - mean(dz) - yhat*mean(dz*yhat)) = sc*dz + k1*y + k0 with yhat = (y - mu)*rs
+  // — four constants per channel instead of six keep the kernel at 3 blocks per SM (it is latency-bound on its two loads)
+  float sc[8], shf[8], c2[8], c3[8];  // sums pass: c2 = mu, c3 = rs;  apply pass: c2 = k1, c3 = k0
   if (pl < npl) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       sc[k] = p.scale[cg * 8 + k];
       shf[k] = p.shift[cg * 8 + k];
-      mu[k] = p.mean[cg * 8 + k];
-      rs[k] = p.rstd[cg * 8 + k];
+      const float mu = p.mean[cg * 8 + k], rs = p.rstd[cg * 8 + k];
       if (APPLY) {
-        m_dz[k] = p.sum_dz[cg * 8 + k] * p.inv_count;
-        m_dzy[k] = p.sum_dzy[cg * 8 + k] * p.inv_count;
+        const float m_dz = p.sum_dz[cg * 8 + k] * p.inv_count, m_dzy = p.sum_dzy[cg * 8 + k] * p.inv_count;
+        c2[k] = -sc[k] * rs * m_dzy;
+        c3[k] = -sc[k] * m_dz - c2[k] * mu;
+      } else {
+        c2[k] = mu;
+        c3[k] = rs;
       }
     }
+#pragma unroll 2
     for (long long px = static_cast<long long>(blockIdx.x) * npl + pl; px < pixels; px += static_cast<long long>(gridDim.x) * npl) {
       const int x = static_cast<int>(px % p.w);
       const long long t = px / p.w;
@@ -218,10 +224,10 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BnBwdArgs p) {
       for (int k = 0; k < 8; ++k) {
         const float z = fmaf(yv[k], sc[k], shf[k]);
         const float dz = d[k] * silu_grad(z);
-        const float yh = (yv[k] - mu[k]) * rs[k];
         if (APPLY) {
-          o[k] = sc[k] * (dz - m_dz[k] - yh * m_dzy[k]);
+          o[k] = fmaf(sc[k], dz, fmaf(c2[k], yv[k], c3[k]));
         } else {
+          const float yh = (yv[k] - c2[k]) * c3[k];
           a_dz[k] += dz;
           a_dzy[k] += dz * yh;
         }
