@@ -48,10 +48,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code) {
+// sleep_ns > 0: back off between polls (the GPU runs the conv stack power-capped; 18 warps spinning on try_wait cost
+// issue slots and power that the tensor pipe could use — Y3_CONV_POLL_NS, measured in profiles/)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code, unsigned sleep_ns = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    if (sleep_ns) __nanosleep(sleep_ns);
     if (clock64() - t0 > Y3_WATCHDOG_CYCLES) {
       if (err) atomicExch(err, code);
       __threadfence_system();

@@ -483,7 +483,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         // the staging rows are free (the issuer has waited for the store that last read them)
         if (kPairSync) named_bar_sync(pair_bar, 64); else __syncwarp();
-        mbar_wait(&tfull_bar[as], aphase, p.err, 4);
+        mbar_wait(&tfull_bar[as], aphase, p.err, 4, p.poll_ns);
         tc_fence_after();
         if (p.res && active) mbar_wait(&my_res_bar[sb], rphase, p.err, 5);  // residual rows landed (idle warps own none)
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
@@ -561,7 +561,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int q = 0; q < 4; ++q) rcur[q] = __ldg(reinterpret_cast<const uint4*>(res_ptr + c_begin) + q);
       }
 
-      mbar_wait(&tfull_bar[as], aphase, p.err, 4);  // accumulator complete
+      mbar_wait(&tfull_bar[as], aphase, p.err, 4, p.poll_ns);  // accumulator complete
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
       if (active) {
@@ -663,6 +663,15 @@ int launch_cfg(const ConvTcPlan& plan, cudaStream_t stream) {
   }
   ConvTcArgs args = plan.args;
   args.bres = plan.bres;
+  {
+    static int poll = -1;  // Y3_CONV_POLL_NS: nanosleep between polls of the epilogue's accumulator wait (default 0 = spin)
+    if (poll < 0) {
+      const char* e = getenv("Y3_CONV_POLL_NS");
+      poll = e ? atoi(e) : 0;
+      if (poll < 0) poll = 0;
+    }
+    args.poll_ns = static_cast<unsigned>(poll);
+  }
   args.stages = plan.bres ? C::bres_stages(args.taps * args.kblocks) : C::kStages;
   if (args.stages < 3) {  // not enough ring left beside the resident weights: fall back to streaming them
     args.bres = 0;
