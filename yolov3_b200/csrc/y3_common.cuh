@@ -48,8 +48,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// sleep_ns > 0: back off between polls (the GPU runs the conv stack power-capped; 18 warps spinning on try_wait cost
-// issue slots and power that the tensor pipe could use — Y3_CONV_POLL_NS, measured in profiles/)
+// sleep_ns > 0: back off between polls (Y3_CONV_POLL_NS).  Tried because the GPU runs the conv stack power-capped
+// (sw_power_cap, 1.64-1.70 of 1.97 GHz): 20 / 60 ns of back-off in the epilogue's accumulator wait changed neither the
+// clock nor the step time (5504 / 5430 / 5418 / 5420 img/s for 0 / 20 / 60 / 0 ns, B200 round 1) — spinning is the default.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* err, int code, unsigned sleep_ns = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
