@@ -179,7 +179,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t sbo_
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= static_cast<uint64_t>(1) << 46;
   // base offset stays 0 even for operands that start off the 1 KB pattern: the swizzle XOR uses absolute address bits
-  // (measured, y3_conv_tc.cu halo_mode()); base_off_mode = 1 is only kept as a probe of the other reading of the ISA text
+  // (measured, y3_conv_tc.cu halo_enabled()); base_off_mode = 1 is only kept as a probe of the other reading of the ISA text
   if (base_off_mode) d |= static_cast<uint64_t>((saddr >> 7) & 0x7u) << 49;
   d |= static_cast<uint64_t>(layout) << 61;
   return d;

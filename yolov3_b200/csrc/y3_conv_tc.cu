@@ -31,7 +31,6 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kEpilogueWarps = 8;
-constexpr int kThreads = 64 + 32 * kEpilogueWarps;
 constexpr int kSmemBudget = 221 * 1024;  // ring + epilogue staging; alignment slack, barriers and bias slices come on top (227 KB max)
 
 // STAGED = true: the epilogue converts into a swizzled shared-memory staging tile and ONE thread stores it with TMA
@@ -40,7 +39,7 @@ constexpr int kSmemBudget = 221 * 1024;  // ring + epilogue staging; alignment s
 // HALO = true (stride-1 3x3, BLOCK_K = 64): one pipeline stage covers a whole filter ROW (3 taps): the A operand is ONE
 // TMA box of 128+2 consecutive pixels and the three taps read it at row offsets 0/1/2 through UMMA descriptors whose
 // start address is not aligned to the 1 KB swizzle pattern (the swizzle is a function of the absolute address, so the
-// descriptor's base_offset stays 0 — verified on hardware, see halo_mode()).  A rows fetched per
+// descriptor's base_offset stays 0 — verified on hardware, see halo_enabled()).  A rows fetched per
 // k-block drop from 9*128 to 3*130; the TMA unit's row rate (~1 row / 2.5 clk / SM), not its byte rate, was the limit.
 template <int BLOCK_N, int BLOCK_K, bool PAIR, bool STAGED, bool HALO>
 struct Cfg {
@@ -743,18 +742,18 @@ static bool staged_enabled() {
   return v != 0;
 }
 
-// Y3_CONV_HALO=0 disables the halo-reuse A path.  Default (1): descriptors of the row-shifted taps carry base_offset = 0.
-// Measured on B200 (tools/probe_conv.py, round 1): with base_offset = 0 all 27 conv cases are exact, i.e. the tensor core
-// applies the 128B-swizzle XOR to the ABSOLUTE shared-memory address bits [7,10) exactly as the TMA unit did when it
-// wrote the box; with base_offset = (addr >> 7) & 7 (Y3_CONV_HALO=2) the shifted taps read wrong rows.
-static int halo_mode() {
+// Y3_CONV_HALO=0 disables the halo-reuse A path.  Descriptors of the row-shifted taps carry base_offset = 0: measured on
+// B200 (tools/probe_conv.py, profiles/r01_probe_conv_halo_baseoffset0.jsonl) all conv cases are exact that way, i.e. the
+// tensor core applies the 128B-swizzle XOR to the ABSOLUTE shared-memory address bits [7,10) exactly as the TMA unit did
+// when it wrote the box; with base_offset = (addr >> 7) & 7 — the other reading of the ISA text — the shifted taps read
+// wrong rows (that probe variant has been removed again).
+static bool halo_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("Y3_CONV_HALO");
-    v = e ? (e[0] - '0') : 1;
-    if (v < 0 || v > 2) v = 1;
+    v = (e && e[0] == '0') ? 0 : 1;
   }
-  return v;
+  return v != 0;
 }
 
 // Y3_CONV_BRES=0 streams the weights through the ring everywhere (A/B measurements).
@@ -885,8 +884,7 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     a.m_tiles = static_cast<int>((rows + kBlockM - 1) / kBlockM);
     // halo reuse needs >= 2 stages of (17 KB + 3 B tiles): any N <= 128, N = 256 only as a CTA pair
     const bool pair_ok = bn >= 128 && pair_enabled() && a.m_tiles >= 2;
-    plan->halo = (taps == 9 && (bk == 64 || (bk == 32 && bn <= 64)) && halo_mode() != 0 && (bn <= 128 || pair_ok)) ? 1 : 0;
-    a.desc_mode = halo_mode() == 2 ? 1 : 0;
+    plan->halo = (taps == 9 && (bk == 64 || (bk == 32 && bn <= 64)) && halo_enabled() && (bn <= 128 || pair_ok)) ? 1 : 0;
     const uint32_t a_rows = plan->halo ? kBlockM + 2 : kBlockM;
     a.a_tx_bytes = a_rows * bk * 2;
     const uint64_t dims[2] = {static_cast<uint64_t>(d.in_ld), static_cast<uint64_t>(rows)};
@@ -896,7 +894,6 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     if (rc) return rc;
   } else {
     plan->halo = 0;
-    a.desc_mode = 0;
     a.mode = 1;
     a.ho = d.h / 2;
     a.wo = d.w / 2;

@@ -38,7 +38,6 @@ struct ConvTcArgs {
   int taps, kblocks, cin;
   int a_coff, a_ld;
   uint32_t a_tx_bytes;   // bytes one A box delivers
-  int desc_mode;         // 1: UMMA descriptors carry base_offset = (addr>>7)&7; 0: base_offset = 0 (probe)
   int xpair;             // patch mode with x-paired weights: 6 taps of 2*c_in channels
   unsigned poll_ns;      // back-off between mbarrier polls of the epilogue warps (0 = spin)
   int stages;            // depth of the shared-memory ring (set by the launcher from the tile configuration)

@@ -519,16 +519,17 @@ class Engine:
         _lib.check(_lib.lib().y3_model_forward(self.handle, ptr, _stream()), "y3_model_forward")
         return self.z, self.raw
 
-    def capture(self):
-        """Capture one forward (reading ``static_in``) into a CUDA graph; ``replay()`` then costs one launch."""
+    def capture(self, x: torch.Tensor | None = None):
+        """Capture one forward into a CUDA graph; ``replay()`` then costs one launch.  ``x`` = the (resident, fixed-address)
+        input the graph reads; default: the engine's ``static_in`` staging buffer, which callers fill before each replay."""
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            self.run(None)
+            self.run(x)
         torch.cuda.current_stream().wait_stream(s)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            self.run(None)
+            self.run(x)
         self.graph = g
         return g
 
