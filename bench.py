@@ -351,7 +351,12 @@ def main():
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tf_sustained"], "traffic": None,
                 "kernel": "conv_tc_kernel (74 launches/step)", "kernel_ms_per_step": conv_ms,
-                "kernel_share_of_step": conv_ms / all_ms, "peak_source": pk["source"] + " sustained bf16 (MEASURED_PEAKS.json)"}
+                "kernel_share_of_step": conv_ms / all_ms, "peak_source": pk["source"] + " sustained bf16 (MEASURED_PEAKS.json)",
+                # `traffic` stays null: `achieved` aggregates 74 launches of 23 different shapes.  One ncu --set full capture
+                # of the largest layer group (recorded, not re-measured here): dram read+write vs algorithmic in+res+out+w
+                "traffic_sample": {"kernel": "conv_tc 128->256 3x3 s1 @80x80 bs32 +res (8 of the 74 launches)",
+                                   "dram_bytes_per_launch": 226.9e6, "algorithmic_bytes_per_launch": 262.7e6,
+                                   "source": "profiles/r01_ncu_conv_tc_final_summary.txt"}}
     if args.per_op:
         Path(args.per_op).parent.mkdir(parents=True, exist_ok=True)
         Path(args.per_op).write_text(json.dumps(per_op, indent=1))
