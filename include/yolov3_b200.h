@@ -185,6 +185,11 @@ int y3_nms_batched(const float* pred, const y3_nms_params* params, void* workspa
  * Pairwise IoU.  Replaces box_iou (ultralytics; re-exported utils/metrics.py:10, used val.py:176): xyxy boxes,
  * out[i*m + j] = inter / (area1 + area2 - inter + eps).  box1 [n,4], box2 [m,4] fp32, 16-byte aligned. */
 int y3_box_iou(const float* box1, int32_t n, const float* box2, int32_t m, float eps, float* out, y3_stream_t stream);
+/* scale_boxes + clip_boxes (utils/general.py:613-626; callers detect.py:218, val.py:381-385): in place on columns 0..3
+ * (xyxy) of n rows of `row_stride` floats: v = clamp((v - pad) / gain, 0, max) with pad_x/max_x for x1,x2 and pad_y/max_y
+ * for y1,y2; gain = 1, pad = 0 gives clip_boxes. */
+int y3_scale_boxes(float* boxes, int64_t n, int32_t row_stride, float pad_x, float pad_y, float gain, float max_x,
+                   float max_y, y3_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Training loss, forward + backward.  Replaces ComputeLoss.__call__ / build_targets (utils/loss.py:131-244) with

@@ -426,6 +426,23 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     return outs, srcs
 
 
+def scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=None):
+    """utils/general.py:613-626 (+ ultralytics clip_boxes): un-letterbox xyxy boxes and clip them; numpy float32, every
+    step separately rounded like the torch ops (tensor -= python float, tensor /= python float, clamp)."""
+    b = np.array(boxes, dtype=np.float32, copy=True)
+    if ratio_pad is None:
+        gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+        pad = (img1_shape[1] - img0_shape[1] * gain) / 2, (img1_shape[0] - img0_shape[0] * gain) / 2
+    else:
+        gain, pad = ratio_pad[0][0], ratio_pad[1]
+    b[..., [0, 2]] = (b[..., [0, 2]] - np.float32(pad[0])).astype(np.float32)
+    b[..., [1, 3]] = (b[..., [1, 3]] - np.float32(pad[1])).astype(np.float32)
+    b[..., :4] = (b[..., :4] / np.float32(gain)).astype(np.float32)
+    b[..., [0, 2]] = np.clip(b[..., [0, 2]], np.float32(0), np.float32(img0_shape[1]))
+    b[..., [1, 3]] = np.clip(b[..., [1, 3]], np.float32(0), np.float32(img0_shape[0]))
+    return b
+
+
 def box_iou(box1, box2, eps=1e-7):
     """ultralytics box_iou (re-exported utils/metrics.py:10; used val.py:176): inter/(a1+a2-inter+eps), [N,M]."""
     b1, b2 = torch.as_tensor(box1).float(), torch.as_tensor(box2).float()

@@ -161,6 +161,31 @@ def gen_nms():
     np.savez_compressed(OUT / "nms_cases.npz", **store)
 
 
+SCALE_CASES = [((640, 640), (1080, 810, 3), None), ((384, 640), (720, 1280, 3), None), ((640, 480), (375, 500, 3), None),
+               ((640, 640), (480, 640, 3), ((0.75, 0.75), (16.0, 80.0)))]
+
+
+def gen_scale_boxes():
+    """scale_boxes (utils/general.py:613-626, through the shim's clip_boxes) on seeded xyxy boxes incl. out-of-image ones."""
+    import utils.general as G  # reference
+
+    store = {}
+    for ci, (s1, s0, rp) in enumerate(SCALE_CASES):
+        g = torch.Generator().manual_seed(40 + ci)
+        xy = torch.rand(200, 2, generator=g) * torch.tensor([s1[1], s1[0]]) * 1.2 - 0.1 * torch.tensor([s1[1], s1[0]])
+        wh = torch.rand(200, 2, generator=g) * 300
+        boxes = torch.cat((xy - wh / 2, xy + wh / 2, torch.rand(200, 2, generator=g)), 1)  # [200, 6] like the NMS output
+        ref = boxes.clone()
+        G.scale_boxes(s1, ref[:, :4], s0, rp)
+        ora = O.scale_boxes(s1, boxes[:, :4].numpy(), s0, rp)
+        assert np.array_equal(ref[:, :4].numpy(), ora), (ci, np.abs(ref[:, :4].numpy() - ora).max())
+        store[f"in{ci}"] = boxes.numpy()
+        store[f"out{ci}"] = ref.numpy()
+        store[f"geom{ci}"] = np.array(repr((s1, s0, rp)))  # (img1_shape, img0_shape, ratio_pad) for the tests
+    np.savez_compressed(OUT / "scale_boxes_cases.npz", **store)
+    print("scale_boxes ok")
+
+
 def loss_inputs(case):
     g = torch.Generator().manual_seed(200 + case)
     bs = [2, 3, 1, 2][case]
@@ -253,7 +278,9 @@ if __name__ == "__main__":
     assert ref_shim.reference_available(), "run in the build container: /root/reference is required"
     ref_shim.install()
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["iou", "nms", "loss", "forward"]
+    which = sys.argv[1:] or ["iou", "nms", "loss", "forward", "scale"]
+    if "scale" in which:
+        gen_scale_boxes()
     if "iou" in which:
         gen_iou()
     if "nms" in which:

@@ -84,3 +84,12 @@ def test_iou():
     g = np.load(G / "iou_cases.npz")
     assert np.array_equal(O.box_iou(g["a"], g["b"]).numpy(), g["iou"])
     assert np.allclose(O.ciou_xywh(torch.from_numpy(g["p1"]), torch.from_numpy(g["p2"])).numpy(), g["ciou"], atol=1e-6)
+
+
+def test_scale_boxes_bit_exact():
+    """oracle scale_boxes == reference utils/general.py:613-626 on the committed fixtures (4 letterbox geometries)."""
+    g = np.load(G / "scale_boxes_cases.npz")
+    for ci in range(sum(k.startswith("geom") for k in g.files)):
+        s1, s0, rp = ast.literal_eval(str(g[f"geom{ci}"]))
+        out = O.scale_boxes(s1, g[f"in{ci}"][:, :4], s0, rp)
+        assert np.array_equal(out, g[f"out{ci}"][:, :4])

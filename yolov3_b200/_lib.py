@@ -158,6 +158,7 @@ def _declare(lib):
         "y3_bn_act_bwd": ([C.POINTER(BnBwdDesc), vp], C.c_int),
         "y3_pack_weights": ([vp, i32, i32, i32, vp, vp, vp], C.c_int),
         "y3_zero_stuff": ([vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, vp], C.c_int),
+        "y3_scale_boxes": ([vp, C.c_int64, i32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, vp], C.c_int),
         "y3_conv_wgrad": ([C.POINTER(WgradDesc), vp], C.c_int),
         "y3_conv_wgrad_tap_major": ([i32], C.c_int),
         "y3_add_nhwc": ([vp, i32, i32, vp, i32, i32, i32, i32, i32, i32, i32, vp], C.c_int),

@@ -21,8 +21,39 @@ __global__ void __launch_bounds__(256) box_iou_kernel(const float4* __restrict__
     out[i] = __fdiv_rn(inter, __fadd_rn(__fsub_rn(__fadd_rn(a1, a2), inter), eps));
   }
 }
+
+// scale_boxes / clip_boxes (reference utils/general.py:613-626 + ultralytics clip_boxes): in place on columns 0..3 of
+// every row: x = clamp((x - pad_x) / gain, 0, max_x), y likewise; separately rounded fp32 ops in the reference's order
+// (sub, div, clamp); torch.clamp propagates NaN.
+__device__ __forceinline__ float clamp_like_torch(float v, float hi) { return v != v ? v : fminf(fmaxf(v, 0.0f), hi); }
+
+__global__ void __launch_bounds__(256) scale_boxes_kernel(float* __restrict__ boxes, long long n, int row_stride, float pad_x,
+                                                          float pad_y, float gain, float max_x, float max_y) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float* b = boxes + i * row_stride;
+    b[0] = clamp_like_torch(__fdiv_rn(__fsub_rn(b[0], pad_x), gain), max_x);
+    b[1] = clamp_like_torch(__fdiv_rn(__fsub_rn(b[1], pad_y), gain), max_y);
+    b[2] = clamp_like_torch(__fdiv_rn(__fsub_rn(b[2], pad_x), gain), max_x);
+    b[3] = clamp_like_torch(__fdiv_rn(__fsub_rn(b[3], pad_y), gain), max_y);
+  }
+}
 }  // namespace
 }  // namespace y3
+
+extern "C" int y3_scale_boxes(float* boxes, int64_t n, int32_t row_stride, float pad_x, float pad_y, float gain, float max_x,
+                              float max_y, y3_stream_t stream) {
+  Y3_REQUIRE(n >= 0 && row_stride >= 4, "scale_boxes: bad shape (n=%lld, row stride %d)", static_cast<long long>(n), row_stride);
+  if (n == 0) return Y3_OK;
+  Y3_REQUIRE(boxes != nullptr, "scale_boxes: null pointer");
+  long long blocks = (n + 255) / 256;
+  const long long cap = static_cast<long long>(y3::num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  y3::scale_boxes_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      boxes, n, row_stride, pad_x, pad_y, gain, max_x, max_y);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
 
 extern "C" int y3_box_iou(const float* box1, int32_t n, const float* box2, int32_t m, float eps, float* out,
                           y3_stream_t stream) {
