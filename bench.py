@@ -105,7 +105,6 @@ def aggregate(ms_local: float, dev) -> float:
 def build_model(device):
     import torch
 
-    sys.path.insert(0, str(ROOT / "oracle"))
     from yolov3_b200.model import Model
 
     torch.manual_seed(0)
@@ -314,10 +313,9 @@ def main():
     # ---- NMS sweep (BASELINE config 5): synthetic [bs,25200,85] fp32 resident in HBM, device pipeline only (no D2H)
     from yolov3_b200.nms import nms_batched
 
-    sys.path.insert(0, str(ROOT / "oracle"))
-    import yolo_oracle as O
+    from yolov3_b200.synth import synth_predictions
 
-    pred = O.synth_predictions(BS, n_rows=25200, nc=80, seed=3).to(dev)
+    pred = synth_predictions(BS, n_rows=25200, nc=80, seed=3).to(dev)
     nms_res = {}
     for conf, iou, ml in ((0.25, 0.45, False), (0.001, 0.6, False), (0.001, 0.6, True)):
         for _ in range(3):

@@ -2,12 +2,12 @@
 rank r runs a training step on HALF of a batch with parallel.convert_sync_batchnorm(); rank 0 also runs the full batch
 without it.  The synchronised running statistics must equal the full-batch ones, and the all-reduced (averaged, loss x
 world) gradients must match the full-batch gradients to the step-to-step reproducibility of the bf16 pipeline.
-  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/check_syncbn.py"""
+  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/diag/check_syncbn.py"""
 import os
 import sys
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "oracle"))
 

@@ -1,10 +1,10 @@
-"""Diagnostic: per-parameter gradient error of one training step vs the CPU oracle.  python tools/train_diag.py [size] [bs]"""
+"""Diagnostic: per-parameter gradient error of one training step vs the CPU oracle.  python tests/diag/train_diag.py [size] [bs]"""
 import sys
 from pathlib import Path
 
 import torch
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "oracle"))
 import yolo_oracle as O
 from yolov3_b200.loss import ComputeLoss

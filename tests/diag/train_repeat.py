@@ -1,11 +1,11 @@
 """Diagnostic: run the same training step several times (same images, same targets, no optimizer step) and report how far
 the parameter gradients of step k are from those of step 1 — eager launches first, then through the captured CUDA graphs.
-  python tools/train_repeat.py [--graphs 0|1] [--steps 4]"""
+  python tests/diag/train_repeat.py [--graphs 0|1] [--steps 4]"""
 import argparse
 import sys
 from pathlib import Path
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "oracle"))
 

@@ -203,3 +203,29 @@ def test_xpair_weight_pack_layout():
     ref = w.bfloat16().float()
     assert torch.equal(v[:, :, 0, 0], ref[:, :, :, 0].permute(0, 2, 1)) and torch.equal(v[:, :, 0, 1], ref[:, :, :, 1].permute(0, 2, 1))
     assert torch.equal(v[:, :, 1, 0], ref[:, :, :, 2].permute(0, 2, 1)) and float(v[:, :, 1, 1].abs().max()) == 0.0
+
+
+def test_package_synth_workloads_equal_the_oracle_copies():
+    """bench.py / tools draw their synthetic inputs from yolov3_b200.synth (nothing outside tests/, smoke() and the CPU
+    baseline leg imports oracle/); the tests use the oracle's generators — both must produce identical tensors."""
+    import torch
+
+    import yolo_oracle as O
+    from yolov3_b200 import synth
+
+    assert torch.equal(O.synth_predictions(2, n_rows=300, seed=3), synth.synth_predictions(2, n_rows=300, seed=3))
+    assert torch.equal(O.synth_targets(16, seed=2), synth.synth_targets(16, seed=2))
+    assert O.scaled_hyp() == synth.scaled_hyp() and O.scaled_hyp(nl=2, nc=20, imgsz=320) == synth.scaled_hyp(nl=2, nc=20, imgsz=320)
+
+
+def test_only_tests_smoke_and_bench_cpu_legs_touch_the_oracle():
+    """The oracle is test infrastructure: no file of the package or of tools/ may import it."""
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parents[1]
+    offenders = []
+    for p in list((root / "yolov3_b200").rglob("*.py")) + list((root / "tools").glob("*.py")):
+        txt = p.read_text()
+        if "yolo_oracle" in txt or "ref_shim" in txt:
+            offenders.append(str(p.relative_to(root)))
+    assert not offenders, offenders

@@ -253,7 +253,7 @@ def test_train_step_vs_oracle_autograd(cfg_name):
     # steps 2 and 3 run through the captured CUDA graphs (forward + backward) on the same inputs.  The step is not
     # bit-reproducible: the fp32 atomics of the BatchNorm sums order differently from launch to launch, and a flipped
     # bf16 rounding is amplified by 75 BatchNorm layers over 4x3x3..12x12 pixels (eager launches show the same spread,
-    # tools/train_repeat.py: loss +-1e-3, gradients 0.12-0.18 rel-L2 step to step).  So the replayed step has to meet
+    # tests/diag/train_repeat.py: loss +-1e-3, gradients 0.12-0.18 rel-L2 step to step).  So the replayed step has to meet
     # the same bar against the fp32 oracle as the eager one, not reproduce it.
     for _ in range(2):
         for k in g_o:

@@ -13,9 +13,9 @@ import torch
 import torch.distributed as dist
 
 ROOT = Path(__file__).resolve().parents[1]
-sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "oracle"))
-import yolo_oracle as O  # noqa: E402  (synthetic targets / hyp only)
+sys.path.insert(0, str(ROOT))
 from yolov3_b200 import parallel  # noqa: E402
+from yolov3_b200 import synth as O  # noqa: E402  (synthetic targets / hyp)
 from yolov3_b200.loss import ComputeLoss  # noqa: E402
 from yolov3_b200.model import Model  # noqa: E402
 

@@ -16,5 +16,5 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 420 --c
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tc --launch-skip 84 --launch-count 1 -f \
   -o gpurun_out/ncu_conv_tc python tools/run_forward.py 2 > /dev/null 2>&1
 # 2 GPUs (gpurun --gpus 2): python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-#   bench.py --gpus 2 ; ... tools/bench_train.py ; ... tools/check_syncbn.py
+#   bench.py --gpus 2 ; ... tools/bench_train.py ; ... tests/diag/check_syncbn.py
 tools/gpu_sanity.sh end

@@ -6,7 +6,6 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "oracle"))
 
 
 def main():
@@ -18,8 +17,7 @@ def main():
     ap.add_argument("--iters", type=int, default=3)
     a = ap.parse_args()
     import torch
-    import yolo_oracle as O
-
+    from yolov3_b200 import synth as O
     from yolov3_b200.nms import nms_batched
 
     pred = O.synth_predictions(a.bs, n_rows=25200, nc=80, seed=3).cuda()
