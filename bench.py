@@ -328,8 +328,11 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ms = aggregate(e0.elapsed_time(e1) / reps, dev)
+        # HBM roofline of the whole NMS pipeline: ALGORITHMIC bytes = read z once, 8.568 MB/image
+        gbs = BS * 25200 * 85 * 4 / (ms / 1e3) / 1e9
         nms_res[f"conf{conf}_iou{iou}_{'multi' if ml else 'single'}"] = {
-            "input_boxes_per_s": world * BS * 25200 / (ms / 1e3), "ms_per_batch": ms}
+            "input_boxes_per_s": world * BS * 25200 / (ms / 1e3), "ms_per_batch": ms,
+            "hbm_gbs_per_gpu": gbs, "hbm_frac": gbs / peaks()["hbm"]}
 
     if rank != 0:
         if world > 1:
@@ -355,6 +358,10 @@ def main():
                 "traffic_sample": {"kernel": "conv_tc 128->256 3x3 s1 @80x80 bs32 +res (8 of the 74 launches)",
                                    "dram_bytes_per_launch": 226.9e6, "algorithmic_bytes_per_launch": 262.7e6,
                                    "source": "profiles/r01_ncu_conv_tc_final_summary.txt"}}
+    dec = [o for o in per_op if o["kind"] == "decode"]
+    if dec:  # Detect decode: read the head logits + write z = 17.1 MB/image algorithmic
+        roofline["decode_hbm"] = {"bound": "hbm", "achieved": dec[0]["gbs"], "peak": pk["hbm"], "unit": "GB/s",
+                                  "frac": dec[0]["gbs"] / pk["hbm"], "ms": dec[0]["ms"]}
     if args.per_op:
         Path(args.per_op).parent.mkdir(parents=True, exist_ok=True)
         Path(args.per_op).write_text(json.dumps(per_op, indent=1))
