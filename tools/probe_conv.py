@@ -4,7 +4,6 @@ the others down.  Usage: python tools/probe_conv.py [--out gpurun_out/probe_conv
 import json
 import subprocess
 import sys
-import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
