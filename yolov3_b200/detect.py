@@ -2,7 +2,6 @@
 (reference models/yolo.py:100-110)."""
 from __future__ import annotations
 
-import ctypes as C
 
 import torch
 
