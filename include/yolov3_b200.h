@@ -156,8 +156,8 @@ typedef struct y3_decode_desc {
 int y3_detect_head_decode_fwd(const y3_decode_desc* d, y3_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
- * Batched NMS.  Replaces non_max_suppression (utils/general.py:630-750) incl. torchvision.ops.nms (:733) for nm=0,
- * labels=().  Sync-free: results are padded device arrays plus per-image counts.
+ * Batched NMS.  Replaces non_max_suppression (utils/general.py:630-750) incl. torchvision.ops.nms (:733) for nm=0;
+ * autolabel priors (labels=, :689-695) are appended to `pred` by the caller as obj = 1 / one-hot rows.  Sync-free: results are padded device arrays plus per-image counts.
  *   pred      fp32 [bs, n_rows, 5+nc]  (xywh, obj, cls...)
  *   out       fp32 [bs, max_det, 6]    rows (x1,y1,x2,y2,conf,cls) sorted by conf desc, zero beyond out_count[b]
  *   out_src   int32 [bs, max_det, 2]   optional (pred row, class) of every kept detection
