@@ -79,6 +79,15 @@ int y3_conv_bn_act_fwd(const y3_conv_desc* d, y3_stream_t stream);
 #define Y3_W_TAPS 0
 #define Y3_W_XPAIR 1
 int y3_conv_weight_layout(const y3_conv_desc* d);
+/* The kernel variant y3_conv_bn_act_fwd would launch for a descriptor (host-only query: pointers are checked for
+ * alignment but never dereferenced, no tensor map is encoded, no GPU needed): tile shape, CTA pairs (cta_group::2), TMA-store
+ * epilogue, halo reuse (one A box per filter row), weights resident in shared memory, epilogue warp groups, x-paired
+ * stride-2 weights, tile counts and grid.  For tests and for reading the selection heuristics off a model. */
+typedef struct y3_conv_plan_info {
+  int32_t block_n, block_k, pair, staged, halo, resident_weights, epilogue_groups, xpair;
+  int32_t m_tiles, n_tiles, k_blocks, grid;
+} y3_conv_plan_info;
+int y3_conv_plan(const y3_conv_desc* d, y3_conv_plan_info* out);
 /* Tile N the kernel will use for c_out (weights/bias must be padded to a multiple of it). */
 int y3_conv_cout_pad(int32_t c_out);
 

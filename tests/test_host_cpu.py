@@ -229,3 +229,58 @@ def test_only_tests_smoke_and_bench_cpu_legs_touch_the_oracle():
         if "yolo_oracle" in txt or "ref_shim" in txt:
             offenders.append(str(p.relative_to(root)))
     assert not offenders, offenders
+
+
+def _plan(c_in, c_out, k, s, hw, n=32, res=False, head=False, layout=0):
+    """y3_conv_plan for a conv of the yolov3 graph: host-only query, fake (aligned, never dereferenced) pointers."""
+    import ctypes as C
+
+    from yolov3_b200 import _lib
+
+    L = _lib.lib()
+    d = _lib.ConvDesc()
+    d.n, d.h, d.w, d.c_in, d.c_out, d.ksize, d.stride, d.act = n, hw, hw, c_in, c_out, k, s, 1
+    d.in_, d.in_ld, d.in_coff = 0x10000, c_in, 0
+    d.weight, d.bias = 0x20000, 0x30000
+    if head:
+        d.out_f32, d.out_f32_ld = 0x40000, L.y3_conv_cout_pad(c_out)
+    else:
+        d.out, d.out_ld, d.out_coff = 0x40000, c_out, 0
+    if res:
+        d.res, d.res_ld, d.res_coff = 0x50000, c_out, 0
+    d.weight_layout = layout
+    info = _lib.ConvPlanInfo()
+    _lib.check(L.y3_conv_plan(C.byref(d), C.byref(info)), "y3_conv_plan")
+    return {k_: getattr(info, k_) for k_, _ in info._fields_}
+
+
+def test_conv_kernel_selection_for_the_yolov3_layers():
+    """The variant conv_tc_prepare picks for the distinct conv shapes of yolov3 @640 bs 32: tile N = c_out
+    bucket, CTA pairs for N >= 128, halo reuse for stride-1 3x3 (N = 256 only as a pair), TMA-store epilogue for stride 1
+    except halo + N = 256, resident weights when one N tile's weights fit in 96 KB, two epilogue groups for N <= 128."""
+    from yolov3_b200 import _lib
+
+    shapes = [(32, 64, 3, 2, 640, False), (64, 32, 1, 1, 320, False), (32, 64, 3, 1, 320, True), (64, 128, 3, 2, 320, False),
+              (128, 64, 1, 1, 160, False), (64, 128, 3, 1, 160, True), (128, 256, 3, 2, 160, False), (256, 128, 1, 1, 80, False),
+              (128, 256, 3, 1, 80, True), (256, 512, 3, 2, 80, False), (512, 256, 1, 1, 40, False), (256, 512, 3, 1, 40, True),
+              (512, 1024, 3, 2, 40, False), (1024, 512, 1, 1, 20, False), (512, 1024, 3, 1, 20, True), (768, 256, 1, 1, 40, False),
+              (384, 128, 1, 1, 80, False)]
+    for c_in, c_out, k, s, hw, res in shapes:
+        p = _plan(c_in, c_out, k, s, hw, res=res)
+        bn = 32 if c_out <= 32 else 64 if c_out <= 64 else 128 if c_out <= 128 else 256
+        assert p["block_n"] == bn and p["block_k"] == (64 if c_in % 64 == 0 else 32), (c_in, c_out, p)
+        assert p["pair"] == int(bn >= 128) and p["epilogue_groups"] == (2 if bn <= 128 else 1), (c_in, c_out, p)
+        assert p["halo"] == int(k == 3 and s == 1), (c_in, c_out, p)
+        assert p["staged"] == int(s == 1 and not (p["halo"] and bn == 256)), (c_in, c_out, p)
+        n_tiles = -(-c_out // bn)
+        w_bytes = k * k * c_in * (bn // 2 if p["pair"] else bn) * 2
+        assert p["n_tiles"] == n_tiles and p["resident_weights"] == int(n_tiles == 1 and w_bytes <= 96 * 1024), (c_in, c_out, p)
+        if s == 1:
+            assert p["m_tiles"] == -(-(32 * (hw + 2) * (hw + 2)) // 128)
+        assert 1 <= p["grid"] <= 148 and (p["grid"] % 2 == 0 or not p["pair"])
+    # the first stride-2 layer with x-paired weights: 6 taps of 64 channels, one k-block
+    d = _plan(32, 64, 3, 2, 640, layout=_lib.W_XPAIR)
+    assert d["xpair"] == 1 and d["block_k"] == 64 and d["k_blocks"] == 1 and d["resident_weights"] == 1
+    # Detect head: fp32 pixel-major output, never staged
+    h = _plan(256, 255, 1, 1, 80, head=True)
+    assert h["block_n"] == 256 and h["staged"] == 0 and h["pair"] == 1

@@ -33,6 +33,13 @@ class ConvDesc(C.Structure):
     ]
 
 
+class ConvPlanInfo(C.Structure):
+    """struct y3_conv_plan_info."""
+
+    _fields_ = [(k, C.c_int32) for k in ("block_n", "block_k", "pair", "staged", "halo", "resident_weights", "epilogue_groups",
+                                         "xpair", "m_tiles", "n_tiles", "k_blocks", "grid")]
+
+
 W_TAPS, W_XPAIR = 0, 1
 MAX_LEVELS, MAX_ANCHORS = 5, 6
 
@@ -147,6 +154,7 @@ def _declare(lib):
         "y3_conv_bn_act_fwd": ([C.POINTER(ConvDesc), vp], C.c_int),
         "y3_conv_cout_pad": ([i32], C.c_int),
         "y3_conv_weight_layout": ([C.POINTER(ConvDesc)], C.c_int),
+        "y3_conv_plan": ([C.POINTER(ConvDesc), C.POINTER(ConvPlanInfo)], C.c_int),
         "y3_abi_sizeof": ([i32], C.c_int64),
         "y3_conv_first_fwd": ([C.POINTER(FirstDesc), vp], C.c_int),
         "y3_maxpool_fwd": ([C.POINTER(PoolDesc), vp], C.c_int),

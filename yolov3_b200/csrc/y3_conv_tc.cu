@@ -805,7 +805,8 @@ static bool conv_prefers_xpair(const y3_conv_desc& d) {
   return d.ksize == 3 && d.stride == 2 && (d.c_in == 32 || d.c_in == 16) && d.in_ld == d.c_in && d.in_coff == 0;
 }
 
-int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
+// select_only: tile / mode selection without encoding the tensor maps (y3_conv_plan: host-side tests of the heuristics)
+int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan, bool select_only) {
   Y3_REQUIRE(d.n > 0 && d.h > 0 && d.w > 0, "conv: empty shape");
   Y3_REQUIRE((d.ksize == 1 && d.stride == 1) || (d.ksize == 3 && (d.stride == 1 || d.stride == 2)),
              "conv: ksize/stride %d/%d unsupported (1x1 s1, 3x3 s1, 3x3 s2)", d.ksize, d.stride);
@@ -890,7 +891,7 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     const uint64_t dims[2] = {static_cast<uint64_t>(d.in_ld), static_cast<uint64_t>(rows)};
     const uint64_t strides[2] = {0, static_cast<uint64_t>(d.in_ld) * 2};
     const uint32_t box[2] = {static_cast<uint32_t>(bk), a_rows};
-    rc = encode_tensor_map_bf16(&plan->map_a, d.in, 2, dims, strides, box, bk * 2);
+    rc = select_only ? Y3_OK : encode_tensor_map_bf16(&plan->map_a, d.in, 2, dims, strides, box, bk * 2);
     if (rc) return rc;
   } else {
     plan->halo = 0;
@@ -923,7 +924,7 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     const uint64_t strides[5] = {0, 2 * ld * 2, static_cast<uint64_t>(wp) * ld * 2, 2ull * wp * ld * 2,
                                  static_cast<uint64_t>(hp) * wp * ld * 2};
     const uint32_t box[5] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(a.tw), 1, static_cast<uint32_t>(a.th), 1};
-    rc = encode_tensor_map_bf16(&plan->map_a, d.in, 5, dims, strides, box, bk * 2);
+    rc = select_only ? Y3_OK : encode_tensor_map_bf16(&plan->map_a, d.in, 5, dims, strides, box, bk * 2);
     if (rc) return rc;
   }
   {
@@ -932,7 +933,7 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     const uint64_t strides[2] = {0, ktot * 2};
     plan->pair = (bn >= 128 && pair_enabled() && a.m_tiles >= 2) ? 1 : 0;
     const uint32_t box[2] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(plan->pair ? bn / 2 : bn)};
-    rc = encode_tensor_map_bf16(&plan->map_b, d.weight, 2, dims, strides, box, bk * 2);
+    rc = select_only ? Y3_OK : encode_tensor_map_bf16(&plan->map_b, d.weight, 2, dims, strides, box, bk * 2);
     if (rc) return rc;
   }
   {
@@ -951,12 +952,12 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
     const uint64_t dims[2] = {static_cast<uint64_t>(d.out_coff + d.c_out), static_cast<uint64_t>(a.rows_total)};
     const uint64_t strides[2] = {0, static_cast<uint64_t>(d.out_ld) * 2};
     const uint32_t box[2] = {slab_cols, 32};  // one epilogue warp's rows
-    rc = encode_tensor_map_bf16(&plan->map_out, d.out, 2, dims, strides, box, slab_cols * 2);
+    rc = select_only ? Y3_OK : encode_tensor_map_bf16(&plan->map_out, d.out, 2, dims, strides, box, slab_cols * 2);
     if (rc) return rc;
     if (d.res) {
       const uint64_t rdims[2] = {static_cast<uint64_t>(d.res_ld), static_cast<uint64_t>(a.rows_total)};
       const uint64_t rstrides[2] = {0, static_cast<uint64_t>(d.res_ld) * 2};
-      rc = encode_tensor_map_bf16(&plan->map_res, d.res, 2, rdims, rstrides, box, slab_cols * 2);
+      rc = select_only ? Y3_OK : encode_tensor_map_bf16(&plan->map_res, d.res, 2, rdims, rstrides, box, slab_cols * 2);
       if (rc) return rc;
     }
   }
@@ -975,6 +976,26 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan) {
 }
 
 }  // namespace y3
+
+extern "C" int y3_conv_plan(const y3_conv_desc* d, y3_conv_plan_info* out) {
+  if (!d || !out) return y3::set_error(Y3_ERR_BAD_ARG, "conv_plan: null argument");
+  y3::ConvTcPlan plan;
+  int rc = y3::conv_tc_prepare(*d, &plan, true);
+  if (rc) return rc;
+  out->block_n = plan.block_n;
+  out->block_k = plan.block_k;
+  out->pair = plan.pair;
+  out->staged = plan.staged;
+  out->halo = plan.halo;
+  out->resident_weights = plan.bres;
+  out->epilogue_groups = plan.groups;
+  out->xpair = plan.args.xpair;
+  out->m_tiles = plan.args.m_tiles;
+  out->n_tiles = plan.args.n_tiles;
+  out->k_blocks = plan.args.kblocks;
+  out->grid = plan.grid;
+  return Y3_OK;
+}
 
 extern "C" int y3_conv_weight_layout(const y3_conv_desc* d) {
   if (!d) return y3::set_error(Y3_ERR_BAD_ARG, "conv: null descriptor");

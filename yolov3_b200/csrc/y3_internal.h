@@ -72,7 +72,7 @@ struct ConvTcPlan {
   int grid;
   size_t smem_bytes;
 };
-int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan);
+int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan, bool select_only = false);
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);
 int pool_launch(const y3_pool_desc& d, cudaStream_t stream);
 int wgrad_tc_enabled();
