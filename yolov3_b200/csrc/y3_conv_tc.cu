@@ -33,14 +33,14 @@ constexpr int kBlockM = 128;
 constexpr int kEpilogueWarps = 8;
 constexpr int kSmemBudget = 221 * 1024;  // ring + epilogue staging; alignment slack, barriers and bias slices come on top (227 KB max)
 
-// STAGED = true: the epilogue converts into a swizzled shared-memory staging tile and ONE thread stores it with TMA
-// (and pre-loads the residual tile into the same buffer with TMA), instead of every thread issuing 16-byte global
-// stores to 32 different cache lines per instruction — the thin layers were bound by exactly that (profiles/r01_*).
-// HALO = true (stride-1 3x3, BLOCK_K = 64): one pipeline stage covers a whole filter ROW (3 taps): the A operand is ONE
-// TMA box of 128+2 consecutive pixels and the three taps read it at row offsets 0/1/2 through UMMA descriptors whose
+// STAGED = true (stride 1, bf16 output): each epilogue warp converts its 32 tile rows into a swizzled shared-memory
+// staging tile and stores them with its own TMA box (and pre-loads its residual rows into the same place with TMA),
+// instead of every thread issuing 16-byte global stores to 32 different cache lines per instruction.
+// HALO = true (stride-1 3x3, BLOCK_K = 64 or 32): one pipeline stage covers a whole filter ROW (3 taps): the A operand is
+// ONE TMA box of 128+2 consecutive pixels and the three taps read it at row offsets 0/1/2 through UMMA descriptors whose
 // start address is not aligned to the 1 KB swizzle pattern (the swizzle is a function of the absolute address, so the
-// descriptor's base_offset stays 0 — verified on hardware, see halo_enabled()).  A rows fetched per
-// k-block drop from 9*128 to 3*130; the TMA unit's row rate (~1 row / 2.5 clk / SM), not its byte rate, was the limit.
+// descriptor's base_offset stays 0 — verified on hardware, see halo_enabled()).  A rows fetched per k-block drop from
+// 9*128 to 3*130 and the producer / MMA warps run a third of the pipeline stages.
 template <int BLOCK_N, int BLOCK_K, bool PAIR, bool STAGED, bool HALO>
 struct Cfg {
   static constexpr uint32_t kARows = HALO ? kBlockM + 2 : kBlockM;
