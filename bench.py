@@ -193,6 +193,19 @@ def run_reference(args, rank):
             om(x)
         dt = time.perf_counter() - t0
     v = per_step * args.steps / dt
+    # the reference's NMS on the host cores (config 5, conf 0.25 / IoU 0.45): oracle candidate pipeline (numpy) + the
+    # reference's own torchvision.ops.nms call, 8 images
+    nms_ref = None
+    try:
+        pred = O.synth_predictions(8, n_rows=25200, nc=80, seed=3)
+        O.non_max_suppression(pred[:1], 0.25, 0.45, use_torchvision=True)
+        t1 = time.perf_counter()
+        O.non_max_suppression(pred, 0.25, 0.45, use_torchvision=True)
+        t_nms = time.perf_counter() - t1
+        nms_ref = {"conf0.25_iou0.45_single": {"input_boxes_per_s": 8 * 25200 / t_nms, "ms_per_batch_of_8": t_nms * 1e3},
+                   "impl": "oracle candidate pipeline (numpy) + torchvision.ops.nms, the reference's call at general.py:733"}
+    except Exception as e:  # torchvision missing: report why instead of failing the arm
+        nms_ref = {"unavailable": repr(e)[:200]}
     sample = (f"{per_step} of the {BS} images of each step (fp32, fused BN, torch CPU ops, {cores} threads of "
               f"{os.cpu_count()} host cores: fastest of 4 thread counts tried)")
     print(json.dumps({
@@ -202,6 +215,7 @@ def run_reference(args, rank):
         "config": {"workload": f"yolov3.yaml forward+decode {IMG}x{IMG}, CPU sample", "imgsz": IMG, "batch_per_step": per_step},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "nms": nms_ref,
         "gpu_launches": 0,
     }), flush=True)
 

@@ -357,7 +357,8 @@ def greedy_nms(boxes, scores, iou_thres):
     return order[np.asarray(keep, dtype=np.int64)]
 
 
-def nms_image(x, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False, max_det=300, lb=None):
+def nms_image(x, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False, max_det=300, lb=None,
+              use_torchvision=False):
     """One image of non_max_suppression (utils/general.py:683-743).  x: [n, 5+nc] float32.
 
     Returns (det[k,6] float32 = xyxy,conf,cls sorted by conf desc; src[k,2] int64 = (row, cls) of each kept detection).
@@ -405,12 +406,17 @@ def nms_image(x, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, 
     det, src = det[order], src[order]
     c = (det[:, 5:6] * (np.float32(0) if agnostic else MAX_WH)).astype(np.float32)  # :731
     boxes = (det[:, :4] + c).astype(np.float32)  # :732
-    keep = greedy_nms(boxes, det[:, 4], iou_thres)[:max_det]  # :733-734
+    if use_torchvision:  # the reference's own call (general.py:733); same kept set as greedy_nms on tie-free scores
+        import torchvision
+
+        keep = torchvision.ops.nms(torch.from_numpy(boxes), torch.from_numpy(np.ascontiguousarray(det[:, 4])), iou_thres).numpy()[:max_det]
+    else:
+        keep = greedy_nms(boxes, det[:, 4], iou_thres)[:max_det]  # :733-734
     return det[keep].astype(np.float32), src[keep].astype(np.int64)
 
 
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
-                        max_det=300, labels=()):
+                        max_det=300, labels=(), use_torchvision=False):
     """Batch wrapper; the reference's wall-clock ``time_limit`` break (utils/general.py:675,746-748) is NOT restated:
     it is a hazard, not a result."""
     assert 0 <= conf_thres <= 1 and 0 <= iou_thres <= 1
@@ -420,7 +426,7 @@ def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=Non
     outs, srcs = [], []
     for xi in range(pred.shape[0]):
         d, s = nms_image(pred[xi], conf_thres, iou_thres, classes, agnostic, multi_label, max_det,
-                         lb=labels[xi] if labels else None)
+                         lb=labels[xi] if labels else None, use_torchvision=use_torchvision)
         outs.append(d)
         srcs.append(s)
     return outs, srcs

@@ -93,3 +93,14 @@ def test_scale_boxes_bit_exact():
         s1, s0, rp = ast.literal_eval(str(g[f"geom{ci}"]))
         out = O.scale_boxes(s1, g[f"in{ci}"][:, :4], s0, rp)
         assert np.array_equal(out, g[f"out{ci}"][:, :4])
+
+
+def test_oracle_greedy_nms_equals_torchvision():
+    """The numpy greedy pass of the oracle and torchvision.ops.nms (what the reference calls, general.py:733) keep the same
+    boxes in the same order on the config-5 workload."""
+    pred = O.synth_predictions(2, n_rows=25200, nc=80, seed=3)
+    for conf, iou, ml in ((0.25, 0.45, False), (0.05, 0.45, True)):
+        a, sa = O.non_max_suppression(pred, conf, iou, multi_label=ml)
+        b, sb = O.non_max_suppression(pred, conf, iou, multi_label=ml, use_torchvision=True)
+        for x, y, sx, sy in zip(a, b, sa, sb):
+            assert np.array_equal(x, y) and np.array_equal(sx, sy)
