@@ -104,3 +104,29 @@ def test_oracle_greedy_nms_equals_torchvision():
         b, sb = O.non_max_suppression(pred, conf, iou, multi_label=ml, use_torchvision=True)
         for x, y, sx, sy in zip(a, b, sa, sb):
             assert np.array_equal(x, y) and np.array_equal(sx, sy)
+
+
+def test_oracle_nms_properties():
+    """Size-independent properties of the checker itself: rows sorted by confidence, every kept score above the
+    threshold, kept boxes of one class never overlap above the IoU threshold, idempotence (NMS of its own output keeps
+    everything), and invariance of the kept set under a permutation of the prediction rows."""
+    pred = O.synth_predictions(1, n_rows=4000, nc=80, seed=9)
+    conf, iou = 0.1, 0.45
+    (out,), (src,) = O.non_max_suppression(pred, conf, iou, max_det=1000)
+    assert out.shape[0] > 10 and np.all(out[:-1, 4] >= out[1:, 4]) and np.all(out[:, 4] > conf)
+    for c in np.unique(out[:, 5]):
+        b = out[out[:, 5] == c][:, :4]
+        if len(b) > 1:
+            m = O.box_iou(torch.from_numpy(b), torch.from_numpy(b)).numpy()
+            np.fill_diagonal(m, 0.0)
+            assert m.max() <= iou + 1e-6
+    again = torch.zeros(1, out.shape[0], 85)
+    again[0, :, 0:2] = torch.from_numpy((out[:, 0:2] + out[:, 2:4]) / 2)
+    again[0, :, 2:4] = torch.from_numpy(out[:, 2:4] - out[:, 0:2])
+    again[0, :, 4] = 1.0
+    again[0, torch.arange(out.shape[0]), 5 + torch.from_numpy(out[:, 5]).long()] = torch.from_numpy(out[:, 4])
+    (out2,), _ = O.non_max_suppression(again, conf, iou, max_det=1000)
+    assert out2.shape[0] == out.shape[0]
+    perm = torch.randperm(pred.shape[1], generator=torch.Generator().manual_seed(1))
+    (out3,), (src3,) = O.non_max_suppression(pred[:, perm], conf, iou, max_det=1000)
+    assert np.array_equal(out3, out) and np.array_equal(perm.numpy()[src3[:, 0]], src[:, 0])
