@@ -303,3 +303,20 @@ def test_reference_arm_json_contract():
     assert d["higher_is_better"] is True and d["steps"] == 1 and d["value"] > 0 and d["n_gpus"] == 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+
+
+def test_detect_multi_backend_seam():
+    """The reference's backend-plugin point (models/common.py:435): same attributes as its ``pt`` branch, loud failure on a
+    CPU device, checkpoint dict {"cfg", "state_dict"} accepted."""
+    import torch
+
+    from yolov3_b200.backend import DetectMultiBackend, _load
+    from yolov3_b200.model import Model
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        DetectMultiBackend(Model(CFG / "yolov3-tiny.yaml", device="cpu"), device=torch.device("cpu"))
+    src = Model(CFG / "yolov3-tiny.yaml", device="cpu")
+    m = _load({"cfg": str(CFG / "yolov3-tiny.yaml"), "state_dict": src.state_dict(), "names": ["a"] * 80}, "cpu")
+    assert m.names == ["a"] * 80 and all(torch.equal(v, m.state_dict()[k]) for k, v in src.state_dict().items())
+    for attr in ("forward", "warmup", "from_numpy", "__call__"):
+        assert callable(getattr(DetectMultiBackend, attr))
