@@ -320,3 +320,12 @@ def test_detect_multi_backend_seam():
     assert m.names == ["a"] * 80 and all(torch.equal(v, m.state_dict()[k]) for k, v in src.state_dict().items())
     for attr in ("forward", "warmup", "from_numpy", "__call__"):
         assert callable(getattr(DetectMultiBackend, attr))
+    # checkpoint round trip through a file
+    import tempfile
+
+    from yolov3_b200.backend import save_checkpoint
+
+    with tempfile.TemporaryDirectory() as td:
+        save_checkpoint(src, td + "/tiny.pt")
+        back = _load(td + "/tiny.pt", "cpu")
+    assert back.yaml == src.yaml and all(torch.equal(v, back.state_dict()[k]) for k, v in src.state_dict().items())

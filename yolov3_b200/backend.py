@@ -37,6 +37,15 @@ def _load(weights, device, cfg=None) -> Model:
     return m
 
 
+def save_checkpoint(model: Model, path) -> None:
+    """Write the checkpoint format ``DetectMultiBackend`` / ``_load`` read: the YAML dict, reference-named fp32 tensors,
+    class names (the reference pickles whole nn.Modules instead, train.py:445-462)."""
+    if model.training:
+        model.eval()  # pulls the trained master parameters back from the device
+    torch.save({"cfg": model.yaml, "state_dict": {k: v.detach().float().cpu() for k, v in model.state_dict().items()},
+                "names": list(model.names)}, str(path))
+
+
 class DetectMultiBackend:
     def __init__(self, weights="yolov3.pt", device=torch.device("cuda"), dnn=False, data=None, fp16=False, fuse=True):  # noqa: B008
         device = torch.device(device)
