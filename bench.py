@@ -1,16 +1,25 @@
 #!/usr/bin/env python
-"""bench.py — BASELINE.json metric on the BASELINE config, one JSON line on stdout (rank 0).
+"""bench.py — BASELINE.json metric on the BASELINE configs, one JSON line on stdout (rank 0).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-  torchrun ... bench.py --gpus N ...        (one rank per GPU; weak scaling: bs 32 per GPU, no data-path collective)
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--only infer,train,spp_nms,nms,lib,cpu]
+  torchrun ... bench.py --gpus N ...        (one rank per GPU)
 
-A step = one pass of the hot path (Model.forward + Detect decode, reference models/yolo.py) over one synthetic batch:
-configs[1] "YOLOv3 640x640 bs=32 inference on 1 B200, synthetic input, random-init weights".
+Headline (config 2, `metric`/`value`/`e2e`/`roofline`): a step = one pass of the hot path (Model.forward + Detect decode,
+reference models/yolo.py) over one synthetic batch "YOLOv3 640x640 bs=32 inference on 1 B200, synthetic input, random-init
+weights"; weak scaling: bs 32 per GPU, no data-path collective.
   value      images/s, inputs resident in HBM (fp32 NCHW), CUDA-graph replay, CUDA-event timing, max over ranks
   e2e        images/s through yolov3_b200.Pipeline with HOST uint8 images: H2D + forward + decode + NMS + D2H per step
   roofline   conv kernels (tensor bound): algorithmic conv FLOPs / event-timed conv_tc launch time, vs MEASURED_PEAKS
-  cpu_baseline / --impl reference: the CPU oracle port of the reference forward (oracle/yolo_oracle.py, torch CPU ops,
-             all host threads) on a bounded sample of the same workload.
+  parity_rel_l2   z of the timed bs-32 engine vs the CPU reference/oracle forward on the same images and weights (the run
+                  fails above 2e-2)
+Extra keys (the other BASELINE configs, tools/bench_workloads.py):
+  train      config 4: training step (fwd / loss / bwd + overlapped bucketed all-reduce / fused clip+SGD+EMA), bs 8 per GPU —
+             the one path with a collective: its per-N values are the scaling curve of the gradient exchange
+  spp_nms    config 3: yolov3-spp forward + decode + NMS(0.25/0.45/1000), bs 8 per GPU, host images in, boxes out
+  nms        config 5: five thresholds x single/multi-label on synthetic [32,25200,85]
+  gpu_library_baseline   the reference itself on this GPU through PyTorch+cuDNN / torchvision / torch DDP (informational)
+  cpu_baseline / --impl reference: the reference's own torch-CPU Model + non_max_suppression from the staged copy
+             (baseline/_ref, kind "reference"), else the oracle port (kind "port"), on the host cores, bounded sample.
 """
 from __future__ import annotations
 
@@ -26,6 +35,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tools"))
 
 CFG = "yolov3.yaml"
 IMG, BS = 640, 32
@@ -33,15 +43,19 @@ GFLOP_PER_IMG = 155.891          # 2*MAC over the 75 nn.Conv2d of
 GFLOP_LAYER0 = 0.708             # layer 0 runs on CUDA cores (c_in=3); excluded from the tensor roofline
 METRIC = "images/sec @640 bs32 YOLOv3"
 UNIT = "images/s"
+PARITY_TOL = 2e-2
 
 
 def peaks():
-    p = ROOT / "MEASURED_PEAKS.json"
-    if p.exists():
-        d = json.loads(p.read_text())
-        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
-                    source="measured")
-    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+    from bench_workloads import peaks as _p
+
+    return _p()
+
+
+def workload_config(world):
+    return {"workload": f"yolov3.yaml forward+decode, {IMG}x{IMG}, bs {BS}/GPU, random-init weights, folded BN",
+            "imgsz": IMG, "batch_per_gpu": BS, "global_batch": BS * world, "parallelism": f"replicas x{world} (no collective)",
+            "l2": "inputs larger than L2: two 157 MB fp32 batches alternated; activations 6 GB/step", "cuda_graph": True}
 
 
 class ClockSampler:
@@ -121,103 +135,238 @@ def build_model(device):
     return m
 
 
-_BEST_THREADS = None
+# ------------------------------------------------------------------------------------------ CPU legs (checker / baseline only)
+class CpuReference:
+    """The reference's torch-CPU forward for the bench model: the reference's OWN ``Model`` from the staged copy
+    (baseline/_ref, ``kind = "reference"``) when present, else the oracle port (``kind = "port"``), holding the same weights
+    as the GPU model (``params``), fused, fp32, inference mode.  Thread count: calibrated AT the batch that is timed."""
 
+    def __init__(self, params=None):
+        import torch
 
-def best_threads(om):
-    """The reference leaves torch's intra-op thread count at its default; on many-core hosts that default can be far
-    from the fastest setting for this conv stack, so the baseline uses the fastest of a few candidates (stated in the
-    output)."""
-    global _BEST_THREADS
-    import torch
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import ref_shim
+        import yolo_oracle as O
 
-    if _BEST_THREADS is None:
+        self.O = O
+        self.kind = "port"
+        self.nms = None
+        if ref_shim.reference_available():
+            try:
+                ref_shim.install()
+                from models.yolo import Model as RefModel
+                from utils.general import non_max_suppression as ref_nms
+
+                m = RefModel(str(ref_shim.REFERENCE_ROOT / "models" / CFG))
+                if params is not None:
+                    missing, unexpected = m.load_state_dict(params, strict=False)
+                    assert not unexpected and all("num_batches_tracked" in k for k in missing), (missing[:3], unexpected[:3])
+                self.model = m.eval().fuse()
+                self.nms = ref_nms
+                self.kind = "reference"
+            except Exception as e:  # noqa: BLE001  (a broken staged copy must not take the bench down: say so and use the port)
+                print(f"bench: staged reference unusable ({e!r}); using the oracle port", file=sys.stderr)
+        if self.kind == "port":
+            self.model = O.OracleModel(ROOT / "yolov3_b200" / "cfg" / CFG, params=params, seed=0, fused=True)
+        self.threads = None
+        self.torch = torch
+
+    def forward(self, x):
+        with self.torch.inference_mode():
+            y = self.model(x)
+        return y[0]
+
+    def calibrate(self, x):
+        """fastest of {cores, cores/2, cores/4} intra-op threads on THIS batch (one pass each after one warm-up pass)"""
+        torch = self.torch
         cores = os.cpu_count() or 1
-        x = torch.rand(1, 3, IMG, IMG)
         best = (None, 1e30)
-        with torch.inference_mode():
-            for t in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 16)}, reverse=True):
-                torch.set_num_threads(t)
-                om(x)
-                t0 = time.perf_counter()
-                om(x)
-                dt = time.perf_counter() - t0
-                if dt < best[1]:
-                    best = (t, dt)
-        _BEST_THREADS = best[0]
-    torch.set_num_threads(_BEST_THREADS)
-    return _BEST_THREADS
+        tried = {}
+        for t in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
+            torch.set_num_threads(t)
+            self.forward(x[:2])
+            t0 = time.perf_counter()
+            self.forward(x)
+            dt = time.perf_counter() - t0
+            tried[t] = round(x.shape[0] / dt, 2)
+            if dt < best[1]:
+                best = (t, dt)
+        self.threads, self.tried = best[0], tried
+        torch.set_num_threads(self.threads)
+        return self.threads
 
+    def nms_rate(self, n_img=8, conf=0.25, iou=0.45):
+        """reference non_max_suppression on the host cores (config 5).  Called per image: the reference's wall-clock break
+        (utils/general.py:675,746-748) would otherwise silently drop the rest of a slow batch."""
+        from yolov3_b200.synth import synth_predictions
 
-def cpu_forward_rate(n_img, iters, warmup=1):
-    """Oracle port of the reference forward on the host cores; returns (images/s, threads used)."""
-    import torch
-
-    sys.path.insert(0, str(ROOT / "oracle"))
-    import yolo_oracle as O
-
-    om = O.OracleModel(ROOT / "yolov3_b200" / "cfg" / CFG, seed=0, fused=True)
-    cores = best_threads(om)
-    x = torch.rand(n_img, 3, IMG, IMG, generator=torch.Generator().manual_seed(1))
-    with torch.inference_mode():
-        for _ in range(warmup):
-            om(x)
+        pred = synth_predictions(n_img, n_rows=25200, nc=80, seed=3)
+        fn = self.nms if self.nms is not None else (lambda p, c, i: self.O.non_max_suppression(p, c, i, use_torchvision=True))
+        fn(pred[:1], conf, iou)
         t0 = time.perf_counter()
-        for _ in range(iters):
-            om(x)
+        for i in range(n_img):
+            fn(pred[i:i + 1], conf, iou)
         dt = time.perf_counter() - t0
-    return n_img * iters / dt, cores
+        return {"input_boxes_per_s": n_img * 25200 / dt, "ms_per_image": dt * 1e3 / n_img, "images": n_img,
+                "impl": "reference utils.general.non_max_suppression (torch CPU + torchvision.ops.nms)" if self.nms is not None
+                else "oracle candidate pipeline (numpy) + torchvision.ops.nms"}
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's torch-CPU forward (oracle port) on rank 0's host cores."""
+    """--impl reference: the reference's torch-CPU forward on rank 0's host cores, a bounded sample of each step's batch."""
     if rank != 0:
         return
-    n_img = 2
-    rate, cores = cpu_forward_rate(n_img, 1, warmup=1)  # calibration
-    budget = 150.0
-    per_step = max(1, min(BS, int(budget / max(1, args.steps + args.warmup) * rate)))
     import torch
 
-    sys.path.insert(0, str(ROOT / "oracle"))
-    import yolo_oracle as O
-
-    om = O.OracleModel(ROOT / "yolov3_b200" / "cfg" / CFG, seed=0, fused=True)
-    cores = best_threads(om)
-    x = torch.rand(per_step, 3, IMG, IMG, generator=torch.Generator().manual_seed(1))
-    with torch.inference_mode():
-        for _ in range(args.warmup):
-            om(x)
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            om(x)
-        dt = time.perf_counter() - t0
+    model = build_model("cpu")  # parameters only: nothing of yolov3_b200's compute path runs in this arm
+    ref = CpuReference(params=model.state_dict())
+    gen = torch.Generator().manual_seed(1)
+    probe = torch.rand(8, 3, IMG, IMG, generator=gen)
+    ref.calibrate(probe)
+    t0 = time.perf_counter()
+    ref.forward(probe)
+    rate = 8 / (time.perf_counter() - t0)
+    budget = 170.0
+    per_step = max(1, min(BS, int(budget / max(1, args.steps + args.warmup) * rate)))
+    x = torch.rand(per_step, 3, IMG, IMG, generator=gen)
+    for _ in range(args.warmup):
+        ref.forward(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ref.forward(x)
+    dt = time.perf_counter() - t0
     v = per_step * args.steps / dt
-    # the reference's NMS on the host cores (config 5, conf 0.25 / IoU 0.45): oracle candidate pipeline (numpy) + the
-    # reference's own torchvision.ops.nms call, 8 images
-    nms_ref = None
     try:
-        pred = O.synth_predictions(8, n_rows=25200, nc=80, seed=3)
-        O.non_max_suppression(pred[:1], 0.25, 0.45, use_torchvision=True)
-        t1 = time.perf_counter()
-        O.non_max_suppression(pred, 0.25, 0.45, use_torchvision=True)
-        t_nms = time.perf_counter() - t1
-        nms_ref = {"conf0.25_iou0.45_single": {"input_boxes_per_s": 8 * 25200 / t_nms, "ms_per_batch_of_8": t_nms * 1e3},
-                   "impl": "oracle candidate pipeline (numpy) + torchvision.ops.nms, the reference's call at general.py:733"}
-    except Exception as e:  # torchvision missing: report why instead of failing the arm
+        nms_ref = {"conf0.25_iou0.45_single": ref.nms_rate(8, 0.25, 0.45), "conf0.001_iou0.6_single": ref.nms_rate(4, 0.001, 0.6)}
+    except Exception as e:  # noqa: BLE001
         nms_ref = {"unavailable": repr(e)[:200]}
-    sample = (f"{per_step} of the {BS} images of each step (fp32, fused BN, torch CPU ops, {cores} threads of "
-              f"{os.cpu_count()} host cores: fastest of 4 thread counts tried)")
+    sample = (f"{per_step} of the {BS} images of each step (reference {'Model' if ref.kind == 'reference' else 'forward, oracle port'}, "
+              f"fp32, fused BN, torch CPU, {ref.threads} threads of {os.cpu_count()} host cores — img/s by thread count at bs 8: {ref.tried})")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"yolov3.yaml forward+decode {IMG}x{IMG}, CPU sample", "imgsz": IMG, "batch_per_step": per_step},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(max(1, args.gpus)),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": ref.threads, "kind": ref.kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "nms": nms_ref,
         "gpu_launches": 0,
     }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ reference on the GPU
+def _reference_modules():
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import ref_shim
+
+    if not ref_shim.reference_available():
+        return None
+    ref_shim.install()
+    return ref_shim
+
+
+def library_baseline(dev, rank, world, bs=32, img=640, steps=10, train_bs=8):
+    """The reference's own code on this GPU through PyTorch's libraries: Model(yolov3.yaml).fuse() in bf16 channels_last
+    (cuDNN), utils.general.non_max_suppression (torch ops + torchvision CUDA nms), ComputeLoss + DistributedDataParallel +
+    torch.optim.SGD under bf16 autocast.  Informational: this is the bar a kernel library sets on the same hardware."""
+    shim = _reference_modules()
+    if shim is None:
+        return {"unavailable": "reference not staged (baseline/_ref missing: run oracle/stage_reference.py in the build container)"}
+    from models.yolo import Model as RefModel
+    from utils.general import non_max_suppression as ref_nms
+    from utils.loss import ComputeLoss as RefLoss
+
+    import torch
+    import torch.distributed as dist
+
+    from yolov3_b200 import synth
+
+    res = {"impl": "ultralytics/yolov3 @ 97b87b1 (staged copy) on torch " + torch.__version__ + " / cuDNN " + str(torch.backends.cudnn.version())}
+    torch.backends.cudnn.benchmark = True
+    cfg = str(shim.REFERENCE_ROOT / "models" / "yolov3.yaml")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        torch.manual_seed(0)
+        m = RefModel(cfg).to(dev).eval().fuse().to(torch.bfloat16).to(memory_format=torch.channels_last)
+        x = torch.rand(bs, 3, img, img, device=dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        with torch.inference_mode():
+            for _ in range(5):
+                m(x)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(steps):
+                m(x)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = aggregate(e0.elapsed_time(e1) / steps, dev)
+        res["forward"] = {"images_per_s": world * bs / (ms / 1e3), "ms_per_step": ms, "batch_per_gpu": bs,
+                          "what": "reference Model.fuse() forward+decode, bf16, channels_last, cuDNN (benchmark mode), resident input"}
+        del m, x
+    except Exception as e:  # noqa: BLE001
+        res["forward"] = {"error": repr(e)[:300]}
+    try:
+        pred = synth.synth_predictions(bs, n_rows=25200, nc=80, seed=3).to(dev)
+        nms = {}
+        for conf, iou, ml in ((0.25, 0.45, False), (0.001, 0.6, False), (0.001, 0.6, True)):
+            ref_nms(pred[:2], conf, iou, multi_label=ml, max_det=300)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_done = 0
+            for i in range(0, bs, 4):  # 4 images per call keeps the reference's wall-clock break (general.py:746) out of reach
+                ref_nms(pred[i:i + 4], conf, iou, multi_label=ml, max_det=300)
+                n_done += 4
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            nms[f"conf{conf}_iou{iou}_{'multi' if ml else 'single'}"] = {"input_boxes_per_s": world * n_done * 25200 / dt,
+                                                                         "ms_per_batch_of_32": dt * 1e3 * 32 / n_done}
+        res["nms"] = {"what": "reference non_max_suppression on the CUDA tensor (torchvision.ops.nms CUDA kernel), wall clock incl. "
+                              "its host syncs", **nms}
+        del pred
+    except Exception as e:  # noqa: BLE001
+        res["nms"] = {"error": repr(e)[:300]}
+    try:
+        torch.manual_seed(0)
+        m = RefModel(cfg).to(dev)
+        hyp = synth.scaled_hyp()
+        m.hyp, m.nc = hyp, 80
+        m.train()
+        net = m
+        if world > 1:
+            net = torch.nn.parallel.DistributedDataParallel(m, device_ids=[dev.index], output_device=dev.index)
+        opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.937, nesterov=True)
+        loss_fn = RefLoss(m)
+        x = torch.rand(train_bs, 3, img, img, device=dev)
+        targets = synth.synth_targets(train_bs, seed=2 + rank).to(dev)
+
+        def step():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                pred = net(x)
+                loss, _ = loss_fn(pred, targets)
+                loss = loss * world
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), max_norm=10.0)
+            opt.step()
+            opt.zero_grad()
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        n = max(3, steps // 2)
+        for _ in range(n):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = aggregate(e0.elapsed_time(e1) / n, dev)
+        res["train"] = {"images_per_s": world * train_bs / (ms / 1e3), "ms_per_step": ms, "batch_per_gpu": train_bs,
+                        "what": "reference Model + ComputeLoss, torch.autocast(bf16), DistributedDataParallel (NCCL), clip + torch SGD; "
+                                "no EMA, no H2D"}
+    except Exception as e:  # noqa: BLE001
+        res["train"] = {"error": repr(e)[:300]}
+    torch.cuda.empty_cache()
+    return res
 
 
 def main():
@@ -227,9 +376,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only", default="all", help="comma list of legs besides the headline: train,spp_nms,nms,lib,cpu (default all)")
     ap.add_argument("--per-op", default=None, help="write the per-launch timing table (JSON) to this path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    legs = {"train", "spp_nms", "nms", "lib", "cpu"} if args.only == "all" else set(filter(None, args.only.split(",")))
+    if args.no_cpu_baseline:
+        legs.discard("cpu")
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -247,14 +400,19 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
+    import bench_workloads as W
     from yolov3_b200 import _lib
     from yolov3_b200.pipeline import Pipeline
 
     model = build_model(dev)
     eng = model.engine(BS, IMG, IMG, torch.float32)
     n_launch = _lib.lib().y3_model_num_launches(eng.handle)
-    # two distinct resident input batches (157 MB each > 126 MB L2), alternated so no step re-reads a cached input
+    # two distinct resident input batches (157 MB each > 126 MB L2), alternated so no step re-reads a cached input.  The first
+    # images of batch 0 come from a CPU generator: the parity leg runs the CPU reference on exactly those images.
+    n_par = 2
+    x_par = torch.rand(n_par, 3, IMG, IMG, generator=torch.Generator().manual_seed(1))
     xs = [torch.rand(BS, 3, IMG, IMG, device=dev, generator=torch.Generator(device=dev).manual_seed(1 + i)) for i in range(2)]
+    xs[0][:n_par] = x_par.to(dev)
     graphs = [eng.capture(x) for x in xs]  # one graph per resident input: a step is exactly the 76 launches of a forward
 
     def step(i):
@@ -295,6 +453,12 @@ def main():
     if world > 1:
         dist.barrier()
     value = world * BS * args.steps / (ms_total / 1e3)
+    # output of the timed engine on the parity images (graph 0 = batch 0), kept for the parity leg below
+    graphs[0].replay()
+    torch.cuda.synchronize()
+    eng.check_errors()
+    z_par = eng.z[:n_par].detach().cpu().clone()
+    z_finite = bool(torch.isfinite(eng.z).all())
 
     # ---- e2e: host uint8 images -> H2D -> forward -> decode -> NMS -> D2H, through the public Pipeline
     pipe = Pipeline(model, BS, IMG, IMG, conf_thres=0.25, iou_thres=0.45, max_det=300)
@@ -324,29 +488,31 @@ def main():
     ms_e2e = aggregate(ms_e2e, dev)
     e2e = world * BS * args.steps / (ms_e2e / 1e3)
 
-    # ---- NMS sweep (BASELINE config 5): synthetic [bs,25200,85] fp32 resident in HBM, device pipeline only (no D2H)
-    from yolov3_b200.nms import nms_batched
+    # ---- roofline of the dominant kernel (conv_tc): per-launch CUDA events on the launching stream (rank 0's GPU)
+    per_op = None
+    if rank == 0:
+        from yolov3_b200.profile import time_ops
 
-    from yolov3_b200.synth import synth_predictions
+        per_op = time_ops(eng, xs[0], iters=max(3, min(10, args.steps)))
+    del pipe, graphs
+    model._engines.clear()
+    del eng
+    torch.cuda.empty_cache()
 
-    pred = synth_predictions(BS, n_rows=25200, nc=80, seed=3).to(dev)
-    nms_res = {}
-    for conf, iou, ml in ((0.25, 0.45, False), (0.001, 0.6, False), (0.001, 0.6, True)):
-        for _ in range(3):
-            nms_batched(pred, conf, iou, multi_label=ml, max_det=300)
-        torch.cuda.synchronize()
-        e0.record()
-        reps = 10
-        for _ in range(reps):
-            nms_batched(pred, conf, iou, multi_label=ml, max_det=300)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = aggregate(e0.elapsed_time(e1) / reps, dev)
-        # HBM roofline of the whole NMS pipeline: ALGORITHMIC bytes = read z once, 8.568 MB/image
-        gbs = BS * 25200 * 85 * 4 / (ms / 1e3) / 1e9
-        nms_res[f"conf{conf}_iou{iou}_{'multi' if ml else 'single'}"] = {
-            "input_boxes_per_s": world * BS * 25200 / (ms / 1e3), "ms_per_batch": ms,
-            "hbm_gbs_per_gpu": gbs, "hbm_frac": gbs / peaks()["hbm"]}
+    # ---- the other BASELINE configs (every rank takes part: the training step has the collective)
+    extra = {}
+    if "nms" in legs:
+        extra["nms"] = {"workload": f"synthetic [bs {BS}/GPU, 25200, 85] fp32 (SURVEY §8d config 5), max_det 300, device-resident, "
+                                    "sync-free y3_nms_batched; iou 0.6 at conf <= 0.01 else 0.45", "unit": "input boxes/s",
+                        **W.nms_sweep_workload(dev, rank, world, bs=BS)}
+    if "spp_nms" in legs:
+        extra["spp_nms"] = W.spp_nms_workload(dev, rank, world, bs=8, img=IMG, steps=max(10, args.steps), warmup=args.warmup)
+        torch.cuda.empty_cache()
+    if "train" in legs:
+        extra["train"] = W.train_step_workload(dev, rank, world, bs=8, img=IMG, steps=max(5, min(10, args.steps)), warmup=3)
+        torch.cuda.empty_cache()
+    if "lib" in legs:
+        extra["gpu_library_baseline"] = library_baseline(dev, rank, world, bs=BS, img=IMG, steps=max(5, min(10, args.steps)))
 
     if rank != 0:
         if world > 1:
@@ -354,10 +520,6 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (conv_tc): per-launch CUDA events on the launching stream
-    from yolov3_b200.profile import time_ops
-
-    per_op = time_ops(eng, xs[0], iters=max(3, min(10, args.steps)))
     conv_ms = sum(o["ms"] for o in per_op if o["kind"] == "conv_tc")
     all_ms = sum(o["ms"] for o in per_op)
     conv_tflop = (GFLOP_PER_IMG - GFLOP_LAYER0) * BS / 1e3
@@ -365,13 +527,12 @@ def main():
     achieved = conv_tflop / (conv_ms / 1e3)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["tf_sustained"], "traffic": None,
-                "kernel": "conv_tc_kernel (74 launches/step)", "kernel_ms_per_step": conv_ms,
-                "kernel_share_of_step": conv_ms / all_ms, "peak_source": pk["source"] + " sustained bf16 (MEASURED_PEAKS.json)",
-                # `traffic` stays null: `achieved` aggregates 74 launches of 23 different shapes.  One ncu --set full capture
-                # of the largest layer group (recorded, not re-measured here): dram read+write vs algorithmic in+res+out+w
-                "traffic_sample": {"kernel": "conv_tc 128->256 3x3 s1 @80x80 bs32 +res (8 of the 74 launches)",
-                                   "dram_bytes_per_launch": 226.9e6, "algorithmic_bytes_per_launch": 262.7e6,
-                                   "source": "profiles/r01_ncu_conv_tc_final_summary.txt"}}
+                "kernel": f"conv_tc_kernel ({sum(1 for o in per_op if o['kind'] == 'conv_tc')} launches/step)",
+                "kernel_ms_per_step": conv_ms, "kernel_share_of_step": conv_ms / all_ms,
+                "whole_step_frac": GFLOP_PER_IMG * 1e9 * (value / world) / (pk["tf_sustained"] * 1e12),
+                "peak_source": pk["source"] + " sustained bf16 (MEASURED_PEAKS.json)",
+                "traffic_note": "null: `achieved` aggregates launches of 23 shapes; per-kernel DRAM bytes are in the ncu --set full "
+                                "summaries under profiles/ (not re-measured per run)"}
     dec = [o for o in per_op if o["kind"] == "decode"]
     if dec:  # Detect decode: read the head logits + write z = 17.1 MB/image algorithmic
         roofline["decode_hbm"] = {"bound": "hbm", "achieved": dec[0]["gbs"], "peak": pk["hbm"], "unit": "GB/s",
@@ -380,32 +541,45 @@ def main():
         Path(args.per_op).parent.mkdir(parents=True, exist_ok=True)
         Path(args.per_op).write_text(json.dumps(per_op, indent=1))
 
-    cpu = None
-    if not args.no_cpu_baseline:
-        n_img = 4
-        rate, cores = cpu_forward_rate(n_img, 2, warmup=1)
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_img} of the {BS} images per step, 2 timed passes after 1 warm-up (oracle port, torch CPU fp32)"}
+    cpu, parity = None, None
+    if "cpu" in legs:
+        ref = CpuReference(params=model.state_dict())
+        probe = torch.cat([x_par, torch.rand(6, 3, IMG, IMG, generator=torch.Generator().manual_seed(2))])
+        ref.calibrate(probe)
+        ref.forward(probe[:2])
+        t0 = time.perf_counter()
+        z_ref = ref.forward(probe)
+        dt = time.perf_counter() - t0
+        cpu = {"value": probe.shape[0] / dt, "unit": UNIT, "cores": ref.threads, "kind": ref.kind,
+               "sample": f"8 of the {BS} images of a step, one timed pass after warm-up and thread calibration "
+                         f"(img/s by thread count: {ref.tried}); "
+                         + ("reference models.yolo.Model from baseline/_ref" if ref.kind == "reference" else "oracle port")}
+        zr = z_ref[:n_par].double()
+        parity = float((z_par.double() - zr).norm() / zr.norm())
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"yolov3.yaml forward+decode, {IMG}x{IMG}, bs {BS}/GPU, random-init weights, folded BN",
-                   "imgsz": IMG, "batch_per_gpu": BS, "global_batch": BS * world, "parallelism": f"replicas x{world} (no collective)",
-                   "l2": "inputs larger than L2: two 157 MB fp32 batches alternated; activations 6 GB/step",
-                   "cuda_graph": True},
+        "config": workload_config(world),
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes, "d2h_bytes_per_step": pipe.d2h_bytes,
+        "parity_rel_l2": parity, "parity": {"what": f"z[:{n_par}] of the timed bs-{BS} CUDA-graph engine vs the CPU {cpu['kind'] if cpu else 'reference'} "
+                                                    "forward on the same images and weights", "tolerance": PARITY_TOL, "z_all_finite": z_finite},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": BS * 3 * IMG * IMG, "d2h_bytes_per_step": BS * 300 * 6 * 4 + 2 * BS * 4,
                 "ms_per_step": ms_e2e / args.steps, "path": "Pipeline.stream: uint8 H2D -> forward -> decode -> NMS(0.25/0.45/300) -> D2H, two batches in flight",
                 "sync_call_ms_per_step": ms_e2e_sync / args.steps},
         "gpu_launches": n_launch * args.steps,
         "clocks": clocks,
-        "nms": {"workload": f"synthetic [bs {BS}/GPU, 25200, 85] fp32 (SURVEY §8d config 5), max_det 300, device-resident, "
-                            "sync-free y3_nms_batched", "unit": "input boxes/s", **nms_res},
+        **extra,
     }
     print(json.dumps(line), flush=True)
+    if not z_finite or (parity is not None and not parity <= PARITY_TOL):
+        print(f"bench: PARITY FAILURE: rel-L2 {parity} (tolerance {PARITY_TOL}), finite {z_finite}", file=sys.stderr)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        sys.exit(3)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

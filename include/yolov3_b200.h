@@ -231,13 +231,19 @@ int y3_loss_fwd_bwd(const y3_loss_desc* d, void* workspace, int64_t workspace_by
  * (forward; dgrad = convolution with the transposed, tap-flipped weights) is y3_conv_bn_act_fwd with zero bias and
  * Y3_ACT_NONE; these entry points are the bandwidth-bound parts around it.  All activations: padded NHWC bf16 slices.
  */
-/* per-channel sum and sum of squares of y over all `rows` = n*(h+2)*(w+2) padded pixels (halo = 0); sum/sumsq must be
- * zeroed by the caller */
-int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, int64_t rows, float* sum, float* sumsq,
+/* Two-stage, atomic-free (bit-reproducible) reductions: a first-stage kernel writes one partial row per block into a
+ * caller-owned workspace [y3_bn_partial_blocks(n, h)][width], a fixed-order second stage adds the rows. */
+int32_t y3_bn_partial_blocks(int32_t n, int32_t h);
+/* per-channel sum and sum of squares of the conv output y over its n*h*w interior pixels:
+ * partial[blocks][2][c] = (sum | sumsq).  c: power of two in [8, 2048]. */
+int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, int32_t n, int32_t h, int32_t w, float* partial,
                 y3_stream_t stream);
-/* batch statistics -> scale = gamma*rstd, shift = beta - mean*scale, saved mean/rstd; running stats updated in place
- * with the unbiased variance when non-NULL (nn.BatchNorm2d semantics).  count = n*h*w. */
-int y3_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, int32_t c, float count,
+/* out[j] (+)= sum_b partial[b][j] for j < width, rows added in index order (SyncBatchNorm: sums before the all-reduce) */
+int y3_colreduce_f32(const float* partial, int32_t nblk, int32_t width, float* out, int32_t accumulate, y3_stream_t stream);
+/* batch statistics (given as nblk partial rows [2][c]; nblk = 1: already reduced) -> scale = gamma*rstd, shift = beta -
+ * mean*scale, saved mean/rstd; running stats updated in place with the unbiased variance when non-NULL (nn.BatchNorm2d
+ * semantics).  count = pixels behind the sums (n*h*w, times the world size under SyncBatchNorm). */
+int y3_bn_finalize(const float* partial, int32_t nblk, const float* gamma, const float* beta, int32_t c, float count,
                    float eps, float momentum, float* scale, float* shift, float* mean, float* rstd, float* running_mean,
                    float* running_var, y3_stream_t stream);
 typedef struct y3_bn_act_desc {
@@ -253,8 +259,10 @@ typedef struct y3_bn_bwd_desc {
   const void* da; int32_t da_ld, da_coff;      /* gradient w.r.t. the block output (2x geometry when upsample) */
   void* dy;       int32_t dy_ld, dy_coff;      /* gradient w.r.t. the conv output (input of dgrad / wgrad) */
   const float* scale; const float* shift; const float* mean; const float* rstd;
-  float* sum_dz;   /* [c] phase 0/1: out, dbeta = sum dz;  phase 2: in, the (all-reduced) sum */
-  float* sum_dzy;  /* [c] phase 0/1: out, dgamma = sum dz*xhat;  phase 2: in */
+  float* sums;       /* [2][c] = (sum dz | sum dz*xhat): phase 0/1 out, phase 2 in (the all-reduced sums) */
+  float* partial;    /* workspace [y3_bn_partial_blocks(n, h)][2][c] of the reduction phase (phases 0, 1) */
+  float* dbeta_acc;  /* optional [c]: += sum dz      (the bn.bias gradient, accumulated like autograd does) */
+  float* dgamma_acc; /* optional [c]: += sum dz*xhat (the bn.weight gradient) */
   int32_t n, h, w, c, upsample;
   int32_t phase;   /* 0: sums then apply (single GPU); 1: sums only; 2: apply only — SyncBatchNorm (train.py:270-272) puts
                       an all-reduce of the two sums between 1 and 2 */
@@ -264,6 +272,27 @@ int y3_bn_act_bwd(const y3_bn_bwd_desc* d, y3_stream_t stream);
 /* fp32 master weights [co, ci, k, k] -> bf16 forward pack [co_pad, k*k*ci] and/or dgrad pack [ci_pad, k*k*co] (taps
  * flipped, channels swapped); pad rows must already be zero */
 int y3_pack_weights(const float* w, int32_t co, int32_t ci, int32_t k, void* fwd, void* dgrad, y3_stream_t stream);
+/* Batched form used by the training engine: the fp32 masters live in ONE flat buffer with every conv weight stored
+ * [co][kh][kw][ci] (channels_last strides of the [co,ci,k,k] parameter == the forward pack's order), so
+ *   y3_f32_to_bf16        converts the whole buffer once per step (forward packs are views of the copy), and
+ *   y3_pack_dgrad_batched transposes every layer of a device-resident table into its dgrad pack in one launch. */
+int y3_f32_to_bf16(const float* src, void* dst, int64_t n, y3_stream_t stream);
+typedef struct y3_pack_item {
+  int64_t src_off;   /* element offset of this layer's [co_rows][k*k][ci] weights inside the bf16 flat copy */
+  void* dst;         /* dgrad pack, bf16 [ci_pad][k*k][dst_co] (rows >= ci stay zero) */
+  int32_t co_rows;   /* rows present in the source (c_out, or the padded 256 of a Detect head) */
+  int32_t ci, k;
+  int32_t dst_co;    /* row pitch of the pack = c_out the dgrad conv reduces over */
+  int32_t tile_begin;/* first 32x32 transpose tile of this layer: k*k * ceil(co_rows/32) * ceil(ci/32) tiles each, consecutive */
+  int32_t reserved;
+} y3_pack_item;
+int y3_pack_dgrad_batched(const y3_pack_item* items_dev, int32_t n_items, const void* wbf, int32_t total_tiles,
+                          y3_stream_t stream);
+/* Detect-head gradient: g = dL/draw fp32 [n, na, ny, nx, no] (ComputeLoss output) -> dy bf16 padded NHWC channel a*no+o
+ * (the head conv's output order; channels >= na*no zeroed) and partial[y3_bn_partial_blocks(n, ny)][256] column sums
+ * (bias gradient = y3_colreduce_f32 over them). */
+int y3_head_grad_pack(const float* g, int32_t n, int32_t na, int32_t ny, int32_t nx, int32_t no, void* dy, int32_t dy_ld,
+                      int32_t dy_coff, float* partial, y3_stream_t stream);
 /* dy of a stride-2 conv scattered onto the even positions of a zeroed [n, 2ho+2, 2wo+2, dst_ld] buffer */
 int y3_zero_stuff(const void* src, int32_t src_ld, int32_t src_coff, void* dst, int32_t dst_ld, int32_t dst_coff, int32_t n,
                   int32_t ho, int32_t wo, int32_t c, y3_stream_t stream);
@@ -274,12 +303,16 @@ int y3_zero_stuff(const void* src, int32_t src_ld, int32_t src_coff, void* dst, 
  * permutes once when it hands the gradient to the optimizer.  Needs c_in % 32 == 0 (y3_conv_wgrad_tap_major tells). */
 #define Y3_DW_OIHW 0
 #define Y3_DW_TAP_MAJOR 1
+#define Y3_DW_OHWI 2       /* [co, k*k, ci] == the channels_last strides of a [co, ci, k, k] tensor: the training engine's
+                              flat gradient buffer (the gradient IS the parameter's .grad view, no permute) */
 typedef struct y3_wgrad_desc {
   const void* dy; int32_t dy_ld, dy_coff;
   const void* x;  int32_t x_ld, x_coff;
   float* dw;
   int32_t co, ci, ksize, n, h, w;
   int32_t dw_layout;
+  int32_t accumulate;     /* 1: dw holds earlier contributions that must be kept (always reduce, never plain-store) */
+  int32_t deterministic;  /* 1: no split over pixels — one CTA per dW tile, bit-reproducible, slower on the early layers */
 } y3_wgrad_desc;
 int y3_conv_wgrad(const y3_wgrad_desc* d, y3_stream_t stream);
 /* 1 if y3_conv_wgrad accepts Y3_DW_TAP_MAJOR for this c_in (the tcgen05 kernel is in use), else 0 */
@@ -293,6 +326,23 @@ int y3_im2col_first(const void* in, int32_t in_dtype, float in_div, int32_t n, i
                     int32_t out_ld, int32_t out_coff, y3_stream_t stream);
 /* out[c] += sum over rows of g[row, c] (fp32 pixel-major; Detect-head bias gradients) */
 int y3_colsum_f32(const float* g, int32_t ld, int32_t c, int64_t rows, float* out, y3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Optimizer step over ONE flat fp32 parameter buffer (train.py:411-421: clip_grad_norm_(10.0), SGD-nesterov with the three
+ * parameter groups of smart_optimizer utils/torch_utils.py:207-237, ModelEMA.update) — csrc/y3_optim.cu.
+ * Layout contract: every parameter occupies a slot whose length is a multiple of 256 elements; group[i] is the group of
+ * elements [256 i, 256 i + 256): 0 = weights with decay, 1 = BatchNorm weights, 2 = biases, >= 3 = not trained (buffers).
+ * hp_dev: DEVICE float[11] = lr[3], weight_decay[3], momentum, nesterov, max_norm (0: no clipping), ema decay of this
+ * update, gradient pre-scale (1/world_size after a SUM all-reduce) — read at run time, so the launches can sit in a CUDA
+ * graph while the scheduler changes them.
+ */
+int32_t y3_sumsq_blocks(void);  /* floats of workspace y3_grad_sumsq needs */
+/* out[0] = sum g[i]^2 (two-stage, fixed order: bit-reproducible); n % 4 == 0 */
+int y3_grad_sumsq(const float* g, int64_t n, float* partial, float* out, y3_stream_t stream);
+/* p, m (momentum buffer, zero-initialised), ema (optional) updated in place from g; gsumsq (from y3_grad_sumsq) is read
+ * only when hp_dev[8] > 0.  n = elements of p (and of ema); g and m are only touched where group < 3. */
+int y3_sgd_step(float* p, const float* g, float* m, float* ema, const uint8_t* group, int64_t n, const float* hp_dev,
+                const float* gsumsq, y3_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Whole-graph executor.  Replaces BaseModel._forward_once (models/yolo.py:135-147): the Python loop over nn.Modules

@@ -7,11 +7,13 @@ utils/__init__.py:6, models/common.py, models/experimental.py, utils/plots.py, u
 utils/augmentations.py) so that the reference files import UNMODIFIED.  The arithmetic symbols (``bbox_iou``, ``box_iou``,
 ``fuse_conv_and_bn``, ``xywh2xyxy`` ...) are third-party code that is absent from ``/root/reference``; they are restated
 here from the published ultralytics 8.x formulas and unit-tested independently in
-``tests/test_oracle_shim.py`` (float64 cross-checks, torchvision.ops.box_iou, fused-vs-unfused forward).
+``tests/golden/make_golden.py`` (``gen_iou``: float64 CIoU cross-check, ``torchvision.ops.box_iou``; ``gen_forward``: fused
+vs unfused forward through ``fuse_conv_and_bn``) and re-checked from the fixtures by ``tests/test_oracle_golden.py``.
 
-Only ``tests/golden/make_golden.py`` (golden-vector generation, run in the build container) uses this.  Nothing on the
-product path, nothing in ``-m gpu`` tests, ``smoke()`` or ``bench.py`` imports it: ``/root/reference`` does not exist
-on the GPU box.
+Consumers: ``tests/golden/make_golden.py`` (golden-vector generation in the build container, reference at
+``/root/reference``); ``bench.py --impl reference`` / its ``cpu_baseline`` leg and ``tests/test_zz_reference_seam_gpu.py``,
+which run the reference from the byte-for-byte staged copy ``baseline/_ref/`` (``oracle/stage_reference.py``; git-ignored,
+travels to the GPU box with the snapshot).  Nothing under ``yolov3_b200/`` imports this.
 """
 from __future__ import annotations
 
@@ -27,7 +29,9 @@ from pathlib import Path
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = Path("/root/reference")
+_REPO = Path(__file__).resolve().parents[1]
+# the read-only checkout in the build container, else the staged copy that ships to the GPU box
+REFERENCE_ROOT = Path("/root/reference") if (Path("/root/reference") / "models" / "yolo.py").exists() else _REPO / "baseline" / "_ref"
 
 
 # ----------------------------------------------------------------------------------------------------------------------

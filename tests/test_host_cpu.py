@@ -302,7 +302,13 @@ def test_reference_arm_json_contract():
     assert d["impl"] == "reference" and d["metric"].startswith("images/sec @640 bs32 YOLOv3") and d["unit"] == "images/s"
     assert d["higher_is_better"] is True and d["steps"] == 1 and d["value"] > 0 and d["n_gpus"] == 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the reference's own Model from the staged copy (baseline/_ref) when it is there, else the oracle port — and it says which
+    sys.path.insert(0, str(root / "oracle"))
+    import ref_shim
+
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_shim.reference_available() else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["config"]["batch_per_gpu"] == 32 and "nms" in d
 
 
 def test_detect_multi_backend_seam():

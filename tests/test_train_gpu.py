@@ -49,18 +49,34 @@ def test_bn_forward_and_backward(c, ld, coff, upsample, res):
     dev = "cuda"
     yp = _padded(y, ld, coff)
     f32 = lambda: torch.zeros(c, device=dev)  # noqa: E731
-    s, q, scale, shift, mean, rstd, dbeta, dgamma = (f32() for _ in range(8))
+    st = {k: f32() for k in ("scale", "shift", "mean", "rstd")}
+    dbeta, dgamma = torch.full((c,), 2.0, device=dev), torch.full((c,), -1.0, device=dev)  # gradients are ACCUMULATED into
+    sums = torch.zeros(2 * c, device=dev)
     rmean, rvar = torch.zeros(c, device=dev), torch.ones(c, device=dev)
-    T.bn_stats(yp, s, q)
-    T.bn_finalize(s, q, gamma.to(dev), beta.to(dev), n * h * w, scale, shift, mean, rstd, rmean, rvar)
+    nblk = T.partial_blocks(n, h)
+    partial = torch.full((nblk * 2 * c,), float("nan"), device=dev)  # every entry the second stage reads must be written
+    T.bn_stats(yp, partial)
+    T.bn_finalize(partial, nblk, gamma.to(dev), beta.to(dev), n * h * w, st["scale"], st["shift"], st["mean"], st["rstd"], rmean, rvar)
     out = PaddedNHWC.zeros(n, h * u, w * u, c)
-    T.bn_act_fwd(yp, scale, shift, out, _padded(r) if res else None, upsample)
+    T.bn_act_fwd(yp, st["scale"], st["shift"], out, _padded(r) if res else None, upsample)
     assert rel_l2(out.to_nchw(), a.detach()) < 6e-3
     assert torch.allclose(rmean.cpu(), rm, atol=1e-5) and torch.allclose(rvar.cpu(), rv, rtol=1e-4)
     dy = PaddedNHWC.zeros(n, h, w, c)
-    T.bn_act_bwd(yp, _padded(da), dy, scale, shift, mean, rstd, dbeta, dgamma, upsample)
+    partial.fill_(float("nan"))
+    dap = _padded(da)
+    T.bn_act_bwd(yp, dap, dy, st, sums, partial, dbeta, dgamma, upsample)
     assert rel_l2(dy.to_nchw(), yt.grad) < 1e-2
-    assert rel_l2(dgamma, gt.grad) < 5e-3 and rel_l2(dbeta, bt.grad) < 5e-3
+    assert rel_l2(dgamma + 1.0, gt.grad) < 5e-3 and rel_l2(dbeta - 2.0, bt.grad) < 5e-3
+    assert rel_l2(sums[c:], gt.grad) < 5e-3 and rel_l2(sums[:c], bt.grad) < 5e-3
+    # two-stage reductions have a fixed summation order: a second run reproduces every bit
+    dy2, sums2 = PaddedNHWC.zeros(n, h, w, c), torch.zeros(2 * c, device=dev)
+    T.bn_act_bwd(yp, dap, dy2, st, sums2, partial, None, None, upsample)
+    assert torch.equal(sums2, sums) and torch.equal(dy2.buf, dy.buf)
+    # SyncBatchNorm split: phase 1 (sums) + phase 2 (apply) == phase 0
+    dy3, sums3 = PaddedNHWC.zeros(n, h, w, c), torch.zeros(2 * c, device=dev)
+    T.bn_act_bwd(yp, dap, dy3, st, sums3, partial, None, None, upsample, phase=1)
+    T.bn_act_bwd(yp, dap, dy3, st, sums3, None, None, None, upsample, phase=2, count=n * h * w)
+    assert torch.equal(dy3.buf, dy.buf)
     halo = dy.buf.float().clone()
     halo[:, 1:-1, 1:-1] = 0
     assert (halo == 0).all()
@@ -96,6 +112,19 @@ def test_dgrad_and_wgrad_stride1(ci, co, k):
         dwt = torch.zeros(k * k, co, ci, device=dev)
         T.conv_wgrad(dyp, _padded(x), dwt, k, tap_major=True)
         assert rel_l2(dwt.permute(1, 2, 0).reshape(co, ci, k, k), wtt.grad) < 3e-3
+        # [co, k*k, ci] = channels_last strides of the parameter: the training engine's flat gradient buffer.  accumulate:
+        # added on top of what is there; deterministic: no split over pixels, so two runs agree bit for bit
+        from yolov3_b200 import _lib
+
+        base = torch.randn(co, k * k, ci, device=dev)
+        d1, d2 = base.clone(), base.clone()
+        T.conv_wgrad(dyp, _padded(x), d1, k, layout=_lib.DW_OHWI, accumulate=True, deterministic=1)
+        T.conv_wgrad(dyp, _padded(x), d2, k, layout=_lib.DW_OHWI, accumulate=True, deterministic=1)
+        assert torch.equal(d1, d2)
+        assert rel_l2((d1 - base).view(co, k, k, ci).permute(0, 3, 1, 2), wtt.grad) < 3e-3
+        d3 = base.clone()
+        T.conv_wgrad(dyp, _padded(x), d3, k, layout=_lib.DW_OHWI, accumulate=True)
+        assert rel_l2(d3 - base, d1 - base) < 1e-4
     # accumulation into an existing gradient (second consumer of the same tensor)
     prev = torch.randn(n, ci, h, w, generator=g).bfloat16().float()
     acc = _padded(prev)

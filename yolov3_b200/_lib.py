@@ -130,7 +130,7 @@ class BnBwdDesc(C.Structure):
                 ("da", C.c_void_p), ("da_ld", C.c_int32), ("da_coff", C.c_int32),
                 ("dy", C.c_void_p), ("dy_ld", C.c_int32), ("dy_coff", C.c_int32),
                 ("scale", C.c_void_p), ("shift", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
-                ("sum_dz", C.c_void_p), ("sum_dzy", C.c_void_p),
+                ("sums", C.c_void_p), ("partial", C.c_void_p), ("dbeta_acc", C.c_void_p), ("dgamma_acc", C.c_void_p),
                 ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("c", C.c_int32), ("upsample", C.c_int32),
                 ("phase", C.c_int32), ("count", C.c_float)]
 
@@ -142,7 +142,17 @@ class WgradDesc(C.Structure):
                 ("x", C.c_void_p), ("x_ld", C.c_int32), ("x_coff", C.c_int32),
                 ("dw", C.c_void_p),
                 ("co", C.c_int32), ("ci", C.c_int32), ("ksize", C.c_int32), ("n", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
-                ("dw_layout", C.c_int32)]
+                ("dw_layout", C.c_int32), ("accumulate", C.c_int32), ("deterministic", C.c_int32)]
+
+
+DW_OIHW, DW_TAP_MAJOR, DW_OHWI = 0, 1, 2
+
+
+class PackItem(C.Structure):
+    """struct y3_pack_item."""
+
+    _fields_ = [("src_off", C.c_int64), ("dst", C.c_void_p), ("co_rows", C.c_int32), ("ci", C.c_int32), ("k", C.c_int32),
+                ("dst_co", C.c_int32), ("tile_begin", C.c_int32), ("reserved", C.c_int32)]
 
 
 def _declare(lib):
@@ -160,8 +170,16 @@ def _declare(lib):
         "y3_maxpool_fwd": ([C.POINTER(PoolDesc), vp], C.c_int),
         "y3_maxpool_train_fwd": ([C.POINTER(PoolDesc), vp, vp], C.c_int),
         "y3_maxpool_bwd": ([C.POINTER(PoolDesc), vp, i32, vp], C.c_int),
-        "y3_bn_stats": ([vp, i32, i32, i32, C.c_int64, vp, vp, vp], C.c_int),
-        "y3_bn_finalize": ([vp, vp, vp, vp, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp], C.c_int),
+        "y3_bn_partial_blocks": ([i32, i32], i32),
+        "y3_bn_stats": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], C.c_int),
+        "y3_colreduce_f32": ([vp, i32, i32, vp, i32, vp], C.c_int),
+        "y3_bn_finalize": ([vp, i32, vp, vp, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp], C.c_int),
+        "y3_f32_to_bf16": ([vp, vp, C.c_int64, vp], C.c_int),
+        "y3_pack_dgrad_batched": ([vp, i32, vp, i32, vp], C.c_int),
+        "y3_head_grad_pack": ([vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp], C.c_int),
+        "y3_sumsq_blocks": ([], i32),
+        "y3_grad_sumsq": ([vp, C.c_int64, vp, vp, vp], C.c_int),
+        "y3_sgd_step": ([vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp], C.c_int),
         "y3_bn_act_fwd": ([C.POINTER(BnActDesc), vp], C.c_int),
         "y3_bn_act_bwd": ([C.POINTER(BnBwdDesc), vp], C.c_int),
         "y3_pack_weights": ([vp, i32, i32, i32, vp, vp, vp], C.c_int),
@@ -208,7 +226,8 @@ def lib():
             )
         _lib = C.CDLL(str(_LIB_PATH))
         SYMBOLS.update(_declare(_lib))
-        for which, st in enumerate((ConvDesc, FirstDesc, PoolDesc, DetectLevel, DecodeDesc, Op, NmsParams, LossDesc)):
+        for which, st in enumerate((ConvDesc, FirstDesc, PoolDesc, DetectLevel, DecodeDesc, Op, NmsParams, LossDesc, BnActDesc,
+                                    BnBwdDesc, WgradDesc, PackItem)):
             if _lib.y3_abi_sizeof(which) != C.sizeof(st):
                 raise Y3Error(f"ABI mismatch: sizeof({st.__name__}) is {C.sizeof(st)} here, "
                               f"{_lib.y3_abi_sizeof(which)} in {_LIB_PATH.name}; rebuild the library")

@@ -12,6 +12,9 @@ import torch
 from .model import Model
 
 
+ALLOW_PICKLED_CHECKPOINTS = False  # opt-in: reference-pickled modules run arbitrary code in torch.load
+
+
 def _load(weights, device, cfg=None) -> Model:
     if isinstance(weights, Model):
         return weights.to(device)
@@ -23,7 +26,14 @@ def _load(weights, device, cfg=None) -> Model:
         # a checkpoint written by this package: {"cfg": yaml name / path / dict, "state_dict": reference-named tensors}.
         # Reference *.pt files pickle the reference's nn.Module classes; with the reference importable they load too
         # (ckpt["ema"] or ckpt["model"], models/experimental.py:87-101).
-        ckpt = torch.load(str(weights), map_location="cpu", weights_only=False)
+        try:  # this package's own checkpoints hold only tensors / dicts / lists / strings: no pickle execution needed
+            ckpt = torch.load(str(weights), map_location="cpu", weights_only=True)
+        except Exception as e:
+            if not ALLOW_PICKLED_CHECKPOINTS:
+                raise RuntimeError(f"{weights}: not a tensors-only checkpoint ({type(e).__name__}).  Reference *.pt files pickle "
+                                   "whole nn.Modules (train.py:445-462) and execute code on load; set "
+                                   "yolov3_b200.backend.ALLOW_PICKLED_CHECKPOINTS = True to load a file you trust") from e
+            ckpt = torch.load(str(weights), map_location="cpu", weights_only=False)
     if isinstance(ckpt, dict) and "state_dict" in ckpt:
         m = Model(ckpt.get("cfg", cfg or "yolov3.yaml"), device=device)
         m.load_state_dict(ckpt["state_dict"])
@@ -40,8 +50,7 @@ def _load(weights, device, cfg=None) -> Model:
 def save_checkpoint(model: Model, path) -> None:
     """Write the checkpoint format ``DetectMultiBackend`` / ``_load`` read: the YAML dict, reference-named fp32 tensors,
     class names (the reference pickles whole nn.Modules instead, train.py:445-462)."""
-    if model.training:
-        model.eval()  # pulls the trained master parameters back from the device
+    # state_dict() reads the device masters while they exist: no mode flip, a mid-epoch save leaves training undisturbed
     torch.save({"cfg": model.yaml, "state_dict": {k: v.detach().float().cpu() for k, v in model.state_dict().items()},
                 "names": list(model.names)}, str(path))
 

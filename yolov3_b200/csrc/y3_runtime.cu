@@ -112,6 +112,10 @@ extern "C" int64_t y3_abi_sizeof(int32_t which) {
     case 5: return sizeof(y3_op);
     case 6: return sizeof(y3_nms_params);
     case 7: return sizeof(y3_loss_desc);
+    case 8: return sizeof(y3_bn_act_desc);
+    case 9: return sizeof(y3_bn_bwd_desc);
+    case 10: return sizeof(y3_wgrad_desc);
+    case 11: return sizeof(y3_pack_item);
   }
   return -1;
 }

@@ -29,28 +29,34 @@ struct SliceW {
   int ld, coff;
 };
 
-// ---------------------------------------------------------------------------------------------- bn_stats
-// grid: (row blocks); block = 256 threads = (C/8 channel groups) x (256/(C/8) row lanes); rows = all padded pixels
-__global__ void __launch_bounds__(256) bn_stats_kernel(Slice y, int c8, long long rows, int rows_per_block, float* sum,
-                                                       float* sumsq) {
-  extern __shared__ float sh[];  // [2][256][8]
-  const int cg = threadIdx.x % c8, rl = threadIdx.x / c8, nrl = blockDim.x / c8;
-  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
-  const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
-  if (rl < nrl) {
-#pragma unroll 4
-    for (long long r = r0 + rl; r < r1; r += nrl) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(y.p + r * y.ld + y.coff + cg * 8));
-      float f[8];
-      unpack8(u, f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s[i] += f[i];
-        q[i] += f[i] * f[i];
-      }
-    }
+// ---------------------------------------------------------------------------------------------- row iteration
+// Every elementwise / reduction kernel below walks INTERIOR image rows: row r of n*h -> (image, y) with one 32-bit division
+// per row, then 16-byte items e = x*c8 + cg inside the row (c8 = channels/8 is a power of two for every BatchNorm of the
+// YOLOv3 graphs, so x = e >> log2(c8)).  The first version derived (n, y, x) from a 64-bit flat index with two 64-bit
+// divisions per 16 bytes and ran 4-8x above its HBM floor (profiles/r01_train_launches_summary.txt).
+struct Rows {
+  int n, h, w, c8, c8_shift;  // c8_shift = log2(c8), or -1 when c8 is not a power of two (generic division)
+};
+__device__ __forceinline__ void split_item(const Rows& g, int e, int& x, int& cg) {
+  if (g.c8_shift >= 0) {
+    x = e >> g.c8_shift;
+    cg = e & (g.c8 - 1);
+  } else {
+    x = e / g.c8;
+    cg = e - x * g.c8;
   }
+}
+__device__ __forceinline__ long long row_base(const Rows& g, int r, int scale = 1) {
+  // padded pixel index of interior pixel (y, x=0) of image n; scale = 2: the 2x-upsampled geometry's pixel (2y, 0)
+  const int n = r / g.h, y = r - n * g.h;
+  const int hp = g.h * scale + 2, wp = g.w * scale + 2;
+  return (static_cast<long long>(n) * hp + y * scale + 1) * wp + 1;
+}
+
+// block-level reduction of per-thread 8-channel accumulators over the threads that share a channel group, written as ONE
+// partial row per block (no atomics: the second stage adds the rows in a fixed order, so results are bit-reproducible)
+__device__ __forceinline__ void block_reduce_store(float (&s)[8], float (&q)[8], int c8, float* sh, float* partial_row, int c) {
+  const int cg = threadIdx.x % c8, rl = threadIdx.x / c8, nrl = blockDim.x / c8;
   float* ss = sh + threadIdx.x * 8;
   float* qq = sh + 256 * 8 + threadIdx.x * 8;
 #pragma unroll
@@ -69,20 +75,61 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(Slice y, int c8, long lon
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(sum + cg * 8 + i, s[i]);
-      atomicAdd(sumsq + cg * 8 + i, q[i]);
+      partial_row[cg * 8 + i] = s[i];
+      partial_row[c + cg * 8 + i] = q[i];
     }
   }
 }
 
+// ---------------------------------------------------------------------------------------------- bn_stats
+// grid: nblk blocks of 256 threads; block b walks rows b, b+nblk, ...; partial[b] = [sum(c) | sumsq(c)]
+__global__ void __launch_bounds__(256) bn_stats_kernel(Slice y, Rows g, float* __restrict__ partial) {
+  extern __shared__ float sh[];  // [2][256][8]
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int items = g.w * g.c8, rows = g.n * g.h;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const __nv_bfloat16* base = y.p + row_base(g, r) * y.ld + y.coff;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < items; e += 256) {
+      int x, cg;
+      split_item(g, e, x, cg);
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(x) * y.ld + cg * 8)), f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        q[i] = fmaf(f[i], f[i], q[i]);
+      }
+    }
+  }
+  block_reduce_store(s, q, g.c8, sh, partial + static_cast<long long>(blockIdx.x) * 2 * g.c8 * 8, g.c8 * 8);
+}
+
+// out[j] (+)= sum_b partial[b][j], j < width, fixed order (second stage of every two-stage reduction here)
+__global__ void colreduce_kernel(const float* __restrict__ partial, int nblk, int width, float* __restrict__ out, int accumulate,
+                                 float* __restrict__ out2, int accumulate2) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= width) return;
+  float a = 0.f;
+  for (int b = 0; b < nblk; ++b) a += partial[static_cast<long long>(b) * width + j];
+  if (out) out[j] = accumulate ? out[j] + a : a;
+  if (out2) out2[j] = accumulate2 ? out2[j] + a : a;
+}
+
 // ---------------------------------------------------------------------------------------------- bn_finalize
-__global__ void bn_finalize_kernel(const float* sum, const float* sumsq, const float* gamma, const float* beta, int c,
+// sums[2][c] given as `nblk` partial rows (nblk = 1: already reduced, e.g. after SyncBatchNorm's all-reduce)
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, const float* gamma, const float* beta, int c,
                                    float count, float eps, float momentum, float* scale, float* shift, float* mean_out,
                                    float* rstd_out, float* running_mean, float* running_var) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c) return;
-  const float mean = sum[i] / count;
-  float var = sumsq[i] / count - mean * mean;
+  float sum = 0.f, sumsq = 0.f;
+  for (int b = 0; b < nblk; ++b) {
+    sum += partial[static_cast<long long>(b) * 2 * c + i];
+    sumsq += partial[static_cast<long long>(b) * 2 * c + c + i];
+  }
+  const float mean = sum / count;
+  float var = sumsq / count - mean * mean;
   var = var > 0.f ? var : 0.f;
   const float rstd = rsqrtf(var + eps);
   const float sc = gamma[i] * rstd;
@@ -98,55 +145,57 @@ __global__ void bn_finalize_kernel(const float* sum, const float* sumsq, const f
 }
 
 // ---------------------------------------------------------------------------------------------- bn_act_fwd
-// one thread = one interior pixel x 8 channels
+// one thread = one interior pixel x 8 channels per item
 struct BnActArgs {
   Slice y;        // conv output (pre-BN)
   Slice res;      // optional residual (p == nullptr: none), geometry of y
   SliceW out;     // activation; padded (h*u+2, w*u+2) when upsample
   const float* scale;
   const float* shift;
-  int n, h, w, c8, upsample;
+  Rows g;
+  int upsample;
 };
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const BnActArgs p) {
-  const long long total = static_cast<long long>(p.n) * p.h * p.w * p.c8;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(i % p.c8);
-    long long t = i / p.c8;
-    const int x = static_cast<int>(t % p.w);
-    t /= p.w;
-    const int yy = static_cast<int>(t % p.h);
-    const int n = static_cast<int>(t / p.h);
-    const long long row = (static_cast<long long>(n) * (p.h + 2) + yy + 1) * (p.w + 2) + x + 1;
-    float f[8], r[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(p.y.p + row * p.y.ld + p.y.coff + cg * 8)), f);
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + cg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + cg * 8 + 4));
-    const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift + cg * 8)), h1 = __ldg(reinterpret_cast<const float4*>(p.shift + cg * 8 + 4));
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+  const Rows g = p.g;
+  const int items = g.w * g.c8, rows = g.n * g.h;
+  const int u = p.upsample ? 2 : 1;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const long long rb = row_base(g, r);
+    const long long ob = p.upsample ? row_base(g, r, 2) : rb;
+    const long long up_row = static_cast<long long>(2 * g.w + 2) * p.out.ld;
+#pragma unroll 2
+    for (int e = threadIdx.x; e < items; e += 256) {
+      int x, cg;
+      split_item(g, e, x, cg);
+      float f[8], rr[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.y.p + (rb + x) * p.y.ld + p.y.coff + cg * 8)), f);
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + cg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + cg * 8 + 4));
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift + cg * 8)), h1 = __ldg(reinterpret_cast<const float4*>(p.shift + cg * 8 + 4));
+      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = silu_f(fmaf(f[k], sc[k], sh[k]));
-    if (p.res.p) {
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.res.p + row * p.res.ld + p.res.coff + cg * 8)), r);
+      for (int k = 0; k < 8; ++k) f[k] = silu_f(fmaf(f[k], sc[k], sh[k]));
+      if (p.res.p) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(p.res.p + (rb + x) * p.res.ld + p.res.coff + cg * 8)), rr);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] += r[k];
-    }
-    const uint4 o = pack8(f);
-    if (p.upsample) {
-      const int w2 = 2 * p.w + 2;
-      const long long r00 = (static_cast<long long>(n) * (2 * p.h + 2) + 2 * yy + 1) * w2 + 2 * x + 1;
-#pragma unroll
-      for (int rep = 0; rep < 4; ++rep)
-        *reinterpret_cast<uint4*>(p.out.p + (r00 + (rep >> 1) * w2 + (rep & 1)) * p.out.ld + p.out.coff + cg * 8) = o;
-    } else {
-      *reinterpret_cast<uint4*>(p.out.p + row * p.out.ld + p.out.coff + cg * 8) = o;
+        for (int k = 0; k < 8; ++k) f[k] += rr[k];
+      }
+      const uint4 o = pack8(f);
+      __nv_bfloat16* dst = p.out.p + (ob + static_cast<long long>(x) * u) * p.out.ld + p.out.coff + cg * 8;
+      *reinterpret_cast<uint4*>(dst) = o;
+      if (p.upsample) {
+        *reinterpret_cast<uint4*>(dst + p.out.ld) = o;
+        *reinterpret_cast<uint4*>(dst + up_row) = o;
+        *reinterpret_cast<uint4*>(dst + up_row + p.out.ld) = o;
+      }
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------- bn_act_bwd
 // da: gradient w.r.t. the block output a (geometry of `out` in the forward, i.e. 2x when upsample: the 4 replicas are
-// summed).  Pass 1 (reduce) accumulates sum(dz), sum(dz*yhat); pass 2 (apply) writes dy.
+// summed).  Pass 1 (reduce) writes per-block partial sums of dz and dz*yhat; a fixed-order second stage turns them into
+// (sum_dz, sum_dzy) — and adds them to the beta / gamma gradients; pass 2 (apply) writes dy.
 struct BnBwdArgs {
   Slice y;
   Slice da;
@@ -155,27 +204,26 @@ struct BnBwdArgs {
   const float* shift;  // beta - mean*scale
   const float* mean;
   const float* rstd;
-  float* sum_dz;       // [c] (= dbeta)
-  float* sum_dzy;      // [c] (= dgamma)
-  int n, h, w, c8, upsample;
+  const float* sum_dz;   // [c]  apply pass
+  const float* sum_dzy;  // [c]
+  float* partial;        // [nblk][2][c]  reduce pass
+  Rows g;
+  int upsample;
   float inv_count;
 };
-__device__ __forceinline__ void load_da(const BnBwdArgs& p, int n, int yy, int x, int cg, float (&d)[8]) {
+__device__ __forceinline__ void load_da(const BnBwdArgs& p, long long rb, long long ub, int x, int cg, float (&d)[8]) {
   if (p.upsample) {
-    const int w2 = 2 * p.w + 2;
-    const long long r00 = (static_cast<long long>(n) * (2 * p.h + 2) + 2 * yy + 1) * w2 + 2 * x + 1;
+    const long long w2 = 2 * p.g.w + 2;
+    const __nv_bfloat16* q = p.da.p + (ub + 2ll * x) * p.da.ld + p.da.coff + cg * 8;
+    float t0[8], t1[8], t2[8], t3[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(q)), t0);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(q + p.da.ld)), t1);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(q + w2 * p.da.ld)), t2);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(q + (w2 + 1) * p.da.ld)), t3);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) d[k] = 0.f;
-#pragma unroll
-    for (int rep = 0; rep < 4; ++rep) {
-      float t[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.da.p + (r00 + (rep >> 1) * w2 + (rep & 1)) * p.da.ld + p.da.coff + cg * 8)), t);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) d[k] += t[k];
-    }
+    for (int k = 0; k < 8; ++k) d[k] = (t0[k] + t1[k]) + (t2[k] + t3[k]);
   } else {
-    const long long row = (static_cast<long long>(n) * (p.h + 2) + yy + 1) * (p.w + 2) + x + 1;
-    unpack8(__ldg(reinterpret_cast<const uint4*>(p.da.p + row * p.da.ld + p.da.coff + cg * 8)), d);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p.da.p + (rb + x) * p.da.ld + p.da.coff + cg * 8)), d);
   }
 }
 // dz = da * d/dz[z*sigmoid(z)] = da * s*(1 + z*(1-s))
@@ -186,39 +234,37 @@ __device__ __forceinline__ float silu_grad(float z) {
 
 template <bool APPLY>
 __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BnBwdArgs p) {
-  // block = 256 threads = c8 channel groups x (256/c8) pixel lanes (c8 <= 256); grid-stride over pixels
+  // block = 256 threads; thread t keeps channel group t % c8 for the whole kernel (256 % c8 == 0)
   extern __shared__ float sh[];
-  const int cg = threadIdx.x % p.c8, pl = threadIdx.x / p.c8, npl = blockDim.x / p.c8;
-  const long long pixels = static_cast<long long>(p.n) * p.h * p.w;
+  const Rows g = p.g;
+  const int cg = threadIdx.x % g.c8;
+  const int items = g.w * g.c8, rows = g.n * g.h;
   float a_dz[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a_dzy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // per-channel constants.  APPLY: dy = sc*(dz - mean(dz) - yhat*mean(dz*yhat)) = sc*dz + k1*y + k0 with yhat = (y - mu)*rs
-  // — four constants per channel instead of six keep the kernel at 3 blocks per SM (it is latency-bound on its two loads)
   float sc[8], shf[8], c2[8], c3[8];  // sums pass: c2 = mu, c3 = rs;  apply pass: c2 = k1, c3 = k0
-  if (pl < npl) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      sc[k] = p.scale[cg * 8 + k];
-      shf[k] = p.shift[cg * 8 + k];
-      const float mu = p.mean[cg * 8 + k], rs = p.rstd[cg * 8 + k];
-      if (APPLY) {
-        const float m_dz = p.sum_dz[cg * 8 + k] * p.inv_count, m_dzy = p.sum_dzy[cg * 8 + k] * p.inv_count;
-        c2[k] = -sc[k] * rs * m_dzy;
-        c3[k] = -sc[k] * m_dz - c2[k] * mu;
-      } else {
-        c2[k] = mu;
-        c3[k] = rs;
-      }
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = p.scale[cg * 8 + k];
+    shf[k] = p.shift[cg * 8 + k];
+    const float mu = p.mean[cg * 8 + k], rs = p.rstd[cg * 8 + k];
+    if (APPLY) {
+      const float m_dz = p.sum_dz[cg * 8 + k] * p.inv_count, m_dzy = p.sum_dzy[cg * 8 + k] * p.inv_count;
+      c2[k] = -sc[k] * rs * m_dzy;
+      c3[k] = -sc[k] * m_dz - c2[k] * mu;
+    } else {
+      c2[k] = mu;
+      c3[k] = rs;
     }
+  }
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const long long rb = row_base(g, r);
+    const long long ub = p.upsample ? row_base(g, r, 2) : rb;
 #pragma unroll 2
-    for (long long px = static_cast<long long>(blockIdx.x) * npl + pl; px < pixels; px += static_cast<long long>(gridDim.x) * npl) {
-      const int x = static_cast<int>(px % p.w);
-      const long long t = px / p.w;
-      const int yy = static_cast<int>(t % p.h);
-      const int n = static_cast<int>(t / p.h);
-      const long long row = (static_cast<long long>(n) * (p.h + 2) + yy + 1) * (p.w + 2) + x + 1;
+    for (int e = threadIdx.x; e < items; e += 256) {
+      const int x = g.c8_shift >= 0 ? e >> g.c8_shift : e / g.c8;  // cg is loop-invariant: 256 % c8 == 0
       float yv[8], d[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.y.p + row * p.y.ld + p.y.coff + cg * 8)), yv);
-      load_da(p, n, yy, x, cg, d);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(p.y.p + (rb + x) * p.y.ld + p.y.coff + cg * 8)), yv);
+      load_da(p, rb, ub, x, cg, d);
       float o[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -229,36 +275,14 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BnBwdArgs p) {
         } else {
           const float yh = (yv[k] - c2[k]) * c3[k];
           a_dz[k] += dz;
-          a_dzy[k] += dz * yh;
+          a_dzy[k] = fmaf(dz, yh, a_dzy[k]);
         }
       }
-      if (APPLY) *reinterpret_cast<uint4*>(p.dy.p + row * p.dy.ld + p.dy.coff + cg * 8) = pack8(o);
+      if (APPLY) *reinterpret_cast<uint4*>(p.dy.p + (rb + x) * p.dy.ld + p.dy.coff + cg * 8) = pack8(o);
     }
   }
-  if (!APPLY) {
-    float* s0 = sh + threadIdx.x * 8;
-    float* s1 = sh + 256 * 8 + threadIdx.x * 8;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      s0[k] = a_dz[k];
-      s1[k] = a_dzy[k];
-    }
-    __syncthreads();
-    if (pl == 0) {
-      for (int j = 1; j < npl; ++j) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          a_dz[k] += sh[(j * p.c8 + cg) * 8 + k];
-          a_dzy[k] += sh[256 * 8 + (j * p.c8 + cg) * 8 + k];
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        atomicAdd(p.sum_dz + cg * 8 + k, a_dz[k]);
-        atomicAdd(p.sum_dzy + cg * 8 + k, a_dzy[k]);
-      }
-    }
-  }
+  if (!APPLY)
+    block_reduce_store(a_dz, a_dzy, g.c8, sh, p.partial + static_cast<long long>(blockIdx.x) * 2 * g.c8 * 8, g.c8 * 8);
 }
 
 // ---------------------------------------------------------------------------------------------- pack_weights
@@ -500,6 +524,82 @@ __global__ void __launch_bounds__(256) im2col_first_kernel(const TIN* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------- batched weight packs
+// The fp32 master weights live in ONE flat buffer, every conv weight stored [co][kh][kw][ci] (PyTorch channels_last
+// strides of the [co,ci,k,k] parameter) — which IS the forward pack's order.  Per optimizer step the whole buffer is
+// converted to bf16 by one elementwise kernel (the forward packs are views of that copy) and ONE launch of the kernel
+// below transposes every layer into its dgrad pack [ci_pad][(k-1-kh)*k + (k-1-kw)][co].  71 per-layer launches with
+// scattered 2-byte stores (0.96 ms / step, profiles/r01_train_launches_summary.txt) become two bandwidth-bound ones.
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n8) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    const float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    reinterpret_cast<uint4*>(dst)[i] = pack8(f);
+  }
+}
+
+// one 32(co) x 32(ci) transpose tile per block iteration; tiles of all layers are numbered consecutively (tile_begin)
+__global__ void __launch_bounds__(256) pack_dgrad_batched_kernel(const y3_pack_item* __restrict__ items, int n_items,
+                                                                 const __nv_bfloat16* __restrict__ wbf, int total_tiles) {
+  __shared__ __nv_bfloat16 tile[32][34];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    int lo = 0, hi = n_items - 1;  // the layer this tile belongs to
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (items[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
+    }
+    const y3_pack_item it = items[lo];
+    const int taps = it.k * it.k;
+    const int tiles_ci = (it.ci + 31) / 32, tiles_co = (it.co_rows + 31) / 32;
+    int local = t - it.tile_begin;
+    const int tap = local / (tiles_ci * tiles_co);
+    local -= tap * tiles_ci * tiles_co;
+    const int co0 = (local / tiles_ci) * 32, ci0 = (local % tiles_ci) * 32;
+    const __nv_bfloat16* src = wbf + it.src_off;  // [co_rows][taps][ci]
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(it.dst);  // [ci_pad][taps][dst_co]
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + ty + j * 8, ci = ci0 + tx;
+      tile[ty + j * 8][tx] = (co < it.co_rows && ci < it.ci) ? src[(static_cast<long long>(co) * taps + tap) * it.ci + ci]
+                                                             : __float2bfloat16(0.f);
+    }
+    __syncthreads();
+    const int ftap = taps - 1 - tap;  // (k-1-kh)*k + (k-1-kw)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int ci = ci0 + ty + j * 8, co = co0 + tx;
+      if (ci < it.ci && co < it.dst_co) dst[(static_cast<long long>(ci) * taps + ftap) * it.dst_co + co] = tile[tx][ty + j * 8];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- Detect-head gradient
+// g: dL/draw fp32 [n, na, ny, nx, no] (the loss kernel's output) -> dy bf16 padded NHWC [n, ny+2, nx+2, ld], channel a*no+o
+// (the head conv's output order), plus per-block partial column sums (bias gradient; second stage = colreduce_kernel).
+// Thread t owns channel t: consecutive threads read consecutive o of one anchor (coalesced) and write consecutive channels.
+__global__ void __launch_bounds__(256) head_grad_pack_kernel(const float* __restrict__ g, int n, int na, int ny, int nx, int no,
+                                                             SliceW dy, float* __restrict__ partial) {
+  const int ch = threadIdx.x, co = na * no;
+  const int a = ch / no, o = ch - a * no;
+  float acc = 0.f;
+  const int rows = n * ny;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int b = r / ny, y = r - b * ny;
+    const long long drow = (static_cast<long long>(b) * (ny + 2) + y + 1) * (nx + 2) + 1;
+    const float* src = g + ((static_cast<long long>(b) * na + a) * ny + y) * nx * no + o;
+    for (int x = 0; x < nx; ++x) {
+      float v = 0.f;
+      if (ch < co) v = __ldg(src + static_cast<long long>(x) * no);
+      acc += v;
+      if (ch < dy.ld - dy.coff) dy.p[(drow + x) * dy.ld + dy.coff + ch] = __float2bfloat16(v);
+    }
+  }
+  partial[static_cast<long long>(blockIdx.x) * 256 + ch] = acc;
+}
+
 int grid_for(long long total, int per_block = 256, int cap_mult = 32) {
   long long b = (total + per_block - 1) / per_block;
   const long long cap = static_cast<long long>(num_sms()) * cap_mult;
@@ -515,31 +615,71 @@ int grid_for(long long total, int per_block = 256, int cap_mult = 32) {
 using y3::Slice;
 using y3::SliceW;
 
-extern "C" int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, int64_t rows, float* sum, float* sumsq,
+namespace y3 {
+namespace {
+int log2_or_neg(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return (1 << l) == v ? l : -1;
+}
+Rows make_rows(int n, int h, int w, int c) {
+  Rows g;
+  g.n = n;
+  g.h = h;
+  g.w = w;
+  g.c8 = c / 8;
+  g.c8_shift = log2_or_neg(g.c8);
+  return g;
+}
+constexpr int kMaxPartialBlocks = 296;  // two blocks per SM on B200; a fixed cap keeps workspace sizes device-independent
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int c, float* __restrict__ sums,
+                                       float* __restrict__ dbeta_acc, float* __restrict__ dgamma_acc) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= 2 * c) return;
+  float a = 0.f;
+  for (int b = 0; b < nblk; ++b) a += partial[static_cast<long long>(b) * 2 * c + j];
+  sums[j] = a;
+  if (j < c) {
+    if (dbeta_acc) dbeta_acc[j] += a;
+  } else if (dgamma_acc) {
+    dgamma_acc[j - c] += a;
+  }
+}
+}  // namespace
+}  // namespace y3
+
+extern "C" int32_t y3_bn_partial_blocks(int32_t n, int32_t h) {
+  const long long rows = static_cast<long long>(n) * h;
+  return static_cast<int32_t>(rows < y3::kMaxPartialBlocks ? (rows > 0 ? rows : 1) : y3::kMaxPartialBlocks);
+}
+
+extern "C" int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, int32_t n, int32_t h, int32_t w, float* partial,
                            y3_stream_t stream) {
-  Y3_REQUIRE(y && sum && sumsq && c > 0 && c % 8 == 0 && c / 8 <= 256 && rows > 0 && ld % 8 == 0 && coff % 8 == 0,
-             "bn_stats: bad arguments");
-  // ~4 blocks per SM, each walking a long row range: with fixed 512-row blocks the 640x640 layers launched 6441 blocks whose
-  // 64 atomics each all hit the same 64 addresses (283 us for 211 MB), and the 1024-channel layers ran 8 blocks
-  // (profiles/r01_train_launches_summary.txt)
-  const int nrl = 256 / (c / 8) > 0 ? 256 / (c / 8) : 1;
-  long long rpb = (rows + 4ll * y3::num_sms() - 1) / (4ll * y3::num_sms());
-  rpb = (rpb + nrl - 1) / nrl * nrl;
-  if (rpb < 4ll * nrl) rpb = 4ll * nrl;
-  const int rows_per_block = static_cast<int>(rpb);
-  const long long blocks = (rows + rows_per_block - 1) / rows_per_block;
-  y3::bn_stats_kernel<<<static_cast<unsigned>(blocks), 256, 2 * 256 * 8 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      Slice{static_cast<const __nv_bfloat16*>(y), ld, coff}, c / 8, rows, rows_per_block, sum, sumsq);
+  Y3_REQUIRE(y && partial && c > 0 && c % 8 == 0 && 256 % (c / 8) == 0 && n > 0 && h > 0 && w > 0 && ld % 8 == 0 && coff % 8 == 0,
+             "bn_stats: bad arguments (c must be a power of two in [8, 2048])");
+  const int nblk = y3_bn_partial_blocks(n, h);
+  y3::bn_stats_kernel<<<nblk, 256, 2 * 256 * 8 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      Slice{static_cast<const __nv_bfloat16*>(y), ld, coff}, y3::make_rows(n, h, w, c), partial);
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
 
-extern "C" int y3_bn_finalize(const float* sum, const float* sumsq, const float* gamma, const float* beta, int32_t c,
-                              float count, float eps, float momentum, float* scale, float* shift, float* mean, float* rstd,
+extern "C" int y3_colreduce_f32(const float* partial, int32_t nblk, int32_t width, float* out, int32_t accumulate,
+                                y3_stream_t stream) {
+  Y3_REQUIRE(partial && out && nblk > 0 && width > 0, "colreduce: bad arguments");
+  y3::colreduce_kernel<<<(width + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(partial, nblk, width, out, accumulate,
+                                                                                          nullptr, 0);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+extern "C" int y3_bn_finalize(const float* partial, int32_t nblk, const float* gamma, const float* beta, int32_t c, float count,
+                              float eps, float momentum, float* scale, float* shift, float* mean, float* rstd,
                               float* running_mean, float* running_var, y3_stream_t stream) {
-  Y3_REQUIRE(sum && sumsq && gamma && beta && scale && shift && mean && rstd && c > 0 && count > 0, "bn_finalize: bad arguments");
+  Y3_REQUIRE(partial && nblk > 0 && gamma && beta && scale && shift && mean && rstd && c > 0 && count > 0, "bn_finalize: bad arguments");
   y3::bn_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-      sum, sumsq, gamma, beta, c, count, eps, momentum, scale, shift, mean, rstd, running_mean, running_var);
+      partial, nblk, gamma, beta, c, count, eps, momentum, scale, shift, mean, rstd, running_mean, running_var);
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -553,21 +693,21 @@ extern "C" int y3_bn_act_fwd(const y3_bn_act_desc* d, y3_stream_t stream) {
   a.out = SliceW{static_cast<__nv_bfloat16*>(d->out), d->out_ld, d->out_coff};
   a.scale = d->scale;
   a.shift = d->shift;
-  a.n = d->n;
-  a.h = d->h;
-  a.w = d->w;
-  a.c8 = d->c / 8;
+  a.g = y3::make_rows(d->n, d->h, d->w, d->c);
   a.upsample = d->upsample;
-  const long long total = static_cast<long long>(d->n) * d->h * d->w * a.c8;
-  y3::bn_act_fwd_kernel<<<y3::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  const long long rows = static_cast<long long>(d->n) * d->h;
+  const long long cap = 8ll * y3::num_sms();
+  y3::bn_act_fwd_kernel<<<static_cast<unsigned>(rows < cap ? rows : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
 
 extern "C" int y3_bn_act_bwd(const y3_bn_bwd_desc* d, y3_stream_t stream_) {
-  Y3_REQUIRE(d && d->y && d->da && d->dy && d->scale && d->shift && d->mean && d->rstd && d->sum_dz && d->sum_dzy,
-             "bn_act_bwd: null pointer");
-  Y3_REQUIRE(d->c % 8 == 0 && d->c / 8 <= 256 && d->n > 0 && d->h > 0 && d->w > 0, "bn_act_bwd: bad shape");
+  Y3_REQUIRE(d && d->y && d->da && d->dy && d->scale && d->shift && d->mean && d->rstd && d->sums, "bn_act_bwd: null pointer");
+  Y3_REQUIRE(d->c % 8 == 0 && 256 % (d->c / 8) == 0 && d->n > 0 && d->h > 0 && d->w > 0,
+             "bn_act_bwd: bad shape (c must be a power of two in [8, 2048])");
+  Y3_REQUIRE(d->phase >= 0 && d->phase <= 2 && d->count >= 0.f, "bn_act_bwd: bad phase/count");
+  Y3_REQUIRE(d->phase == 2 || d->partial, "bn_act_bwd: the reduction phase needs the partial-sum workspace");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   y3::BnBwdArgs a;
   a.y = Slice{static_cast<const __nv_bfloat16*>(d->y), d->y_ld, d->y_coff};
@@ -577,24 +717,54 @@ extern "C" int y3_bn_act_bwd(const y3_bn_bwd_desc* d, y3_stream_t stream_) {
   a.shift = d->shift;
   a.mean = d->mean;
   a.rstd = d->rstd;
-  a.sum_dz = d->sum_dz;
-  a.sum_dzy = d->sum_dzy;
-  a.n = d->n;
-  a.h = d->h;
-  a.w = d->w;
-  a.c8 = d->c / 8;
+  a.sum_dz = d->sums;
+  a.sum_dzy = d->sums + d->c;
+  a.partial = d->partial;
+  a.g = y3::make_rows(d->n, d->h, d->w, d->c);
   a.upsample = d->upsample;
   const long long pixels = static_cast<long long>(d->n) * d->h * d->w;
-  Y3_REQUIRE(d->phase >= 0 && d->phase <= 2 && d->count >= 0.f, "bn_act_bwd: bad phase/count");
   a.inv_count = 1.0f / (d->count > 0.f ? d->count : static_cast<float>(pixels));
-  const int npl = 256 / a.c8;
-  const int grid = y3::grid_for((pixels + npl - 1) / npl, 8, 8);
+  const int nblk = y3_bn_partial_blocks(d->n, d->h);
   if (d->phase != 2) {
-    Y3_CHECK_CUDA(cudaMemsetAsync(d->sum_dz, 0, sizeof(float) * d->c, stream));
-    Y3_CHECK_CUDA(cudaMemsetAsync(d->sum_dzy, 0, sizeof(float) * d->c, stream));
-    y3::bn_act_bwd_kernel<false><<<grid, 256, 2 * 256 * 8 * sizeof(float), stream>>>(a);
+    y3::bn_act_bwd_kernel<false><<<nblk, 256, 2 * 256 * 8 * sizeof(float), stream>>>(a);
+    y3::bn_bwd_finalize_kernel<<<(2 * d->c + 127) / 128, 128, 0, stream>>>(d->partial, nblk, d->c, d->sums, d->dbeta_acc,
+                                                                          d->dgamma_acc);
   }
-  if (d->phase != 1) y3::bn_act_bwd_kernel<true><<<grid, 256, 2 * 256 * 8 * sizeof(float), stream>>>(a);
+  if (d->phase != 1) {
+    const long long rows = static_cast<long long>(d->n) * d->h;
+    const long long cap = 8ll * y3::num_sms();
+    y3::bn_act_bwd_kernel<true><<<static_cast<unsigned>(rows < cap ? rows : cap), 256, 0, stream>>>(a);
+  }
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+extern "C" int y3_f32_to_bf16(const float* src, void* dst, int64_t n, y3_stream_t stream) {
+  Y3_REQUIRE(src && dst && n > 0 && n % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "f32_to_bf16: n must be a multiple of 8, pointers 16-byte aligned");
+  y3::f32_to_bf16_kernel<<<y3::grid_for(n / 8, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), n / 8);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+extern "C" int y3_pack_dgrad_batched(const y3_pack_item* items_dev, int32_t n_items, const void* wbf, int32_t total_tiles,
+                                     y3_stream_t stream) {
+  Y3_REQUIRE(items_dev && wbf && n_items > 0 && total_tiles > 0, "pack_dgrad_batched: bad arguments");
+  const int cap = 16 * y3::num_sms();
+  y3::pack_dgrad_batched_kernel<<<total_tiles < cap ? total_tiles : cap, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      items_dev, n_items, static_cast<const __nv_bfloat16*>(wbf), total_tiles);
+  Y3_CHECK_CUDA(cudaGetLastError());
+  return Y3_OK;
+}
+
+extern "C" int y3_head_grad_pack(const float* g, int32_t n, int32_t na, int32_t ny, int32_t nx, int32_t no, void* dy,
+                                 int32_t dy_ld, int32_t dy_coff, float* partial, y3_stream_t stream) {
+  Y3_REQUIRE(g && dy && partial && n > 0 && na > 0 && ny > 0 && nx > 0 && no > 0 && na * no <= 256 && dy_ld - dy_coff <= 256,
+             "head_grad_pack: bad arguments (na*no <= 256)");
+  const int nblk = y3_bn_partial_blocks(n, ny);
+  y3::head_grad_pack_kernel<<<nblk, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      g, n, na, ny, nx, no, SliceW{static_cast<__nv_bfloat16*>(dy), dy_ld, dy_coff}, partial);
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }

@@ -30,8 +30,8 @@ struct WgTcArgs {
   int kblocks_per_cta;  // pixel blocks one CTA accumulates (split-K)
   int dy_coff, x_coff;
   float* dw;
-  int tap_major;        // dw is [taps][co][ci] (vector reductions) instead of [co][ci][taps]
-  int single;           // 1: this CTA is the only contributor to its dW tile (plain stores)
+  int layout;           // Y3_DW_OIHW [co][ci][taps] | Y3_DW_TAP_MAJOR [taps][co][ci] | Y3_DW_OHWI [co][taps][ci] (vector reductions)
+  int single;           // 1: this CTA is the only contributor to its dW tile AND dw need not be accumulated into (plain stores)
   int* err;
   uint32_t lbo_a, lbo_b, sbo_a, sbo_b;  // descriptor strides in bytes (probe-able, see Y3_WGRAD_VARIANT)
 };
@@ -143,9 +143,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       const int co = co0 + quarter * 32 + lane;
       mbar_wait(done_bar, 0, p.err, 13);
       tc_fence_after();
-      const bool rows_contig = p.tap_major || p.taps == 1;  // this thread's ci run is contiguous in memory
-      float* dst = rows_contig ? p.dw + (static_cast<long long>(tap) * p.co + co) * p.ci + ci0
-                               : p.dw + (static_cast<long long>(co) * p.ci + ci0) * p.taps + tap;
+      const bool rows_contig = p.layout != Y3_DW_OIHW || p.taps == 1;  // this thread's ci run is contiguous in memory
+      float* dst = p.layout == Y3_DW_OHWI ? p.dw + (static_cast<long long>(co) * p.taps + tap) * p.ci + ci0
+                   : rows_contig          ? p.dw + (static_cast<long long>(tap) * p.co + co) * p.ci + ci0
+                                          : p.dw + (static_cast<long long>(co) * p.ci + ci0) * p.taps + tap;
 #pragma unroll 1
       for (int c = 0; c < N; c += 32) {
         uint32_t v[32];
@@ -275,10 +276,11 @@ int wgrad_tc(const y3_wgrad_desc& d, cudaStream_t stream) {
   long long max_split = (a.kblocks_total + 7) / 8;
   if (want > max_split) want = max_split;
   if (want < 1) want = 1;
+  if (d.deterministic) want = 1;  // one CTA per dW tile: a single adder per address, bit-reproducible (slow on early layers)
   a.kblocks_per_cta = static_cast<int>((a.kblocks_total + want - 1) / want);
   const unsigned splits = static_cast<unsigned>((a.kblocks_total + a.kblocks_per_cta - 1) / a.kblocks_per_cta);
-  a.tap_major = d.dw_layout == Y3_DW_TAP_MAJOR ? 1 : 0;
-  a.single = splits == 1 ? 1 : 0;
+  a.layout = d.dw_layout;
+  a.single = (splits == 1 && !d.accumulate) ? 1 : 0;
   const dim3 grid(splits, static_cast<unsigned>(tiles), static_cast<unsigned>(taps));
   switch (n_tile) {
     case 256: return wgrad_tc_launch<256>(mdy, mx, a, grid, stream);

@@ -81,9 +81,12 @@ class Model:
         self.hyp = None
         self.params = self._init_params()
         self._packed = None
-        self._engines: dict = {}
+        self._engines: "OrderedDict" = OrderedDict()  # LRU over input shapes, at most MAX_ENGINES alive
         self._dev = None
+        self._store = None
+        self.ddp = None  # parallel.DDP(model): overlapped gradient exchange
         self._train_engines: dict = {}
+        self._wver = 0  # bumped whenever the weights an Engine baked into its TMA descriptors may have changed
 
     # ------------------------------------------------------------------------------------------------ parameters
     def _init_params(self):
@@ -108,12 +111,21 @@ class Model:
             p[f"model.{d.i}.m.{j}.bias"] = b.view(-1)
         return p
 
+    MAX_ENGINES = 4  # lowered inference engines kept alive (one per input shape/dtype); older ones are destroyed
+
+    def _invalidate(self):
+        """The packed bf16 weights (whose device addresses live inside every Engine's TMA descriptors) are stale."""
+        self._wver += 1
+        self._packed = None
+        self._engines.clear()
+
     def state_dict(self):
+        """Reference-named fp32 tensors (host copies).  While device masters exist (training) they are the truth."""
+        if self._dev is not None:
+            return OrderedDict((k, v.detach().float().cpu().contiguous().clone()) for k, v in self._dev.items())
         return OrderedDict((k, v.clone()) for k, v in self.params.items())
 
     def load_state_dict(self, sd, strict=True):
-        self._dev = None
-        self._train_engines.clear()
         missing = [k for k in self.params if k not in sd]
         unexpected = [k for k in sd if k not in self.params and not k.endswith("num_batches_tracked")]
         if strict and (missing or unexpected):
@@ -123,36 +135,49 @@ class Model:
                 v = sd[k].detach().float().cpu()
                 assert v.shape == self.params[k].shape, (k, v.shape, self.params[k].shape)
                 self.params[k] = v.clone()
+                if self._dev is not None:
+                    # device masters are updated IN PLACE: an optimizer / EMA built on parameters() keeps valid tensors
+                    with torch.no_grad():
+                        self._dev[k].copy_(v)
         self.detect.anchors = self.params[f"model.{self.detect.i}.anchors"]
-        self._packed = None
-        self._engines.clear()
+        self._invalidate()
         return missing, unexpected
 
     def parameters(self):
-        """Trainable parameters.  Before training starts these are the host fp32 tensors; after ``train()`` +
-        ``device_params()`` they are the device-resident fp32 master tensors an optimizer updates."""
-        if self._dev is not None:
-            return iter([v for v in self._dev.values() if v.requires_grad])
-        return iter(self.params.values())
+        """Trainable parameters: ALWAYS the device-resident fp32 master tensors (created on first use), so an optimizer
+        built before the first forward — the reference order, train.py:252-262 before :403 — updates what the training
+        engine reads.  Their addresses never change for the life of the model (load_state_dict copies in place)."""
+        return iter([v for v in self.device_params().values() if v.requires_grad])
+
+    def named_parameters(self):
+        return iter([(k, v) for k, v in self.device_params().items() if v.requires_grad])
+
+    def store(self):
+        """The flat device store of every parameter / buffer (``params.ParamStore``), created on first use."""
+        if self._store is None:
+            from .params import ParamStore
+
+            self._store = ParamStore(self, ops.cout_pad)
+            self._dev = self._store.views
+        return self._store
 
     def device_params(self):
-        """fp32 master copy of every parameter/buffer on the device (leaf tensors, requires_grad for the trainable
-        ones): what ``TrainEngine`` reads each step and what ``optimizer.step()`` writes."""
-        if self._dev is None:
-            self._dev = OrderedDict()
-            for k, v in self.params.items():
-                t = v.detach().to(self.device, torch.float32).contiguous()
-                trainable = not (k.endswith("running_mean") or k.endswith("running_var") or k.endswith("anchors"))
-                self._dev[k] = t.requires_grad_(trainable)
-        return self._dev
+        """fp32 master copy of every parameter/buffer on the device — views of ONE flat buffer (leaf tensors, requires_grad
+        for the trainable ones): what ``TrainEngine`` reads each step and what ``optimizer.step()`` writes."""
+        return self.store().views
+
+    def zero_grad(self, set_to_none: bool = True):
+        """One memset over the flat gradient buffer (instead of one fill per parameter)."""
+        if self._store is not None:
+            self._store.zero_grad(set_to_none)
 
     def sync_from_device(self):
         """Copy the trained master parameters back into ``self.params`` (invalidates packed weights and engines)."""
         if self._dev is not None:
             for k, v in self._dev.items():
-                self.params[k] = v.detach().float().cpu().clone()
-            self._packed = None
-            self._engines.clear()
+                self.params[k] = v.detach().float().cpu().contiguous().clone()
+            self.detect.anchors = self.params[f"model.{self.detect.i}.anchors"]
+            self._invalidate()
 
     # reference-surface no-ops / bookkeeping
     def fuse(self):
@@ -165,7 +190,9 @@ class Model:
         return self
 
     def train(self, mode=True):
-        self.training = bool(mode)
+        if not mode:
+            return self.eval()  # train(False) == eval(): pulls the trained masters back like eval() does
+        self.training = True
         return self
 
     def half(self):
@@ -175,9 +202,13 @@ class Model:
         return self
 
     def to(self, device):
-        self.device = torch.device(device)
-        self._packed = None
-        self._engines.clear()
+        device = torch.device(device)
+        if device != self.device:
+            if self._dev is not None:
+                raise RuntimeError("Model.to(): device masters exist (an optimizer may hold them); build the model on its "
+                                   "final device instead of moving it after parameters() / train()")
+            self.device = device
+            self._invalidate()
         return self
 
     def info(self, verbose=False, img_size=640):
@@ -226,6 +257,10 @@ class Model:
         e = self._engines.get(key)
         if e is None:
             e = self._engines[key] = Engine(self, n, h, w, in_dtype, in_div)
+            while len(self._engines) > self.MAX_ENGINES:  # variable-shape inference (rect / auto-letterbox): bounded memory
+                self._engines.popitem(last=False)
+        else:
+            self._engines.move_to_end(key)
         return e
 
     def forward(self, x, augment=False, profile=False, visualize=False):
@@ -284,6 +319,10 @@ class Engine:
     def _lower(self, model, n, h, w, in_dtype, in_div, dev, L):
         nodes = model.nodes
         W = model.packed()
+        # the TMA descriptors built below hold raw device addresses of these tensors: the engine owns a reference, and
+        # remembers which weight version it was lowered from (run()/replay() refuse to use stale weights)
+        self._weights = W
+        self.wver = model._wver
         det = model.detect
         gs = int(max(det.stride.tolist()))
         if h % gs or w % gs:
@@ -512,6 +551,7 @@ class Engine:
         """Launch the whole graph on the current stream.  x: [n,ch,h,w] device tensor (fp32 or uint8 as built)."""
         if self.handle is None:
             raise _lib.Y3Error("dry-run engine: nothing to launch")
+        self._check_fresh()
         ptr = None
         if x is not None:
             assert x.is_cuda and x.is_contiguous() and x.dtype == self.static_in.dtype and x.shape == self.static_in.shape
@@ -533,7 +573,17 @@ class Engine:
         self.graph = g
         return g
 
+    def _check_fresh(self):
+        if self.wver != self.model._wver:
+            raise _lib.Y3Error("this Engine was lowered from weights that have since changed (load_state_dict / training "
+                               "/ to()): fetch a new one with model.engine(...)")
+
+    @property
+    def stale(self) -> bool:
+        return self.wver != self.model._wver
+
     def replay(self):
+        self._check_fresh()
         self.graph.replay()
         return self.z, self.raw
 

@@ -18,6 +18,7 @@ class Pipeline:
     def __init__(self, model: Model, n, h, w, conf_thres=0.25, iou_thres=0.45, max_det=300, multi_label=False,
                  agnostic=False, classes=None, use_graph=True):
         self.model = model
+        self.shape = (n, h, w)
         self.engine = model.engine(n, h, w, torch.uint8, 255.0)
         self.kw = dict(conf_thres=conf_thres, iou_thres=iou_thres, max_det=max_det, multi_label=multi_label,
                        agnostic=agnostic, classes=classes)
@@ -32,9 +33,19 @@ class Pipeline:
         self.dev = dev
         self._stream_state = None
 
+    def _fresh_engine(self):
+        """The engine this pipeline launches; re-lowered (and re-captured) when the model's weights changed since it was
+        built (load_state_dict, a training phase followed by eval()): an Engine never runs on stale packed weights."""
+        if self.engine.stale:
+            self.engine = self.model.engine(*self.shape, torch.uint8, 255.0)
+            if self.use_graph and self.engine.graph is None:
+                self.engine.capture()
+        return self.engine
+
     def __call__(self, images_u8: torch.Tensor):
-        """images_u8: HOST uint8 [n,3,h,w] (pinned for an async copy).  Returns list of host tensors [k,6]."""
-        e = self.engine
+        """images_u8: HOST uint8 [n,3,h,w] (pinned for an async copy).  Returns list of host tensors [k,6] (copies: the
+        pinned read-back buffer is reused by the next call)."""
+        e = self._fresh_engine()
         e.static_in.copy_(images_u8, non_blocking=True)
         if self.use_graph:
             e.replay()
@@ -47,7 +58,7 @@ class Pipeline:
         torch.cuda.current_stream().synchronize()
         if int(self.host_cnt[1].max()):
             raise RuntimeError("NMS candidate capacity exceeded; rerun through non_max_suppression() for the exact retry")
-        return [self.host_out[i, : int(self.host_cnt[0, i])] for i in range(self.host_out.shape[0])]
+        return [self.host_out[i, : int(self.host_cnt[0, i])].clone() for i in range(self.host_out.shape[0])]
 
     # ------------------------------------------------------------------------------------------------ streaming
     def _slots(self):
@@ -74,7 +85,7 @@ class Pipeline:
         """Generator over per-batch detections (same values as ``self(batch)``) for an iterable of HOST uint8 batches
         (pinned for a truly asynchronous copy)."""
         st = self._slots()
-        e, cs = self.engine, st["copy"]
+        e, cs = self._fresh_engine(), st["copy"]
         main = torch.cuda.current_stream()
         pending = None
         for i, images_u8 in enumerate(batches):

@@ -4,14 +4,23 @@ Mirrors what the reference runs in ``train.py:401-411`` — ``pred = model(imgs)
 statistics, eps 1e-3 / momentum 0.03; ``Detect`` returning the raw ``[bs,na,ny,nx,no]`` maps, models/yolo.py:110), then
 ``loss.backward()`` through every Conv block — without autograd graphs or cuDNN:
 
-  forward  per Conv block:  conv (tcgen05 implicit GEMM, identity epilogue) -> bn_stats -> bn_finalize -> bn_act_fwd
-  backward per Conv block:  bn_act_bwd (dgamma, dbeta, dy) -> wgrad (bf16 MMA, split over pixels) -> dgrad, which is the
-                            SAME conv kernel run on dy with the transposed, tap-flipped weight pack (stride-2 layers:
-                            on the zero-stuffed dy), accumulating into the input's gradient through the residual port.
+  forward  per Conv block:  conv (tcgen05 implicit GEMM, identity epilogue) -> bn_stats (per-block partial sums)
+                            -> bn_finalize (fixed-order second stage, running statistics) -> bn_act_fwd
+  backward per Conv block:  bn_act_bwd (partial sums -> dgamma/dbeta accumulated into the flat gradient buffer -> dy)
+                            -> wgrad (tcgen05, accumulating straight into the parameter's .grad view)
+                            -> dgrad, which is the SAME conv kernel run on dy with the transposed, tap-flipped weight pack
+                               (stride-2 layers: on the zero-stuffed dy), accumulating into the input's gradient through
+                               the residual port (the Bottleneck shortcut's gradient rides on that port too).
+
+Parameters, gradients and the bf16 weight copy live in ONE flat buffer each (``params.ParamStore``): the forward re-packs
+all weights with two launches, the backward writes every gradient in place, and the data-parallel exchange all-reduces
+contiguous ranges of the gradient buffer on a side stream while the remaining layers are still being back-propagated
+(``parallel.DDP``; reference: DistributedDataParallel buckets, utils/torch_utils.py:60-72).  Every reduction is two-stage
+with a fixed summation order — no floating-point atomics — except the split-K wgrad (``deterministic=True`` removes that too).
 
 ``TrainEngine.forward/backward`` are wrapped in one ``torch.autograd.Function`` so that the reference's
 ``loss.backward(); optimizer.step()`` work unchanged on the fp32 master parameters (``Model.parameters()``).
-Supported layer types in train mode: Conv, Bottleneck, nn.Upsample, Concat, Detect (= yolov3.yaml).
+Supported layer types in train mode: Conv, Bottleneck, SPP, nn.Upsample, Concat, Detect (= yolov3.yaml, yolov3-spp.yaml).
 """
 from __future__ import annotations
 
@@ -28,22 +37,33 @@ from .tensors import PaddedNHWC, _stream
 class _Block:
     """One Conv+BN+SiLU block (models/common.py:57-81) with everything its forward and backward need."""
 
-    __slots__ = ("prefix", "c1", "c2", "k", "s", "x", "y", "a", "res", "upsample", "wf", "wd", "zero_b", "zero_bi", "st",
-                 "dw", "dw_tm", "first", "dy", "dy_up", "post_fwd", "pre_bwd")
+    __slots__ = ("prefix", "c1", "c2", "k", "s", "x", "y", "a", "res", "upsample", "wf", "wd", "st", "dw", "first", "dy",
+                 "dy_up", "post_fwd", "pre_bwd", "gamma", "beta", "rmean", "rvar", "dgamma", "dbeta", "nblk")
 
 
 class TrainEngine:
-    def __init__(self, model, n, h, w):
+    use_graphs = True        # replay forward / backward segments as CUDA graphs after one eager warm-up step
+    deterministic = False    # True: wgrad without split-K (bit-reproducible steps; slower on the early layers)
+    n_buckets = 4            # gradient ranges all-reduced separately, each as soon as its layers are done
+
+    def __init__(self, model, n, h, w, keep_all=False):
+        """keep_all=True gives every block its own dy buffer (per-layer gradient checks in the tests); the default shares
+        one scratch buffer per shape."""
         dev = model.device
         self.model, self.n, self.h, self.w = model, n, h, w
         det = model.detect
         nodes = model.nodes
+        gs = int(max(det.stride.tolist()))
+        if h % gs or w % gs:  # same rule as the inference Engine (utils/general.py:281-292 check_img_size)
+            raise ValueError(f"image size {h}x{w} must be a multiple of the max stride {gs}")
+        self.fwd_gen = 0  # activations live in this engine's buffers: a backward must belong to the LAST forward
         for nd in nodes[:-1]:
             if nd.type not in ("Conv", "Bottleneck", "Upsample", "Concat", "SPP"):
                 raise NotImplementedError(f"training-mode {nd.type} is not built (yolov3.yaml / yolov3-spp.yaml need "
                                           "Conv/Bottleneck/Upsample/Concat/SPP)")
-        P = model.device_params()
-        self.P = P
+        store = model.store()
+        self.store = store
+        self.P = model.device_params()
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.sync_bn = bool(getattr(model, "sync_bn", False)) and self.world > 1
         if self.sync_bn:
@@ -52,6 +72,9 @@ class TrainEngine:
         self.keep = []
         self.grad_bufs: dict[int, PaddedNHWC] = {}
         self.scratch: dict[tuple, PaddedNHWC] = {}
+        self.keep_all = keep_all
+        self.zero_bias = torch.zeros(4096, dtype=torch.float32, device=dev)  # identity-epilogue convs (forward and dgrad)
+        max_partial = 0
 
         def buf(c, hh, ww, ld=None):
             b = PaddedNHWC.zeros(n, hh, ww, c, device=dev, ld=ld)
@@ -64,23 +87,22 @@ class TrainEngine:
             return t
 
         def new_block(prefix, c1, c2, k, s, x, a, res=None, upsample=False, first=False):
+            nonlocal max_partial
             b = _Block()
             b.prefix, b.c1, b.c2, b.k, b.s, b.x, b.a, b.res, b.upsample, b.first = prefix, c1, c2, k, s, x, a, res, upsample, first
             ho, wo = x.h // s, x.w // s
             b.y = buf(c2, ho, wo)
-            kk = 1 if first else k
-            ci = 32 if first else c1
-            b.wf = torch.zeros(ops.cout_pad(c2), kk * kk * ci, dtype=torch.bfloat16, device=dev)
+            b.wf = store.weight_rows_bf16(prefix + ".conv.weight")
             b.wd = None if first else torch.zeros(ops.cout_pad(c1), k * k * c2, dtype=torch.bfloat16, device=dev)
-            b.zero_b = f32(ops.cout_pad(c2))
-            b.zero_bi = None if first else f32(ops.cout_pad(c1))
+            b.dw = store.grad_rows(prefix + ".conv.weight")
+            b.gamma, b.beta = store.flat(prefix + ".bn.weight"), store.flat(prefix + ".bn.bias")
+            b.dgamma, b.dbeta = store.flat(prefix + ".bn.weight", grad=True), store.flat(prefix + ".bn.bias", grad=True)
+            b.rmean, b.rvar = store.flat(prefix + ".bn.running_mean"), store.flat(prefix + ".bn.running_var")
             b.st = {name: f32(c2) for name in ("scale", "shift", "mean", "rstd")}
-            sums, dsums, gsums = f32(2 * c2).view(2, c2), f32(2 * c2).view(2, c2), f32(2 * c2).view(2, c2)
-            b.st.update(sums=sums, sum=sums[0], sumsq=sums[1], dsums=dsums, dbeta=dsums[0], dgamma=dsums[1], gsums=gsums)
-            # wgrad accumulator: [k*k, co, ci] when the tensor-core kernel is in use (vector reductions), else PyTorch's layout
-            b.dw_tm = T.wgrad_tap_major(ci)
-            b.dw = torch.zeros((kk * kk, c2, ci) if b.dw_tm else (c2, ci, kk, kk), dtype=torch.float32, device=dev)
-            b.dy = self._scratch(c2, ho, wo, dev)
+            b.st.update(sums=f32(2 * c2), gsums=f32(2 * c2))  # [sum | sumsq] forward, [sum dz | sum dz*xhat] backward
+            b.nblk = T.partial_blocks(n, ho)
+            max_partial = max(max_partial, b.nblk * 2 * c2)
+            b.dy = buf(c2, ho, wo) if keep_all else self._scratch(c2, ho, wo, dev)
             b.dy_up = self._scratch(c2, x.h, x.w, dev, tag="up") if s == 2 else None
             b.post_fwd, b.pre_bwd = [], []  # extra launches after this block's forward / before its backward (SPP pools)
             self.blocks.append(b)
@@ -146,7 +168,7 @@ class TrainEngine:
                     if x is None:
                         assert c1 == 3 and k == 3 and s_ == 1
                         a = out_of(nd.i) if last else buf(c2, h, w)
-                        new_block(r, c1, c2, k, 1, self.im2col, a, first=True)
+                        new_block(r, 32, c2, 1, 1, self.im2col, a, first=True)  # layer 0 = 1x1 conv over the im2col
                     elif last and nd.i in up_alias:
                         a = up_alias[nd.i]
                         new_block(r, c1, c2, k, s_, x, a, upsample=True)
@@ -196,15 +218,18 @@ class TrainEngine:
         dec = _lib.DecodeDesc()
         for j, s in enumerate(nodes[-1].srcs):
             x = tens[s]
-            hd = dict(x=x, c1=x.c, j=j)
+            wname, bname = f"model.{det.i}.m.{j}.weight", f"model.{det.i}.m.{j}.bias"
+            hd = dict(x=x, c1=x.c, j=j, wname=wname, bname=bname)
             hd["out"] = torch.zeros(n * x.h * x.w, head_ld, dtype=torch.float32, device=dev)
             hd["raw"] = torch.zeros(n, det.na, x.h, x.w, det.no, dtype=torch.float32, device=dev)
-            hd["wf"] = torch.zeros(head_ld, x.c, dtype=torch.bfloat16, device=dev)
+            hd["wf"] = store.weight_rows_bf16(wname)                   # [256, c1]: row 255 is the zero pad row of the slot
             hd["wd"] = torch.zeros(ops.cout_pad(x.c), head_ld, dtype=torch.bfloat16, device=dev)
-            hd["bias"] = torch.zeros(head_ld, dtype=torch.float32, device=dev)
-            hd["zero_bi"] = torch.zeros(ops.cout_pad(x.c), dtype=torch.float32, device=dev)
+            hd["bias"] = store.flat(bname, padded=True)[:head_ld]      # fp32 master bias read in place (pad entry = 0)
             hd["dy"] = buf(head_ld, x.h, x.w)
-            hd["dw"] = torch.zeros(head_ld, x.c, 1, 1, dtype=torch.float32, device=dev)
+            hd["dw"] = store.grad_rows(wname)                          # [256, 1, c1]
+            hd["db"] = store.flat(bname, grad=True, padded=True)[:head_ld]
+            hd["nblk"] = T.partial_blocks(n, x.h)
+            max_partial = max(max_partial, hd["nblk"] * 256)
             self.heads.append(hd)
             lv = dec.levels[j]
             lv.head, lv.head_ld, lv.raw_out = hd["out"].data_ptr(), head_ld, hd["raw"].data_ptr()
@@ -212,13 +237,44 @@ class TrainEngine:
         dec.nl, dec.bs, dec.na, dec.no, dec.z = det.nl, n, det.na, det.no, None
         self.dec = dec
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.partial = torch.zeros(max_partial, dtype=torch.float32, device=dev)  # first-stage rows of every reduction
 
-        # ---- static backward plan: for every activation tensor, is the first gradient contribution a write?
+        # ---- one table for the batched dgrad re-pack (y3_pack_dgrad_batched)
+        items, tile = [], 0
+        for hd in self.heads:
+            s = store.slots[hd["wname"]]
+            items.append((s.offset, hd["wd"], s.rows, s.ci, 1, head_ld))
+        for b in self.blocks:
+            if b.wd is not None:
+                s = store.slots[b.prefix + ".conv.weight"]
+                items.append((s.offset, b.wd, s.rows, s.ci, b.k, b.c2))
+        arr = (_lib.PackItem * len(items))()
+        for i, (off, dst, rows, ci, k, dst_co) in enumerate(items):
+            it = arr[i]
+            rows = min(rows, dst_co)
+            it.src_off, it.dst, it.co_rows, it.ci, it.k, it.dst_co, it.tile_begin = off, dst.data_ptr(), rows, ci, k, dst_co, tile
+            tile += k * k * ((rows + 31) // 32) * ((ci + 31) // 32)
+        self.pack_items = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        self.n_pack_items, self.pack_tiles = len(items), tile
+
         self.param_names = []
         for b in self.blocks:
             self.param_names += [b.prefix + ".conv.weight", b.prefix + ".bn.weight", b.prefix + ".bn.bias"]
         for hd in self.heads:
-            self.param_names += [f"model.{det.i}.m.{hd['j']}.weight", f"model.{det.i}.m.{hd['j']}.bias"]
+            self.param_names += [hd["wname"], hd["bname"]]
+
+        # ---- backward segments: [heads + last blocks | ... | first blocks], cut where the gradient buckets end
+        self.buckets = store.bucket_ranges(self.n_buckets)
+        ends = [e for _, e in self.buckets]
+        self.segments: list[list[_Block]] = [[] for _ in ends]
+        si = 0
+        for b in reversed(self.blocks):
+            off = store.slots[b.prefix + ".conv.weight"].offset
+            while off >= ends[si]:
+                si += 1
+            self.segments[si].append(b)
+        self.comm = None          # side stream of the gradient exchange (parallel.DDP)
+        self._graphs: dict = {}
 
     # ------------------------------------------------------------------------------------------------ helpers
     def _scratch(self, c, hh, ww, dev, tag=""):
@@ -235,19 +291,34 @@ class TrainEngine:
             g = self.grad_bufs[key] = PaddedNHWC(torch.zeros_like(t.buf), 0, t.buf.shape[3])
         return g.slice(t.coff, t.c)
 
-    # ------------------------------------------------------------------------------------------------ CUDA graphs
-    # Every launch of a step is stream-ordered with no host synchronisation, so after one eager (warm-up) step the whole
-    # forward and the whole backward are each captured into a CUDA graph and replayed: ~700 launches per step cost two
-    # graph launches on the host.  Master parameters, running statistics and all buffers keep their addresses.
-    use_graphs = True
-
-    def forward(self, x: torch.Tensor, in_div=0.0):
+    def _run(self, key, fn):
+        """Run ``fn`` eagerly the first time (function attributes, lazy allocations), capture AND replay it the second time,
+        replay it afterwards.  Every launch inside is stream-ordered with no host synchronisation and all buffers keep their
+        addresses."""
         if not self.use_graphs:
-            return self._forward_impl(x, in_div)
-        st = self.__dict__.setdefault("_gf", {"n": 0})
+            return fn()
+        st = self._graphs.setdefault(key, {"n": 0})
         if st["n"] == 0:
             st["n"] = 1
-            return self._forward_impl(x, in_div)  # eager warm-up (function attributes, lazy allocations)
+            return fn()
+        if "graph" not in st:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                st["out"] = fn()
+            st["graph"] = g
+        st["graph"].replay()
+        return st["out"]
+
+    # ------------------------------------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, in_div=0.0):
+        self.fwd_gen += 1
+        if not self.use_graphs:
+            return self._forward_impl(x, in_div)
+        st = self._graphs.setdefault("fwd", {"n": 0})
+        if st["n"] == 0:
+            st["n"] = 1
+            return self._forward_impl(x, in_div)
         if "graph" not in st:
             st["x"], st["div"] = x.clone(), in_div
             torch.cuda.synchronize()
@@ -260,129 +331,143 @@ class TrainEngine:
         st["graph"].replay()
         return st["out"]
 
-    def backward(self, graws):
-        if not self.use_graphs:
-            return self._backward_impl(graws)
-        st = self.__dict__.setdefault("_gb", {"n": 0})
-        if st["n"] == 0:
-            st["n"] = 1
-            return self._backward_impl(graws)
-        if "graph" not in st:
-            st["g"] = [g.detach().float().contiguous().clone() for g in graws]
-            torch.cuda.synchronize()
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr):
-                st["out"] = self._backward_impl(st["g"])
-            st["graph"] = gr
-        for dst, src in zip(st["g"], graws):
-            dst.copy_(src)
-        st["graph"].replay()
-        return [o.clone() for o in st["out"]]  # .grad must not alias buffers the next replay overwrites
+    def refresh_packs(self):
+        """bf16 forward packs (views of the flat bf16 copy) and dgrad packs from the current fp32 masters: two launches."""
+        s = self.store
+        T.f32_to_bf16(s.P[:s.n_train], s.Wbf)
+        T.pack_dgrad_batched(self.pack_items, self.n_pack_items, s.Wbf, self.pack_tiles)
 
-    # ------------------------------------------------------------------------------------------------ forward
     def _forward_impl(self, x: torch.Tensor, in_div=0.0):
-        P, det = self.P, self.model.detect
+        det = self.model.detect
+        self.refresh_packs()
         T.im2col_first(x, self.im2col, in_div)
+        zb = self.zero_bias
         for b in self.blocks:
-            w = P[b.prefix + ".conv.weight"]
-            if b.first:
-                b.wf.zero_()
-                b.wf[: b.c2, :27] = w.detach().reshape(b.c2, 27).to(torch.bfloat16)
-                ops.conv_bn_act(b.x, b.wf, b.zero_b, b.c2, 1, 1, ops.ACT_NONE, out=b.y, err=self.err)
-            else:
-                T.pack_weights(w.detach(), b.wf, b.wd)
-                ops.conv_bn_act(b.x, b.wf, b.zero_b, b.c2, b.k, b.s, ops.ACT_NONE, out=b.y, err=self.err)
+            ops.conv_bn_act(b.x, b.wf, zb, b.c2, b.k, b.s, ops.ACT_NONE, out=b.y, err=self.err)
             st = b.st
-            T.bn_stats(b.y, st["sum"], st["sumsq"])
+            T.bn_stats(b.y, self.partial)
             count = self.n * b.y.h * b.y.w
             if self.sync_bn:  # nn.SyncBatchNorm (train.py:270-272): batch statistics over every rank's pixels
+                T.colreduce(self.partial, b.nblk, 2 * b.c2, st["sums"])
                 dist.all_reduce(st["sums"])  # [sum | sumsq] share one buffer: one collective per layer
-                count *= self.world
-            T.bn_finalize(st["sum"], st["sumsq"], P[b.prefix + ".bn.weight"].detach(), P[b.prefix + ".bn.bias"].detach(),
-                          count, st["scale"], st["shift"], st["mean"], st["rstd"],
-                          P[b.prefix + ".bn.running_mean"], P[b.prefix + ".bn.running_var"])
+                T.bn_finalize(st["sums"], 1, b.gamma, b.beta, count * self.world, st["scale"], st["shift"], st["mean"],
+                              st["rstd"], b.rmean, b.rvar)
+            else:
+                T.bn_finalize(self.partial, b.nblk, b.gamma, b.beta, count, st["scale"], st["shift"], st["mean"], st["rstd"],
+                              b.rmean, b.rvar)
             T.bn_act_fwd(b.y, st["scale"], st["shift"], b.a, b.res, b.upsample)
             for fn in b.post_fwd:
                 fn()
+        co = det.na * det.no
         for hd in self.heads:
-            w = P[f"model.{det.i}.m.{hd['j']}.weight"].detach()
-            co = det.na * det.no
-            hd["wf"][:co] = w.reshape(co, hd["c1"]).to(torch.bfloat16)
-            hd["wd"][: hd["c1"], :co] = w.reshape(co, hd["c1"]).t().to(torch.bfloat16)
-            hd["bias"][:co] = P[f"model.{det.i}.m.{hd['j']}.bias"].detach()
             ops.conv_bn_act(hd["x"], hd["wf"], hd["bias"], co, 1, 1, ops.ACT_NONE, out_f32=hd["out"], err=self.err)
         _lib.check(_lib.lib().y3_detect_head_decode_fwd(C.byref(self.dec), _stream()), "y3_detect_head_decode_fwd")
         return [hd["raw"] for hd in self.heads]
 
     # ------------------------------------------------------------------------------------------------ backward
-    def _backward_impl(self, graws):
-        """graws: dL/draw per level (fp32 [n,na,ny,nx,no]).  Returns gradients aligned with ``self.param_names``."""
+    def backward(self, graws):
+        """graws: dL/draw per level (fp32 [n,na,ny,nx,no]).  Gradients are ACCUMULATED into the flat gradient buffer
+        (``store.G``; zeroed first unless earlier gradients are live, like autograd's .grad semantics) and attached to the
+        parameters as ``.grad`` views.  With ``parallel.DDP`` enabled, each gradient bucket is all-reduced on a side stream as
+        soon as the segment producing it has been enqueued."""
+        store = self.store
+        if not store.grads_are_live():
+            store.G.zero_()
+        ddp = getattr(self.model, "ddp", None)
+        exchange = ddp is not None and ddp.require_sync and self.world > 1
+        if exchange and self.comm is None:
+            self.comm = torch.cuda.Stream(device=self.model.device)
+        main = torch.cuda.current_stream()
+        if self.use_graphs:
+            st = self._graphs.setdefault("bwd_in", {})
+            if "g" not in st:
+                st["g"] = [g.detach().float().contiguous().clone() for g in graws]
+            for dst, src in zip(st["g"], graws):
+                dst.copy_(src)
+            graws = st["g"]
+        else:
+            graws = [g.detach().float().contiguous() for g in graws]
+        self._written, self._pending_res, self._pending_add = set(), {}, {}
+        for si, seg in enumerate(self.segments):
+            self._run(("bwd", si), lambda si=si, seg=seg: self._backward_segment(si, seg, graws))
+            if exchange:
+                lo, hi = self.buckets[si]
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self.comm.wait_event(ev)
+                with torch.cuda.stream(self.comm):
+                    dist.all_reduce(store.G[lo:hi], op=dist.ReduceOp.SUM)
+        if exchange:
+            main.wait_stream(self.comm)
+            ddp.pending_average = True  # G holds SUMS over ranks: the optimizer folds 1/world into its update, or
+            #                             parallel.DDP.finish() divides in place for a plain torch.optim optimizer
+        store.attach_grads()
+
+    def _contribute_conv(self, dy, wd, c_in, k, x):
+        gx = self.grad_of(x)
+        key = (x.buf.data_ptr(), x.coff, x.c)
+        first = key not in self._written and not self._overlaps(self._written, key)
+        pend = self._pending_res.pop(key, None)
+        if first:
+            # the Bottleneck shortcut's gradient (da of the block that added x) rides on the residual port of this dgrad
+            ops.conv_bn_act(dy, wd, self.zero_bias, c_in, k, 1, ops.ACT_NONE, out=gx, res=pend, err=self.err)
+        else:
+            ops.conv_bn_act(dy, wd, self.zero_bias, c_in, k, 1, ops.ACT_NONE, out=gx, res=gx, err=self.err)
+            if pend is not None:
+                T.add_nhwc(pend, gx, accumulate=True)
+        self._written.add(key)
+
+    def _flush_pending(self):
+        for key, (src, dst) in list(self._pending_add.items()):
+            first = key not in self._written and not self._overlaps(self._written, key)
+            T.add_nhwc(src, self.grad_of(dst), accumulate=not first)
+            self._written.add(key)
+            self._pending_res.pop(key, None)
+        self._pending_add.clear()
+
+    def _backward_segment(self, si, seg, graws):
         det = self.model.detect
-        co = det.na * det.no
-        written: set = set()
-
-        def contribute_conv(dy, wd, zero_b, c_in, k, x):
-            gx = self.grad_of(x)
-            key = (x.buf.data_ptr(), x.coff, x.c)
-            first = key not in written and not self._overlaps(written, key)
-            ops.conv_bn_act(dy, wd, zero_b, c_in, k, 1, ops.ACT_NONE, out=gx, res=None if first else gx, err=self.err)
-            written.add(key)
-
-        def contribute_add(src, x):
-            gx = self.grad_of(x)
-            key = (x.buf.data_ptr(), x.coff, x.c)
-            first = key not in written and not self._overlaps(written, key)
-            T.add_nhwc(src, gx, accumulate=not first)
-            written.add(key)
-
-        head_grads = []
-        for hd, g in zip(self.heads, graws):
-            x = hd["x"]
-            g = g.detach().float().contiguous()
-            hd["dy"].buf[:, 1:-1, 1:-1, :co] = g.permute(0, 2, 3, 1, 4).reshape(self.n, x.h, x.w, co).to(torch.bfloat16)
-            db = g.sum(dim=(0, 2, 3)).reshape(co)
-            hd["dw"].zero_()
-            T.conv_wgrad(hd["dy"], x, hd["dw"], 1)
-            contribute_conv(hd["dy"], hd["wd"], hd["zero_bi"], hd["c1"], 1, x)
-            head_grads.append((hd["dw"][:co].clone(), db))
-
-        grads = {}
-        for b in reversed(self.blocks):
+        det_flag = 1 if self.deterministic else 0
+        if si == 0:
+            for hd, g in zip(self.heads, graws):
+                x = hd["x"]
+                T.head_grad_pack(g, hd["dy"], self.partial)
+                T.colreduce(self.partial, hd["nblk"], 256, hd["db"], accumulate=True)
+                T.conv_wgrad(hd["dy"], x, hd["dw"], 1, layout=_lib.DW_OHWI, accumulate=True, deterministic=det_flag)
+                self._contribute_conv(hd["dy"], hd["wd"], hd["c1"], 1, x)
+        for b in seg:
             st = b.st
             for fn in b.pre_bwd:
                 fn()
             da = self.grad_of(b.a)
             if self.sync_bn:
                 # local sums are the (rank-local) gamma/beta gradients; dy needs the sums over all ranks
-                T.bn_act_bwd(b.y, da, b.dy, st["scale"], st["shift"], st["mean"], st["rstd"], st["dbeta"], st["dgamma"],
-                             b.upsample, phase=1)
-                st["gsums"].copy_(st["dsums"])
+                T.bn_act_bwd(b.y, da, b.dy, st, st["sums"], self.partial, b.dbeta, b.dgamma, b.upsample, phase=1)
+                st["gsums"].copy_(st["sums"])
                 dist.all_reduce(st["gsums"])
-                T.bn_act_bwd(b.y, da, b.dy, st["scale"], st["shift"], st["mean"], st["rstd"], st["gsums"][0], st["gsums"][1],
-                             b.upsample, phase=2, count=self.n * b.y.h * b.y.w * self.world)
+                T.bn_act_bwd(b.y, da, b.dy, st, st["gsums"], None, None, None, b.upsample, phase=2,
+                             count=self.n * b.y.h * b.y.w * self.world)
             else:
-                T.bn_act_bwd(b.y, da, b.dy, st["scale"], st["shift"], st["mean"], st["rstd"], st["dbeta"], st["dgamma"],
-                             b.upsample)
-            b.dw.zero_()
+                T.bn_act_bwd(b.y, da, b.dy, st, st["sums"], self.partial, b.dbeta, b.dgamma, b.upsample)
             src = b.dy
             if b.s == 2:
                 src = T.zero_stuff(b.dy, b.dy_up)
-            kk = 1 if b.first else b.k
-            T.conv_wgrad(src, b.x, b.dw, kk, tap_major=b.dw_tm)
-            dw = b.dw.permute(1, 2, 0).reshape(b.c2, -1, kk, kk) if b.dw_tm else b.dw  # -> [co, ci, k, k]
-            if b.first:
-                grads[b.prefix + ".conv.weight"] = dw[:, :27].reshape(b.c2, 3, 3, 3).clone()
-            else:
-                grads[b.prefix + ".conv.weight"] = dw.contiguous().clone() if b.dw_tm and kk > 1 else dw.clone()
-                contribute_conv(src, b.wd, b.zero_bi, b.c1, b.k, b.x)
-            grads[b.prefix + ".bn.weight"] = st["dgamma"].clone()
-            grads[b.prefix + ".bn.bias"] = st["dbeta"].clone()
+            T.conv_wgrad(src, b.x, b.dw, b.k, layout=_lib.DW_OHWI, accumulate=True, deterministic=det_flag)
             if b.res is not None:
-                contribute_add(da, b.res)  # Bottleneck shortcut: the block output's gradient also flows to its input
-        for hd, (dwh, dbh) in zip(self.heads, head_grads):
-            grads[f"model.{det.i}.m.{hd['j']}.weight"] = dwh
-            grads[f"model.{det.i}.m.{hd['j']}.bias"] = dbh
-        return [grads[k] for k in self.param_names]
+                # Bottleneck shortcut: the block output's gradient also flows to its input.  It is folded into the next
+                # dgrad into that tensor (cv1 of the same Bottleneck: the very next block) through the residual port, or
+                # added by a separate launch if no such dgrad arrives before the segment ends.
+                self._flush_pending()
+                r = b.res
+                key = (r.buf.data_ptr(), r.coff, r.c)
+                self._pending_res[key] = da
+                self._pending_add[key] = (da, r)
+            if not b.first:
+                key = (b.x.buf.data_ptr(), b.x.coff, b.x.c)
+                self._contribute_conv(src, b.wd, b.c1, b.k, b.x)
+                self._pending_add.pop(key, None)
+        self._flush_pending()  # a segment is one CUDA graph: nothing may stay pending across its end
+        return None
 
     @staticmethod
     def _overlaps(written, key):
@@ -396,15 +481,21 @@ class TrainEngine:
 
 
 class TrainFn(torch.autograd.Function):
-    """pred = model(imgs) in train mode as ONE autograd node: backward() runs TrainEngine.backward."""
+    """pred = model(imgs) in train mode as ONE autograd node: backward() runs TrainEngine.backward, which leaves every
+    parameter gradient in the flat gradient buffer and attaches the ``.grad`` views itself (autograd sees None)."""
 
     @staticmethod
     def forward(ctx, engine, x, in_div, *params):
         ctx.engine = engine
         raws = engine.forward(x, in_div)
+        ctx.gen = engine.fwd_gen
+        ctx.n_params = len(params)
         return tuple(r.clone() for r in raws)
 
     @staticmethod
     def backward(ctx, *graws):
-        grads = ctx.engine.backward(graws)
-        return (None, None, None, *grads)
+        if ctx.gen != ctx.engine.fwd_gen:
+            raise RuntimeError("backward() of a train-mode forward whose activations were overwritten by a later forward of the "
+                               "same shape: call loss.backward() before the next model(imgs) (one forward in flight per shape)")
+        ctx.engine.backward(graws)
+        return (None, None, None) + (None,) * ctx.n_params

@@ -12,18 +12,32 @@ from .tensors import PaddedNHWC, _stream
 BN_EPS, BN_MOMENTUM = 1e-3, 0.03  # ultralytics initialize_weights (models/yolo.py:229)
 
 
-def bn_stats(y: PaddedNHWC, sum_: torch.Tensor, sumsq: torch.Tensor):
-    """sum/sumsq (fp32 [c], zeroed here) of the conv output over all padded pixels (the halo is zero)."""
-    sum_.zero_()
-    sumsq.zero_()
-    rows = y.n * (y.h + 2) * (y.w + 2)
-    _lib.check(_lib.lib().y3_bn_stats(y.ptr, y.ld, y.coff, y.c, rows, sum_.data_ptr(), sumsq.data_ptr(), _stream()), "y3_bn_stats")
+def partial_blocks(n: int, h: int) -> int:
+    """Rows the first stage of a two-stage reduction writes for an [n, h, w] activation (y3_bn_partial_blocks)."""
+    return int(_lib.lib().y3_bn_partial_blocks(int(n), int(h)))
 
 
-def bn_finalize(sum_, sumsq, gamma, beta, count, scale, shift, mean, rstd, running_mean=None, running_var=None,
+def bn_stats(y: PaddedNHWC, partial: torch.Tensor):
+    """First stage of the batch statistics: partial[blocks][2][c] = (sum | sumsq) of the conv output over its interior
+    pixels; ``bn_finalize`` (or ``colreduce``) adds the rows in a fixed order — no atomics, bit-reproducible."""
+    assert partial.dtype == torch.float32 and partial.numel() >= partial_blocks(y.n, y.h) * 2 * y.c
+    _lib.check(_lib.lib().y3_bn_stats(y.ptr, y.ld, y.coff, y.c, y.n, y.h, y.w, partial.data_ptr(), _stream()), "y3_bn_stats")
+    return partial
+
+
+def colreduce(partial: torch.Tensor, nblk: int, width: int, out: torch.Tensor, accumulate: bool = False):
+    """out[j] (+)= sum_b partial[b][j] in index order."""
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.numel() >= width
+    _lib.check(_lib.lib().y3_colreduce_f32(partial.data_ptr(), int(nblk), int(width), out.data_ptr(), int(bool(accumulate)),
+                                           _stream()), "y3_colreduce_f32")
+    return out
+
+
+def bn_finalize(partial, nblk, gamma, beta, count, scale, shift, mean, rstd, running_mean=None, running_var=None,
                 eps=BN_EPS, momentum=BN_MOMENTUM):
+    """partial: ``nblk`` rows of [sum(c) | sumsq(c)] (nblk = 1: already reduced sums)."""
     c = gamma.numel()
-    _lib.check(_lib.lib().y3_bn_finalize(sum_.data_ptr(), sumsq.data_ptr(), gamma.data_ptr(), beta.data_ptr(), c, float(count),
+    _lib.check(_lib.lib().y3_bn_finalize(partial.data_ptr(), int(nblk), gamma.data_ptr(), beta.data_ptr(), c, float(count),
                                          eps, momentum, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                          running_mean.data_ptr() if running_mean is not None else None,
                                          running_var.data_ptr() if running_var is not None else None, _stream()),
@@ -42,20 +56,45 @@ def bn_act_fwd(y: PaddedNHWC, scale, shift, out: PaddedNHWC, res: PaddedNHWC | N
     return out
 
 
-def bn_act_bwd(y: PaddedNHWC, da: PaddedNHWC, dy: PaddedNHWC, scale, shift, mean, rstd, dbeta, dgamma, upsample=False,
-               phase=0, count=0.0):
-    """phase 0: sums (-> dbeta, dgamma) then dy.  SyncBatchNorm: phase 1 (local sums), all-reduce, phase 2 (dy from the
-    global sums passed as dbeta/dgamma, ``count`` = pixels over all ranks)."""
+def bn_act_bwd(y: PaddedNHWC, da: PaddedNHWC, dy: PaddedNHWC, st: dict, sums: torch.Tensor, partial, dbeta_acc, dgamma_acc,
+               upsample=False, phase=0, count=0.0):
+    """st: the block's saved (scale, shift, mean, rstd).  sums: fp32 [2*c] = (sum dz | sum dz*xhat), written by the reduction
+    phase and read by the apply phase.  dbeta_acc / dgamma_acc (optional fp32 [c]): the bn.bias / bn.weight gradients, ADDED to.
+    phase 0: sums then dy.  SyncBatchNorm: phase 1 (local sums), all-reduce, phase 2 (dy from the global sums in ``sums``,
+    ``count`` = pixels over all ranks)."""
     d = _lib.BnBwdDesc()
     d.phase, d.count = int(phase), float(count)
     d.y, d.y_ld, d.y_coff = y.ptr, y.ld, y.coff
     d.da, d.da_ld, d.da_coff = da.ptr, da.ld, da.coff
     d.dy, d.dy_ld, d.dy_coff = dy.ptr, dy.ld, dy.coff
-    d.scale, d.shift, d.mean, d.rstd = scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), rstd.data_ptr()
-    d.sum_dz, d.sum_dzy = dbeta.data_ptr(), dgamma.data_ptr()
+    d.scale, d.shift, d.mean, d.rstd = st["scale"].data_ptr(), st["shift"].data_ptr(), st["mean"].data_ptr(), st["rstd"].data_ptr()
+    d.sums = sums.data_ptr()
+    d.partial = partial.data_ptr() if partial is not None else None
+    d.dbeta_acc = dbeta_acc.data_ptr() if dbeta_acc is not None else None
+    d.dgamma_acc = dgamma_acc.data_ptr() if dgamma_acc is not None else None
     d.n, d.h, d.w, d.c, d.upsample = y.n, y.h, y.w, y.c, int(bool(upsample))
     _lib.check(_lib.lib().y3_bn_act_bwd(C.byref(d), _stream()), "y3_bn_act_bwd")
     return dy
+
+
+def f32_to_bf16(src: torch.Tensor, dst: torch.Tensor):
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel() and src.is_contiguous()
+    _lib.check(_lib.lib().y3_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream()), "y3_f32_to_bf16")
+    return dst
+
+
+def pack_dgrad_batched(items_dev: torch.Tensor, n_items: int, wbf: torch.Tensor, total_tiles: int):
+    _lib.check(_lib.lib().y3_pack_dgrad_batched(items_dev.data_ptr(), int(n_items), wbf.data_ptr(), int(total_tiles), _stream()),
+               "y3_pack_dgrad_batched")
+
+
+def head_grad_pack(g: torch.Tensor, dy: PaddedNHWC, partial: torch.Tensor):
+    """dL/draw fp32 [n,na,ny,nx,no] -> dy (bf16 padded NHWC, channel a*no+o) + first-stage column sums partial[blocks][256]."""
+    assert g.dtype == torch.float32 and g.is_contiguous() and g.dim() == 5
+    n, na, ny, nx, no = g.shape
+    assert (dy.n, dy.h, dy.w) == (n, ny, nx) and partial.numel() >= partial_blocks(n, ny) * 256
+    _lib.check(_lib.lib().y3_head_grad_pack(g.data_ptr(), n, na, ny, nx, no, dy.ptr, dy.ld, dy.coff, partial.data_ptr(), _stream()),
+               "y3_head_grad_pack")
 
 
 def pack_weights(w: torch.Tensor, fwd: torch.Tensor | None, dgrad: torch.Tensor | None):
@@ -78,11 +117,15 @@ def wgrad_tap_major(ci: int) -> bool:
     return bool(_lib.lib().y3_conv_wgrad_tap_major(int(ci)))
 
 
-def conv_wgrad(dy: PaddedNHWC, x: PaddedNHWC, dw: torch.Tensor, ksize: int, tap_major: bool = False):
-    """dw (fp32, accumulated into; [co,ci,k,k] or, tap_major, [k*k,co,ci]) from dy and x on the same stride-1 padded grid."""
+def conv_wgrad(dy: PaddedNHWC, x: PaddedNHWC, dw: torch.Tensor, ksize: int, tap_major: bool = False, layout: int | None = None,
+               accumulate: bool = False, deterministic: int = 0):
+    """dw (fp32, accumulated into) from dy and x on the same stride-1 padded grid.  Layouts: [co,ci,k,k] (default),
+    tap_major [k*k,co,ci], or ``layout=_lib.DW_OHWI`` [co,k*k,ci] (the flat gradient buffer's).  ``accumulate``: dw already holds
+    gradient that must be kept; ``deterministic``: no split over pixels (bit-reproducible)."""
     assert dy.n == x.n and dy.h == x.h and dy.w == x.w and dw.dtype == torch.float32 and dw.is_contiguous()
     d = _lib.WgradDesc()
-    d.dw_layout = 1 if tap_major else 0
+    d.dw_layout = layout if layout is not None else (1 if tap_major else 0)
+    d.accumulate, d.deterministic = int(bool(accumulate)), int(deterministic)
     d.dy, d.dy_ld, d.dy_coff = dy.ptr, dy.ld, dy.coff
     d.x, d.x_ld, d.x_coff = x.ptr, x.ld, x.coff
     d.dw, d.co, d.ci, d.ksize = dw.data_ptr(), dy.c, x.c, ksize
