@@ -232,8 +232,8 @@ int y3_loss_fwd_bwd(const y3_loss_desc* d, void* workspace, int64_t workspace_by
  * Y3_ACT_NONE; these entry points are the bandwidth-bound parts around it.  All activations: padded NHWC bf16 slices.
  */
 /* Two-stage, atomic-free (bit-reproducible) reductions: a first-stage kernel writes one partial row per block into a
- * caller-owned workspace [y3_bn_partial_blocks(n, h)][width], a fixed-order second stage adds the rows. */
-int32_t y3_bn_partial_blocks(int32_t n, int32_t h);
+ * caller-owned workspace [y3_bn_partial_blocks(n, h, w, c)][width], a fixed-order second stage adds the rows. */
+int32_t y3_bn_partial_blocks(int32_t n, int32_t h, int32_t w, int32_t c);  /* c = 0: one unit per image row (head gradient) */
 /* per-channel sum and sum of squares of the conv output y over its n*h*w interior pixels:
  * partial[blocks][2][c] = (sum | sumsq).  c: power of two in [8, 2048]. */
 int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, int32_t n, int32_t h, int32_t w, float* partial,
@@ -260,7 +260,7 @@ typedef struct y3_bn_bwd_desc {
   void* dy;       int32_t dy_ld, dy_coff;      /* gradient w.r.t. the conv output (input of dgrad / wgrad) */
   const float* scale; const float* shift; const float* mean; const float* rstd;
   float* sums;       /* [2][c] = (sum dz | sum dz*xhat): phase 0/1 out, phase 2 in (the all-reduced sums) */
-  float* partial;    /* workspace [y3_bn_partial_blocks(n, h)][2][c] of the reduction phase (phases 0, 1) */
+  float* partial;    /* workspace [y3_bn_partial_blocks(n, h, w, c)][2][c] of the reduction phase (phases 0, 1) */
   float* dbeta_acc;  /* optional [c]: += sum dz      (the bn.bias gradient, accumulated like autograd does) */
   float* dgamma_acc; /* optional [c]: += sum dz*xhat (the bn.weight gradient) */
   int32_t n, h, w, c, upsample;
@@ -289,7 +289,7 @@ typedef struct y3_pack_item {
 int y3_pack_dgrad_batched(const y3_pack_item* items_dev, int32_t n_items, const void* wbf, int32_t total_tiles,
                           y3_stream_t stream);
 /* Detect-head gradient: g = dL/draw fp32 [n, na, ny, nx, no] (ComputeLoss output) -> dy bf16 padded NHWC channel a*no+o
- * (the head conv's output order; channels >= na*no zeroed) and partial[y3_bn_partial_blocks(n, ny)][256] column sums
+ * (the head conv's output order; channels >= na*no zeroed) and partial[y3_bn_partial_blocks(n, ny, 0, 0)][256] column sums
  * (bias gradient = y3_colreduce_f32 over them). */
 int y3_head_grad_pack(const float* g, int32_t n, int32_t na, int32_t ny, int32_t nx, int32_t no, void* dy, int32_t dy_ld,
                       int32_t dy_coff, float* partial, y3_stream_t stream);

@@ -53,7 +53,7 @@ def test_bn_forward_and_backward(c, ld, coff, upsample, res):
     dbeta, dgamma = torch.full((c,), 2.0, device=dev), torch.full((c,), -1.0, device=dev)  # gradients are ACCUMULATED into
     sums = torch.zeros(2 * c, device=dev)
     rmean, rvar = torch.zeros(c, device=dev), torch.ones(c, device=dev)
-    nblk = T.partial_blocks(n, h)
+    nblk = T.partial_blocks(n, h, w, c)
     partial = torch.full((nblk * 2 * c,), float("nan"), device=dev)  # every entry the second stage reads must be written
     T.bn_stats(yp, partial)
     T.bn_finalize(partial, nblk, gamma.to(dev), beta.to(dev), n * h * w, st["scale"], st["shift"], st["mean"], st["rstd"], rmean, rvar)

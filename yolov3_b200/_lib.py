@@ -170,7 +170,7 @@ def _declare(lib):
         "y3_maxpool_fwd": ([C.POINTER(PoolDesc), vp], C.c_int),
         "y3_maxpool_train_fwd": ([C.POINTER(PoolDesc), vp, vp], C.c_int),
         "y3_maxpool_bwd": ([C.POINTER(PoolDesc), vp, i32, vp], C.c_int),
-        "y3_bn_partial_blocks": ([i32, i32], i32),
+        "y3_bn_partial_blocks": ([i32, i32, i32, i32], i32),
         "y3_bn_stats": ([vp, i32, i32, i32, i32, i32, i32, vp, vp], C.c_int),
         "y3_colreduce_f32": ([vp, i32, i32, vp, i32, vp], C.c_int),
         "y3_bn_finalize": ([vp, i32, vp, vp, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp], C.c_int),

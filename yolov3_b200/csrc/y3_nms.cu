@@ -15,6 +15,7 @@
 // violate that bound (or agnostic=True) take the single-segment path over all candidates.
 // The reference's wall-clock time_limit break (general.py:675,746-748) is deliberately not reproduced.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "y3_common.cuh"
@@ -44,6 +45,15 @@ struct NmsArgs {
   float* det;                // [bs, kRankCap, 6]
   uint32_t* seg_keys;        // [bs, kRankCap]
   uint8_t* keep;             // [bs, kRankCap]
+  // v2 (class-bucketed) workspace
+  int* seg_off;                  // [bs, nc + 1] first member of every class segment (conf-unordered members)
+  unsigned long long* seg_key2;  // [bs, kRankCap] candidate keys grouped by class
+  float4* box4;                  // [bs, kRankCap] xyxy of the member at the same position
+  int* surv_cnt;                 // [bs] members that survived the greedy pass
+  unsigned long long* surv_key;  // [bs, kRankCap]
+  int* surv_pos;                 // [bs, kRankCap] position of the survivor in seg_key2 / box4
+  int* done_cnt;                 // [bs] blocks that finished ranking a single-segment image (last one runs the greedy pass)
+  uint16_t* ord;                 // [bs, kRankCap] large segments: member index by confidence rank
   // outputs
   float* out;     // [bs, max_det, 6]
   int* out_src;   // [bs, max_det, 2] or null
@@ -544,6 +554,444 @@ __global__ void __launch_bounds__(1024) nms_compact_kernel(const NmsArgs p) {
   for (int i = total * 6 + threadIdx.x; i < p.max_det * 6; i += blockDim.x) out[i] = 0.f;
 }
 
+// ================================================================================================ v2 pipeline
+// The first version sorted every candidate twice with global bitonic networks (conf, then (class, rank)): ~25 launches, the
+// two sorts 60 % of the 0.37 ms at conf 0.25 (profiles/r01_nms_launches_summary.txt).  Nothing needs a GLOBAL order except
+// the <= max_det rows that are returned, so v2 is:
+//   K1 candidates (unchanged)           keys (conf bits | ~id), unordered, per image
+//   K2 nms_bucket_kernel   1 CTA/image  max_nms cut (exact radix select, only when count > max_nms), xywh -> xyxy, counting
+//                                       sort of the candidates by class (shared-memory histogram + scan + scatter)
+//   K3 nms_seg_warp_kernel 1 warp/(image,class): rank the <= 512 members by key (counting in shared memory), boxes to
+//                                       registers in that order, greedy suppression (exact division-free IoU), survivors
+//                                       appended to the image's survivor list
+//      nms_seg_block_kernel             segments > 512 members (multi-label at low conf; agnostic / out-of-range images, whose
+//                                       single segment is ranked by all the image's CTAs and finished by the last one)
+//   K4 nms_output_kernel   1 CTA/image  top max_det survivors by key: shared-memory bitonic sort (<= 4096 survivors) or exact
+//                                       radix select + sort of the selected, rows + (row, class) sources + counts
+// Same exactness contract as v1: all arithmetic in the reference's order, ties broken by candidate id (stable).
+constexpr int kBucketThreads = 1024;
+constexpr int kOutSortMax = 4096;
+
+__device__ __forceinline__ void key_to_rowcls(unsigned long long key, int nc, int& row, int& cls) {
+  const uint32_t id = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
+  row = static_cast<int>(id / static_cast<uint32_t>(nc));
+  cls = static_cast<int>(id - static_cast<uint32_t>(row) * nc);
+}
+
+// k-th largest (k >= 1) of n UNIQUE 64-bit keys in global memory, by one CTA: 8 passes over 8-bit digits, MSB first.
+// Returns the key itself: exactly k keys are >= it.
+__device__ unsigned long long block_select_kth(const unsigned long long* keys, int n, int k, int* s_hist, unsigned long long* s_prefix,
+                                               int* s_k) {
+  if (threadIdx.x == 0) {
+    *s_prefix = 0ull;
+    *s_k = k;
+  }
+  __syncthreads();
+  for (int pass = 7; pass >= 0; --pass) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    const unsigned long long prefix = *s_prefix;
+    const int shift = pass * 8;
+    const unsigned long long hi_mask = pass == 7 ? 0ull : (~0ull << (shift + 8));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long v = keys[i];
+      if ((v & hi_mask) == prefix) atomicAdd(&s_hist[static_cast<int>((v >> shift) & 0xFFull)], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int kk = *s_k, d = 255;
+      for (; d > 0; --d) {  // walk down from the largest digit
+        if (s_hist[d] >= kk) break;
+        kk -= s_hist[d];
+      }
+      *s_k = kk;
+      *s_prefix = prefix | (static_cast<unsigned long long>(d) << shift);
+    }
+    __syncthreads();
+  }
+  return *s_prefix;
+}
+
+__global__ void __launch_bounds__(kBucketThreads) nms_bucket_kernel(const NmsArgs p) {
+  __shared__ int s_hist[1024];   // class histogram, then exclusive offsets
+  __shared__ int s_cur[1024];    // scatter cursors
+  __shared__ int s_sel[256];
+  __shared__ int s_warp[32];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_k, s_outside;
+  const int img = blockIdx.x;
+  int c = p.count[img];
+  c = c < p.cap ? c : p.cap;
+  const int n = c < p.max_nms ? c : p.max_nms;
+  const unsigned long long* keys = p.keys + static_cast<size_t>(img) * p.cap;
+  int* off = p.seg_off + static_cast<size_t>(img) * (p.nc + 1);
+  if (threadIdx.x == 0) {
+    s_outside = 0;
+    p.surv_cnt[img] = 0;
+    p.done_cnt[img] = 0;
+  }
+  unsigned long long thr = 0ull;  // candidates below the max_nms-th key are dropped (general.py:728)
+  if (c > p.max_nms) thr = block_select_kth(keys, c, p.max_nms, s_sel, &s_prefix, &s_k);
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+    s_hist[i] = 0;
+    s_cur[i] = 0;
+  }
+  __syncthreads();
+  const float lim = p.max_wh * 0.5f;
+  const float* base = p.pred + static_cast<size_t>(img) * p.n_rows * p.no;
+  // pass A: class histogram + "class-split is exact" check (offset boxes of different classes cannot intersect)
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    const unsigned long long key = keys[i];
+    if (key < thr) continue;
+    int row, cls;
+    key_to_rowcls(key, p.nc, row, cls);
+    const float* x = base + static_cast<size_t>(row) * p.no;
+    const float cx = __ldg(x), w = __ldg(x + 2);
+    const float hw = __fdiv_rn(w, 2.0f);
+    const float x1 = __fsub_rn(cx, hw), x2 = __fadd_rn(cx, hw);
+    if (!((x1 > -lim) && (x2 < lim) && (x1 <= x2))) s_outside = 1;
+    atomicAdd(&s_hist[cls], 1);
+  }
+  __syncthreads();
+  const bool single = p.agnostic || s_outside;
+  // exclusive scan of the class counts (nc <= 1024 = one per thread)
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v = (threadIdx.x < p.nc && !single) ? s_hist[threadIdx.x] : 0;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int excl = incl - v + (warp ? s_warp[warp - 1] : 0);
+    __syncthreads();
+    if (threadIdx.x < p.nc) {
+      const int o = single ? (threadIdx.x == 0 ? 0 : n) : excl;
+      s_hist[threadIdx.x] = o;
+      off[threadIdx.x] = o;
+    }
+    if (threadIdx.x == 0) {
+      off[p.nc] = n;
+      p.flags[img] = single ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  // pass B: scatter (order inside a segment is arbitrary: the segment kernels rank by key)
+  unsigned long long* k2 = p.seg_key2 + static_cast<size_t>(img) * kRankCap;
+  float4* b4 = p.box4 + static_cast<size_t>(img) * kRankCap;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    const unsigned long long key = keys[i];
+    if (key < thr) continue;
+    int row, cls;
+    key_to_rowcls(key, p.nc, row, cls);
+    const int seg = single ? 0 : cls;
+    const int pos = s_hist[seg] + atomicAdd(&s_cur[seg], 1);
+    const float* x = base + static_cast<size_t>(row) * p.no;
+    const float cx = __ldg(x), cy = __ldg(x + 1), w = __ldg(x + 2), h = __ldg(x + 3);
+    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
+    k2[pos] = key;
+    b4[pos] = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+  }
+}
+
+__device__ __forceinline__ float4 offset_box(const float4& b, int cls, const NmsArgs& p) {
+  const float off = p.agnostic ? 0.0f : __fmul_rn(static_cast<float>(cls), p.max_wh);  // general.py:731-732
+  return make_float4(__fadd_rn(b.x, off), __fadd_rn(b.y, off), __fadd_rn(b.z, off), __fadd_rn(b.w, off));
+}
+
+__device__ __forceinline__ void append_survivors(const NmsArgs& p, int img, bool kept, unsigned long long key, int pos, int lane) {
+  const unsigned full = 0xffffffffu;
+  const unsigned b = __ballot_sync(full, kept);
+  if (b == 0u) return;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(&p.surv_cnt[img], __popc(b));
+  base = __shfl_sync(full, base, 0);
+  if (kept) {
+    const int at = base + __popc(b & ((1u << lane) - 1u));
+    p.surv_key[static_cast<size_t>(img) * kRankCap + at] = key;
+    p.surv_pos[static_cast<size_t>(img) * kRankCap + at] = pos;
+  }
+}
+
+// One WARP per (image, class) segment of up to 512 members.
+__global__ void __launch_bounds__(256) nms_seg_warp_kernel(const NmsArgs p) {
+  __shared__ unsigned long long s_key[8][kWarpSegMax];
+  __shared__ uint16_t s_ord[8][kWarpSegMax];
+  const unsigned full = 0xffffffffu;
+  const int img = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seg = blockIdx.x * 8 + warp;
+  if (seg >= p.nc) return;
+  const int* off = p.seg_off + static_cast<size_t>(img) * (p.nc + 1);
+  const int lo = off[seg], hi = off[seg + 1];
+  const int m = hi - lo;
+  if (m <= 0 || m > kWarpSegMax) return;  // larger segments: nms_seg_block_kernel
+  const unsigned long long* k2 = p.seg_key2 + static_cast<size_t>(img) * kRankCap + lo;
+  const float4* b4 = p.box4 + static_cast<size_t>(img) * kRankCap + lo;
+  const int slots = (m + 31) >> 5;
+  unsigned long long k[kWarpSlots];
+#pragma unroll
+  for (int s = 0; s < kWarpSlots; ++s) {
+    const int j = s * 32 + lane;
+    k[s] = (s < slots && j < m) ? k2[j] : 0ull;
+    if (s < slots && j < m) s_key[warp][j] = k[s];
+  }
+  __syncwarp();
+  // rank of my members = number of members with a larger key (keys are unique)
+  int r[kWarpSlots];
+#pragma unroll
+  for (int s = 0; s < kWarpSlots; ++s) r[s] = 0;
+  for (int t = 0; t < m; ++t) {
+    const unsigned long long kt = s_key[warp][t];  // broadcast read
+#pragma unroll
+    for (int s = 0; s < kWarpSlots; ++s)
+      if (s < slots) r[s] += (kt > k[s]) ? 1 : 0;
+  }
+#pragma unroll
+  for (int s = 0; s < kWarpSlots; ++s) {
+    const int j = s * 32 + lane;
+    if (s < slots && j < m) s_ord[warp][r[s]] = static_cast<uint16_t>(j);
+  }
+  __syncwarp();
+  // boxes in confidence order: rank q -> lane q % 32, slot q / 32
+  float4 b[kWarpSlots];
+  uint32_t supp = 0;
+  int mj[kWarpSlots];
+#pragma unroll
+  for (int s = 0; s < kWarpSlots; ++s) {
+    const int q = s * 32 + lane;
+    b[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    mj[s] = 0;
+    if (s < slots && q < m) {
+      const int j = s_ord[warp][q];
+      mj[s] = j;
+      int row, cls;
+      key_to_rowcls(s_key[warp][j], p.nc, row, cls);
+      b[s] = offset_box(b4[j], cls, p);
+    } else {
+      supp |= 1u << s;
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < kWarpSlots; ++s) {
+    if (s * 32 >= m) break;
+    unsigned dead = __ballot_sync(full, (supp >> s) & 1u);
+    const int cnt = min(32, m - s * 32);
+    for (int l = 0; l < cnt; ++l) {
+      if ((dead >> l) & 1u) continue;
+      float4 bi;
+      bi.x = __shfl_sync(full, b[s].x, l);
+      bi.y = __shfl_sync(full, b[s].y, l);
+      bi.z = __shfl_sync(full, b[s].z, l);
+      bi.w = __shfl_sync(full, b[s].w, l);
+      const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+      const bool hit = lane > l && !((supp >> s) & 1u) && box_suppresses(bi, ai, b[s], p);
+      if (hit) supp |= 1u << s;
+      dead |= __ballot_sync(full, hit);
+#pragma unroll
+      for (int s2 = s + 1; s2 < kWarpSlots; ++s2) {
+        if (s2 * 32 >= m) break;
+        if (!((supp >> s2) & 1u) && box_suppresses(bi, ai, b[s2], p)) supp |= 1u << s2;
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < kWarpSlots; ++s) {
+    if (s * 32 >= m) break;
+    const int q = s * 32 + lane;
+    const bool kept = q < m && !((supp >> s) & 1u);
+    append_survivors(p, img, kept, kept ? s_key[warp][mj[s]] : 0ull, lo + mj[s], lane);
+  }
+}
+
+// Segments with more than 512 members.  Class segments: one CTA ranks its members (keys tiled through shared memory) and runs
+// the greedy pass.  Single-segment images (agnostic, or boxes outside the class-offset bound): every CTA of the image ranks a
+// share of the members; the last one to finish (atomic ticket, no waiting) runs the greedy pass over the whole segment.
+constexpr int kRankTile = 1024;
+
+__global__ void __launch_bounds__(256) nms_seg_block_kernel(const NmsArgs p) {
+  __shared__ unsigned long long s_tile[kRankTile];
+  __shared__ float4 s_box[kSegSmemBoxes];
+  __shared__ uint32_t s_supp[(kRankCap + 31) / 32];
+  __shared__ int s_last;
+  const int img = blockIdx.y, seg = blockIdx.x;
+  const int* off = p.seg_off + static_cast<size_t>(img) * (p.nc + 1);
+  const bool single = p.flags[img] & 1;
+  const int lo = single ? 0 : off[seg], hi = single ? off[p.nc] : off[seg + 1];
+  const int m = hi - lo;
+  if (m <= kWarpSegMax) return;  // empty, or done by the warp kernel (a single segment sits in class slot 0 there)
+  const unsigned long long* k2 = p.seg_key2 + static_cast<size_t>(img) * kRankCap + lo;
+  const float4* b4 = p.box4 + static_cast<size_t>(img) * kRankCap + lo;
+  uint16_t* ord = p.ord + static_cast<size_t>(img) * kRankCap + lo;
+  // ---- rank my share of the members: rank = number of larger keys
+  const int share = single ? gridDim.x : 1, me = single ? seg : 0;
+  for (int j0 = me * blockDim.x; j0 < m; j0 += share * blockDim.x) {
+    const int j = j0 + threadIdx.x;
+    const unsigned long long kj = j < m ? k2[j] : ~0ull;
+    int r = 0;
+    for (int t0 = 0; t0 < m; t0 += kRankTile) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < kRankTile && t0 + t < m; t += blockDim.x) s_tile[t] = k2[t0 + t];
+      __syncthreads();
+      const int tn = min(kRankTile, m - t0);
+      for (int t = 0; t < tn; ++t) r += (s_tile[t] > kj) ? 1 : 0;
+    }
+    if (j < m) ord[r] = static_cast<uint16_t>(j);
+  }
+  if (single) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(&p.done_cnt[img], 1) == static_cast<int>(gridDim.x) - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+  } else {
+    __syncthreads();
+  }
+  // ---- greedy pass in confidence order
+  auto load_box = [&](int q) -> float4 {
+    const int j = ord[q];
+    int row, cls;
+    key_to_rowcls(k2[j], p.nc, row, cls);
+    return offset_box(b4[j], cls, p);
+  };
+  const bool in_smem = m <= kSegSmemBoxes;
+  for (int q = threadIdx.x; q < (m + 31) / 32; q += blockDim.x) s_supp[q] = 0;
+  if (in_smem)
+    for (int q = threadIdx.x; q < m; q += blockDim.x) s_box[q] = load_box(q);
+  __syncthreads();
+  for (int i = 0; i < m; ++i) {
+    if ((s_supp[i >> 5] >> (i & 31)) & 1u) continue;  // uniform
+    const float4 bi = in_smem ? s_box[i] : load_box(i);
+    const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+    if (i + 1 >= m) break;
+    for (int q = i + 1 + threadIdx.x; q < m; q += blockDim.x) {
+      if ((s_supp[q >> 5] >> (q & 31)) & 1u) continue;
+      const float4 bj = in_smem ? s_box[q] : load_box(q);
+      if (box_suppresses(bi, ai, bj, p)) atomicOr(&s_supp[q >> 5], 1u << (q & 31));
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int q0 = 0; q0 < m; q0 += blockDim.x) {
+    const int q = q0 + threadIdx.x;
+    const bool kept = q < m && !((s_supp[q >> 5] >> (q & 31)) & 1u);
+    const int j = q < m ? ord[q] : 0;
+    append_survivors(p, img, kept, kept ? k2[j] : 0ull, lo + j, lane);
+  }
+}
+
+__global__ void __launch_bounds__(1024) nms_output_kernel(const NmsArgs p) {
+  __shared__ unsigned long long s_k[kOutSortMax];
+  __shared__ uint16_t s_p[kOutSortMax];  // positions < kRankCap = 32768
+  __shared__ int s_sel[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_k_, s_n;
+  const int img = blockIdx.x;
+  const int c = p.count[img];
+  if (p.overflow && threadIdx.x == 0) p.overflow[img] = c > p.cap ? c : 0;
+  const int S = p.surv_cnt[img];
+  const int D = S < p.max_det ? S : p.max_det;
+  const unsigned long long* sk = p.surv_key + static_cast<size_t>(img) * kRankCap;
+  const int* sp = p.surv_pos + static_cast<size_t>(img) * kRankCap;
+  float* out = p.out + static_cast<size_t>(img) * p.max_det * 6;
+  const float4* b4 = p.box4 + static_cast<size_t>(img) * kRankCap;
+  auto emit = [&](int rank, unsigned long long key, int pos) {
+    int row, cls;
+    key_to_rowcls(key, p.nc, row, cls);
+    const float4 b = b4[pos];
+    float* o = out + static_cast<size_t>(rank) * 6;
+    o[0] = b.x;
+    o[1] = b.y;
+    o[2] = b.z;
+    o[3] = b.w;
+    o[4] = __uint_as_float(static_cast<uint32_t>(key >> 32));
+    o[5] = static_cast<float>(cls);
+    if (p.out_src) {
+      p.out_src[(static_cast<size_t>(img) * p.max_det + rank) * 2 + 0] = row;
+      p.out_src[(static_cast<size_t>(img) * p.max_det + rank) * 2 + 1] = cls;
+    }
+  };
+  if (D > 0) {
+    unsigned long long thr = 0ull;
+    int cnt = S;  // survivors that enter the sort
+    if (S > kOutSortMax) {
+      thr = block_select_kth(sk, S, D, s_sel, &s_prefix, &s_k_);  // exactly D survivors have key >= thr
+      cnt = D;
+    }
+    if (cnt <= kOutSortMax) {
+      int npad = next_pow2(cnt);
+      npad = npad < 32 ? 32 : npad;
+      if (threadIdx.x == 0) s_n = 0;
+      __syncthreads();
+      if (S > kOutSortMax) {
+        for (int i = threadIdx.x; i < S; i += blockDim.x) {
+          const unsigned long long key = sk[i];
+          if (key >= thr) {
+            const int at = atomicAdd(&s_n, 1);
+            s_k[at] = key;
+            s_p[at] = static_cast<uint16_t>(sp[i]);
+          }
+        }
+      } else {
+        for (int i = threadIdx.x; i < S; i += blockDim.x) {
+          s_k[i] = sk[i];
+          s_p[i] = static_cast<uint16_t>(sp[i]);
+        }
+      }
+      __syncthreads();
+      for (int i = cnt + threadIdx.x; i < npad; i += blockDim.x) {
+        s_k[i] = 0ull;
+        s_p[i] = 0;
+      }
+      __syncthreads();
+      for (int k = 2; k <= npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int t = threadIdx.x; t < npad / 2; t += blockDim.x) {
+            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+            const bool up = ((i & k) == 0);  // descending overall: "up" halves end with the larger key first
+            const unsigned long long a = s_k[i], b = s_k[i | j];
+            if (up ? a < b : a > b) {
+              s_k[i] = b;
+              s_k[i | j] = a;
+              const uint16_t t2 = s_p[i];
+              s_p[i] = s_p[i | j];
+              s_p[i | j] = t2;
+            }
+          }
+          __syncthreads();
+        }
+      }
+      for (int rnk = threadIdx.x; rnk < D; rnk += blockDim.x) emit(rnk, s_k[rnk], s_p[rnk]);
+    } else {
+      // more than 4096 rows requested AND available: rank by counting straight from global memory (exact, slow, rare)
+      for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        const unsigned long long key = sk[i];
+        if (key < thr) continue;
+        int rnk = 0;
+        for (int t = 0; t < S; ++t) rnk += (sk[t] > key) ? 1 : 0;
+        emit(rnk, key, sp[i]);
+      }
+    }
+  }
+  if (threadIdx.x == 0) p.out_count[img] = D;
+  for (int i = D * 6 + threadIdx.x; i < p.max_det * 6; i += blockDim.x) out[i] = 0.f;
+}
+
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
@@ -557,6 +1005,14 @@ extern "C" int64_t y3_nms_workspace_bytes(int32_t bs, int32_t cap) {
   b += y3::align_up(sizeof(float) * size_t(bs) * y3::kRankCap * 6, 256);
   b += y3::align_up(sizeof(uint32_t) * size_t(bs) * y3::kRankCap, 256);
   b += y3::align_up(size_t(bs) * y3::kRankCap, 256);
+  // v2: seg_off, seg_key2, box4, surv_cnt + done_cnt, surv_key, surv_pos, ord
+  b += y3::align_up(sizeof(int) * size_t(bs) * 1025, 256);
+  b += y3::align_up(sizeof(unsigned long long) * size_t(bs) * y3::kRankCap, 256);
+  b += y3::align_up(sizeof(float4) * size_t(bs) * y3::kRankCap, 256);
+  b += y3::align_up(sizeof(int) * size_t(bs) * 2, 256);
+  b += y3::align_up(sizeof(unsigned long long) * size_t(bs) * y3::kRankCap, 256);
+  b += y3::align_up(sizeof(int) * size_t(bs) * y3::kRankCap, 256);
+  b += y3::align_up(sizeof(uint16_t) * size_t(bs) * y3::kRankCap, 256);
   return static_cast<int64_t>(b);
 }
 
@@ -623,6 +1079,21 @@ extern "C" int y3_nms_batched(const float* pred, const y3_nms_params* q, void* w
   a.seg_keys = reinterpret_cast<uint32_t*>(w);
   w += align_up(sizeof(uint32_t) * size_t(a.bs) * kRankCap, 256);
   a.keep = w;
+  w += align_up(size_t(a.bs) * kRankCap, 256);
+  a.seg_off = reinterpret_cast<int*>(w);
+  w += align_up(sizeof(int) * size_t(a.bs) * 1025, 256);
+  a.seg_key2 = reinterpret_cast<unsigned long long*>(w);
+  w += align_up(sizeof(unsigned long long) * size_t(a.bs) * kRankCap, 256);
+  a.box4 = reinterpret_cast<float4*>(w);
+  w += align_up(sizeof(float4) * size_t(a.bs) * kRankCap, 256);
+  a.surv_cnt = reinterpret_cast<int*>(w);
+  a.done_cnt = a.surv_cnt + a.bs;
+  w += align_up(sizeof(int) * size_t(a.bs) * 2, 256);
+  a.surv_key = reinterpret_cast<unsigned long long*>(w);
+  w += align_up(sizeof(unsigned long long) * size_t(a.bs) * kRankCap, 256);
+  a.surv_pos = reinterpret_cast<int*>(w);
+  w += align_up(sizeof(int) * size_t(a.bs) * kRankCap, 256);
+  a.ord = reinterpret_cast<uint16_t*>(w);
   a.out = out;
   a.out_src = out_src;
   a.out_count = out_count;
@@ -631,6 +1102,19 @@ extern "C" int y3_nms_batched(const float* pred, const y3_nms_params* q, void* w
   Y3_CHECK_CUDA(cudaMemsetAsync(a.count, 0, sizeof(int) * size_t(a.bs) * 2, stream));
   // K1
   nms_candidates_kernel<<<dim3((a.n_rows + 32 * kCandWarps - 1) / (32 * kCandWarps), a.bs), 32 * kCandWarps, 0, stream>>>(a);
+  static int v1 = -1;  // Y3_NMS_V1=1: the round-1 pipeline (two global bitonic sorts), kept for A/B measurements
+  if (v1 < 0) {
+    const char* e = getenv("Y3_NMS_V1");
+    v1 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (!v1) {
+    nms_bucket_kernel<<<a.bs, kBucketThreads, 0, stream>>>(a);
+    nms_seg_warp_kernel<<<dim3((a.nc + 7) / 8, a.bs), 256, 0, stream>>>(a);
+    nms_seg_block_kernel<<<dim3(a.nc, a.bs), 256, 0, stream>>>(a);
+    nms_output_kernel<<<a.bs, 1024, 0, stream>>>(a);
+    Y3_CHECK_CUDA(cudaGetLastError());
+    return Y3_OK;
+  }
   pad_keys_kernel<<<dim3(8, a.bs), 256, 0, stream>>>(a);
   // K2: sort candidates by confidence (descending)
   {

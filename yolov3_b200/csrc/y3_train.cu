@@ -36,7 +36,12 @@ struct SliceW {
 // divisions per 16 bytes and ran 4-8x above its HBM floor (profiles/r01_train_launches_summary.txt).
 struct Rows {
   int n, h, w, c8, c8_shift;  // c8_shift = log2(c8), or -1 when c8 is not a power of two (generic division)
+  int upr;                    // work units per image row: a unit = kUnitIters x 256 consecutive 16-byte items of one row
 };
+// Every thread of a unit issues all of its (kUnitIters x loads-per-item) 16-byte loads before it consumes any: with one whole
+// row per block (10 dependent iterations per thread) the small layers ran at a fifth of HBM speed on latency alone
+// (gpurun r2j2 launch list: 21 us for 26 MB).
+constexpr int kUnitIters = 2;
 __device__ __forceinline__ void split_item(const Rows& g, int e, int& x, int& cg) {
   if (g.c8_shift >= 0) {
     x = e >> g.c8_shift;
@@ -83,18 +88,25 @@ __device__ __forceinline__ void block_reduce_store(float (&s)[8], float (&q)[8],
 
 // ---------------------------------------------------------------------------------------------- bn_stats
 // grid: nblk blocks of 256 threads; block b walks rows b, b+nblk, ...; partial[b] = [sum(c) | sumsq(c)]
-__global__ void __launch_bounds__(256) bn_stats_kernel(Slice y, Rows g, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256, 4) bn_stats_kernel(Slice y, Rows g, float* __restrict__ partial) {
   extern __shared__ float sh[];  // [2][256][8]
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const int items = g.w * g.c8, rows = g.n * g.h;
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+  const int items = g.w * g.c8, units = g.n * g.h * g.upr;
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int r = u / g.upr, e0 = (u - r * g.upr) * (256 * kUnitIters) + threadIdx.x;
     const __nv_bfloat16* base = y.p + row_base(g, r) * y.ld + y.coff;
-#pragma unroll 4
-    for (int e = threadIdx.x; e < items; e += 256) {
+    uint4 v[kUnitIters];
+#pragma unroll
+    for (int k = 0; k < kUnitIters; ++k) {
+      const int e = e0 + k * 256;
       int x, cg;
       split_item(g, e, x, cg);
+      v[k] = e < items ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(x) * y.ld + cg * 8)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < kUnitIters; ++k) {
       float f[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(x) * y.ld + cg * 8)), f);
+      unpack8(v[k], f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s[i] += f[i];
@@ -105,29 +117,43 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(Slice y, Rows g, float* _
   block_reduce_store(s, q, g.c8, sh, partial + static_cast<long long>(blockIdx.x) * 2 * g.c8 * 8, g.c8 * 8);
 }
 
-// out[j] (+)= sum_b partial[b][j], j < width, fixed order (second stage of every two-stage reduction here)
-__global__ void colreduce_kernel(const float* __restrict__ partial, int nblk, int width, float* __restrict__ out, int accumulate,
-                                 float* __restrict__ out2, int accumulate2) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= width) return;
+// Second stage of every two-stage reduction here: column sums of the nblk partial rows in a FIXED order (bit-reproducible).
+// Block = 32 columns x 32 row lanes: lane ty adds rows ty, ty+32, ... (coalesced 128-byte reads across tx), then the 32 lane
+// sums are added in index order.  The first version gave each column to one thread that walked all ~300 rows serially:
+// 37 us per BatchNorm layer, 2.7 ms of a 17 ms step (gpurun r2j2 launch list).
+__device__ __forceinline__ float colsum_32x32(const float* __restrict__ partial, int nblk, long long pitch, int col, bool valid,
+                                              float (*sh)[33]) {
   float a = 0.f;
-  for (int b = 0; b < nblk; ++b) a += partial[static_cast<long long>(b) * width + j];
-  if (out) out[j] = accumulate ? out[j] + a : a;
-  if (out2) out2[j] = accumulate2 ? out2[j] + a : a;
+  if (valid)
+    for (int b = threadIdx.y; b < nblk; b += 32) a += partial[static_cast<long long>(b) * pitch + col];
+  sh[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  float tot = 0.f;
+  if (threadIdx.y == 0)
+    for (int r = 0; r < 32; ++r) tot += sh[r][threadIdx.x];
+  __syncthreads();
+  return tot;  // meaningful on threadIdx.y == 0
+}
+
+__global__ void __launch_bounds__(1024) colreduce_kernel(const float* __restrict__ partial, int nblk, int width,
+                                                         float* __restrict__ out, int accumulate) {
+  __shared__ float sh[32][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const float a = colsum_32x32(partial, nblk, width, j, j < width, sh);
+  if (threadIdx.y == 0 && j < width) out[j] = accumulate ? out[j] + a : a;
 }
 
 // ---------------------------------------------------------------------------------------------- bn_finalize
 // sums[2][c] given as `nblk` partial rows (nblk = 1: already reduced, e.g. after SyncBatchNorm's all-reduce)
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblk, const float* gamma, const float* beta, int c,
-                                   float count, float eps, float momentum, float* scale, float* shift, float* mean_out,
-                                   float* rstd_out, float* running_mean, float* running_var) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
-  float sum = 0.f, sumsq = 0.f;
-  for (int b = 0; b < nblk; ++b) {
-    sum += partial[static_cast<long long>(b) * 2 * c + i];
-    sumsq += partial[static_cast<long long>(b) * 2 * c + c + i];
-  }
+__global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restrict__ partial, int nblk, const float* gamma,
+                                                           const float* beta, int c, float count, float eps, float momentum,
+                                                           float* scale, float* shift, float* mean_out, float* rstd_out,
+                                                           float* running_mean, float* running_var) {
+  __shared__ float sh[32][33];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  const float sum = colsum_32x32(partial, nblk, 2ll * c, i, i < c, sh);
+  const float sumsq = colsum_32x32(partial, nblk, 2ll * c, c + i, i < c, sh);
+  if (threadIdx.y != 0 || i >= c) return;
   const float mean = sum / count;
   float var = sumsq / count - mean * mean;
   var = var > 0.f ? var : 0.f;
@@ -157,31 +183,46 @@ struct BnActArgs {
 };
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const BnActArgs p) {
   const Rows g = p.g;
-  const int items = g.w * g.c8, rows = g.n * g.h;
-  const int u = p.upsample ? 2 : 1;
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+  const int items = g.w * g.c8, units = g.n * g.h * g.upr;
+  const int us = p.upsample ? 2 : 1;
+  const long long up_row = static_cast<long long>(2 * g.w + 2) * p.out.ld;
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int r = u / g.upr, e0 = (u - r * g.upr) * (256 * kUnitIters) + threadIdx.x;
     const long long rb = row_base(g, r);
     const long long ob = p.upsample ? row_base(g, r, 2) : rb;
-    const long long up_row = static_cast<long long>(2 * g.w + 2) * p.out.ld;
-#pragma unroll 2
-    for (int e = threadIdx.x; e < items; e += 256) {
+    uint4 vy[kUnitIters], vr[kUnitIters];
+#pragma unroll
+    for (int k = 0; k < kUnitIters; ++k) {
+      const int e = e0 + k * 256;
+      int x, cg;
+      split_item(g, e, x, cg);
+      vy[k] = vr[k] = make_uint4(0, 0, 0, 0);
+      if (e < items) {
+        vy[k] = __ldg(reinterpret_cast<const uint4*>(p.y.p + (rb + x) * p.y.ld + p.y.coff + cg * 8));
+        if (p.res.p) vr[k] = __ldg(reinterpret_cast<const uint4*>(p.res.p + (rb + x) * p.res.ld + p.res.coff + cg * 8));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kUnitIters; ++k) {
+      const int e = e0 + k * 256;
+      if (e >= items) continue;
       int x, cg;
       split_item(g, e, x, cg);
       float f[8], rr[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.y.p + (rb + x) * p.y.ld + p.y.coff + cg * 8)), f);
+      unpack8(vy[k], f);
       const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + cg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + cg * 8 + 4));
       const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift + cg * 8)), h1 = __ldg(reinterpret_cast<const float4*>(p.shift + cg * 8 + 4));
       const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
       const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = silu_f(fmaf(f[k], sc[k], sh[k]));
+      for (int q = 0; q < 8; ++q) f[q] = silu_f(fmaf(f[q], sc[q], sh[q]));
       if (p.res.p) {
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p.res.p + (rb + x) * p.res.ld + p.res.coff + cg * 8)), rr);
+        unpack8(vr[k], rr);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] += rr[k];
+        for (int q = 0; q < 8; ++q) f[q] += rr[q];
       }
       const uint4 o = pack8(f);
-      __nv_bfloat16* dst = p.out.p + (ob + static_cast<long long>(x) * u) * p.out.ld + p.out.coff + cg * 8;
+      __nv_bfloat16* dst = p.out.p + (ob + static_cast<long long>(x) * us) * p.out.ld + p.out.coff + cg * 8;
       *reinterpret_cast<uint4*>(dst) = o;
       if (p.upsample) {
         *reinterpret_cast<uint4*>(dst + p.out.ld) = o;
@@ -232,13 +273,13 @@ __device__ __forceinline__ float silu_grad(float z) {
   return s * fmaf(z, 1.0f - s, 1.0f);
 }
 
-template <bool APPLY>
-__global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BnBwdArgs p) {
+template <bool APPLY, bool UPS>
+__global__ void __launch_bounds__(256, UPS ? 2 : 3) bn_act_bwd_kernel(const BnBwdArgs p) {
   // block = 256 threads; thread t keeps channel group t % c8 for the whole kernel (256 % c8 == 0)
   extern __shared__ float sh[];
   const Rows g = p.g;
   const int cg = threadIdx.x % g.c8;
-  const int items = g.w * g.c8, rows = g.n * g.h;
+  const int items = g.w * g.c8, units = g.n * g.h * g.upr;
   float a_dz[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a_dzy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // per-channel constants.  APPLY: dy = sc*(dz - mean(dz) - yhat*mean(dz*yhat)) = sc*dz + k1*y + k0 with yhat = (y - mu)*rs
   float sc[8], shf[8], c2[8], c3[8];  // sums pass: c2 = mu, c3 = rs;  apply pass: c2 = k1, c3 = k0
@@ -256,29 +297,56 @@ __global__ void __launch_bounds__(256) bn_act_bwd_kernel(const BnBwdArgs p) {
       c3[k] = rs;
     }
   }
-  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int r = u / g.upr, e0 = (u - r * g.upr) * (256 * kUnitIters) + threadIdx.x;
     const long long rb = row_base(g, r);
     const long long ub = p.upsample ? row_base(g, r, 2) : rb;
-#pragma unroll 2
-    for (int e = threadIdx.x; e < items; e += 256) {
-      const int x = g.c8_shift >= 0 ? e >> g.c8_shift : e / g.c8;  // cg is loop-invariant: 256 % c8 == 0
-      float yv[8], d[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.y.p + (rb + x) * p.y.ld + p.y.coff + cg * 8)), yv);
-      load_da(p, rb, ub, x, cg, d);
-      float o[8];
+    // raw 16-byte vectors stay packed until they are consumed (registers: the reduction pass keeps 48 per-channel values);
+    // only the 2x-upsample variant (2 layers) sums its four da replicas right away
+    uint4 vy[kUnitIters], vd[kUnitIters];
+    float du[UPS ? kUnitIters : 1][8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float z = fmaf(yv[k], sc[k], shf[k]);
-        const float dz = d[k] * silu_grad(z);
+    for (int k = 0; k < kUnitIters; ++k) {
+      const int e = e0 + k * 256;
+      const int x = g.c8_shift >= 0 ? e >> g.c8_shift : e / g.c8;  // cg is loop-invariant: 256 % c8 == 0
+      vy[k] = vd[k] = make_uint4(0, 0, 0, 0);  // dz = 0 beyond the row: adds nothing to the sums
+      if (UPS) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) du[UPS ? k : 0][q] = 0.f;
+      }
+      if (e < items) {
+        vy[k] = __ldg(reinterpret_cast<const uint4*>(p.y.p + (rb + x) * p.y.ld + p.y.coff + cg * 8));
+        if (UPS)
+          load_da(p, rb, ub, x, cg, du[UPS ? k : 0]);
+        else
+          vd[k] = __ldg(reinterpret_cast<const uint4*>(p.da.p + (rb + x) * p.da.ld + p.da.coff + cg * 8));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kUnitIters; ++k) {
+      const int e = e0 + k * 256;
+      const int x = g.c8_shift >= 0 ? e >> g.c8_shift : e / g.c8;
+      float yv[8], d[8], o[8];
+      unpack8(vy[k], yv);
+      if (UPS) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) d[q] = du[UPS ? k : 0][q];
+      } else {
+        unpack8(vd[k], d);
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float z = fmaf(yv[q], sc[q], shf[q]);
+        const float dz = d[q] * silu_grad(z);
         if (APPLY) {
-          o[k] = fmaf(sc[k], dz, fmaf(c2[k], yv[k], c3[k]));
+          o[q] = fmaf(sc[q], dz, fmaf(c2[q], yv[q], c3[q]));
         } else {
-          const float yh = (yv[k] - c2[k]) * c3[k];
-          a_dz[k] += dz;
-          a_dzy[k] = fmaf(dz, yh, a_dzy[k]);
+          const float yh = (yv[q] - c2[q]) * c3[q];
+          a_dz[q] += dz;
+          a_dzy[q] = fmaf(dz, yh, a_dzy[q]);
         }
       }
-      if (APPLY) *reinterpret_cast<uint4*>(p.dy.p + (rb + x) * p.dy.ld + p.dy.coff + cg * 8) = pack8(o);
+      if (APPLY && e < items) *reinterpret_cast<uint4*>(p.dy.p + (rb + x) * p.dy.ld + p.dy.coff + cg * 8) = pack8(o);
     }
   }
   if (!APPLY)
@@ -629,16 +697,18 @@ Rows make_rows(int n, int h, int w, int c) {
   g.w = w;
   g.c8 = c / 8;
   g.c8_shift = log2_or_neg(g.c8);
+  g.upr = (w * g.c8 + 256 * kUnitIters - 1) / (256 * kUnitIters);
   return g;
 }
-constexpr int kMaxPartialBlocks = 296;  // two blocks per SM on B200; a fixed cap keeps workspace sizes device-independent
+constexpr int kMaxPartialBlocks = 592;  // four blocks per SM on B200; a fixed cap keeps workspace sizes device-independent
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int c, float* __restrict__ sums,
-                                       float* __restrict__ dbeta_acc, float* __restrict__ dgamma_acc) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= 2 * c) return;
-  float a = 0.f;
-  for (int b = 0; b < nblk; ++b) a += partial[static_cast<long long>(b) * 2 * c + j];
+__global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int c,
+                                                               float* __restrict__ sums, float* __restrict__ dbeta_acc,
+                                                               float* __restrict__ dgamma_acc) {
+  __shared__ float sh[32][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const float a = colsum_32x32(partial, nblk, 2ll * c, j, j < 2 * c, sh);
+  if (threadIdx.y != 0 || j >= 2 * c) return;
   sums[j] = a;
   if (j < c) {
     if (dbeta_acc) dbeta_acc[j] += a;
@@ -649,16 +719,18 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int nb
 }  // namespace
 }  // namespace y3
 
-extern "C" int32_t y3_bn_partial_blocks(int32_t n, int32_t h) {
-  const long long rows = static_cast<long long>(n) * h;
-  return static_cast<int32_t>(rows < y3::kMaxPartialBlocks ? (rows > 0 ? rows : 1) : y3::kMaxPartialBlocks);
+extern "C" int32_t y3_bn_partial_blocks(int32_t n, int32_t h, int32_t w, int32_t c) {
+  // work units of the streaming kernels (c == 0: one unit per image row, the Detect-head gradient pack), capped
+  long long units = static_cast<long long>(n) * h;
+  if (c > 0) units *= (static_cast<long long>(w) * (c / 8) + 256 * y3::kUnitIters - 1) / (256 * y3::kUnitIters);
+  return static_cast<int32_t>(units < y3::kMaxPartialBlocks ? (units > 0 ? units : 1) : y3::kMaxPartialBlocks);
 }
 
 extern "C" int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, int32_t n, int32_t h, int32_t w, float* partial,
                            y3_stream_t stream) {
   Y3_REQUIRE(y && partial && c > 0 && c % 8 == 0 && 256 % (c / 8) == 0 && n > 0 && h > 0 && w > 0 && ld % 8 == 0 && coff % 8 == 0,
              "bn_stats: bad arguments (c must be a power of two in [8, 2048])");
-  const int nblk = y3_bn_partial_blocks(n, h);
+  const int nblk = y3_bn_partial_blocks(n, h, w, c);
   y3::bn_stats_kernel<<<nblk, 256, 2 * 256 * 8 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       Slice{static_cast<const __nv_bfloat16*>(y), ld, coff}, y3::make_rows(n, h, w, c), partial);
   Y3_CHECK_CUDA(cudaGetLastError());
@@ -668,8 +740,7 @@ extern "C" int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, i
 extern "C" int y3_colreduce_f32(const float* partial, int32_t nblk, int32_t width, float* out, int32_t accumulate,
                                 y3_stream_t stream) {
   Y3_REQUIRE(partial && out && nblk > 0 && width > 0, "colreduce: bad arguments");
-  y3::colreduce_kernel<<<(width + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(partial, nblk, width, out, accumulate,
-                                                                                          nullptr, 0);
+  y3::colreduce_kernel<<<(width + 31) / 32, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(partial, nblk, width, out, accumulate);
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -678,7 +749,7 @@ extern "C" int y3_bn_finalize(const float* partial, int32_t nblk, const float* g
                               float eps, float momentum, float* scale, float* shift, float* mean, float* rstd,
                               float* running_mean, float* running_var, y3_stream_t stream) {
   Y3_REQUIRE(partial && nblk > 0 && gamma && beta && scale && shift && mean && rstd && c > 0 && count > 0, "bn_finalize: bad arguments");
-  y3::bn_finalize_kernel<<<(c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  y3::bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(
       partial, nblk, gamma, beta, c, count, eps, momentum, scale, shift, mean, rstd, running_mean, running_var);
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
@@ -695,9 +766,9 @@ extern "C" int y3_bn_act_fwd(const y3_bn_act_desc* d, y3_stream_t stream) {
   a.shift = d->shift;
   a.g = y3::make_rows(d->n, d->h, d->w, d->c);
   a.upsample = d->upsample;
-  const long long rows = static_cast<long long>(d->n) * d->h;
+  const long long units = static_cast<long long>(d->n) * d->h * a.g.upr;
   const long long cap = 8ll * y3::num_sms();
-  y3::bn_act_fwd_kernel<<<static_cast<unsigned>(rows < cap ? rows : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  y3::bn_act_fwd_kernel<<<static_cast<unsigned>(units < cap ? units : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -724,16 +795,22 @@ extern "C" int y3_bn_act_bwd(const y3_bn_bwd_desc* d, y3_stream_t stream_) {
   a.upsample = d->upsample;
   const long long pixels = static_cast<long long>(d->n) * d->h * d->w;
   a.inv_count = 1.0f / (d->count > 0.f ? d->count : static_cast<float>(pixels));
-  const int nblk = y3_bn_partial_blocks(d->n, d->h);
+  const int nblk = y3_bn_partial_blocks(d->n, d->h, d->w, d->c);
   if (d->phase != 2) {
-    y3::bn_act_bwd_kernel<false><<<nblk, 256, 2 * 256 * 8 * sizeof(float), stream>>>(a);
-    y3::bn_bwd_finalize_kernel<<<(2 * d->c + 127) / 128, 128, 0, stream>>>(d->partial, nblk, d->c, d->sums, d->dbeta_acc,
-                                                                          d->dgamma_acc);
+    if (d->upsample)
+      y3::bn_act_bwd_kernel<false, true><<<nblk, 256, 2 * 256 * 8 * sizeof(float), stream>>>(a);
+    else
+      y3::bn_act_bwd_kernel<false, false><<<nblk, 256, 2 * 256 * 8 * sizeof(float), stream>>>(a);
+    y3::bn_bwd_finalize_kernel<<<(2 * d->c + 31) / 32, dim3(32, 32), 0, stream>>>(d->partial, nblk, d->c, d->sums, d->dbeta_acc,
+                                                                                  d->dgamma_acc);
   }
   if (d->phase != 1) {
-    const long long rows = static_cast<long long>(d->n) * d->h;
+    const long long units = static_cast<long long>(d->n) * d->h * a.g.upr;
     const long long cap = 8ll * y3::num_sms();
-    y3::bn_act_bwd_kernel<true><<<static_cast<unsigned>(rows < cap ? rows : cap), 256, 0, stream>>>(a);
+    if (d->upsample)
+      y3::bn_act_bwd_kernel<true, true><<<static_cast<unsigned>(units < cap ? units : cap), 256, 0, stream>>>(a);
+    else
+      y3::bn_act_bwd_kernel<true, false><<<static_cast<unsigned>(units < cap ? units : cap), 256, 0, stream>>>(a);
   }
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
@@ -762,7 +839,7 @@ extern "C" int y3_head_grad_pack(const float* g, int32_t n, int32_t na, int32_t 
                                  int32_t dy_ld, int32_t dy_coff, float* partial, y3_stream_t stream) {
   Y3_REQUIRE(g && dy && partial && n > 0 && na > 0 && ny > 0 && nx > 0 && no > 0 && na * no <= 256 && dy_ld - dy_coff <= 256,
              "head_grad_pack: bad arguments (na*no <= 256)");
-  const int nblk = y3_bn_partial_blocks(n, ny);
+  const int nblk = y3_bn_partial_blocks(n, ny, 0, 0);
   y3::head_grad_pack_kernel<<<nblk, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       g, n, na, ny, nx, no, SliceW{static_cast<__nv_bfloat16*>(dy), dy_ld, dy_coff}, partial);
   Y3_CHECK_CUDA(cudaGetLastError());

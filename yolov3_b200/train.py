@@ -100,7 +100,7 @@ class TrainEngine:
             b.rmean, b.rvar = store.flat(prefix + ".bn.running_mean"), store.flat(prefix + ".bn.running_var")
             b.st = {name: f32(c2) for name in ("scale", "shift", "mean", "rstd")}
             b.st.update(sums=f32(2 * c2), gsums=f32(2 * c2))  # [sum | sumsq] forward, [sum dz | sum dz*xhat] backward
-            b.nblk = T.partial_blocks(n, ho)
+            b.nblk = T.partial_blocks(n, ho, wo, c2)
             max_partial = max(max_partial, b.nblk * 2 * c2)
             b.dy = buf(c2, ho, wo) if keep_all else self._scratch(c2, ho, wo, dev)
             b.dy_up = self._scratch(c2, x.h, x.w, dev, tag="up") if s == 2 else None

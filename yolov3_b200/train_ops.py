@@ -12,15 +12,16 @@ from .tensors import PaddedNHWC, _stream
 BN_EPS, BN_MOMENTUM = 1e-3, 0.03  # ultralytics initialize_weights (models/yolo.py:229)
 
 
-def partial_blocks(n: int, h: int) -> int:
-    """Rows the first stage of a two-stage reduction writes for an [n, h, w] activation (y3_bn_partial_blocks)."""
-    return int(_lib.lib().y3_bn_partial_blocks(int(n), int(h)))
+def partial_blocks(n: int, h: int, w: int = 0, c: int = 0) -> int:
+    """Rows the first stage of a two-stage reduction writes for an [n, h, w, c] activation (y3_bn_partial_blocks); c = 0: the
+    Detect-head gradient pack (one unit per image row)."""
+    return int(_lib.lib().y3_bn_partial_blocks(int(n), int(h), int(w), int(c)))
 
 
 def bn_stats(y: PaddedNHWC, partial: torch.Tensor):
     """First stage of the batch statistics: partial[blocks][2][c] = (sum | sumsq) of the conv output over its interior
     pixels; ``bn_finalize`` (or ``colreduce``) adds the rows in a fixed order — no atomics, bit-reproducible."""
-    assert partial.dtype == torch.float32 and partial.numel() >= partial_blocks(y.n, y.h) * 2 * y.c
+    assert partial.dtype == torch.float32 and partial.numel() >= partial_blocks(y.n, y.h, y.w, y.c) * 2 * y.c
     _lib.check(_lib.lib().y3_bn_stats(y.ptr, y.ld, y.coff, y.c, y.n, y.h, y.w, partial.data_ptr(), _stream()), "y3_bn_stats")
     return partial
 
