@@ -328,6 +328,19 @@ int y3_im2col_first(const void* in, int32_t in_dtype, float in_div, int32_t n, i
 int y3_colsum_f32(const float* g, int32_t ld, int32_t c, int64_t rows, float* out, y3_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Validation matching (val.process_batch, val.py:147-188) for a whole batch and all IoU thresholds in one launch.
+ * det: [bs, det_stride, 6] rows (x1,y1,x2,y2,conf,cls) in confidence order (the NMS output), det_count[bs] valid rows per image
+ * (NULL: max_det each); labels: [nl, 6] rows (image, cls, x1,y1,x2,y2) in the same coordinate space as det; iouv: [niou]
+ * thresholds (val.py:301: linspace(0.5, 0.95, 10)).  correct[bs, max_det, niou] (bytes 0/1):
+ *   correct[d, t] = 1  <=>  detection d's best same-class label l (IoU >= iouv[t], highest IoU) exists and d is the
+ *   lowest-index detection whose best label is l  — the result of the reference's sort / np.unique / np.unique sequence.
+ * IoU = inter / (area_label + area_det - inter + eps), the reference box_iou's fp32 operation order (eps 1e-7).
+ * At most 1024 labels per image are matched; overflow[bs] (optional) reports how many were ignored. */
+int y3_val_match(const float* det, const int32_t* det_count, int32_t bs, int32_t max_det, int32_t det_stride,
+                 const float* labels, int32_t nl, const float* iouv, int32_t niou, float eps, uint8_t* correct,
+                 int32_t* overflow, y3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Optimizer step over ONE flat fp32 parameter buffer (train.py:411-421: clip_grad_norm_(10.0), SGD-nesterov with the three
  * parameter groups of smart_optimizer utils/torch_utils.py:207-237, ModelEMA.update) — csrc/y3_optim.cu.
  * Layout contract: every parameter occupies a slot whose length is a multiple of 256 elements; group[i] is the group of

@@ -449,6 +449,44 @@ def scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=None):
     return b
 
 
+def process_batch(detections, labels, iouv):
+    """val.process_batch (reference val.py:147-188) restated with the same torch / numpy calls in the same order:
+    detections [N,6] (xyxy, conf, cls), labels [M,5] (cls, xyxy), iouv [T] -> bool [N,T]."""
+    correct = np.zeros((detections.shape[0], iouv.shape[0])).astype(bool)
+    iou = box_iou(labels[:, 1:], detections[:, :4])
+    correct_class = labels[:, 0:1] == detections[:, 5]
+    for i in range(len(iouv)):
+        x = torch.where((iou >= iouv[i]) & correct_class)  # val.py:179
+        if x[0].shape[0]:
+            matches = torch.cat((torch.stack(x, 1), iou[x[0], x[1]][:, None]), 1).cpu().numpy()  # [label, detect, iou]
+            if x[0].shape[0] > 1:
+                matches = matches[matches[:, 2].argsort()[::-1]]
+                matches = matches[np.unique(matches[:, 1], return_index=True)[1]]
+                matches = matches[np.unique(matches[:, 0], return_index=True)[1]]
+            correct[matches[:, 1].astype(int), i] = True
+    return torch.tensor(correct, dtype=torch.bool)
+
+
+def synth_val_case(n_det=120, n_lab=25, nc=6, seed=0, jitter=12.0, size=640.0):
+    """Seeded detections/labels for the matching tests: labels are random boxes, most detections are jittered copies of a
+    label (several per label, some with the wrong class), the rest random; detections sorted by confidence like NMS output."""
+    g = torch.Generator().manual_seed(seed)
+    xy = torch.rand(n_lab, 2, generator=g) * (size - 200) + 20
+    wh = torch.rand(n_lab, 2, generator=g) * 160 + 20
+    lab = torch.cat((torch.randint(0, nc, (n_lab, 1), generator=g).float(), xy, xy + wh), 1)
+    src = torch.randint(0, max(n_lab, 1), (n_det,), generator=g)
+    box = lab[src, 1:] + torch.randn(n_det, 4, generator=g) * jitter if n_lab else torch.zeros(n_det, 4)
+    rnd = torch.rand(n_det, generator=g) < 0.2
+    rxy = torch.rand(n_det, 2, generator=g) * (size - 100)
+    box[rnd] = torch.cat((rxy, rxy + torch.rand(n_det, 2, generator=g) * 90 + 10), 1)[rnd]
+    cls = lab[src, 0].clone() if n_lab else torch.zeros(n_det)
+    wrong = torch.rand(n_det, generator=g) < 0.15
+    cls[wrong] = torch.randint(0, nc, (int(wrong.sum()),), generator=g).float()
+    conf = torch.rand(n_det, generator=g).sort(descending=True).values
+    det = torch.cat((box, conf[:, None], cls[:, None]), 1)
+    return det, lab
+
+
 def box_iou(box1, box2, eps=1e-7):
     """ultralytics box_iou (re-exported utils/metrics.py:10; used val.py:176): inter/(a1+a2-inter+eps), [N,M]."""
     b1, b2 = torch.as_tensor(box1).float(), torch.as_tensor(box2).float()

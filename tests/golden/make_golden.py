@@ -9,6 +9,7 @@ What is pinned:
   nms_cases.npz         non_max_suppression outputs for a sweep + adversarial cases       (utils/general.py:630-750)
   loss_cases.npz        ComputeLoss loss / loss_items / dL/dp and build_targets           (utils/loss.py:131-244)
   iou_cases.npz         box_iou, bbox_iou(CIoU) values                                    (ultralytics, via shim)
+  val_cases.npz         val.process_batch correct[N,10] on seeded detections / labels     (val.py:147-188)
 """
 from __future__ import annotations
 
@@ -274,11 +275,38 @@ def gen_iou():
     print("iou ok")
 
 
+def val_case_list():
+    """(name, n_det, n_lab, nc, seed, jitter): crowded / sparse / empty-side / single-pair / many-duplicates cases"""
+    return [("typical", 120, 25, 6, 0, 12.0), ("crowded", 300, 60, 3, 1, 6.0), ("sparse", 40, 5, 20, 2, 25.0),
+            ("one_pair", 1, 1, 1, 3, 1.0), ("no_labels", 30, 0, 4, 4, 5.0), ("one_label_many_dets", 80, 1, 1, 5, 4.0),
+            ("many_labels_one_det", 1, 40, 2, 6, 8.0), ("tight", 200, 30, 2, 7, 2.0)]
+
+
+def gen_val():
+    import val as V  # reference val.py (process_batch)
+
+    iouv = torch.linspace(0.5, 0.95, 10)  # val.py:301
+    store = {"iouv": iouv.numpy()}
+    for name, nd, nl, nc, seed, jit in val_case_list():
+        det, lab = O.synth_val_case(nd, nl, nc, seed, jit)
+        if nl == 0:
+            ref = torch.zeros(nd, 10, dtype=torch.bool)  # val.py:372-376 never calls process_batch without labels
+        else:
+            ref = V.process_batch(det, lab, iouv)
+        ora = O.process_batch(det, lab, iouv) if nl else ref
+        assert torch.equal(ref, ora), name
+        store[f"{name}/det"], store[f"{name}/lab"], store[f"{name}/correct"] = det.numpy(), lab.numpy(), ref.numpy()
+        print("val", name, int(ref.sum()), "true of", ref.numel())
+    np.savez_compressed(OUT / "val_cases.npz", **store)
+
+
 if __name__ == "__main__":
     assert ref_shim.reference_available(), "run in the build container: /root/reference is required"
     ref_shim.install()
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["iou", "nms", "loss", "forward", "scale"]
+    which = sys.argv[1:] or ["iou", "nms", "loss", "forward", "scale", "val"]
+    if "val" in which:
+        gen_val()
     if "scale" in which:
         gen_scale_boxes()
     if "iou" in which:

@@ -130,3 +130,17 @@ def test_oracle_nms_properties():
     perm = torch.randperm(pred.shape[1], generator=torch.Generator().manual_seed(1))
     (out3,), (src3,) = O.non_max_suppression(pred[:, perm], conf, iou, max_det=1000)
     assert np.array_equal(out3, out) and np.array_equal(perm.numpy()[src3[:, 0]], src[:, 0])
+
+
+def test_process_batch_oracle_vs_reference_golden():
+    """oracle.process_batch (restatement of val.py:147-188) against the matrices the reference's own val.process_batch produced."""
+    g = np.load(G / "val_cases.npz")
+    iouv = torch.from_numpy(g["iouv"])
+    for case in sorted({k.split("/")[0] for k in g.files if "/" in k}):
+        det, lab = torch.from_numpy(g[f"{case}/det"]), torch.from_numpy(g[f"{case}/lab"])
+        if lab.shape[0] == 0:
+            continue
+        assert np.array_equal(O.process_batch(det, lab, iouv).numpy(), g[f"{case}/correct"]), case
+        d2, l2 = O.synth_val_case(det.shape[0], lab.shape[0], 6, seed=0)  # the generator is part of the fixture contract
+    d0, l0 = O.synth_val_case(120, 25, 6, 0, 12.0)
+    assert np.array_equal(d0.numpy(), g["typical/det"]) and np.array_equal(l0.numpy(), g["typical/lab"])

@@ -2,7 +2,7 @@
 # round-2 GPU job 3: NMS v2 (class-bucketed pipeline), parallel BN finalize + unit-based BN streams
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_nms_gpu.py tests/test_pipeline_gpu.py tests/test_train_gpu.py tests/test_train_layers_gpu.py -m gpu -q -x --timeout 600 -p no:cacheprovider 2>&1 | tail -30 > gpurun_out/r2j3_pytest.log
+timeout 900 python -m pytest tests/test_val_gpu.py tests/test_nms_gpu.py tests/test_pipeline_gpu.py tests/test_train_gpu.py tests/test_train_layers_gpu.py -m gpu -q -x --timeout 600 -p no:cacheprovider 2>&1 | tail -30 > gpurun_out/r2j3_pytest.log
 tail -8 gpurun_out/r2j3_pytest.log
 for c in "0.25 0.45 0" "0.001 0.6 0" "0.25 0.45 1" "0.001 0.6 1"; do set -- $c; timeout 120 python tools/run_nms.py --conf $1 --iou $2 --ml $3 --iters 10 2>&1 | tail -1; done | tee gpurun_out/r2j3_nms.log
 Y3_NMS_V1=1 timeout 120 python tools/run_nms.py --conf 0.25 --iou 0.45 --ml 0 --iters 10 2>&1 | tail -1 | tee -a gpurun_out/r2j3_nms.log

@@ -177,6 +177,7 @@ def _declare(lib):
         "y3_f32_to_bf16": ([vp, vp, C.c_int64, vp], C.c_int),
         "y3_pack_dgrad_batched": ([vp, i32, vp, i32, vp], C.c_int),
         "y3_head_grad_pack": ([vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp], C.c_int),
+        "y3_val_match": ([vp, vp, i32, i32, i32, vp, i32, vp, i32, C.c_float, vp, vp, vp], C.c_int),
         "y3_sumsq_blocks": ([], i32),
         "y3_grad_sumsq": ([vp, C.c_int64, vp, vp, vp], C.c_int),
         "y3_sgd_step": ([vp, vp, vp, vp, vp, C.c_int64, vp, vp, vp], C.c_int),
