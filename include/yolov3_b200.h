@@ -328,6 +328,35 @@ int y3_im2col_first(const void* in, int32_t in_dtype, float in_div, int32_t n, i
 int y3_colsum_f32(const float* g, int32_t ld, int32_t c, int64_t rows, float* out, y3_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Image pre-processing on the device: letterbox (utils/augmentations.py:104-134: cv2.resize
+ * INTER_LINEAR to new_w x new_h, then a constant border) fused with the HWC->CHW / BGR->RGB step of the loaders
+ * (utils/dataloaders.py:308-310).  src: uint8 [src_h, src_w, 3] with row pitch src_pitch bytes (a decoded BGR frame);
+ * dst: uint8 [out_h, out_w, 3] (out_chw = 0) or [3, out_h, out_w] (out_chw = 1), channel order reversed when swap_rb.
+ * The resized image sits at (top, left); everything else is pad[] (given in SOURCE channel order, 114 in the reference).
+ * The resize reproduces OpenCV's 8-bit INTER_LINEAR bit for bit (incl. its 2x-shrink INTER_AREA shortcut and the plain copy
+ * when no resize is needed).  The geometry (new size, offsets) is the caller's: letterbox's scalar arithmetic stays on the host. */
+typedef struct y3_letterbox_desc {
+  const void* src; int32_t src_h, src_w, src_pitch;
+  int32_t new_h, new_w, top, left;
+  void* dst;       int32_t out_h, out_w;
+  int32_t out_chw, swap_rb;
+  uint8_t pad[4];
+} y3_letterbox_desc;
+int y3_letterbox_u8(const y3_letterbox_desc* d, y3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Test-time augmentation (Model._forward_augment, models/yolo.py:239-280).
+ * y3_scale_img_f32: scale_img (ultralytics; yolo.py:246) — bilinear (align_corners = false) resample of fp32 [n,c,h,w] (read
+ *   left-right flipped when flip_lr) to rh x rw inside an [n,c,oh,ow] output whose right / bottom remainder is pad_value (0.447).
+ * y3_tta_merge: rows [row_begin, row_end) of one view's decoded z [bs, rows, no] go to rows [out_row_off, ...) of the merged
+ *   output [bs, out_rows, no] with _descale_pred applied (xywh /= scale; x = img_w - x when the view was flipped): the
+ *   _clip_augmented row selection and the torch.cat of the reference are the addressing of this copy. */
+int y3_scale_img_f32(const float* in, int32_t n, int32_t c, int32_t h, int32_t w, int32_t rh, int32_t rw, int32_t oh, int32_t ow,
+                     int32_t flip_lr, float pad_value, float* out, y3_stream_t stream);
+int y3_tta_merge(const float* z, int32_t bs, int32_t rows, int32_t no, int32_t row_begin, int32_t row_end, float scale,
+                 int32_t flip_lr, float img_w, float* out, int32_t out_rows, int32_t out_row_off, y3_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Validation matching (val.process_batch, val.py:147-188) for a whole batch and all IoU thresholds in one launch.
  * det: [bs, det_stride, 6] rows (x1,y1,x2,y2,conf,cls) in confidence order (the NMS output), det_count[bs] valid rows per image
  * (NULL: max_det each); labels: [nl, 6] rows (image, cls, x1,y1,x2,y2) in the same coordinate space as det; iouv: [niou]

@@ -449,6 +449,122 @@ def scale_boxes(img1_shape, boxes, img0_shape, ratio_pad=None):
     return b
 
 
+# ------------------------------------------------------------------------------------------------ TTA
+def scale_img(img, ratio=1.0, same_shape=False, gs=32):
+    """ultralytics scale_img (third-party; used by models/yolo.py:246): bilinear resize to int(h*r) x int(w*r), right/bottom pad
+    with 0.447 to a gs multiple."""
+    if ratio == 1.0:
+        return img
+    h, w = img.shape[2:]
+    s = (int(h * ratio), int(w * ratio))
+    img = F.interpolate(img, size=s, mode="bilinear", align_corners=False)
+    if not same_shape:
+        h, w = (math.ceil(x * ratio / gs) * gs for x in (h, w))
+    return F.pad(img, [0, w - s[1], 0, h - s[0]], value=0.447)
+
+
+def forward_augment(om, x):
+    """Model._forward_augment + _descale_pred + _clip_augmented (models/yolo.py:239-278) on an OracleModel: returns z_aug."""
+    img_size = x.shape[-2:]
+    y = []
+    for si, fi in zip([1, 0.83, 0.67], [None, 3, None]):
+        xi = scale_img(x.flip(fi) if fi else x, si, gs=int(max(om.stride)))
+        yi = om(xi)[0].clone()
+        yi[..., :4] /= si
+        if fi == 3:
+            yi[..., 0] = img_size[1] - yi[..., 0]
+        y.append(yi)
+    nl = len(om.stride)
+    g = sum(4 ** q for q in range(nl))
+    i = (y[0].shape[1] // g) * 1
+    y[0] = y[0][:, :-i]
+    i = (y[-1].shape[1] // g) * 4 ** (nl - 1)
+    y[-1] = y[-1][:, i:]
+    return torch.cat(y, 1)
+
+
+# ------------------------------------------------------------------------------------------------ pre-processing
+def _cv_round(x):
+    """cvRound / saturate_cast<short>(float): round half to even."""
+    return np.rint(x).astype(np.int64)
+
+
+def resize_linear_u8(src, dw, dh):
+    """cv2.resize(src, (dw, dh), interpolation=cv2.INTER_LINEAR) for uint8 HWC images, restated bit-exactly from OpenCV's
+    fixed-point path (third-party: opencv-python 4.13 is what the reference's letterbox calls, utils/augmentations.py:127;
+    resize.cpp: 11-bit coefficients, HResizeLinear -> int, VResizeLinear ((b*(S>>4))>>16 ... +2)>>2; the exact 2x shrink takes
+    the INTER_AREA 2x2 average).  Pinned against cv2 itself in tests/test_oracle_golden.py."""
+    sh, sw = src.shape[:2]
+    if (dw, dh) == (sw, sh):
+        return src.copy()
+    scale_x, scale_y = 1.0 / (dw / sw), 1.0 / (dh / sh)
+    isx, isy = int(np.rint(scale_x)), int(np.rint(scale_y))
+    eps = np.finfo(np.float64).eps
+    if abs(scale_x - isx) < eps and abs(scale_y - isy) < eps and isx == 2 and isy == 2:
+        s = src.astype(np.int32)
+        return ((s[0:2 * dh:2, 0:2 * dw:2] + s[0:2 * dh:2, 1:2 * dw:2] + s[1:2 * dh:2, 0:2 * dw:2] + s[1:2 * dh:2, 1:2 * dw:2] + 2)
+                >> 2).astype(np.uint8)
+
+    def frac(dn, scale):
+        f = ((np.arange(dn) + 0.5) * scale - 0.5).astype(np.float32)
+        s0 = np.floor(f).astype(np.int64)
+        return s0, (f - s0.astype(np.float32)).astype(np.float32)
+
+    sx, fx = frac(dw, scale_x)
+    lo, hi = sx < 0, sx >= sw - 1
+    fx[lo], sx[lo] = 0, 0
+    fx[hi], sx[hi] = 0, sw - 1
+    ax0, ax1 = _cv_round((np.float32(1.0) - fx) * np.float32(2048)), _cv_round(fx * np.float32(2048))
+    sy, fy = frac(dh, scale_y)
+    b0, b1 = _cv_round((np.float32(1.0) - fy) * np.float32(2048)), _cv_round(fy * np.float32(2048))
+    s = src.astype(np.int64)
+    hrow = s[:, sx] * ax0[None, :, None] + s[:, np.minimum(sx + 1, sw - 1)] * ax1[None, :, None]
+    s0, s1 = hrow[np.clip(sy, 0, sh - 1)], hrow[np.clip(sy + 1, 0, sh - 1)]
+    out = (((b0[:, None, None] * (s0 >> 4)) >> 16) + ((b1[:, None, None] * (s1 >> 4)) >> 16) + 2) >> 2
+    return out.astype(np.uint8)
+
+
+def letterbox_geometry(shape, new_shape=(640, 640), auto=True, scaleFill=False, scaleup=True, stride=32):
+    """The scalar part of letterbox (utils/augmentations.py:104-132): returns (new_unpad (w, h), ratio, (dw, dh), top, bottom,
+    left, right)."""
+    if isinstance(new_shape, int):
+        new_shape = (new_shape, new_shape)
+    r = min(new_shape[0] / shape[0], new_shape[1] / shape[1])
+    if not scaleup:
+        r = min(r, 1.0)
+    ratio = r, r
+    new_unpad = round(shape[1] * r), round(shape[0] * r)
+    dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
+    if auto:
+        dw, dh = np.mod(dw, stride), np.mod(dh, stride)
+    elif scaleFill:
+        dw, dh = 0.0, 0.0
+        new_unpad = (new_shape[1], new_shape[0])
+        ratio = new_shape[1] / shape[1], new_shape[0] / shape[0]
+    dw /= 2
+    dh /= 2
+    top, bottom = round(dh - 0.1), round(dh + 0.1)
+    left, right = round(dw - 0.1), round(dw + 0.1)
+    return new_unpad, ratio, (dw, dh), top, bottom, left, right
+
+
+def letterbox(im, new_shape=(640, 640), color=(114, 114, 114), auto=True, scaleFill=False, scaleup=True, stride=32):
+    """letterbox (utils/augmentations.py:104-134) on a uint8 HWC numpy image: cv2.resize(INTER_LINEAR) + constant border."""
+    new_unpad, ratio, (dw, dh), top, bottom, left, right = letterbox_geometry(im.shape[:2], new_shape, auto, scaleFill, scaleup, stride)
+    if im.shape[:2][::-1] != new_unpad:
+        im = resize_linear_u8(im, new_unpad[0], new_unpad[1])
+    out = np.empty((im.shape[0] + top + bottom, im.shape[1] + left + right, im.shape[2]), np.uint8)
+    out[...] = np.asarray(color, np.uint8)
+    out[top:top + im.shape[0], left:left + im.shape[1]] = im
+    return out, ratio, (dw, dh)
+
+
+def preprocess(im0, img_size=640, stride=32, auto=True):
+    """LoadImages.__next__ (utils/dataloaders.py:305-310): letterbox -> HWC to CHW, BGR to RGB -> contiguous uint8."""
+    im = letterbox(im0, img_size, stride=stride, auto=auto)[0]
+    return np.ascontiguousarray(im.transpose((2, 0, 1))[::-1])
+
+
 def process_batch(detections, labels, iouv):
     """val.process_batch (reference val.py:147-188) restated with the same torch / numpy calls in the same order:
     detections [N,6] (xyxy, conf, cls), labels [M,5] (cls, xyxy), iouv [T] -> bool [N,T]."""

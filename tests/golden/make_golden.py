@@ -10,6 +10,7 @@ What is pinned:
   loss_cases.npz        ComputeLoss loss / loss_items / dL/dp and build_targets           (utils/loss.py:131-244)
   iou_cases.npz         box_iou, bbox_iou(CIoU) values                                    (ultralytics, via shim)
   val_cases.npz         val.process_batch correct[N,10] on seeded detections / labels     (val.py:147-188)
+  tta_cases.npz         Model.forward(x, augment=True) rows (scale / flip views merged)    (models/yolo.py:239-280)
 """
 from __future__ import annotations
 
@@ -275,6 +276,24 @@ def gen_iou():
     print("iou ok")
 
 
+def gen_tta():
+    """Model.forward(x, augment=True) (models/yolo.py:233-280) of the reference vs the oracle restatement."""
+    store = {}
+    for name, shape in (("yolov3-tiny", (2, 3, 96, 128)), ("yolov3", (1, 3, 128, 96))):
+        params = O.init_params(CFG / f"{name}.yaml", seed=0)
+        m = ref_model(name, params)
+        x = torch.rand(*shape, generator=torch.Generator().manual_seed(41))
+        with torch.no_grad():
+            z_ref = m(x.clone(), augment=True)[0]
+            z_ora = O.forward_augment(O.OracleModel(CFG / f"{name}.yaml", params=params, fused=False), x)
+        assert z_ref.shape == z_ora.shape, (z_ref.shape, z_ora.shape)
+        err = float((z_ref - z_ora).abs().max() / z_ref.abs().max())
+        assert err < 2e-5, (name, err)
+        store[f"{name}/shape"], store[f"{name}/z_aug"] = np.array(shape), z_ref.numpy().astype(np.float32)
+        print("tta", name, tuple(z_ref.shape), err)
+    np.savez_compressed(OUT / "tta_cases.npz", **store)
+
+
 def val_case_list():
     """(name, n_det, n_lab, nc, seed, jitter): crowded / sparse / empty-side / single-pair / many-duplicates cases"""
     return [("typical", 120, 25, 6, 0, 12.0), ("crowded", 300, 60, 3, 1, 6.0), ("sparse", 40, 5, 20, 2, 25.0),
@@ -304,7 +323,9 @@ if __name__ == "__main__":
     assert ref_shim.reference_available(), "run in the build container: /root/reference is required"
     ref_shim.install()
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["iou", "nms", "loss", "forward", "scale", "val"]
+    which = sys.argv[1:] or ["iou", "nms", "loss", "forward", "scale", "val", "tta"]
+    if "tta" in which:
+        gen_tta()
     if "val" in which:
         gen_val()
     if "scale" in which:

@@ -144,3 +144,28 @@ def test_process_batch_oracle_vs_reference_golden():
         d2, l2 = O.synth_val_case(det.shape[0], lab.shape[0], 6, seed=0)  # the generator is part of the fixture contract
     d0, l0 = O.synth_val_case(120, 25, 6, 0, 12.0)
     assert np.array_equal(d0.numpy(), g["typical/det"]) and np.array_equal(l0.numpy(), g["typical/lab"])
+
+
+def test_letterbox_oracle_vs_cv2_and_reference():
+    """oracle.resize_linear_u8 / letterbox (restating OpenCV's 8-bit INTER_LINEAR and utils/augmentations.py:104-134) against
+    cv2 itself (third-party, installed: opencv-python 4.13) and, when the reference is importable, its own letterbox()."""
+    import sys
+
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(0)
+    for (h, w, nh, nw) in [(480, 640, 480, 640), (1080, 810, 640, 480), (720, 1280, 360, 640), (375, 500, 480, 640), (100, 133, 640, 851),
+                           (501, 333, 417, 277), (64, 64, 200, 31), (33, 77, 32, 75)]:
+        im = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(O.resize_linear_u8(im, nw, nh), cv2.resize(im, (nw, nh), interpolation=cv2.INTER_LINEAR)), (h, w, nh, nw)
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "oracle"))
+    import ref_shim
+
+    if ref_shim.reference_available():
+        ref_shim.install()
+        from utils.augmentations import letterbox as ref_letterbox
+
+        for (h, w) in [(1080, 810), (375, 500), (333, 1000)]:
+            im = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            for kw in [dict(auto=True), dict(auto=False), dict(auto=False, scaleFill=True), dict(auto=True, scaleup=False)]:
+                a, b = ref_letterbox(im.copy(), **kw), O.letterbox(im.copy(), **kw)
+                assert np.array_equal(a[0], b[0]) and a[1] == b[1] and tuple(a[2]) == tuple(b[2])

@@ -180,17 +180,23 @@ def nms_sweep_workload(dev, rank, world, bs=32, reps=10):
     for conf in (0.001, 0.01, 0.05, 0.1, 0.25):
         iou = 0.6 if conf <= 0.01 else 0.45
         for ml in (False, True):
+            # size the candidate capacity like non_max_suppression's exact retry does (multi-label at low conf: > 4 per row)
+            cap = None
+            _, _, overflow, _ = nms_batched(pred, conf, iou, multi_label=ml, max_det=300)
+            worst = int(overflow.max())
+            if worst:
+                cap = 1 << (worst - 1).bit_length()
             for _ in range(3):
-                nms_batched(pred, conf, iou, multi_label=ml, max_det=300)
+                nms_batched(pred, conf, iou, multi_label=ml, max_det=300, cap=cap)
             torch.cuda.synchronize()
             e0.record()
             for _ in range(reps):
-                _, counts, overflow, _ = nms_batched(pred, conf, iou, multi_label=ml, max_det=300)
+                _, counts, overflow, _ = nms_batched(pred, conf, iou, multi_label=ml, max_det=300, cap=cap)
             e1.record()
             torch.cuda.synchronize()
             ms = _max_over_ranks(e0.elapsed_time(e1) / reps, dev)
             gbs = bs * 25200 * 85 * 4 / (ms / 1e3) / 1e9  # ALGORITHMIC bytes: z read once, 8.568 MB/image
             out[f"conf{conf}_iou{iou}_{'multi' if ml else 'single'}"] = {
                 "input_boxes_per_s": world * bs * 25200 / (ms / 1e3), "ms_per_batch": ms, "hbm_gbs_per_gpu": gbs,
-                "hbm_frac": gbs / hbm, "kept_per_image": float(counts.float().mean()), "overflow": int(overflow.max())}
+                "hbm_frac": gbs / hbm, "kept_per_image": float(counts.float().mean()), "overflow": int(overflow.max()), "candidate_capacity": cap or "default"}
     return out

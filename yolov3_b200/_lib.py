@@ -148,6 +148,15 @@ class WgradDesc(C.Structure):
 DW_OIHW, DW_TAP_MAJOR, DW_OHWI = 0, 1, 2
 
 
+class LetterboxDesc(C.Structure):
+    """struct y3_letterbox_desc."""
+
+    _fields_ = [("src", C.c_void_p), ("src_h", C.c_int32), ("src_w", C.c_int32), ("src_pitch", C.c_int32),
+                ("new_h", C.c_int32), ("new_w", C.c_int32), ("top", C.c_int32), ("left", C.c_int32),
+                ("dst", C.c_void_p), ("out_h", C.c_int32), ("out_w", C.c_int32),
+                ("out_chw", C.c_int32), ("swap_rb", C.c_int32), ("pad", C.c_uint8 * 4)]
+
+
 class PackItem(C.Structure):
     """struct y3_pack_item."""
 
@@ -177,6 +186,9 @@ def _declare(lib):
         "y3_f32_to_bf16": ([vp, vp, C.c_int64, vp], C.c_int),
         "y3_pack_dgrad_batched": ([vp, i32, vp, i32, vp], C.c_int),
         "y3_head_grad_pack": ([vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp], C.c_int),
+        "y3_letterbox_u8": ([C.POINTER(LetterboxDesc), vp], C.c_int),
+        "y3_scale_img_f32": ([vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, C.c_float, vp, vp], C.c_int),
+        "y3_tta_merge": ([vp, i32, i32, i32, i32, i32, C.c_float, i32, C.c_float, vp, i32, i32, vp], C.c_int),
         "y3_val_match": ([vp, vp, i32, i32, i32, vp, i32, vp, i32, C.c_float, vp, vp, vp], C.c_int),
         "y3_sumsq_blocks": ([], i32),
         "y3_grad_sumsq": ([vp, C.c_int64, vp, vp, vp], C.c_int),
@@ -228,7 +240,7 @@ def lib():
         _lib = C.CDLL(str(_LIB_PATH))
         SYMBOLS.update(_declare(_lib))
         for which, st in enumerate((ConvDesc, FirstDesc, PoolDesc, DetectLevel, DecodeDesc, Op, NmsParams, LossDesc, BnActDesc,
-                                    BnBwdDesc, WgradDesc, PackItem)):
+                                    BnBwdDesc, WgradDesc, PackItem, LetterboxDesc)):
             if _lib.y3_abi_sizeof(which) != C.sizeof(st):
                 raise Y3Error(f"ABI mismatch: sizeof({st.__name__}) is {C.sizeof(st)} here, "
                               f"{_lib.y3_abi_sizeof(which)} in {_LIB_PATH.name}; rebuild the library")

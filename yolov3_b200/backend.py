@@ -19,7 +19,7 @@ def _load(weights, device, cfg=None) -> Model:
     if isinstance(weights, Model):
         return weights.to(device)
     if isinstance(weights, (list, tuple)):
-        assert len(weights) == 1, "model ensembles (models/experimental.py:74-85) are outside the accelerated path"
+        assert len(weights) == 1, "_load takes one checkpoint; several -> tta.attempt_load builds an Ensemble"
         weights = weights[0]
     ckpt = weights
     if isinstance(weights, (str, Path)):
@@ -62,10 +62,15 @@ class DetectMultiBackend:
             raise RuntimeError("yolov3_b200 has no CPU path: DetectMultiBackend needs a CUDA (B200) device")
         if dnn:
             raise NotImplementedError("only the PyTorch ('pt') role of DetectMultiBackend is accelerated")
-        model = _load(weights, device)
-        model.eval()
-        if fuse:
-            model.fuse()
+        if isinstance(weights, (list, tuple)) and len(weights) > 1:  # models/common.py:471: attempt_load(weights list) -> Ensemble
+            from .tta import attempt_load
+
+            model = attempt_load(list(weights), device=device, inplace=True, fuse=fuse)
+        else:
+            model = _load(weights, device)
+            model.eval()
+            if fuse:
+                model.fuse()
         self.model = model
         self.stride = max(int(model.stride.max()), 32)
         self.names = model.names

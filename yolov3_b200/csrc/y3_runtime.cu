@@ -116,6 +116,7 @@ extern "C" int64_t y3_abi_sizeof(int32_t which) {
     case 9: return sizeof(y3_bn_bwd_desc);
     case 10: return sizeof(y3_wgrad_desc);
     case 11: return sizeof(y3_pack_item);
+    case 12: return sizeof(y3_letterbox_desc);
   }
   return -1;
 }

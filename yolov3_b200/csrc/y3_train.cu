@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const BnActArgs p) {
       const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
       const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-      for (int q = 0; q < 8; ++q) f[q] = silu_f(fmaf(f[q], sc[q], sh[q]));
+      for (int q = 0; q < 8; ++q) f[q] = silu_fast(fmaf(f[q], sc[q], sh[q]));
       if (p.res.p) {
         unpack8(vr[k], rr);
 #pragma unroll
@@ -267,9 +267,16 @@ __device__ __forceinline__ void load_da(const BnBwdArgs& p, long long rb, long l
     unpack8(__ldg(reinterpret_cast<const uint4*>(p.da.p + (rb + x) * p.da.ld + p.da.coff + cg * 8)), d);
   }
 }
-// dz = da * d/dz[z*sigmoid(z)] = da * s*(1 + z*(1-s))
+// dz = da * d/dz[z*sigmoid(z)] = da * s*(1 + z*(1-s)); sigmoid(z) = 0.5*tanh(z/2) + 0.5: ONE MUFU op (tanh.approx, abs error
+// ~5e-4 — below the bf16 rounding of dy) instead of ex2 + rcp; these kernels sit close to the MUFU roof (2 ops x 8 elements
+// per 16 bytes loaded)
+__device__ __forceinline__ float sigmoid_fast(float z) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+  return fmaf(0.5f, t, 0.5f);
+}
 __device__ __forceinline__ float silu_grad(float z) {
-  const float s = __fdividef(1.0f, 1.0f + __expf(-z));
+  const float s = sigmoid_fast(z);
   return s * fmaf(z, 1.0f - s, 1.0f);
 }
 
@@ -700,7 +707,8 @@ Rows make_rows(int n, int h, int w, int c) {
   g.upr = (w * g.c8 + 256 * kUnitIters - 1) / (256 * kUnitIters);
   return g;
 }
-constexpr int kMaxPartialBlocks = 592;  // four blocks per SM on B200; a fixed cap keeps workspace sizes device-independent
+constexpr int kMaxPartialBlocks = 444;  // = 3 resident 256-thread blocks per SM x 148 SMs: exactly one wave of the reduction kernels
+                                        // (592 ran 1.33 waves: the tail block set doubled the small layers' time); fixed: sizes stay device-independent
 
 __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int c,
                                                                float* __restrict__ sums, float* __restrict__ dbeta_acc,
@@ -806,7 +814,7 @@ extern "C" int y3_bn_act_bwd(const y3_bn_bwd_desc* d, y3_stream_t stream_) {
   }
   if (d->phase != 1) {
     const long long units = static_cast<long long>(d->n) * d->h * a.g.upr;
-    const long long cap = 8ll * y3::num_sms();
+    const long long cap = 3ll * y3::num_sms();  // one wave at the kernel's 3 resident blocks per SM
     if (d->upsample)
       y3::bn_act_bwd_kernel<true, true><<<static_cast<unsigned>(units < cap ? units : cap), 256, 0, stream>>>(a);
     else

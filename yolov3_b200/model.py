@@ -265,10 +265,16 @@ class Model:
 
     def forward(self, x, augment=False, profile=False, visualize=False):
         """Eval-mode Model.forward (models/yolo.py:233-237): returns (z[bs, rows, no], [p_i[bs,na,ny,nx,no]])."""
-        if augment or profile or visualize:
-            raise NotImplementedError("augment/profile/visualize are outside the accelerated path (SURVEY §8a)")
+        if profile or visualize:
+            raise NotImplementedError("profile/visualize are outside the accelerated path (SURVEY §8a)")
         if not x.is_cuda:
             raise RuntimeError("yolov3_b200 has no CPU path: move the input to the B200 (x.cuda())")
+        if augment:  # models/yolo.py:235-236: augmented inference returns (z_aug, None)
+            if self.training:
+                raise RuntimeError("augment=True is an inference option (models/yolo.py:233-237)")
+            from .tta import forward_augment
+
+            return forward_augment(self, x)
         if x.dtype not in (torch.float32, torch.uint8):
             x = x.float()
         x = x.contiguous()

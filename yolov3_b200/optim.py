@@ -82,6 +82,7 @@ class SGD:
                        "y3_grad_sumsq")
         _lib.check(L.y3_sgd_step(s.P.data_ptr(), s.G.data_ptr(), self.M.data_ptr(), ema_ptr, s.group.data_ptr(), s.n_total,
                                  self._hp.data_ptr(), self.grad_sumsq.data_ptr(), st), "y3_sgd_step")
+        s.kernel_writes += 1
 
     def grad_norm(self) -> torch.Tensor:
         """total gradient norm seen by the last step's clipping (before the 1/world_size average when DDP left sums)."""

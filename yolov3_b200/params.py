@@ -105,10 +105,17 @@ class ParamStore:
             with torch.no_grad():
                 v.copy_(model.params[name].to(dev))
             trainable = s.group != G_FROZEN
-            self.views[name] = v.requires_grad_(trainable)
+            # trainables are nn.Parameter objects (aliases of the flat storage, same strides) so that the nn.Module facade
+            # (module.DetectionModel) can register THE SAME objects: an optimizer built on either surface sees the gradients
+            self.views[name] = torch.nn.Parameter(v, requires_grad=True) if trainable else v
             if trainable:
                 self.grads[name] = torch.as_strided(self.G, s.shape, s.stride, s.offset)
         self.grads_live = False  # True: G holds gradients of earlier backward passes that the next one must add to
+        self.kernel_writes = 0   # bumped by our own kernels that write P (torch's in-place ops bump P._version themselves)
+
+    def version(self):
+        """Changes whenever any parameter / buffer value may have changed (torch in-place op on a view, or a fused kernel)."""
+        return (self.P._version, self.kernel_writes)
 
     # ------------------------------------------------------------------------------------------------ raw slot views
     def weight_rows_bf16(self, name) -> torch.Tensor:
