@@ -313,8 +313,13 @@ typedef struct y3_wgrad_desc {
   int32_t dw_layout;
   int32_t accumulate;     /* 1: dw holds earlier contributions that must be kept (always reduce, never plain-store) */
   int32_t deterministic;  /* 1: no split over pixels — one CTA per dW tile, bit-reproducible, slower on the early layers */
+  int32_t stride;         /* 0/1: dy on x's grid (a stride-2 conv passes the zero-stuffed dy).  2: DIRECT stride-2 — dy is the
+                             conv's own [n, h/2+2, w/2+2, dy_ld] output-grid gradient, x is read through its row/column parity view;
+                             3x3 only, needs y3_conv_wgrad_s2_supported(h, w) and c_in % 32 == 0 */
 } y3_wgrad_desc;
 int y3_conv_wgrad(const y3_wgrad_desc* d, y3_stream_t stream);
+/* 1 if the direct stride-2 form (stride = 2) can tile an input of h x w (an 80-pixel tw x th patch must divide the output) */
+int y3_conv_wgrad_s2_supported(int32_t h, int32_t w);
 /* 1 if y3_conv_wgrad accepts Y3_DW_TAP_MAJOR for this c_in (the tcgen05 kernel is in use), else 0 */
 int y3_conv_wgrad_tap_major(int32_t c_in);
 /* dst (+)= src over the interior pixels of two padded NHWC bf16 slices of equal [n,h,w,c] (gradient fan-in) */

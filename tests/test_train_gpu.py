@@ -155,6 +155,38 @@ def test_dgrad_and_wgrad_stride2(ci, co):
     dw = torch.zeros(co, ci, 3, 3, device=dev)
     T.conv_wgrad(up, _padded(x), dw, 3)
     assert rel_l2(dw, wtt.grad) < 3e-3
+    assert not T.wgrad_s2_supported(h, w)  # 8 x 12 outputs: no 80-pixel patch -> the zero-stuffed form above is the path
+
+
+@pytest.mark.parametrize("ci,co,hw", [(32, 64, (160, 160)), (64, 128, (80, 80)), (128, 256, (40, 40)), (256, 512, (40, 80)), (32, 64, (16, 320))])
+def test_wgrad_stride2_direct(ci, co, hw):
+    """Direct stride-2 wgrad (dy on the OUTPUT grid, x through its parity view; 80-pixel tw x th patches: 80x1, 40x2, 20x4 ...)
+    against torch, and against the zero-stuffed stride-1 formulation it replaces in the training engine."""
+    from yolov3_b200 import _lib
+    from yolov3_b200 import train_ops as T
+    from yolov3_b200.tensors import PaddedNHWC
+
+    g = torch.Generator().manual_seed(5)
+    n, (h, w) = 2, hw
+    assert T.wgrad_s2_supported(h, w)
+    x = torch.randn(n, ci, h, w, generator=g).bfloat16().float()
+    dy = torch.randn(n, co, h // 2, w // 2, generator=g).bfloat16().float()
+    ref = torch.nn.grad.conv2d_weight(x, (co, ci, 3, 3), dy, stride=2, padding=1)
+    xp, dyp = _padded(x), _padded(dy)
+    base = torch.randn(co, 9, ci, device="cuda")
+    d1 = base.clone()
+    T.conv_wgrad(dyp, xp, d1, 3, layout=_lib.DW_OHWI, accumulate=True, stride=2)
+    got = (d1 - base).view(co, 3, 3, ci).permute(0, 3, 1, 2)
+    assert rel_l2(got, ref) < 3e-3
+    up = PaddedNHWC.zeros(n, h, w, co)
+    T.zero_stuff(dyp, up)
+    d2 = torch.zeros(co, 9, ci, device="cuda")
+    T.conv_wgrad(up, xp, d2, 3, layout=_lib.DW_OHWI, accumulate=True)
+    assert rel_l2(d1 - base, d2) < 1e-3
+    d3, d4 = base.clone(), base.clone()
+    T.conv_wgrad(dyp, xp, d3, 3, layout=_lib.DW_OHWI, accumulate=True, deterministic=1, stride=2)
+    T.conv_wgrad(dyp, xp, d4, 3, layout=_lib.DW_OHWI, accumulate=True, deterministic=1, stride=2)
+    assert torch.equal(d3, d4)
 
 
 @pytest.mark.parametrize("k", [5, 9, 13])

@@ -891,6 +891,8 @@ extern "C" int y3_conv_wgrad(const y3_wgrad_desc* d, y3_stream_t stream) {
   Y3_REQUIRE(d->co % 8 == 0 && d->ci % 8 == 0 && (d->ksize == 1 || d->ksize == 3) && d->n > 0 && d->h > 0 && d->w > 0,
              "wgrad: c_out/c_in must be multiples of 8 (got %d/%d), ksize 1|3", d->co, d->ci);
   Y3_REQUIRE(d->dy_ld % 8 == 0 && d->dy_coff % 8 == 0 && d->x_ld % 8 == 0 && d->x_coff % 8 == 0, "wgrad: bad slices");
+  Y3_REQUIRE(d->stride == 0 || d->stride == 1 || (d->stride == 2 && y3::wgrad_tc_enabled() && d->ci % 32 == 0),
+             "wgrad: stride must be 1, or 2 with the tensor-core kernel (c_in % 32 == 0)");
   // tcgen05 kernel (csrc/y3_wgrad_tc.cu) whenever its tiling fits; the warp-level MMA kernel below otherwise
   if (y3::wgrad_tc_enabled() && d->ci % 32 == 0 && (reinterpret_cast<uintptr_t>(d->dy) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(d->x) & 15) == 0)
@@ -921,6 +923,8 @@ extern "C" int y3_conv_wgrad(const y3_wgrad_desc* d, y3_stream_t stream) {
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
+
+extern "C" int y3_conv_wgrad_s2_supported(int32_t h, int32_t w) { return y3::wgrad_tc_enabled() ? y3::wgrad_tc_s2_supported(h, w) : 0; }
 
 extern "C" int y3_conv_wgrad_tap_major(int32_t c_in) { return (y3::wgrad_tc_enabled() && c_in % 32 == 0) ? 1 : 0; }
 

@@ -20,7 +20,7 @@ namespace y3 {
 namespace {
 
 constexpr int kWgM = 128;     // co per tile (TMEM lanes)
-constexpr int kWgK = 64;      // pixels per pipeline stage
+constexpr int kWgK = 64;      // pixels per pipeline stage (flat mode); the stride-2 patch mode uses 80 = tw x th
 constexpr int kWgThreads = 192;  // warp 0 producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue
 
 struct WgTcArgs {
@@ -34,17 +34,20 @@ struct WgTcArgs {
   int single;           // 1: this CTA is the only contributor to its dW tile AND dw need not be accumulated into (plain stores)
   int* err;
   uint32_t lbo_a, lbo_b, sbo_a, sbo_b;  // descriptor strides in bytes (probe-able, see Y3_WGRAD_VARIANT)
+  // stride-2 "patch" mode (KB = 80): a K block is a tw x th patch of OUTPUT pixels; dy comes through a 4-D map of its padded
+  // grid, x through the 5-D parity view the forward stride-2 conv uses (one box per tap)
+  int s2, tw, th, tiles_w, tiles_per_img, x_ld;
 };
 
-// N = ci tile width (32 .. 256); SWZ = bytes of one smem row = min(N, 64) * 2 for B, 128 for A
-template <int N>
+// N = ci tile width (32 .. 256); SWZ = bytes of one smem row = min(N, 64) * 2 for B, 128 for A; KB = pixels per K block
+template <int N, int KB>
 __global__ void __launch_bounds__(kWgThreads, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x, const WgTcArgs p) {
   constexpr int kBCols = N >= 64 ? 64 : N;            // channels per B box
   constexpr int kBBoxes = N / kBCols;
-  constexpr uint32_t kABox = kWgK * 128;              // one A box: 64 pixel rows x 64 channels
+  constexpr uint32_t kABox = KB * 128;                // one A box: KB pixel rows x 64 channels
   constexpr uint32_t kABytes = 2 * kABox;             // co 0-63 | co 64-127
-  constexpr uint32_t kBBox = kWgK * kBCols * 2;
+  constexpr uint32_t kBBox = KB * kBCols * 2;
   constexpr uint32_t kBBytes = kBBoxes * kBBox;
   constexpr uint32_t kStage = kABytes + kBBytes;
   // <= ~100 KB of ring: two CTAs per SM, so one CTA's prologue / atomic epilogue overlaps the other's main loop
@@ -97,13 +100,26 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         if (elect_one()) {
           uint8_t* a_dst = smem + stage * kStage;
           uint8_t* b_dst = a_dst + kABytes;
-          const int row = (kb0 + it) * kWgK;
           mbar_expect_tx(&full_bar[stage], kStage);
-          tma_load_2d(a_dst, &map_dy, &full_bar[stage], p.dy_coff + co0, row);
-          tma_load_2d(a_dst + kABox, &map_dy, &full_bar[stage], p.dy_coff + co0 + 64, row);
+          if (KB == 80) {  // stride-2 patch mode
+            const int kb = kb0 + it;
+            const int img = kb / p.tiles_per_img, t = kb - img * p.tiles_per_img;
+            const int oy0 = (t / p.tiles_w) * p.th, ox0 = (t % p.tiles_w) * p.tw;
+            const int r = tap / 3, sx = tap - r * 3;
+            tma_load_4d(a_dst, &map_dy, &full_bar[stage], p.dy_coff + co0, 1 + ox0, 1 + oy0, img);
+            tma_load_4d(a_dst + kABox, &map_dy, &full_bar[stage], p.dy_coff + co0 + 64, 1 + ox0, 1 + oy0, img);
 #pragma unroll
-          for (int b = 0; b < kBBoxes; ++b)
-            tma_load_2d(b_dst + b * kBBox, &map_x, &full_bar[stage], p.x_coff + ci0 + b * kBCols, row + shift);
+            for (int b = 0; b < kBBoxes; ++b)  // input pixel of output (oy, ox), tap (r, sx): padded (2 oy + r, 2 ox + sx)
+              tma_load_5d(b_dst + b * kBBox, &map_x, &full_bar[stage], (sx & 1) * p.x_ld + p.x_coff + ci0 + b * kBCols,
+                          ox0 + (sx >> 1), r & 1, oy0 + (r >> 1), img);
+          } else {
+            const int row = (kb0 + it) * KB;
+            tma_load_2d(a_dst, &map_dy, &full_bar[stage], p.dy_coff + co0, row);
+            tma_load_2d(a_dst + kABox, &map_dy, &full_bar[stage], p.dy_coff + co0 + 64, row);
+#pragma unroll
+            for (int b = 0; b < kBBoxes; ++b)
+              tma_load_2d(b_dst + b * kBBox, &map_x, &full_bar[stage], p.x_coff + ci0 + b * kBCols, row + shift);
+          }
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -123,7 +139,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < kWgK / 16; ++ks) {
+          for (int ks = 0; ks < KB / 16; ++ks) {
             const uint64_t adesc = (uint64_t(hi_a) << 32) | (lo_a0 + ((stage * kStage + ks * 16 * kRowA) >> 4));
             const uint64_t bdesc = (uint64_t(hi_b) << 32) | (lo_b0 + ((stage * kStage + ks * 16 * kRowB) >> 4));
             umma_bf16_ss(tmem_base, adesc, bdesc, IDESC, (it | ks) != 0 ? 1u : 0u);
@@ -183,13 +199,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   }
 }
 
-template <int N>
+template <int N, int KB>
 int wgrad_tc_launch(const CUtensorMap& mdy, const CUtensorMap& mx, const WgTcArgs& a, dim3 grid, cudaStream_t stream) {
   constexpr int kBCols = N >= 64 ? 64 : N;
-  constexpr uint32_t kStage = 2 * kWgK * 128 + (N / kBCols) * kWgK * kBCols * 2;
+  constexpr uint32_t kStage = 2 * KB * 128 + (N / kBCols) * KB * kBCols * 2;
   constexpr int STAGES = N >= 256 ? 3 : ((100 * 1024) / kStage > 4 ? 4 : (100 * 1024) / kStage);
+  static_assert(STAGES >= 2, "wgrad: the ring needs two stages");
   constexpr size_t smem = size_t(STAGES) * kStage + 1024 + 256;
-  auto kern = wgrad_tc_kernel<N>;
+  auto kern = wgrad_tc_kernel<N, KB>;
   static bool attr_set = false;
   if (!attr_set) {
     Y3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -213,7 +230,95 @@ int wgrad_tc_enabled() {
   return v;
 }
 
+// (tw, th) with tw * th == 80, tw | wo, th | ho for the stride-2 patch mode; false: no such tiling (caller zero-stuffs)
+static bool s2_patch(int ho, int wo, int* tw, int* th) {
+  for (int cand_th = 1; cand_th <= 80; ++cand_th) {
+    if (80 % cand_th) continue;
+    const int cand_tw = 80 / cand_th;
+    if (cand_tw <= 256 && wo % cand_tw == 0 && ho % cand_th == 0) {
+      *tw = cand_tw;
+      *th = cand_th;
+      return true;
+    }
+  }
+  return false;
+}
+
+int wgrad_tc_s2_supported(int h, int w) {
+  int tw, th;
+  return (h % 2 == 0 && w % 2 == 0 && s2_patch(h / 2, w / 2, &tw, &th)) ? 1 : 0;
+}
+
+static int wgrad_tc_s2(const y3_wgrad_desc& d, cudaStream_t stream) {
+  // dW[co, tap, ci] += sum over OUTPUT pixels p of dy[p, co] * x[2p + tap, ci]: no zero-stuffed copy of dy, a quarter of the
+  // K extent of the stride-1 formulation on the input grid (which multiplied 75 % zeros)
+  const int ho = d.h / 2, wo = d.w / 2;
+  int tw = 0, th = 0;
+  Y3_REQUIRE(d.ksize == 3 && d.h % 2 == 0 && d.w % 2 == 0 && s2_patch(ho, wo, &tw, &th),
+             "wgrad: no 80-pixel patch tiling for a %dx%d stride-2 output (ask y3_conv_wgrad_s2_supported first)", ho, wo);
+  Y3_REQUIRE(d.ci % 32 == 0, "wgrad_tc: c_in=%d must be a multiple of 32", d.ci);
+  const int n_tile = d.ci >= 128 ? 128 : (d.ci >= 64 ? 64 : 32);
+  const uint32_t bcols = n_tile >= 64 ? 64 : n_tile;
+  CUtensorMap mdy, mx;
+  {
+    const uint64_t ld = static_cast<uint64_t>(d.dy_ld);
+    const uint64_t dims[4] = {static_cast<uint64_t>(d.dy_coff + d.co), static_cast<uint64_t>(wo + 2), static_cast<uint64_t>(ho + 2),
+                              static_cast<uint64_t>(d.n)};
+    const uint64_t strides[4] = {0, ld * 2, static_cast<uint64_t>(wo + 2) * ld * 2, static_cast<uint64_t>(ho + 2) * (wo + 2) * ld * 2};
+    const uint32_t box[4] = {64, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), 1};
+    int rc = encode_tensor_map_bf16(&mdy, d.dy, 4, dims, strides, box, 128);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t ld = static_cast<uint64_t>(d.x_ld);
+    const int hp = d.h + 2, wp = d.w + 2;
+    const uint64_t dims[5] = {2 * ld, static_cast<uint64_t>(wp / 2), 2, static_cast<uint64_t>(hp / 2), static_cast<uint64_t>(d.n)};
+    const uint64_t strides[5] = {0, 2 * ld * 2, static_cast<uint64_t>(wp) * ld * 2, 2ull * wp * ld * 2,
+                                 static_cast<uint64_t>(hp) * wp * ld * 2};
+    const uint32_t box[5] = {bcols, static_cast<uint32_t>(tw), 1, static_cast<uint32_t>(th), 1};
+    int rc = encode_tensor_map_bf16(&mx, d.x, 5, dims, strides, box, bcols * 2);
+    if (rc) return rc;
+  }
+  WgTcArgs a{};
+  a.co = d.co;
+  a.ci = d.ci;
+  a.taps = 9;
+  a.wp = d.w + 2;
+  a.n_ci_tiles = (d.ci + n_tile - 1) / n_tile;
+  a.s2 = 1;
+  a.tw = tw;
+  a.th = th;
+  a.tiles_w = wo / tw;
+  a.tiles_per_img = (wo / tw) * (ho / th);
+  a.x_ld = d.x_ld;
+  a.kblocks_total = d.n * a.tiles_per_img;
+  a.dy_coff = d.dy_coff;
+  a.x_coff = d.x_coff;
+  a.dw = d.dw;
+  a.err = nullptr;
+  a.lbo_a = 80 * 128;
+  a.lbo_b = 80 * bcols * 2;
+  a.sbo_a = 1024;
+  a.sbo_b = 8 * bcols * 2;
+  const int tiles = ((d.co + kWgM - 1) / kWgM) * a.n_ci_tiles;
+  long long want = (2ll * num_sms() + static_cast<long long>(tiles) * 9 - 1) / (static_cast<long long>(tiles) * 9);
+  long long max_split = (a.kblocks_total + 7) / 8;
+  if (want > max_split) want = max_split;
+  if (want < 1 || d.deterministic) want = 1;
+  a.kblocks_per_cta = static_cast<int>((a.kblocks_total + want - 1) / want);
+  const unsigned splits = static_cast<unsigned>((a.kblocks_total + a.kblocks_per_cta - 1) / a.kblocks_per_cta);
+  a.layout = d.dw_layout;
+  a.single = (splits == 1 && !d.accumulate) ? 1 : 0;
+  const dim3 grid(splits, static_cast<unsigned>(tiles), 9u);
+  switch (n_tile) {
+    case 128: return wgrad_tc_launch<128, 80>(mdy, mx, a, grid, stream);
+    case 64: return wgrad_tc_launch<64, 80>(mdy, mx, a, grid, stream);
+    default: return wgrad_tc_launch<32, 80>(mdy, mx, a, grid, stream);
+  }
+}
+
 int wgrad_tc(const y3_wgrad_desc& d, cudaStream_t stream) {
+  if (d.stride == 2) return wgrad_tc_s2(d, stream);
   const int taps = d.ksize * d.ksize;
   const long long rows = static_cast<long long>(d.n) * (d.h + 2) * (d.w + 2);
   Y3_REQUIRE(rows < (1ll << 31) - 4096, "wgrad: too many pixels");
@@ -283,10 +388,10 @@ int wgrad_tc(const y3_wgrad_desc& d, cudaStream_t stream) {
   a.single = (splits == 1 && !d.accumulate) ? 1 : 0;
   const dim3 grid(splits, static_cast<unsigned>(tiles), static_cast<unsigned>(taps));
   switch (n_tile) {
-    case 256: return wgrad_tc_launch<256>(mdy, mx, a, grid, stream);
-    case 128: return wgrad_tc_launch<128>(mdy, mx, a, grid, stream);
-    case 64: return wgrad_tc_launch<64>(mdy, mx, a, grid, stream);
-    default: return wgrad_tc_launch<32>(mdy, mx, a, grid, stream);
+    case 256: return wgrad_tc_launch<256, kWgK>(mdy, mx, a, grid, stream);
+    case 128: return wgrad_tc_launch<128, kWgK>(mdy, mx, a, grid, stream);
+    case 64: return wgrad_tc_launch<64, kWgK>(mdy, mx, a, grid, stream);
+    default: return wgrad_tc_launch<32, kWgK>(mdy, mx, a, grid, stream);
   }
 }
 

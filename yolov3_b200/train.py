@@ -451,8 +451,12 @@ class TrainEngine:
                 T.bn_act_bwd(b.y, da, b.dy, st, st["sums"], self.partial, b.dbeta, b.dgamma, b.upsample)
             src = b.dy
             if b.s == 2:
-                src = T.zero_stuff(b.dy, b.dy_up)
-            T.conv_wgrad(src, b.x, b.dw, b.k, layout=_lib.DW_OHWI, accumulate=True, deterministic=det_flag)
+                src = T.zero_stuff(b.dy, b.dy_up)  # dgrad of a stride-2 conv = stride-1 conv of the zero-stuffed dy
+            if b.s == 2 and T.wgrad_s2_supported(b.x.h, b.x.w):
+                # wgrad straight from the un-stuffed dy (x through its parity view): a quarter of the pixels, no zeros multiplied
+                T.conv_wgrad(b.dy, b.x, b.dw, b.k, layout=_lib.DW_OHWI, accumulate=True, deterministic=det_flag, stride=2)
+            else:
+                T.conv_wgrad(src, b.x, b.dw, b.k, layout=_lib.DW_OHWI, accumulate=True, deterministic=det_flag)
             if b.res is not None:
                 # Bottleneck shortcut: the block output's gradient also flows to its input.  It is folded into the next
                 # dgrad into that tensor (cv1 of the same Bottleneck: the very next block) through the residual port, or

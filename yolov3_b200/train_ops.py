@@ -118,13 +118,19 @@ def wgrad_tap_major(ci: int) -> bool:
     return bool(_lib.lib().y3_conv_wgrad_tap_major(int(ci)))
 
 
+def wgrad_s2_supported(h: int, w: int) -> bool:
+    """True when the direct stride-2 wgrad (no zero-stuffed dy) can tile an h x w input (y3_conv_wgrad_s2_supported)."""
+    return bool(_lib.lib().y3_conv_wgrad_s2_supported(int(h), int(w)))
+
+
 def conv_wgrad(dy: PaddedNHWC, x: PaddedNHWC, dw: torch.Tensor, ksize: int, tap_major: bool = False, layout: int | None = None,
-               accumulate: bool = False, deterministic: int = 0):
+               accumulate: bool = False, deterministic: int = 0, stride: int = 1):
     """dw (fp32, accumulated into) from dy and x on the same stride-1 padded grid.  Layouts: [co,ci,k,k] (default),
     tap_major [k*k,co,ci], or ``layout=_lib.DW_OHWI`` [co,k*k,ci] (the flat gradient buffer's).  ``accumulate``: dw already holds
     gradient that must be kept; ``deterministic``: no split over pixels (bit-reproducible)."""
-    assert dy.n == x.n and dy.h == x.h and dy.w == x.w and dw.dtype == torch.float32 and dw.is_contiguous()
+    assert dy.n == x.n and dy.h * stride == x.h and dy.w * stride == x.w and dw.dtype == torch.float32 and dw.is_contiguous()
     d = _lib.WgradDesc()
+    d.stride = int(stride)
     d.dw_layout = layout if layout is not None else (1 if tap_major else 0)
     d.accumulate, d.deterministic = int(bool(accumulate)), int(deterministic)
     d.dy, d.dy_ld, d.dy_coff = dy.ptr, dy.ld, dy.coff
