@@ -47,7 +47,7 @@ def main():
         if sync:
             parallel.allreduce_gradients(ps)
         torch.cuda.synchronize()
-        return m, {k: P[k].grad.clone() for k in sorted(P) if P[k].grad is not None}, {k: v.clone() for k, v in P.items() if "running" in k}
+        return m, {k: P[k].grad.clone() for k in sorted(P) if P[k].grad is not None}, {k: v.detach().clone() for k, v in P.items() if "running" in k}
 
     lo = rank * 4
     sel = (t[:, 0] >= lo) & (t[:, 0] < lo + 4)

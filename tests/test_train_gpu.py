@@ -218,6 +218,52 @@ def test_maxpool_train_fwd_bwd(k):
     assert torch.equal(gin.to_nchw().cpu() != 0, xt.grad.bfloat16().float() != 0)  # identical routing
 
 
+@pytest.mark.parametrize("mode", ["k2s2", "zeropad_k2s1"])
+def test_maxpool_tiny_fwd_bwd(mode):
+    """The two pools of yolov3-tiny under autograd: nn.MaxPool2d(2, 2) and nn.ZeroPad2d([0,1,0,1]) + nn.MaxPool2d(2, 1, 0)
+    (yolov3-tiny.yaml:20-30): values and gradient routing equal torch on the same bf16 input, ties and pad-wins included."""
+    from yolov3_b200 import train_ops as T
+    from yolov3_b200.tensors import PaddedNHWC
+
+    g = torch.Generator().manual_seed(11)
+    n, c, h, w = 2, 16, 12, 20
+    x = (torch.randn(n, c, h, w, generator=g) * 2).round().div(2).bfloat16().float()  # many ties, many negatives (pad 0 wins)
+    xt = x.clone().requires_grad_(True)
+    if mode == "k2s2":
+        yt = F.max_pool2d(xt, 2, 2)
+        k, stride, oz = 2, 2, False
+    else:
+        yt = F.max_pool2d(F.pad(xt, [0, 1, 0, 1]), 2, 1, 0)
+        k, stride, oz = 2, 1, True
+    dout = torch.randn(*yt.shape, generator=g).bfloat16().float()
+    yt.backward(dout)
+    xin = _padded(x, ld=32, coff=0)  # a 16-channel tensor in a 32-wide buffer, as the training engine allocates it
+    out = PaddedNHWC.zeros(n, yt.shape[2], yt.shape[3], c, ld=32).slice(0, c)
+    idx = torch.zeros(n * yt.shape[2] * yt.shape[3] * c, dtype=torch.uint8, device="cuda")
+    T.maxpool_train_fwd(xin, out, k, idx, stride=stride, off=0, oob_zero=oz)
+    assert torch.equal(out.to_nchw().cpu(), yt.detach())
+    gin = PaddedNHWC.zeros(n, h, w, c, ld=32).slice(0, c)
+    T.maxpool_bwd(_padded(dout, ld=32, coff=0), gin, k, idx, accumulate=False, stride=stride, off=0)
+    assert rel_l2(gin.to_nchw(), xt.grad.bfloat16().float()) < 4e-3
+    assert torch.equal(gin.to_nchw().cpu() != 0, xt.grad.bfloat16().float() != 0)
+
+
+def test_wgrad_small_cin_ohwi():
+    """c_in = 16 (yolov3-tiny layer 2) takes the warp-level MMA kernel: it accumulates into the flat buffer's [co, k*k, ci] layout too."""
+    from yolov3_b200 import _lib
+    from yolov3_b200 import train_ops as T
+
+    g = torch.Generator().manual_seed(12)
+    n, ci, co, h, w = 2, 16, 32, 12, 20
+    x = torch.randn(n, ci, h, w, generator=g).bfloat16().float()
+    dy = torch.randn(n, co, h, w, generator=g).bfloat16().float()
+    ref = torch.nn.grad.conv2d_weight(x, (co, ci, 3, 3), dy, padding=1)
+    base = torch.randn(co, 9, ci, device="cuda")
+    d = base.clone()
+    T.conv_wgrad(_padded(dy), _padded(x, ld=32, coff=0), d, 3, layout=_lib.DW_OHWI, accumulate=True)
+    assert rel_l2((d - base).view(co, 3, 3, ci).permute(0, 3, 1, 2), ref) < 3e-3
+
+
 def test_colsum():
     from yolov3_b200 import train_ops as T
 
@@ -227,7 +273,7 @@ def test_colsum():
     assert torch.allclose(out, g[:, :255].sum(0), rtol=1e-4, atol=1e-3)
 
 
-@pytest.mark.parametrize("cfg_name", ["yolov3.yaml", "yolov3-spp.yaml"])
+@pytest.mark.parametrize("cfg_name", ["yolov3.yaml", "yolov3-spp.yaml", "yolov3-tiny.yaml"])
 def test_train_step_vs_oracle_autograd(cfg_name):
     """One full training step (train-mode forward -> ComputeLoss -> backward) on yolov3(-spp).yaml against the CPU oracle
     (torch autograd, fp32) AND against the same oracle run on the GPU under torch.autocast(bfloat16) — the precision the
@@ -247,7 +293,8 @@ def test_train_step_vs_oracle_autograd(cfg_name):
 
     cfg = Path(__file__).resolve().parents[1] / "yolov3_b200" / "cfg" / cfg_name
     params = O.init_params(cfg, seed=0)
-    hyp = O.scaled_hyp()
+    nl = 2 if "tiny" in cfg_name else 3
+    hyp = O.scaled_hyp(nl=nl)
     x = torch.rand(4, 3, 96, 96, generator=torch.Generator().manual_seed(3))
     targets = O.synth_targets(4, seed=2)
     trainable = lambda k: not ("running" in k or "anchors" in k)  # noqa: E731
@@ -260,7 +307,7 @@ def test_train_step_vs_oracle_autograd(cfg_name):
         raw = [r.float().cpu() for r in raw]
         for r in raw:
             r.retain_grad()
-        loss, items = O.compute_loss(raw, targets, params["model.28.anchors"], hyp)
+        loss, items = O.compute_loss(raw, targets, params[[k for k in params if k.endswith(".anchors")][0]], hyp)
         loss.backward()
         return raw, loss, {k: v.grad.float().cpu() for k, v in po.items() if v.grad is not None}
 
@@ -289,7 +336,9 @@ def test_train_step_vs_oracle_autograd(cfg_name):
         errs, bad = {}, []
         # yolov3.yaml: measured <= 0.08.  yolov3-spp.yaml at 96x96 (3x3 maps under 5/9/13 pools): backbone gradients come
         # out 5-25 % long while their cosine matches or beats torch autocast's (DESIGN.md section 6 lists this as open)
-        ratio_tol = 0.12 if "spp" not in cfg_name else 0.60  # spp: noise-dominated regime (autocast itself: 0.46 median rel-L2)
+        # spp / tiny at 96x96 (3x3 .. 6x6 maps under max-pools): noise-dominated regime (autocast itself: 0.46 median rel-L2);
+        # the tight, per-kernel bar is tests/test_train_layers_gpu.py (every block vs autograd on identical bf16 tensors)
+        ratio_tol = 0.12 if cfg_name == "yolov3.yaml" else 0.60
         for k, ref in g_o.items():
             assert P[k].grad is not None, k
             g = P[k].grad.float().cpu()
@@ -310,7 +359,7 @@ def test_train_step_vs_oracle_autograd(cfg_name):
     # yolov3.yaml: 0.19 vs 0.22 (autocast).  yolov3-spp.yaml at 96x96: 0.48 vs 0.46 — bf16 itself is that far from fp32 there
     assert med <= max(0.30, 1.25 * med_amp + 0.02) and med <= 2.5 * med_amp + 0.02, (med, med_amp)
     # running statistics were updated with momentum 0.03
-    assert not torch.equal(P["model.0.bn.running_mean"].cpu(), params["model.0.bn.running_mean"])
+    assert not torch.equal(P["model.0.bn.running_mean"].detach().cpu(), params["model.0.bn.running_mean"])
     # steps 2 and 3 run through the captured CUDA graphs (forward + backward) on the same inputs.  The step is not
     # bit-reproducible: the fp32 atomics of the BatchNorm sums order differently from launch to launch, and a flipped
     # bf16 rounding is amplified by 75 BatchNorm layers over 4x3x3..12x12 pixels (eager launches show the same spread,

@@ -38,7 +38,7 @@ def _step(cfg_name, hw, bs, deterministic, keep_all=True, seed=3):
     params = O.init_params(cfg, seed=0)
     m = Model(cfg)
     m.load_state_dict(params)
-    m.hyp = O.scaled_hyp()
+    m.hyp = O.scaled_hyp(nl=m.detect.nl)
     m.train()
     te = TrainEngine(m, bs, hw, hw, keep_all=keep_all)
     te.use_graphs = False
@@ -55,7 +55,7 @@ def _step(cfg_name, hw, bs, deterministic, keep_all=True, seed=3):
     return m, te, float(loss.detach())
 
 
-@pytest.mark.parametrize("cfg_name,hw", [("yolov3.yaml", 128), ("yolov3-spp.yaml", 160)])
+@pytest.mark.parametrize("cfg_name,hw", [("yolov3.yaml", 128), ("yolov3-spp.yaml", 160), ("yolov3-tiny.yaml", 128)])
 def test_every_block_vs_autograd_on_identical_tensors(cfg_name, hw):
     m, te, _ = _step(cfg_name, hw, 4, deterministic=True)
     P = m.device_params()

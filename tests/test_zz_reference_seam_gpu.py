@@ -82,10 +82,18 @@ def test_reference_detect_py_runs_on_our_backend(tmp_path):
         assert rel_l2(z, z_ref) <= 2e-2, path
         det_ref = ref_nms(z_ref.clone(), 0.25, 0.45, max_det=50)[0]
         det = nms.non_max_suppression(z_ref.cuda(), 0.25, 0.45, max_det=50)[0]
-        assert np.array_equal(det.cpu().numpy(), det_ref.numpy()), path
-        a = ref_scale(x.shape[2:], det_ref[:, :4].clone(), im0s.shape)
-        b = boxes.scale_boxes(x.shape[2:], det[:, :4].clone(), im0s.shape)
-        assert np.array_equal(b.cpu().numpy(), a.numpy())
+        # real-image predictions with saturating sigmoids contain bit-equal confidences (birthday collisions among ~20 k
+        # candidates): the reference orders such ties by an unstable argsort, we by candidate index — compare row SETS
+        # (rows sorted lexicographically), which is what "identical detections" means when the order is undefined
+        a, b = det_ref.numpy(), det.cpu().numpy()
+        assert a.shape == b.shape, (path, a.shape, b.shape)
+        ka = np.lexsort(a.T[::-1])
+        kb = np.lexsort(b.T[::-1])
+        assert np.array_equal(a[ka], b[kb]), (path, np.abs(a[ka] - b[kb]).max())
+        det = det_ref.cuda()  # continue with identical rows in identical order
+        sa = ref_scale(x.shape[2:], det_ref[:, :4].clone(), im0s.shape)
+        sb = boxes.scale_boxes(x.shape[2:], det[:, :4].clone(), im0s.shape)
+        assert np.array_equal(sb.cpu().numpy(), sa.numpy())
 
 
 @needs_ref

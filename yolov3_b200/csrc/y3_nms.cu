@@ -384,12 +384,15 @@ __device__ __forceinline__ bool iou_exceeds(float inter, float uni, const NmsArg
 }
 
 __device__ __forceinline__ bool box_suppresses(const float4& bi, float ai, const float4& bj, const NmsArgs& p) {
-  const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
-  const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
-  const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
-  const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+  // disjoint boxes (most pairs) leave after 3-4 instructions per axis: inter = w * h = 0 can never exceed a threshold >= 0,
+  // and NaN coordinates do not take these exits (comparisons with NaN are false)
+  const float w = fmaxf(0.0f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
+  if (w == 0.0f) return false;
+  const float h = fmaxf(0.0f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
+  if (h == 0.0f) return false;
   const float inter = __fmul_rn(w, h);
-  if (inter == 0.0f) return false;  // disjoint boxes (most pairs): 0 / anything is never > thr >= 0 (NaN operands do not land here)
+  if (inter == 0.0f) return false;  // underflow of w * h
+  const float aj = __fmul_rn(__fsub_rn(bj.z, bj.x), __fsub_rn(bj.w, bj.y));
   return iou_exceeds(inter, __fsub_rn(__fadd_rn(ai, aj), inter), p);
 }
 
@@ -775,6 +778,7 @@ __device__ __forceinline__ void append_survivors(const NmsArgs& p, int img, bool
 // One WARP per (image, class) segment of up to kSegWarpMax members.  8 register slots (not the 16 of the v1 kernel): at 125
 // registers only 16 warps fit an SM, and 80 classes x 32 images = 17.3 warps per SM ran as two waves (93 us at conf 0.25,
 // gpurun r2j3); larger segments take the block kernel.
+constexpr int kMaskSmall = 128;  // segments up to this size take the suppression-matrix kernel (nms_seg_mask_kernel)
 constexpr int kSegSlots = 8;
 constexpr int kSegWarpMax = 32 * kSegSlots;
 
@@ -789,7 +793,7 @@ __global__ void __launch_bounds__(256, 3) nms_seg_warp_kernel(const NmsArgs p) {
   const int* off = p.seg_off + static_cast<size_t>(img) * (p.nc + 1);
   const int lo = off[seg], hi = off[seg + 1];
   const int m = hi - lo;
-  if (m <= 0 || m > kSegWarpMax) return;  // larger segments: nms_seg_block_kernel
+  if (m <= kMaskSmall || m > kSegWarpMax) return;  // smaller: nms_seg_mask_kernel; larger: nms_seg_block_kernel
   const unsigned long long* k2 = p.seg_key2 + static_cast<size_t>(img) * kRankCap + lo;
   const float4* b4 = p.box4 + static_cast<size_t>(img) * kRankCap + lo;
   const int slots = (m + 31) >> 5;
@@ -953,7 +957,6 @@ int launch_seg_mask(const NmsArgs& a, int m_lo, cudaStream_t stream) {
   return Y3_OK;
 }
 
-constexpr int kMaskSmall = 128, kMaskLarge = 768;  // segment sizes of the two suppression-matrix instantiations
 
 // Segments with more than kSegWarpMax members.  Class segments: one CTA ranks its members (keys tiled through shared memory) and runs
 // the greedy pass.  Single-segment images (agnostic, or boxes outside the class-offset bound): every CTA of the image ranks a
@@ -970,7 +973,7 @@ __global__ void __launch_bounds__(256) nms_seg_block_kernel(const NmsArgs p) {
   const bool single = p.flags[img] & 1;
   const int lo = single ? 0 : off[seg], hi = single ? off[p.nc] : off[seg + 1];
   const int m = hi - lo;
-  if (m <= kMaskLarge) return;  // empty, or done by a suppression-matrix kernel (a single segment sits in class slot 0 there)
+  if (m <= kSegWarpMax) return;  // empty, or done by the matrix / warp kernels (a single segment sits in class slot 0 there)
   const unsigned long long* k2 = p.seg_key2 + static_cast<size_t>(img) * kRankCap + lo;
   const float4* b4 = p.box4 + static_cast<size_t>(img) * kRankCap + lo;
   uint16_t* ord = p.ord + static_cast<size_t>(img) * kRankCap + lo;
@@ -1251,8 +1254,11 @@ extern "C" int y3_nms_batched(const float* pred, const y3_nms_params* q, void* w
   }
   if (!v1) {
     nms_bucket_kernel<<<a.bs, kBucketThreads, 0, stream>>>(a);
+    // measured (gpurun r2j5 / r2j6, 32 x 25200 rows): <= 128 members per class (conf 0.25: ~65) -> suppression matrix, 37 us vs
+    // 50 us for the warp kernel; ~215 per class (conf 0.001) -> warp kernel 228 us vs 448 us for a 768-wide matrix kernel
+    // (94 KB of shared memory: 2 CTAs per SM); ~375 (multi-label) -> per-keeper block kernel 782 us vs 1178 us
     if (int rc = launch_seg_mask<kMaskSmall, 128>(a, 0, stream)) return rc;
-    if (int rc = launch_seg_mask<kMaskLarge, 256>(a, kMaskSmall, stream)) return rc;
+    nms_seg_warp_kernel<<<dim3((a.nc + 7) / 8, a.bs), 256, 0, stream>>>(a);
     nms_seg_block_kernel<<<dim3(a.nc, a.bs), 256, 0, stream>>>(a);
     {
       constexpr int kOutSmem = kOutSortMax * (sizeof(unsigned long long) + sizeof(uint16_t));

@@ -87,12 +87,18 @@ __global__ void __launch_bounds__(256) maxpool_idx_kernel(const PoolArgs p, uint
     }
     for (int dy = 0; dy < p.k; ++dy) {
       const int yy = y * p.stride + p.off + dy;
-      if (yy < 0 || yy >= p.h) continue;
+      const bool oob_y = yy < 0 || yy >= p.h;
+      if (oob_y && !p.oob_zero) continue;
       for (int dx = 0; dx < p.k; ++dx) {
         const int xx = x * p.stride + p.off + dx;
-        if (xx < 0 || xx >= p.w) continue;
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(
-            p.in + ((static_cast<long long>(n) * (p.h + 2) + yy + 1) * (p.w + 2) + xx + 1) * p.in_ld + p.in_coff + cg * 8));
+        const bool oob = oob_y || xx < 0 || xx >= p.w;
+        if (oob && !p.oob_zero) continue;
+        // oob_zero: the window reaches into an nn.ZeroPad2d border (yolov3-tiny.yaml:29-30): the pad value 0 competes like any
+        // element; if it wins, the gradient goes to the pad, i.e. nowhere (the backward gathers over real pixels only)
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (!oob)
+          v = __ldg(reinterpret_cast<const uint4*>(
+              p.in + ((static_cast<long long>(n) * (p.h + 2) + yy + 1) * (p.w + 2) + xx + 1) * p.in_ld + p.in_coff + cg * 8));
         float f[8];
         unpack8(v, f);
 #pragma unroll
@@ -210,7 +216,7 @@ static unsigned pool_grid(long long total) {
 int pool_train_fwd(const y3_pool_desc& d, uint8_t* idx, cudaStream_t stream) {
   PoolArgs a;
   if (int rc = pool_args(d, &a)) return rc;
-  Y3_REQUIRE(idx && !d.oob_zero, "pool (train): idx is required; zero-padded windows are not differentiated here");
+  Y3_REQUIRE(idx, "pool (train): idx is required");
   maxpool_idx_kernel<<<pool_grid(static_cast<long long>(a.n) * a.ho * a.wo * a.c8), 256, 0, stream>>>(a, idx);
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;

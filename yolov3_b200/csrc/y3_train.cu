@@ -435,7 +435,8 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
 struct WgradArgs {
   Slice dy;   // [rows, ld] padded pixel list, channels [coff, coff+co)
   Slice x;    // input activation, same padded geometry
-  float* dw;  // fp32 [co, ci, taps] == PyTorch's [co, ci, k, k]
+  float* dw;  // fp32 [co, ci, taps] == PyTorch's [co, ci, k, k], or (ohwi) [co, taps, ci]
+  int ohwi;
   int co, ci, taps, wp;
   long long rows;
   int rows_per_cta;
@@ -516,15 +517,18 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WgradArgs p) {
     for (int nj = 0; nj < 4; ++nj) {
       const int co = co0 + wm + mi * 16 + g, ci = ci0 + wn + nj * 8 + t * 2;
       if (ci >= p.ci) continue;  // ci is a multiple of 8, so ci+1 is in range with ci
+      const long long step = p.ohwi ? 1 : p.taps;  // distance between ci and ci + 1
       if (co < p.co) {
-        float* d0 = p.dw + (static_cast<long long>(co) * p.ci + ci) * p.taps + tap;
+        float* d0 = p.ohwi ? p.dw + (static_cast<long long>(co) * p.taps + tap) * p.ci + ci
+                           : p.dw + (static_cast<long long>(co) * p.ci + ci) * p.taps + tap;
         atomicAdd(d0, acc[mi][nj][0]);
-        atomicAdd(d0 + p.taps, acc[mi][nj][1]);
+        atomicAdd(d0 + step, acc[mi][nj][1]);
       }
       if (co + 8 < p.co) {
-        float* d1 = p.dw + (static_cast<long long>(co + 8) * p.ci + ci) * p.taps + tap;
+        float* d1 = p.ohwi ? p.dw + (static_cast<long long>(co + 8) * p.taps + tap) * p.ci + ci
+                           : p.dw + (static_cast<long long>(co + 8) * p.ci + ci) * p.taps + tap;
         atomicAdd(d1, acc[mi][nj][2]);
-        atomicAdd(d1 + p.taps, acc[mi][nj][3]);
+        atomicAdd(d1 + step, acc[mi][nj][3]);
       }
     }
 }
@@ -897,8 +901,11 @@ extern "C" int y3_conv_wgrad(const y3_wgrad_desc* d, y3_stream_t stream) {
   if (y3::wgrad_tc_enabled() && d->ci % 32 == 0 && (reinterpret_cast<uintptr_t>(d->dy) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(d->x) & 15) == 0)
     return y3::wgrad_tc(*d, static_cast<cudaStream_t>(stream));
-  Y3_REQUIRE(d->dw_layout == Y3_DW_OIHW, "wgrad: the tap-major accumulation layout needs the tensor-core kernel (c_in % 32 == 0)");
+  Y3_REQUIRE(d->dw_layout == Y3_DW_OIHW || d->dw_layout == Y3_DW_OHWI,
+             "wgrad: the tap-major accumulation layout needs the tensor-core kernel (c_in % 32 == 0)");
+  Y3_REQUIRE(d->stride != 2, "wgrad: the direct stride-2 form needs the tensor-core kernel (c_in % 32 == 0)");
   y3::WgradArgs a;
+  a.ohwi = d->dw_layout == Y3_DW_OHWI ? 1 : 0;
   a.dy = Slice{static_cast<const __nv_bfloat16*>(d->dy), d->dy_ld, d->dy_coff};
   a.x = Slice{static_cast<const __nv_bfloat16*>(d->x), d->x_ld, d->x_coff};
   a.dw = d->dw;

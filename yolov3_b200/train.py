@@ -34,6 +34,11 @@ from . import train_ops as T
 from .tensors import PaddedNHWC, _stream
 
 
+def _wide(t: PaddedNHWC) -> PaddedNHWC:
+    """The >= 32-channel view of a 16-channel slice (its buffer was allocated 32 wide with a zero upper half)."""
+    return t if t.c >= 32 else PaddedNHWC(t.buf, t.coff, 32)
+
+
 class _Block:
     """One Conv+BN+SiLU block (models/common.py:57-81) with everything its forward and backward need."""
 
@@ -58,9 +63,8 @@ class TrainEngine:
             raise ValueError(f"image size {h}x{w} must be a multiple of the max stride {gs}")
         self.fwd_gen = 0  # activations live in this engine's buffers: a backward must belong to the LAST forward
         for nd in nodes[:-1]:
-            if nd.type not in ("Conv", "Bottleneck", "Upsample", "Concat", "SPP"):
-                raise NotImplementedError(f"training-mode {nd.type} is not built (yolov3.yaml / yolov3-spp.yaml need "
-                                          "Conv/Bottleneck/Upsample/Concat/SPP)")
+            if nd.type not in ("Conv", "Bottleneck", "Upsample", "Concat", "SPP", "MaxPool2d", "ZeroPad2d"):
+                raise NotImplementedError(f"training-mode {nd.type} is not built")
         store = model.store()
         self.store = store
         self.P = model.device_params()
@@ -77,7 +81,9 @@ class TrainEngine:
         max_partial = 0
 
         def buf(c, hh, ww, ld=None):
-            b = PaddedNHWC.zeros(n, hh, ww, c, device=dev, ld=ld)
+            # the conv kernel produces multiples of 32 output channels: a 16-channel tensor (yolov3-tiny layers 0-2) lives in a
+            # 32-channel buffer whose upper half stays zero (zero weight rows / zero dgrad rows), everything else sees c = 16
+            b = PaddedNHWC.zeros(n, hh, ww, c, device=dev, ld=max(ld or c, 32))
             self.keep.append(b)
             return b
 
@@ -122,6 +128,11 @@ class TrainEngine:
                 shp[nd.i] = (c0, h0 * 2, w0 * 2)
             elif nd.type == "Concat":
                 shp[nd.i] = (sum(s[0] for s in src), h0, w0)
+            elif nd.type == "ZeroPad2d":
+                shp[nd.i] = (c0, h0, w0)  # virtual: folded into the MaxPool2d(2,1,0) that follows (out-of-bounds = 0)
+            elif nd.type == "MaxPool2d":
+                k_, s2_ = nd.args[0], (nd.args[1] if len(nd.args) > 1 else nd.args[0])
+                shp[nd.i] = (c0, h0, w0) if (k_, s2_) == (2, 1) else (c0, h0 // s2_, w0 // s2_)
         consumers = {}
         for nd in nodes:
             for s in nd.srcs:
@@ -211,6 +222,25 @@ class TrainEngine:
                 tens[nd.i] = None
             elif nd.type == "Concat":
                 tens[nd.i] = cat_buf[nd.i]
+            elif nd.type == "ZeroPad2d":  # yolov3-tiny.yaml:29: nn.ZeroPad2d([0,1,0,1]) feeding nn.MaxPool2d(2,1,0)
+                assert tuple(nd.args[0]) == (0, 1, 0, 1) and all(nodes[c].type == "MaxPool2d" for c in consumers.get(nd.i, []))
+                tens[nd.i] = ("zeropad", srcs[0])
+            elif nd.type == "MaxPool2d":
+                k = nd.args[0]
+                s_ = nd.args[1] if len(nd.args) > 1 else k
+                pd = nd.args[2] if len(nd.args) > 2 else 0
+                x, oob_zero = srcs[0], False
+                if isinstance(x, tuple):
+                    assert (k, s_, pd) == (2, 1, 0), "only ZeroPad2d([0,1,0,1]) + MaxPool2d(2,1,0)"
+                    x, oob_zero = x[1], True
+                y = out_of(nd.i)
+                idx = torch.zeros(n * y.h * y.w * x.c, dtype=torch.uint8, device=dev)
+                self.keep.append(idx)
+                host = self.blocks[-1]  # the pool runs after the latest block's forward and before that block's backward
+                host.post_fwd.append(lambda x=x, y=y, k=k, s_=s_, pd=pd, idx=idx, oz=oob_zero:
+                                     T.maxpool_train_fwd(x, y, k, idx, stride=s_, off=-pd, oob_zero=oz))
+                host.pre_bwd.append(lambda x=x, y=y, k=k, s_=s_, pd=pd, idx=idx: self._pool_backward(x, y, k, s_, -pd, idx))
+                tens[nd.i] = y
 
         # ---- Detect heads
         self.heads = []
@@ -343,7 +373,7 @@ class TrainEngine:
         T.im2col_first(x, self.im2col, in_div)
         zb = self.zero_bias
         for b in self.blocks:
-            ops.conv_bn_act(b.x, b.wf, zb, b.c2, b.k, b.s, ops.ACT_NONE, out=b.y, err=self.err)
+            ops.conv_bn_act(b.x, b.wf, zb, max(b.c2, 32), b.k, b.s, ops.ACT_NONE, out=_wide(b.y), err=self.err)
             st = b.st
             T.bn_stats(b.y, self.partial)
             count = self.n * b.y.h * b.y.w
@@ -404,7 +434,8 @@ class TrainEngine:
         store.attach_grads()
 
     def _contribute_conv(self, dy, wd, c_in, k, x):
-        gx = self.grad_of(x)
+        gx = _wide(self.grad_of(x))  # c_in = 16: the dgrad conv writes 32 channels, the upper 16 from zero weight rows
+        c_in = max(c_in, 32)
         key = (x.buf.data_ptr(), x.coff, x.c)
         first = key not in self._written and not self._overlaps(self._written, key)
         pend = self._pending_res.pop(key, None)
@@ -415,6 +446,13 @@ class TrainEngine:
             ops.conv_bn_act(dy, wd, self.zero_bias, c_in, k, 1, ops.ACT_NONE, out=gx, res=gx, err=self.err)
             if pend is not None:
                 T.add_nhwc(pend, gx, accumulate=True)
+        self._written.add(key)
+
+    def _pool_backward(self, x, y, k, stride, off, idx):
+        """grad(x) (+)= gather of grad(y) through the recorded argmax; first contribution writes, later ones accumulate."""
+        key = (x.buf.data_ptr(), x.coff, x.c)
+        first = key not in self._written and not self._overlaps(self._written, key)
+        T.maxpool_bwd(self.grad_of(y), self.grad_of(x), k, idx, accumulate=not first, stride=stride, off=off)
         self._written.add(key)
 
     def _flush_pending(self):

@@ -162,23 +162,26 @@ def im2col_first(x: torch.Tensor, out: PaddedNHWC, in_div=0.0):
     return out
 
 
-def maxpool_train_fwd(x: PaddedNHWC, out: PaddedNHWC, k: int, idx: torch.Tensor):
-    """Stride-1 'same' max-pool (SPP) that also records the argmax idx[n,h,w,c] uint8 for the backward."""
+def maxpool_train_fwd(x: PaddedNHWC, out: PaddedNHWC, k: int, idx: torch.Tensor, stride: int = 1, off: int | None = None,
+                      oob_zero: bool = False):
+    """Max-pool that also records the argmax idx[n,ho,wo,c] uint8 for the backward.  Default: the stride-1 'same' pools of SPP;
+    (stride, off, oob_zero) cover nn.MaxPool2d(2, 2) and nn.ZeroPad2d([0,1,0,1]) + nn.MaxPool2d(2, 1) of yolov3-tiny."""
     from . import ops
 
-    assert idx.dtype == torch.uint8 and idx.numel() == x.n * x.h * x.w * x.c
-    d = ops.pool_desc(x, out, k, 1, -(k // 2), False)
+    assert idx.dtype == torch.uint8 and idx.numel() == out.n * out.h * out.w * x.c
+    d = ops.pool_desc(x, out, k, stride, -(k // 2) if off is None else off, oob_zero)
     _lib.check(_lib.lib().y3_maxpool_train_fwd(C.byref(d), idx.data_ptr(), _stream()), "y3_maxpool_train_fwd")
     return out
 
 
-def maxpool_bwd(dout: PaddedNHWC, din: PaddedNHWC, k: int, idx: torch.Tensor, accumulate: bool):
+def maxpool_bwd(dout: PaddedNHWC, din: PaddedNHWC, k: int, idx: torch.Tensor, accumulate: bool, stride: int = 1,
+                off: int | None = None):
     """din (+)= gather of dout through the recorded argmax (deterministic, no atomics)."""
     d = _lib.PoolDesc()
     d.in_, d.in_ld, d.in_coff = dout.ptr, dout.ld, dout.coff
     d.out, d.out_ld, d.out_coff = din.ptr, din.ld, din.coff
     d.n, d.h, d.w, d.c = din.n, din.h, din.w, din.c
     d.ho, d.wo = dout.h, dout.w
-    d.k, d.stride, d.off, d.oob_zero = k, 1, -(k // 2), 0
+    d.k, d.stride, d.off, d.oob_zero = k, int(stride), -(k // 2) if off is None else int(off), 0
     _lib.check(_lib.lib().y3_maxpool_bwd(C.byref(d), idx.data_ptr(), int(bool(accumulate)), _stream()), "y3_maxpool_bwd")
     return din
