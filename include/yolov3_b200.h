@@ -70,6 +70,12 @@ typedef struct y3_conv_desc {
   int32_t weight_layout; /* Y3_W_*: how `weight` is packed (0 = tap-major as documented above) */
 } y3_conv_desc;
 int y3_conv_bn_act_fwd(const y3_conv_desc* d, y3_stream_t stream);
+/* Input gradient of a STRIDE-2 3x3 conv (training; autograd of Conv.forward, models/common.py:71-75) as four parity-class
+ * convolutions of the un-stuffed output gradient: `in` = dy, padded NHWC [n, h+2, w+2, in_ld] on the conv's OUTPUT grid (h, w =
+ * output size), `weight` = the dgrad pack [c_in_pad rows = dx channels, 9 * c_dy] (taps flipped, y3_pack_weights), `out` = dx, padded
+ * [n, 2h+2, 2w+2, out_ld]; `res` (optional, dx geometry) is added — pass `out` itself to accumulate.  ksize = 3, stride = 1 and
+ * act = Y3_ACT_NONE in the descriptor (it describes the transposed conv on dy's grid). */
+int y3_conv_dgrad_s2(const y3_conv_desc* d, y3_stream_t stream);
 /* Weight layouts.  Y3_W_XPAIR (stride-2 3x3 with c_in in {16,32}, in_ld == c_in, in_coff == 0): bf16
  * [c_out_pad, 3, 2, 2, c_in] with element (kh, sp, par, c) = W[kh][2*sp+par][c] and zeros for the phantom column
  * 2*sp+par == 3 — two horizontally adjacent taps form one 2*c_in-channel GEMM k-block, which turns the 64-byte rows of

@@ -158,6 +158,40 @@ def test_dgrad_and_wgrad_stride2(ci, co):
     assert not T.wgrad_s2_supported(h, w)  # 8 x 12 outputs: no 80-pixel patch -> the zero-stuffed form above is the path
 
 
+@pytest.mark.parametrize("ci,co,hw", [(32, 64, (24, 40)), (64, 128, (16, 16)), (128, 256, (12, 20)), (256, 512, (8, 8)), (512, 1024, (6, 10))])
+def test_dgrad_stride2_by_phases(ci, co, hw):
+    """Input gradient of a stride-2 3x3 conv as four parity-class convolutions of the un-stuffed dy (y3_conv_dgrad_s2) against
+    torch, against the zero-stuffed formulation it replaces, and accumulating onto an existing gradient."""
+    from yolov3_b200 import ops
+    from yolov3_b200 import train_ops as T
+    from yolov3_b200.tensors import PaddedNHWC
+
+    g = torch.Generator().manual_seed(6)
+    n, (h, w) = 2, hw
+    wt = (torch.randn(co, ci, 3, 3, generator=g) / (ci * 9) ** 0.5).bfloat16().float()
+    dy = torch.randn(n, co, h // 2, w // 2, generator=g).bfloat16().float()
+    ref = torch.nn.grad.conv2d_input((n, ci, h, w), wt, dy, stride=2, padding=1)
+    dev = "cuda"
+    dgr = torch.zeros(ops.cout_pad(ci), 9 * co, dtype=torch.bfloat16, device=dev)
+    T.pack_weights(wt.to(dev).contiguous(), None, dgr)
+    zb = torch.zeros(ops.cout_pad(ci), device=dev)
+    dyp = _padded(dy)
+    dx = PaddedNHWC.zeros(n, h, w, ci)
+    ops.conv_dgrad_s2(dyp, dgr, zb, ci, out=dx)
+    assert rel_l2(dx.to_nchw(), ref) < 6e-3
+    halo = dx.buf.float().clone()
+    halo[:, 1:-1, 1:-1] = 0
+    assert (halo == 0).all()
+    up = PaddedNHWC.zeros(n, h, w, co)
+    T.zero_stuff(dyp, up)
+    dx2 = ops.conv_bn_act(up, dgr, zb, ci, 3, 1, ops.ACT_NONE)
+    assert rel_l2(dx.to_nchw(), dx2.to_nchw()) < 2e-3  # same products, different summation order / bf16 rounding points
+    prev = torch.randn(n, ci, h, w, generator=g).bfloat16().float()
+    acc = _padded(prev)
+    ops.conv_dgrad_s2(dyp, dgr, zb, ci, out=acc, res=acc)
+    assert rel_l2(acc.to_nchw(), ref + prev) < 6e-3
+
+
 @pytest.mark.parametrize("ci,co,hw", [(32, 64, (160, 160)), (64, 128, (80, 80)), (128, 256, (40, 40)), (256, 512, (40, 80)), (32, 64, (16, 320))])
 def test_wgrad_stride2_direct(ci, co, hw):
     """Direct stride-2 wgrad (dy on the OUTPUT grid, x through its parity view; 80-pixel tw x th patches: 80x1, 40x2, 20x4 ...)

@@ -20,6 +20,7 @@ ROOT = Path(__file__).resolve().parents[1]
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
+CONV_GFLOP_PER_IMG = {"yolov3.yaml": 155.891, "yolov3-spp.yaml": 156.730, "yolov3-tiny.yaml": 13.172}  # @640
 TRAIN_GFLOP_PER_IMG = 3 * 155.891  # forward + dgrad + wgrad
 
 
@@ -130,7 +131,8 @@ def train_step_workload(dev, rank, world, bs=8, img=640, steps=5, warmup=3, cfg=
         "metric": "train images/sec @640 YOLOv3 (H2D + fwd + loss + bwd/all-reduce + clip/SGD/EMA)", "value": img_s,
         "unit": "images/s", "n_gpus": world, "batch_per_gpu": bs, "global_batch": bs * world, "ms_per_step": ms_step,
         "split_ms": split, "loss": loss_v,
-        "tensor_frac": TRAIN_GFLOP_PER_IMG * 1e9 * (img_s / world) / (pk["tf_sustained"] * 1e12),
+        "tensor_frac": 3 * CONV_GFLOP_PER_IMG.get(Path(str(cfg)).name, 155.891) * (img / 640) ** 2 * 1e9 * (img_s / world)
+        / (pk["tf_sustained"] * 1e12),
         "allreduce": {"bytes_fp32": st.n_train * 4, "buckets_mb": [round((b - a) * 4 / 1e6, 1) for a, b in te.buckets],
                       "overlapped": True, "copies": 0},
         "optimizer": "torch.optim.SGD" if torch_optim else "fused clip_grad_norm(10)+SGD-nesterov(3 groups)+ModelEMA, 3 launches",

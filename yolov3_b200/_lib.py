@@ -171,6 +171,7 @@ def _declare(lib):
         "y3_last_error": ([C.c_char_p, sz], C.c_int),
         "y3_device_check": ([], C.c_int),
         "y3_conv_bn_act_fwd": ([C.POINTER(ConvDesc), vp], C.c_int),
+        "y3_conv_dgrad_s2": ([C.POINTER(ConvDesc), vp], C.c_int),
         "y3_conv_cout_pad": ([i32], C.c_int),
         "y3_conv_weight_layout": ([C.POINTER(ConvDesc)], C.c_int),
         "y3_conv_plan": ([C.POINTER(ConvDesc), C.POINTER(ConvPlanInfo)], C.c_int),

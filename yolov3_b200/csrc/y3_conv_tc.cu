@@ -213,13 +213,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             mbar_arrive_cluster(bar_addr);
           for (int st = 0; st < b_steps; ++st) {
             const int kb = st / p.taps, tap = st - kb * p.taps;
-            tma_load_2d_pair(smem_b + st * C::kBBytes, &map_b, bar_addr, tap * p.cin + kb * BLOCK_K, n0);
+            tma_load_2d_pair(smem_b + st * C::kBBytes, &map_b, bar_addr, (p.custom_taps ? p.tap_wcol[tap] : tap) * p.cin + kb * BLOCK_K, n0);
           }
         } else {
           mbar_expect_tx(bres_bar, bytes);
           for (int st = 0; st < b_steps; ++st) {
             const int kb = st / p.taps, tap = st - kb * p.taps;
-            tma_load_2d(smem_b + st * C::kBBytes, &map_b, bres_bar, tap * p.cin + kb * BLOCK_K, n0);
+            tma_load_2d(smem_b + st * C::kBBytes, &map_b, bres_bar, (p.custom_taps ? p.tap_wcol[tap] : tap) * p.cin + kb * BLOCK_K, n0);
           }
         }
       }
@@ -227,7 +227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // single lane's issue slots (~5 clk per dependent instruction), every instruction in it is paid per pipeline stage
       const int n_tiles = p.n_tiles, kblocks = p.kblocks, wp = p.wp, cin = p.cin, a_coff = p.a_coff, a_ld = p.a_ld;
       const int taps_it = HALO ? 3 : p.taps;  // HALO: tap = filter row r
-      const bool xpair = p.xpair != 0, nine = p.taps == 9;
+      const bool xpair = p.xpair != 0, nine = p.taps == 9, custom = p.custom_taps != 0;
       const int taps_w = xpair ? 2 : 3;       // taps per filter row
       const uint32_t stage_tx = p.a_tx_bytes + (bres ? 0u : kBStage);
       auto run = [&](auto mode_tag) {
@@ -255,12 +255,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               uint8_t* b_dst = smem_b + stage * kBStage;
               const int kcol = kb * BLOCK_K;
               // flat mode: the tap's A box is the tile's pixel rows shifted by (r-1)*wp + (s-1) (HALO: a whole filter row)
-              const int shift = HALO ? (tap - 1) * wp - 1 : (nine ? (r - 1) * wp + (s - 1) : 0);
+              const int shift = HALO ? (tap - 1) * wp - 1 : (custom ? p.tap_shift[tap] : (nine ? (r - 1) * wp + (s - 1) : 0));
               // patch mode: filter row r, column s.  x-paired weights (stride 2, in_ld == c_in): one box covers the two
               // horizontally adjacent taps (r, 2s) and (r, 2s+1), which are contiguous channels of the parity view
               const int c0 = xpair ? a_coff : (s & 1) * a_ld + a_coff + kcol;
               const int c1 = xpair ? s : (s >> 1);
-              const int bcol = (HALO ? tap * 3 : tap) * cin + kcol;
+              const int bcol = (HALO ? tap * 3 : (custom ? p.tap_wcol[tap] : tap)) * cin + kcol;
               if (PAIR) {
                 // all bytes of both CTAs are credited to the LEADER's full barrier; the peer only contributes an arrival
                 const uint32_t bar_addr = mapa_u32(smem_u32(&full_bar[stage]), 0);
@@ -538,7 +538,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       const int oh = p.mode == 0 ? p.hp - 2 : p.ho;  // conv-output height/width (unpadded)
       const int ow = p.mode == 0 ? p.wp - 2 : p.wo;
-      const long long conv_row = (static_cast<long long>(img) * (oh + 2) + oy + 1) * (ow + 2) + ox + 1;
+      long long conv_row = (static_cast<long long>(img) * (oh + 2) + oy + 1) * (ow + 2) + ox + 1;
+      if (p.phase)  // one parity class of a transposed stride-2 conv: (oy, ox) -> (2 oy + a, 2 ox + b) of the 2x grid
+        conv_row = (static_cast<long long>(img) * (2 * oh + 2) + 2 * oy + p.ph_a + 1) * (2 * ow + 2) + 2 * ox + p.ph_b + 1;
       const __nv_bfloat16* res_ptr = (p.res && valid) ? p.res + conv_row * p.res_ld + p.res_coff + n0 : nullptr;
       __nv_bfloat16* out_ptr = nullptr;
       float* f32_ptr = nullptr;
@@ -806,7 +808,7 @@ static bool conv_prefers_xpair(const y3_conv_desc& d) {
 }
 
 // select_only: tile / mode selection without encoding the tensor maps (y3_conv_plan: host-side tests of the heuristics)
-int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan, bool select_only) {
+int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan, bool select_only, const ConvTcExtra* extra) {
   Y3_REQUIRE(d.n > 0 && d.h > 0 && d.w > 0, "conv: empty shape");
   Y3_REQUIRE((d.ksize == 1 && d.stride == 1) || (d.ksize == 3 && (d.stride == 1 || d.stride == 2)),
              "conv: ksize/stride %d/%d unsupported (1x1 s1, 3x3 s1, 3x3 s2)", d.ksize, d.stride);
@@ -839,8 +841,9 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan, bool select_only) {
   const int gemm_cin = xpair ? 2 * d.c_in : d.c_in;
   const int bk = gemm_cin % 64 == 0 ? 64 : (gemm_cin % 32 == 0 ? 32 : 16);
   const int cout_pad = (d.c_out + bn - 1) / bn * bn;
-  const int taps = xpair ? 6 : d.ksize * d.ksize;
+  const int taps = extra ? extra->ntaps : (xpair ? 6 : d.ksize * d.ksize);
   const int hp = d.h + 2, wp = d.w + 2;
+  if (extra) Y3_REQUIRE(d.stride == 1 && !xpair && !head && !d.upsample && extra->ntaps >= 1 && extra->ntaps <= 4, "conv: bad custom tap list");
 
   ConvTcArgs& a = plan->args;
   a = ConvTcArgs{};
@@ -885,7 +888,17 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan, bool select_only) {
     a.m_tiles = static_cast<int>((rows + kBlockM - 1) / kBlockM);
     // halo reuse needs >= 2 stages of (17 KB + 3 B tiles): any N <= 128, N = 256 only as a CTA pair
     const bool pair_ok = bn >= 128 && pair_enabled() && a.m_tiles >= 2;
-    plan->halo = (taps == 9 && (bk == 64 || (bk == 32 && bn <= 64)) && halo_enabled() && (bn <= 128 || pair_ok)) ? 1 : 0;
+    plan->halo = (!extra && taps == 9 && (bk == 64 || (bk == 32 && bn <= 64)) && halo_enabled() && (bn <= 128 || pair_ok)) ? 1 : 0;
+    if (extra) {
+      a.custom_taps = 1;
+      for (int t = 0; t < extra->ntaps; ++t) {
+        a.tap_shift[t] = extra->dr[t] * wp + extra->ds[t];
+        a.tap_wcol[t] = extra->wcol[t];
+      }
+      a.phase = extra->phase;
+      a.ph_a = extra->ph_a;
+      a.ph_b = extra->ph_b;
+    }
     const uint32_t a_rows = plan->halo ? kBlockM + 2 : kBlockM;
     a.a_tx_bytes = a_rows * bk * 2;
     const uint64_t dims[2] = {static_cast<uint64_t>(d.in_ld), static_cast<uint64_t>(rows)};
@@ -928,7 +941,7 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan, bool select_only) {
     if (rc) return rc;
   }
   {
-    const uint64_t ktot = static_cast<uint64_t>(taps) * gemm_cin;
+    const uint64_t ktot = static_cast<uint64_t>(extra ? d.ksize * d.ksize : taps) * gemm_cin;  // the whole weight matrix
     const uint64_t dims[2] = {ktot, static_cast<uint64_t>(cout_pad)};
     const uint64_t strides[2] = {0, ktot * 2};
     plan->pair = (bn >= 128 && pair_enabled() && a.m_tiles >= 2) ? 1 : 0;
@@ -943,7 +956,7 @@ int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan, bool select_only) {
     plan->bres = (a.n_tiles == 1 && b_bytes <= 96 * 1024 && bres_enabled()) ? 1 : 0;
   }
   // staged (TMA-store) epilogue: flat mode, bf16 output, no upsample
-  plan->staged = (a.mode == 0 && !head && !d.upsample && staged_enabled() && !(plan->halo && bn == 256)) ? 1 : 0;
+  plan->staged = (a.mode == 0 && !head && !d.upsample && !(extra && extra->phase) && staged_enabled() && !(plan->halo && bn == 256)) ? 1 : 0;
   plan->map_out = plan->map_a;
   plan->map_res = plan->map_a;
   if (plan->staged) {
@@ -1010,6 +1023,41 @@ extern "C" int y3_conv_weight_layout(const y3_conv_desc* d) {
 extern "C" int y3_conv_cout_pad(int32_t c_out) {
   const int bn = y3::pick_block_n(c_out);
   return (c_out + bn - 1) / bn * bn;
+}
+
+// Input gradient of a stride-2 3x3 conv as FOUR parity-class convolutions on the un-stuffed dy (transposed convolution by
+// phases): dx[2i+a, 2j+b] = sum over the taps (r, s) with r = a+1 (mod 2), s = b+1 (mod 2) of dy[i + (a && r == 0), j + (b && s == 0)]
+// * W[r, s]^T — 1, 2, 2 and 4 taps.  The stride-1 convolution of the zero-stuffed dy it replaces multiplied 75 % zeros.
+extern "C" int y3_conv_dgrad_s2(const y3_conv_desc* d, y3_stream_t stream) {
+  if (!d) return y3::set_error(Y3_ERR_BAD_ARG, "conv: null descriptor");
+  Y3_REQUIRE(d->ksize == 3 && d->stride == 1 && !d->upsample && !d->out_f32 && d->weight_layout == Y3_W_TAPS,
+             "dgrad_s2: describe the 3x3 transposed conv on dy's own grid (stride 1 in the descriptor), bf16 output");
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      y3::ConvTcExtra ex{};
+      ex.phase = 1;
+      ex.ph_a = a;
+      ex.ph_b = b;
+      const int rs[2][2] = {{1, -1}, {0, 2}};  // taps r of parity class a (second entry -1: none)
+      for (int ri = 0; ri < 2; ++ri) {
+        const int r = rs[a][ri];
+        if (r < 0) continue;
+        for (int si = 0; si < 2; ++si) {
+          const int s = rs[b][si];
+          if (s < 0) continue;
+          const int t = ex.ntaps++;
+          ex.dr[t] = (a == 1 && r == 0) ? 1 : 0;
+          ex.ds[t] = (b == 1 && s == 0) ? 1 : 0;
+          ex.wcol[t] = (2 - r) * 3 + (2 - s);  // the dgrad pack stores W[r, s]^T at the flipped tap
+        }
+      }
+      y3::ConvTcPlan plan;
+      int rc = y3::conv_tc_prepare(*d, &plan, false, &ex);
+      if (rc) return rc;
+      rc = y3::conv_tc_launch(plan, static_cast<cudaStream_t>(stream));
+      if (rc) return rc;
+    }
+  return Y3_OK;
 }
 
 extern "C" int y3_conv_bn_act_fwd(const y3_conv_desc* d, y3_stream_t stream) {

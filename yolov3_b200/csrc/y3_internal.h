@@ -58,6 +58,19 @@ struct ConvTcArgs {
   float* out_f32;   // fp32 pixel-major output [n*ho*wo, out_f32_ld] (Detect heads) instead of `out`
   int out_f32_ld;
   int* err;
+  // custom tap list (flat mode, no halo reuse): tap t reads the pixel list shifted by tap_shift[t] rows and the weight
+  // columns [tap_wcol[t] * cin, +cin).  phase = 1: output pixel (oy, ox) is stored at (2 oy + ph_a, 2 ox + ph_b) of a padded
+  // [n, 2 oh + 2, 2 ow + 2] grid (one parity class of a transposed stride-2 convolution; residual read from the same place)
+  int custom_taps;
+  int tap_shift[4], tap_wcol[4];
+  int phase, ph_a, ph_b;
+};
+
+struct ConvTcExtra {  // host side of the above (conv_tc_prepare)
+  int ntaps;
+  int dr[4], ds[4];   // tap offsets in input-pixel units (rows, columns), >= 0 or negative
+  int wcol[4];        // weight tap index of each
+  int phase, ph_a, ph_b;
 };
 
 struct ConvTcPlan {
@@ -72,7 +85,7 @@ struct ConvTcPlan {
   int grid;
   size_t smem_bytes;
 };
-int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan, bool select_only = false);
+int conv_tc_prepare(const y3_conv_desc& d, ConvTcPlan* plan, bool select_only = false, const ConvTcExtra* extra = nullptr);
 int conv_tc_launch(const ConvTcPlan& plan, cudaStream_t stream);
 int pool_launch(const y3_pool_desc& d, cudaStream_t stream);
 int wgrad_tc_enabled();

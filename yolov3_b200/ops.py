@@ -79,6 +79,14 @@ def conv_bn_act(x: PaddedNHWC, weight, bias, c_out, k=1, s=1, act=ACT_SILU, out=
     return out if out_f32 is None else out_f32
 
 
+def conv_dgrad_s2(dy: PaddedNHWC, wd, zero_bias, c_in, out: PaddedNHWC, res: PaddedNHWC | None = None, err=None):
+    """dx (padded [n, 2h+2, 2w+2]) of a stride-2 3x3 conv from the un-stuffed dy: four parity-class convs (y3_conv_dgrad_s2)."""
+    assert out.h == 2 * dy.h and out.w == 2 * dy.w
+    d = conv_desc(dy, wd, zero_bias, c_in, 3, 1, ACT_NONE, out, res, False, None, err)
+    _lib.check(_lib.lib().y3_conv_dgrad_s2(C.byref(d), _stream()), "y3_conv_dgrad_s2")
+    return out
+
+
 def first_desc(x: torch.Tensor, weight27, bias, c_out, out: PaddedNHWC, in_div=0.0):
     from . import tensors as _t
 

@@ -50,6 +50,7 @@ class TrainEngine:
     use_graphs = True        # replay forward / backward segments as CUDA graphs after one eager warm-up step
     deterministic = False    # True: wgrad without split-K (bit-reproducible steps; slower on the early layers)
     n_buckets = 4            # gradient ranges all-reduced separately, each as soon as its layers are done
+    dgrad_phases = True      # stride-2 dgrad as four parity-class convs of the un-stuffed dy (False: conv of the zero-stuffed dy)
 
     def __init__(self, model, n, h, w, keep_all=False):
         """keep_all=True gives every block its own dy buffer (per-layer gradient checks in the tests); the default shares
@@ -433,17 +434,24 @@ class TrainEngine:
             #                             parallel.DDP.finish() divides in place for a plain torch.optim optimizer
         store.attach_grads()
 
-    def _contribute_conv(self, dy, wd, c_in, k, x):
+    def _contribute_conv(self, dy, wd, c_in, k, x, s2=False):
         gx = _wide(self.grad_of(x))  # c_in = 16: the dgrad conv writes 32 channels, the upper 16 from zero weight rows
         c_in = max(c_in, 32)
         key = (x.buf.data_ptr(), x.coff, x.c)
         first = key not in self._written and not self._overlaps(self._written, key)
         pend = self._pending_res.pop(key, None)
+
+        def conv(res):
+            if s2:
+                ops.conv_dgrad_s2(dy, wd, self.zero_bias, c_in, out=gx, res=res, err=self.err)
+            else:
+                ops.conv_bn_act(dy, wd, self.zero_bias, c_in, k, 1, ops.ACT_NONE, out=gx, res=res, err=self.err)
+
         if first:
             # the Bottleneck shortcut's gradient (da of the block that added x) rides on the residual port of this dgrad
-            ops.conv_bn_act(dy, wd, self.zero_bias, c_in, k, 1, ops.ACT_NONE, out=gx, res=pend, err=self.err)
+            conv(pend)
         else:
-            ops.conv_bn_act(dy, wd, self.zero_bias, c_in, k, 1, ops.ACT_NONE, out=gx, res=gx, err=self.err)
+            conv(gx)
             if pend is not None:
                 T.add_nhwc(pend, gx, accumulate=True)
         self._written.add(key)
@@ -488,9 +496,10 @@ class TrainEngine:
             else:
                 T.bn_act_bwd(b.y, da, b.dy, st, st["sums"], self.partial, b.dbeta, b.dgamma, b.upsample)
             src = b.dy
-            if b.s == 2:
-                src = T.zero_stuff(b.dy, b.dy_up)  # dgrad of a stride-2 conv = stride-1 conv of the zero-stuffed dy
-            if b.s == 2 and T.wgrad_s2_supported(b.x.h, b.x.w):
+            direct_w = b.s == 2 and T.wgrad_s2_supported(b.x.h, b.x.w)
+            if b.s == 2 and not (direct_w and self.dgrad_phases):
+                src = T.zero_stuff(b.dy, b.dy_up)  # fallback: stride-1 formulations on the zero-stuffed dy
+            if direct_w:
                 # wgrad straight from the un-stuffed dy (x through its parity view): a quarter of the pixels, no zeros multiplied
                 T.conv_wgrad(b.dy, b.x, b.dw, b.k, layout=_lib.DW_OHWI, accumulate=True, deterministic=det_flag, stride=2)
             else:
@@ -506,7 +515,11 @@ class TrainEngine:
                 self._pending_add[key] = (da, r)
             if not b.first:
                 key = (b.x.buf.data_ptr(), b.x.coff, b.x.c)
-                self._contribute_conv(src, b.wd, b.c1, b.k, b.x)
+                if b.s == 2 and self.dgrad_phases:
+                    # transposed stride-2 conv by parity classes on the un-stuffed dy (4 launches, a quarter of the MMA work)
+                    self._contribute_conv(b.dy, b.wd, b.c1, b.k, b.x, s2=True)
+                else:
+                    self._contribute_conv(src, b.wd, b.c1, b.k, b.x)
                 self._pending_add.pop(key, None)
         self._flush_pending()  # a segment is one CUDA graph: nothing may stay pending across its end
         return None
