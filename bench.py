@@ -52,6 +52,31 @@ def peaks():
     return _p()
 
 
+def recorded_conv_traffic():
+    """`roofline.traffic`: DRAM bytes of the conv_tc launches of ONE forward (bs 32) from the committed ncu capture of
+    tools/run_forward.py (profiles/r02_ncu_conv_tc_dram.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch) — a recorded
+    capture of the same kernels, not a counter of this run (no profiler runs inside the timed process); null when absent."""
+    import csv
+
+    p = ROOT / "profiles" / "r02_ncu_conv_tc_dram.csv"
+    if not p.exists():
+        return {"traffic": None, "traffic_note": "no committed ncu DRAM capture (profiles/r02_ncu_conv_tc_dram.csv)"}
+    try:
+        rows = [r for r in csv.DictReader(l for l in p.read_text().splitlines() if not l.startswith("=="))]
+        tot, n = 0.0, 0
+        for r in rows:
+            if r.get("Metric Name") in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v = float(r["Metric Value"].replace(",", ""))
+                v *= {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r["Metric Unit"], 1)
+                tot += v
+                n += 1
+        launches = n // 2
+        return {"traffic": tot, "traffic_unit": "bytes per step (sum over the conv_tc launches of one forward)",
+                "traffic_launches": launches, "traffic_source": "profiles/r02_ncu_conv_tc_dram.csv (ncu capture, recorded)"}
+    except Exception as e:  # noqa: BLE001
+        return {"traffic": None, "traffic_note": f"could not parse the committed capture: {e!r}"}
+
+
 def workload_config(world):
     return {"workload": f"yolov3.yaml forward+decode, {IMG}x{IMG}, bs {BS}/GPU, random-init weights, folded BN",
             "imgsz": IMG, "batch_per_gpu": BS, "global_batch": BS * world, "parallelism": f"replicas x{world} (no collective)",
@@ -380,7 +405,7 @@ def main():
     ap.add_argument("--per-op", default=None, help="write the per-launch timing table (JSON) to this path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    legs = {"train", "spp_nms", "nms", "lib", "cpu"} if args.only == "all" else set(filter(None, args.only.split(",")))
+    legs = {"train", "spp_nms", "nms", "lib", "cpu"} if args.only == "all" else set(filter(None, args.only.split(","))) - {"none"}
     if args.no_cpu_baseline:
         legs.discard("cpu")
 
@@ -531,8 +556,7 @@ def main():
                 "kernel_ms_per_step": conv_ms, "kernel_share_of_step": conv_ms / all_ms,
                 "whole_step_frac": GFLOP_PER_IMG * 1e9 * (value / world) / (pk["tf_sustained"] * 1e12),
                 "peak_source": pk["source"] + " sustained bf16 (MEASURED_PEAKS.json)",
-                "traffic_note": "null: `achieved` aggregates launches of 23 shapes; per-kernel DRAM bytes are in the ncu --set full "
-                                "summaries under profiles/ (not re-measured per run)"}
+                **recorded_conv_traffic()}
     dec = [o for o in per_op if o["kind"] == "decode"]
     if dec:  # Detect decode: read the head logits + write z = 17.1 MB/image algorithmic
         roofline["decode_hbm"] = {"bound": "hbm", "achieved": dec[0]["gbs"], "peak": pk["hbm"], "unit": "GB/s",

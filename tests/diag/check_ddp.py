@@ -88,7 +88,7 @@ def main():
             opt.step()
             opt.zero_grad()
         torch.cuda.synchronize()
-        chk = st.P.double().sum()
+        chk = st.P[:st.n_train].double().sum()  # trainable range: BatchNorm running statistics stay rank-local (no --sync-bn)
         lo, hi = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)

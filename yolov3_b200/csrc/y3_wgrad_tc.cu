@@ -301,7 +301,9 @@ static int wgrad_tc_s2(const y3_wgrad_desc& d, cudaStream_t stream) {
   a.sbo_a = 1024;
   a.sbo_b = 8 * bcols * 2;
   const int tiles = ((d.co + kWgM - 1) / kWgM) * a.n_ci_tiles;
-  long long want = (2ll * num_sms() + static_cast<long long>(tiles) * 9 - 1) / (static_cast<long long>(tiles) * 9);
+  // split the pixel dimension so that the grid is ONE wave of the 2 CTAs an SM holds (floor, not ceil: 33 splits x 9 taps = 297
+  // CTAs on 296 slots ran a second wave for a single CTA — 196 us instead of ~110, gpurun r2j6)
+  long long want = (2ll * num_sms()) / (static_cast<long long>(tiles) * 9);
   long long max_split = (a.kblocks_total + 7) / 8;
   if (want > max_split) want = max_split;
   if (want < 1 || d.deterministic) want = 1;
@@ -377,7 +379,8 @@ int wgrad_tc(const y3_wgrad_desc& d, cudaStream_t stream) {
   }
   const int tiles = ((d.co + kWgM - 1) / kWgM) * a.n_ci_tiles;
   // split the pixel dimension so that ~2 CTAs per SM exist; at least 8 pixel blocks per CTA
-  long long want = (2ll * num_sms() + static_cast<long long>(tiles) * taps - 1) / (static_cast<long long>(tiles) * taps);
+  // one wave of the 2 resident CTAs per SM (floor: a grid a few CTAs over a wave costs a whole extra wave)
+  long long want = (2ll * num_sms()) / (static_cast<long long>(tiles) * taps);
   long long max_split = (a.kblocks_total + 7) / 8;
   if (want > max_split) want = max_split;
   if (want < 1) want = 1;
