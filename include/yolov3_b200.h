@@ -41,6 +41,10 @@ int y3_device_check(void);
  * 0 y3_conv_desc, 1 y3_first_desc, 2 y3_pool_desc, 3 y3_detect_level, 4 y3_decode_desc, 5 y3_op, 6 y3_nms_params,
  * 7 y3_loss_desc. */
 int64_t y3_abi_sizeof(int32_t which);
+/* Programmatic dependent launch between consecutive kernels of a stream (on by default; env Y3_PDL=0 or on=0 turns it off).
+ * Results are identical either way — only the launch boundaries overlap.  Returns the previous setting.  A tuning switch with
+ * no counterpart in the reference. */
+int y3_set_pdl(int32_t on);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Conv + folded-BN + SiLU (+ residual add, + nearest-2x upsample, + concat-offset store, or fp32 head store).

@@ -61,6 +61,7 @@ template <int COUT, typename TIN, bool VEC>
 __global__ void __launch_bounds__(128) conv_first_kernel(const TIN* __restrict__ in, float in_div, int H, int W,
                                                          const float* __restrict__ wgt, const float* __restrict__ bias,
                                                          __nv_bfloat16* __restrict__ out, int out_ld, int out_coff) {
+  pdl_entry();
   // patch column of image column ww is (ww - w0) + 4: the 128 interior columns start 16-byte aligned, halos at 3 and 132
   constexpr int TW = kFirstTW, R = kFirstRows, NT = COUT / 8, PITCH = TW + 8, C0 = 3;
   __shared__ __align__(16) float s_in[3][R + 2][PITCH];
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const TIN* __restrict__
 
 __global__ void nchw_to_padded_kernel(const float* __restrict__ src, int C, int H, int W, __nv_bfloat16* __restrict__ dst,
                                       int ld, int coff, size_t total) {
+  pdl_entry();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int w = i % W;
@@ -207,6 +209,7 @@ __global__ void nchw_to_padded_kernel(const float* __restrict__ src, int C, int 
 
 __global__ void padded_to_nchw_kernel(const __nv_bfloat16* __restrict__ src, int ld, int coff, int C, int H, int W,
                                       float* __restrict__ dst, size_t total) {
+  pdl_entry();
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int w = i % W;
@@ -234,11 +237,11 @@ extern "C" int y3_conv_first_fwd(const y3_first_desc* d, y3_stream_t stream) {
 #define Y3_FIRST(CO, T)                                                                                                 \
   do {                                                                                                                  \
     if (vec)                                                                                                            \
-      y3::conv_first_kernel<CO, T, true><<<grid, block, 0, s>>>(static_cast<const T*>(d->in), d->in_div, d->h, d->w,    \
-                                                                d->weight, d->bias, o, d->out_ld, d->out_coff);         \
+      Y3_CHECK_CUDA(::y3::launch_pdl(y3::conv_first_kernel<CO, T, true>, dim3(grid), dim3(block), 0, s, static_cast<const T*>(d->in), d->in_div, d->h, d->w,    \
+                                                                d->weight, d->bias, o, d->out_ld, d->out_coff));         \
     else                                                                                                                \
-      y3::conv_first_kernel<CO, T, false><<<grid, block, 0, s>>>(static_cast<const T*>(d->in), d->in_div, d->h, d->w,   \
-                                                                 d->weight, d->bias, o, d->out_ld, d->out_coff);        \
+      Y3_CHECK_CUDA(::y3::launch_pdl(y3::conv_first_kernel<CO, T, false>, dim3(grid), dim3(block), 0, s, static_cast<const T*>(d->in), d->in_div, d->h, d->w,   \
+                                                                 d->weight, d->bias, o, d->out_ld, d->out_coff));        \
   } while (0)
   if (d->c_out == 32) {
     if (d->in_dtype == Y3_IN_F32) Y3_FIRST(32, float); else Y3_FIRST(32, uint8_t);
@@ -254,8 +257,7 @@ extern "C" int y3_nchw_to_padded_nhwc(const float* src, int32_t n, int32_t c, in
                                       int32_t dst_ld, int32_t dst_coff, y3_stream_t stream) {
   Y3_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0 && dst_coff + c <= dst_ld, "nchw_to_padded: bad args");
   const size_t total = static_cast<size_t>(n) * c * h * w;
-  y3::nchw_to_padded_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, c, h, w, static_cast<__nv_bfloat16*>(dst), dst_ld, dst_coff, total);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::nchw_to_padded_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), src, c, h, w, static_cast<__nv_bfloat16*>(dst), dst_ld, dst_coff, total));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -264,8 +266,7 @@ extern "C" int y3_padded_nhwc_to_nchw(const void* src, int32_t src_ld, int32_t s
                                       int32_t w, float* dst, y3_stream_t stream) {
   Y3_REQUIRE(src && dst && n > 0 && c > 0 && h > 0 && w > 0 && src_coff + c <= src_ld, "padded_to_nchw: bad args");
   const size_t total = static_cast<size_t>(n) * c * h * w;
-  y3::padded_to_nchw_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(src), src_ld, src_coff, c, h, w, dst, total);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::padded_to_nchw_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(src), src_ld, src_coff, c, h, w, dst, total));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }

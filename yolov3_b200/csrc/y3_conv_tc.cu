@@ -188,6 +188,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only shared memory, TMEM and the kernel parameters: it may run while the previous kernel of the
+  // stream drains.  From here on global memory is read and written.
+  pdl_wait();
+  pdl_trigger();
 
   const int m_units = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles;  // a pair owns two consecutive M tiles
   const int total_tiles = m_units * p.n_tiles;
@@ -653,15 +657,22 @@ int launch_cfg(const ConvTcPlan& plan, cudaStream_t stream) {
   cfg.blockDim = dim3(64 + 32 * kEpilogueWarps * groups);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
   if (PAIR) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = 2;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
   }
+  if (pdl_enabled()) {  // the kernel parks at pdl_wait() after its prologue (y3_common.cuh)
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n_attr;
   ConvTcArgs args = plan.args;
   args.bres = plan.bres;
   {

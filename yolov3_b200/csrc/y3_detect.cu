@@ -21,6 +21,7 @@ struct DecodeArgs {
 };
 
 __global__ void __launch_bounds__(256) decode_kernel(const DecodeArgs p) {
+  pdl_entry();
   const long long per_img = static_cast<long long>(p.row_off[p.nl]) * p.no;
   const long long total = per_img * p.bs;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -82,6 +83,7 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f,
 // (profiles/r01_ncu_decode_summary.txt).
 template <int NITER>
 __global__ void __launch_bounds__(256, NITER <= 3 ? 3 : 1) head_decode_kernel(const HeadDecodeArgs p) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int rows_per_img = p.row_off[p.nl];
   const int total = rows_per_img * p.bs;  // < 2^31 (checked by the launcher)
@@ -243,11 +245,11 @@ extern "C" int y3_detect_head_decode_fwd(const y3_decode_desc* d, y3_stream_t st
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned g = static_cast<unsigned>(blocks);
   switch (niter) {
-    case 1: y3::head_decode_kernel<1><<<g, 256, 0, st>>>(a); break;
-    case 2: y3::head_decode_kernel<2><<<g, 256, 0, st>>>(a); break;
-    case 3: y3::head_decode_kernel<3><<<g, 256, 0, st>>>(a); break;
-    case 4: y3::head_decode_kernel<4><<<g, 256, 0, st>>>(a); break;
-    default: y3::head_decode_kernel<8><<<g, 256, 0, st>>>(a); break;
+    case 1: Y3_CHECK_CUDA(::y3::launch_pdl(y3::head_decode_kernel<1>, dim3(g), dim3(256), 0, st, a)); break;
+    case 2: Y3_CHECK_CUDA(::y3::launch_pdl(y3::head_decode_kernel<2>, dim3(g), dim3(256), 0, st, a)); break;
+    case 3: Y3_CHECK_CUDA(::y3::launch_pdl(y3::head_decode_kernel<3>, dim3(g), dim3(256), 0, st, a)); break;
+    case 4: Y3_CHECK_CUDA(::y3::launch_pdl(y3::head_decode_kernel<4>, dim3(g), dim3(256), 0, st, a)); break;
+    default: Y3_CHECK_CUDA(::y3::launch_pdl(y3::head_decode_kernel<8>, dim3(g), dim3(256), 0, st, a)); break;
   }
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
@@ -282,7 +284,7 @@ extern "C" int y3_detect_decode_fwd(const y3_detect_level* levels, int32_t nl, i
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(y3::num_sms()) * 16;
   if (blocks > cap) blocks = cap;
-  y3::decode_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::decode_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), a));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }

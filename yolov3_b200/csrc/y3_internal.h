@@ -31,6 +31,8 @@ int encode_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const u
                            const uint32_t* box, int swizzle_bytes);
 
 int num_sms();
+int pdl_enabled();   // programmatic dependent launch on (default; Y3_PDL=0 or y3_set_pdl(0) turns it off)
+void pdl_set(int on);
 
 // ---- tcgen05 conv: kernel arguments (device view) and a prepared launch
 struct ConvTcArgs {

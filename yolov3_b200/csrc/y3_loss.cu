@@ -36,6 +36,7 @@ struct LossArgs {
 
 // ---------------------------------------------------------------------------------------------- K1
 __global__ void __launch_bounds__(256) loss_match_kernel(const LossArgs p) {
+  pdl_entry();
   const y3_loss_desc& d = p.d;
   const int per_level = 5 * d.na * d.nt;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -161,6 +162,7 @@ __device__ __forceinline__ float bce_logits(float x, float t, float pw, float* d
 
 // ---------------------------------------------------------------------------------------------- K2
 __global__ void __launch_bounds__(256) loss_matches_kernel(const LossArgs p, int l) {
+  pdl_entry();
   const y3_loss_desc& d = p.d;
   const int n = p.count[l];
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(256) loss_matches_kernel(const LossArgs p, int
 
 // ---------------------------------------------------------------------------------------------- K3
 __global__ void __launch_bounds__(256) loss_obj_kernel(const LossArgs p, int l) {
+  pdl_entry();
   const y3_loss_desc& d = p.d;
   const int no = d.nc + 5;
   const size_t cells = static_cast<size_t>(d.bs) * d.na * d.ny[l] * d.nx[l];
@@ -233,6 +236,7 @@ __global__ void __launch_bounds__(256) loss_obj_kernel(const LossArgs p, int l) 
 
 // ---------------------------------------------------------------------------------------------- K4
 __global__ void loss_finalize_kernel(const LossArgs p) {
+  pdl_entry();
   const y3_loss_desc& d = p.d;
   float lbox = 0.f, lobj = 0.f, lcls = 0.f;
   for (int l = 0; l < d.nl; ++l) {
@@ -305,10 +309,10 @@ extern "C" int y3_loss_fwd_bwd(const y3_loss_desc* d, void* workspace, int64_t w
   }
   if (d->nt > 0) {
     const int total = 5 * d->na * d->nt * d->nl;
-    loss_match_kernel<<<(total + 255) / 256, 256, 0, stream>>>(a);
+    Y3_CHECK_CUDA(::y3::launch_pdl(loss_match_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, a));
     for (int l = 0; l < d->nl; ++l) {
       const long long threads = static_cast<long long>(a.cap) * 32;  // one warp per potential match
-      loss_matches_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, stream>>>(a, l);
+      Y3_CHECK_CUDA(::y3::launch_pdl(loss_matches_kernel, dim3(static_cast<unsigned>((threads + 255) / 256)), dim3(256), 0, stream, a, l));
     }
   }
   for (int l = 0; l < d->nl; ++l) {
@@ -316,9 +320,9 @@ extern "C" int y3_loss_fwd_bwd(const y3_loss_desc* d, void* workspace, int64_t w
     size_t blocks = (cells + 255) / 256;
     const size_t cap = static_cast<size_t>(num_sms()) * 8;
     if (blocks > cap) blocks = cap;
-    loss_obj_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(a, l);
+    Y3_CHECK_CUDA(::y3::launch_pdl(loss_obj_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, a, l));
   }
-  loss_finalize_kernel<<<1, 1, 0, stream>>>(a);
+  Y3_CHECK_CUDA(::y3::launch_pdl(loss_finalize_kernel, dim3(1), dim3(1), 0, stream, a));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }

@@ -71,6 +71,7 @@ __device__ __forceinline__ int next_pow2(int v) { return v <= 1 ? 1 : 1 << (32 -
 constexpr int kCandWarps = 8;
 
 __global__ void __launch_bounds__(32 * kCandWarps) nms_candidates_kernel(const NmsArgs p) {
+  pdl_entry();
   const unsigned full = 0xffffffffu;
   const int img = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -662,6 +663,7 @@ __device__ unsigned long long block_select_kth(const unsigned long long* keys, i
 }
 
 __global__ void __launch_bounds__(kBucketThreads) nms_bucket_kernel(const NmsArgs p) {
+  pdl_entry();
   __shared__ int s_hist[1024];   // class histogram, then exclusive offsets
   __shared__ int s_cur[1024];    // scatter cursors
   __shared__ int s_sel[256];
@@ -783,6 +785,7 @@ constexpr int kSegSlots = 8;
 constexpr int kSegWarpMax = 32 * kSegSlots;
 
 __global__ void __launch_bounds__(256, 3) nms_seg_warp_kernel(const NmsArgs p) {
+  pdl_entry();
   __shared__ unsigned long long s_key[8][kSegWarpMax];
   __shared__ uint16_t s_ord[8][kSegWarpMax];
   const unsigned full = 0xffffffffu;
@@ -880,6 +883,7 @@ __global__ void __launch_bounds__(256, 3) nms_seg_warp_kernel(const NmsArgs p) {
 // per class and 782 us for ~375 (multi-label) against ~65 us of pair-test work (gpurun r2j5).
 template <int MAXM, int THREADS>
 __global__ void __launch_bounds__(THREADS) nms_seg_mask_kernel(const NmsArgs p, int m_lo) {
+  pdl_entry();
   constexpr int W = MAXM / 32;  // mask words per row
   extern __shared__ unsigned long long s_dyn[];
   unsigned long long* s_key = s_dyn;                                   // [MAXM]
@@ -952,7 +956,7 @@ int launch_seg_mask(const NmsArgs& a, int m_lo, cudaStream_t stream) {
     Y3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     attr_set = true;
   }
-  kern<<<dim3(a.nc, a.bs), THREADS, kSmem, stream>>>(a, m_lo);
+  Y3_CHECK_CUDA(::y3::launch_pdl(kern, dim3(a.nc, a.bs), dim3(THREADS), kSmem, stream, a, m_lo));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -964,6 +968,7 @@ int launch_seg_mask(const NmsArgs& a, int m_lo, cudaStream_t stream) {
 constexpr int kRankTile = 1024;
 
 __global__ void __launch_bounds__(256) nms_seg_block_kernel(const NmsArgs p) {
+  pdl_entry();
   __shared__ unsigned long long s_tile[kRankTile];
   __shared__ float4 s_box[kSegSmemBoxes];
   __shared__ uint32_t s_supp[(kRankCap + 31) / 32];
@@ -1037,6 +1042,7 @@ __global__ void __launch_bounds__(256) nms_seg_block_kernel(const NmsArgs p) {
 }
 
 __global__ void __launch_bounds__(1024) nms_output_kernel(const NmsArgs p) {
+  pdl_entry();
   extern __shared__ unsigned long long s_dyn[];
   unsigned long long* s_k = s_dyn;                                          // [kOutSortMax]
   uint16_t* s_p = reinterpret_cast<uint16_t*>(s_dyn + kOutSortMax);         // [kOutSortMax] positions < kRankCap = 32768
@@ -1246,20 +1252,20 @@ extern "C" int y3_nms_batched(const float* pred, const y3_nms_params* q, void* w
 
   Y3_CHECK_CUDA(cudaMemsetAsync(a.count, 0, sizeof(int) * size_t(a.bs) * 2, stream));
   // K1
-  nms_candidates_kernel<<<dim3((a.n_rows + 32 * kCandWarps - 1) / (32 * kCandWarps), a.bs), 32 * kCandWarps, 0, stream>>>(a);
+  Y3_CHECK_CUDA(::y3::launch_pdl(nms_candidates_kernel, dim3((a.n_rows + 32 * kCandWarps - 1) / (32 * kCandWarps), a.bs), dim3(32 * kCandWarps), 0, stream, a));
   static int v1 = -1;  // Y3_NMS_V1=1: the round-1 pipeline (two global bitonic sorts), kept for A/B measurements
   if (v1 < 0) {
     const char* e = getenv("Y3_NMS_V1");
     v1 = (e && e[0] == '1') ? 1 : 0;
   }
   if (!v1) {
-    nms_bucket_kernel<<<a.bs, kBucketThreads, 0, stream>>>(a);
+    Y3_CHECK_CUDA(::y3::launch_pdl(nms_bucket_kernel, dim3(a.bs), dim3(kBucketThreads), 0, stream, a));
     // measured (gpurun r2j5 / r2j6, 32 x 25200 rows): <= 128 members per class (conf 0.25: ~65) -> suppression matrix, 37 us vs
     // 50 us for the warp kernel; ~215 per class (conf 0.001) -> warp kernel 228 us vs 448 us for a 768-wide matrix kernel
     // (94 KB of shared memory: 2 CTAs per SM); ~375 (multi-label) -> per-keeper block kernel 782 us vs 1178 us
     if (int rc = launch_seg_mask<kMaskSmall, 128>(a, 0, stream)) return rc;
-    nms_seg_warp_kernel<<<dim3((a.nc + 7) / 8, a.bs), 256, 0, stream>>>(a);
-    nms_seg_block_kernel<<<dim3(a.nc, a.bs), 256, 0, stream>>>(a);
+    Y3_CHECK_CUDA(::y3::launch_pdl(nms_seg_warp_kernel, dim3((a.nc + 7) / 8, a.bs), dim3(256), 0, stream, a));
+    Y3_CHECK_CUDA(::y3::launch_pdl(nms_seg_block_kernel, dim3(a.nc, a.bs), dim3(256), 0, stream, a));
     {
       constexpr int kOutSmem = kOutSortMax * (sizeof(unsigned long long) + sizeof(uint16_t));
       static bool attr_set = false;
@@ -1267,7 +1273,7 @@ extern "C" int y3_nms_batched(const float* pred, const y3_nms_params* q, void* w
         Y3_CHECK_CUDA(cudaFuncSetAttribute(nms_output_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOutSmem));
         attr_set = true;
       }
-      nms_output_kernel<<<a.bs, 1024, kOutSmem, stream>>>(a);
+      Y3_CHECK_CUDA(::y3::launch_pdl(nms_output_kernel, dim3(a.bs), dim3(1024), kOutSmem, stream, a));
     }
     Y3_CHECK_CUDA(cudaGetLastError());
     return Y3_OK;

@@ -17,6 +17,7 @@ constexpr int kChunk = 256;  // elements per group-map entry; every parameter's 
 
 // first stage: partial[b] = sum of g^2 over block b's grid-stride range (fixed association order per block)
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, long long n4, float* __restrict__ partial) {
+  pdl_entry();
   float acc = 0.f;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -37,6 +38,7 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
 }
 // second stage (one block): out[0] = sum_b partial[b], pairwise in a fixed order
 __global__ void __launch_bounds__(256) sumsq_final_kernel(const float* __restrict__ partial, int nblk, float* __restrict__ out) {
+  pdl_entry();
   __shared__ float sh[256];
   float acc = 0.f;
   for (int b = threadIdx.x; b < nblk; b += 256) acc += partial[b];
@@ -56,6 +58,7 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ p, co
                                                        float* __restrict__ ema, const uint8_t* __restrict__ group,
                                                        long long n4, const float* __restrict__ hp,
                                                        const float* __restrict__ gsumsq) {
+  pdl_entry();
   const float mom = hp[6], nesterov = hp[7], max_norm = hp[8], d = hp[9], gscale = hp[10];
   float clip = gscale;
   if (max_norm > 0.f) {
@@ -112,8 +115,8 @@ extern "C" int y3_grad_sumsq(const float* g, int64_t n, float* partial, float* o
              "grad_sumsq: n must be a multiple of 4, g 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int nblk = y3_sumsq_blocks();  // fixed: the partial sums — and so the result — do not depend on the device
-  y3::sumsq_partial_kernel<<<nblk, 256, 0, stream>>>(g, n / 4, partial);
-  y3::sumsq_final_kernel<<<1, 256, 0, stream>>>(partial, nblk, out);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::sumsq_partial_kernel, dim3(nblk), dim3(256), 0, stream, g, n / 4, partial));
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::sumsq_final_kernel, dim3(1), dim3(256), 0, stream, partial, nblk, out));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -123,8 +126,8 @@ extern "C" int y3_sgd_step(float* p, const float* g, float* m, float* ema, const
   Y3_REQUIRE(p && g && m && group && hp_dev && n > 0 && n % y3::kChunk == 0, "sgd_step: n must be a multiple of 256");
   Y3_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                reinterpret_cast<uintptr_t>(ema)) & 15) == 0, "sgd_step: buffers must be 16-byte aligned");
-  y3::sgd_step_kernel<<<y3::blocks_for(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, ema, group, n / 4, hp_dev,
-                                                                                            gsumsq);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::sgd_step_kernel, dim3(y3::blocks_for(n / 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), p, g, m, ema, group, n / 4, hp_dev,
+                                                                                            gsumsq));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }

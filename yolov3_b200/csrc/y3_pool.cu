@@ -26,6 +26,7 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
 }
 
 __global__ void __launch_bounds__(256) maxpool_kernel(const PoolArgs p) {
+  pdl_entry();
   const long long total = static_cast<long long>(p.n) * p.ho * p.wo * p.c8;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const PoolArgs p) {
 // Forward with argmax: idx[n, ho, wo, c] (uint8) = dy*k + dx of the FIRST maximum in row-major window order, which is the
 // element torch.nn.MaxPool2d routes the gradient to (ATen max_pool2d_with_indices: `val > maxval || isnan(val)`).
 __global__ void __launch_bounds__(256) maxpool_idx_kernel(const PoolArgs p, uint8_t* __restrict__ idx) {
+  pdl_entry();
   const long long total = static_cast<long long>(p.n) * p.ho * p.wo * p.c8;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -127,6 +129,7 @@ __global__ void __launch_bounds__(256) maxpool_idx_kernel(const PoolArgs p, uint
 // Backward as a gather (no atomics, deterministic): input pixel (yy, xx) collects dy of every window whose recorded argmax
 // is this pixel.  `in`/`out` of PoolArgs are reused as dOut (read) / dIn (written or accumulated).
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const PoolArgs p, const uint8_t* __restrict__ idx, int accumulate) {
+  pdl_entry();
   const long long total = static_cast<long long>(p.n) * p.h * p.w * p.c8;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -217,7 +220,7 @@ int pool_train_fwd(const y3_pool_desc& d, uint8_t* idx, cudaStream_t stream) {
   PoolArgs a;
   if (int rc = pool_args(d, &a)) return rc;
   Y3_REQUIRE(idx, "pool (train): idx is required");
-  maxpool_idx_kernel<<<pool_grid(static_cast<long long>(a.n) * a.ho * a.wo * a.c8), 256, 0, stream>>>(a, idx);
+  Y3_CHECK_CUDA(::y3::launch_pdl(maxpool_idx_kernel, dim3(pool_grid(static_cast<long long>(a.n) * a.ho * a.wo * a.c8)), dim3(256), 0, stream, a, idx));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -226,7 +229,7 @@ int pool_bwd(const y3_pool_desc& d, const uint8_t* idx, int accumulate, cudaStre
   PoolArgs a;
   if (int rc = pool_args(d, &a)) return rc;
   Y3_REQUIRE(idx, "pool_bwd: null idx");
-  maxpool_bwd_kernel<<<pool_grid(static_cast<long long>(a.n) * a.h * a.w * a.c8), 256, 0, stream>>>(a, idx, accumulate);
+  Y3_CHECK_CUDA(::y3::launch_pdl(maxpool_bwd_kernel, dim3(pool_grid(static_cast<long long>(a.n) * a.h * a.w * a.c8)), dim3(256), 0, stream, a, idx, accumulate));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -258,7 +261,7 @@ int pool_launch(const y3_pool_desc& d, cudaStream_t stream) {
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(num_sms()) * 32;
   if (blocks > cap) blocks = cap;
-  maxpool_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(a);
+  Y3_CHECK_CUDA(::y3::launch_pdl(maxpool_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, a));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }

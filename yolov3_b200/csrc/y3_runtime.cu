@@ -1,6 +1,7 @@
 // yolov3_b200 — host runtime glue behind the C ABI: error strings, device probe, TMA descriptor encoding.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -48,6 +49,18 @@ int num_sms() {
   }
   return sms;
 }
+
+namespace {
+int g_pdl = -1;
+}
+int pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("Y3_PDL");
+    g_pdl = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl;
+}
+void pdl_set(int on) { g_pdl = on ? 1 : 0; }
 
 int encode_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                            const uint32_t* box, int swizzle_bytes) {
@@ -100,6 +113,12 @@ extern "C" int y3_device_check(void) {
   Y3_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   if (major != 10) return y3::set_error(Y3_ERR_UNSUPPORTED, "device compute capability %d.x is not sm_100", major);
   return Y3_OK;
+}
+
+extern "C" int y3_set_pdl(int32_t on) {
+  const int prev = y3::pdl_enabled();
+  y3::pdl_set(on);
+  return prev;
 }
 
 extern "C" int64_t y3_abi_sizeof(int32_t which) {

@@ -89,6 +89,7 @@ __device__ __forceinline__ void block_reduce_store(float (&s)[8], float (&q)[8],
 // ---------------------------------------------------------------------------------------------- bn_stats
 // grid: nblk blocks of 256 threads; block b walks rows b, b+nblk, ...; partial[b] = [sum(c) | sumsq(c)]
 __global__ void __launch_bounds__(256, 4) bn_stats_kernel(Slice y, Rows g, float* __restrict__ partial) {
+  pdl_entry();
   extern __shared__ float sh[];  // [2][256][8]
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int items = g.w * g.c8, units = g.n * g.h * g.upr;
@@ -148,6 +149,7 @@ __device__ __forceinline__ float colsum_32x32(const float* __restrict__ partial,
 
 __global__ void __launch_bounds__(1024) colreduce_kernel(const float* __restrict__ partial, int nblk, int width,
                                                          float* __restrict__ out, int accumulate) {
+  pdl_entry();
   __shared__ float sh[32][33];
   const int j = blockIdx.x * 32 + threadIdx.x;
   const float a = colsum_32x32(partial, nblk, width, j, j < width, sh);
@@ -160,6 +162,7 @@ __global__ void __launch_bounds__(1024) bn_finalize_kernel(const float* __restri
                                                            const float* beta, int c, float count, float eps, float momentum,
                                                            float* scale, float* shift, float* mean_out, float* rstd_out,
                                                            float* running_mean, float* running_var) {
+  pdl_entry();
   __shared__ float sh[32][33];
   const int i = blockIdx.x * 32 + threadIdx.x;
   const float sum = colsum_32x32(partial, nblk, 2ll * c, i, i < c, sh);
@@ -193,6 +196,7 @@ struct BnActArgs {
   int upsample;
 };
 __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const BnActArgs p) {
+  pdl_entry();
   const Rows g = p.g;
   const int items = g.w * g.c8, units = g.n * g.h * g.upr;
   const int us = p.upsample ? 2 : 1;
@@ -293,6 +297,7 @@ __device__ __forceinline__ float silu_grad(float z) {
 
 template <bool APPLY, bool UPS>
 __global__ void __launch_bounds__(256, UPS ? 2 : 3) bn_act_bwd_kernel(const BnBwdArgs p) {
+  pdl_entry();
   // block = 256 threads; thread t keeps channel group t % c8 for the whole kernel (256 % c8 == 0)
   extern __shared__ float sh[];
   const Rows g = p.g;
@@ -376,6 +381,7 @@ __global__ void __launch_bounds__(256, UPS ? 2 : 3) bn_act_bwd_kernel(const BnBw
 // with (kh', kw') = (k-1-kh, k-1-kw).  Rows beyond co / ci stay zero (buffers are zero-initialised once).
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, int co, int ci, int k,
                                                            __nv_bfloat16* __restrict__ fwd, __nv_bfloat16* __restrict__ dgr) {
+  pdl_entry();
   const long long total = static_cast<long long>(co) * ci * k * k;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -395,6 +401,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 // src: dy of a stride-2 conv, padded NHWC [n, ho+2, wo+2, ld]; dst: zero-initialised padded [n, 2ho+2, 2wo+2, c]:
 // dst(2*oy, 2*ox) = src(oy, ox)  (unpadded coordinates).  Only the even positions are ever written.
 __global__ void __launch_bounds__(256) zero_stuff_kernel(Slice src, SliceW dst, int n, int ho, int wo, int c8) {
+  pdl_entry();
   const long long total = static_cast<long long>(n) * ho * wo * c8;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -444,6 +451,7 @@ struct WgradArgs {
 
 // grid: (pixel chunks, co/64 * ci/64, taps); block 128 threads (4 warps: 2x2 over the 64x64 tile, 32x32 each)
 __global__ void __launch_bounds__(128) wgrad_kernel(const WgradArgs p) {
+  pdl_entry();
   __shared__ __align__(16) __nv_bfloat16 s_a[kWgPix][kWgTile + 8];  // dy chunk  [pixel][co]   (+8: conflict-free ldmatrix)
   __shared__ __align__(16) __nv_bfloat16 s_b[kWgPix][kWgTile + 8];  // x chunk   [pixel][ci]
   const int tiles_ci = (p.ci + kWgTile - 1) / kWgTile;
@@ -537,6 +545,7 @@ __global__ void __launch_bounds__(128) wgrad_kernel(const WgradArgs p) {
 // g: fp32 pixel-major [rows, ld]; db[c] += sum_rows g[row, c]
 __global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict__ g, int ld, int c, long long rows,
                                                          int rows_per_block, float* __restrict__ db) {
+  pdl_entry();
   const int col = threadIdx.x % c, rl = threadIdx.x / c, nrl = blockDim.x / c;
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long r1 = r0 + rows_per_block < rows ? r0 + rows_per_block : rows;
@@ -550,6 +559,7 @@ __global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict
 // dst (+)= src over the interior pixels of two padded NHWC slices with the same [n,h,w,c] (gradient fan-in:
 // Bottleneck shortcut, tensors with several consumers)
 __global__ void __launch_bounds__(256) add_nhwc_kernel(Slice src, SliceW dst, int n, int h, int w, int c8, int accumulate) {
+  pdl_entry();
   const long long total = static_cast<long long>(n) * h * w * c8;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -580,6 +590,7 @@ __global__ void __launch_bounds__(256) add_nhwc_kernel(Slice src, SliceW dst, in
 template <typename TIN>
 __global__ void __launch_bounds__(256) im2col_first_kernel(const TIN* __restrict__ in, float div, int n, int h, int w,
                                                            SliceW out) {
+  pdl_entry();
   const long long total = static_cast<long long>(n) * h * w;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -621,6 +632,7 @@ __global__ void __launch_bounds__(256) im2col_first_kernel(const TIN* __restrict
 // below transposes every layer into its dgrad pack [ci_pad][(k-1-kh)*k + (k-1-kw)][co].  71 per-layer launches with
 // scattered 2-byte stores (0.96 ms / step, profiles/r01_train_launches_summary.txt) become two bandwidth-bound ones.
 __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n8) {
+  pdl_entry();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
@@ -632,6 +644,7 @@ __global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* __restric
 // one 32(co) x 32(ci) transpose tile per block iteration; tiles of all layers are numbered consecutively (tile_begin)
 __global__ void __launch_bounds__(256) pack_dgrad_batched_kernel(const y3_pack_item* __restrict__ items, int n_items,
                                                                  const __nv_bfloat16* __restrict__ wbf, int total_tiles) {
+  pdl_entry();
   __shared__ __nv_bfloat16 tile[32][34];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -672,6 +685,7 @@ __global__ void __launch_bounds__(256) pack_dgrad_batched_kernel(const y3_pack_i
 // Thread t owns channel t: consecutive threads read consecutive o of one anchor (coalesced) and write consecutive channels.
 __global__ void __launch_bounds__(256) head_grad_pack_kernel(const float* __restrict__ g, int n, int na, int ny, int nx, int no,
                                                              SliceW dy, float* __restrict__ partial) {
+  pdl_entry();
   const int ch = threadIdx.x, co = na * no;
   const int a = ch / no, o = ch - a * no;
   float acc = 0.f;
@@ -728,6 +742,7 @@ constexpr int kMaxPartialBlocks = 444;  // = 3 resident 256-thread blocks per SM
 __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int c,
                                                                float* __restrict__ sums, float* __restrict__ dbeta_acc,
                                                                float* __restrict__ dgamma_acc) {
+  pdl_entry();
   __shared__ float sh[32][33];
   const int j = blockIdx.x * 32 + threadIdx.x;
   const float a = colsum_32x32(partial, nblk, 2ll * c, j, j < 2 * c, sh);
@@ -754,8 +769,7 @@ extern "C" int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, i
   Y3_REQUIRE(y && partial && c > 0 && c % 8 == 0 && 256 % (c / 8) == 0 && n > 0 && h > 0 && w > 0 && ld % 8 == 0 && coff % 8 == 0,
              "bn_stats: bad arguments (c must be a power of two in [8, 2048])");
   const int nblk = y3_bn_partial_blocks(n, h, w, c);
-  y3::bn_stats_kernel<<<nblk, 256, 2 * 256 * 8 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      Slice{static_cast<const __nv_bfloat16*>(y), ld, coff}, y3::make_rows(n, h, w, c), partial);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_stats_kernel, dim3(nblk), dim3(256), 2 * 256 * 8 * sizeof(float), static_cast<cudaStream_t>(stream), Slice{static_cast<const __nv_bfloat16*>(y), ld, coff}, y3::make_rows(n, h, w, c), partial));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -763,7 +777,7 @@ extern "C" int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, i
 extern "C" int y3_colreduce_f32(const float* partial, int32_t nblk, int32_t width, float* out, int32_t accumulate,
                                 y3_stream_t stream) {
   Y3_REQUIRE(partial && out && nblk > 0 && width > 0, "colreduce: bad arguments");
-  y3::colreduce_kernel<<<(width + 31) / 32, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(partial, nblk, width, out, accumulate);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::colreduce_kernel, dim3((width + 31) / 32), dim3(32, 32), 0, static_cast<cudaStream_t>(stream), partial, nblk, width, out, accumulate));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -772,8 +786,7 @@ extern "C" int y3_bn_finalize(const float* partial, int32_t nblk, const float* g
                               float eps, float momentum, float* scale, float* shift, float* mean, float* rstd,
                               float* running_mean, float* running_var, y3_stream_t stream) {
   Y3_REQUIRE(partial && nblk > 0 && gamma && beta && scale && shift && mean && rstd && c > 0 && count > 0, "bn_finalize: bad arguments");
-  y3::bn_finalize_kernel<<<(c + 31) / 32, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(
-      partial, nblk, gamma, beta, c, count, eps, momentum, scale, shift, mean, rstd, running_mean, running_var);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_finalize_kernel, dim3((c + 31) / 32), dim3(32, 32), 0, static_cast<cudaStream_t>(stream), partial, nblk, gamma, beta, c, count, eps, momentum, scale, shift, mean, rstd, running_mean, running_var));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -791,7 +804,7 @@ extern "C" int y3_bn_act_fwd(const y3_bn_act_desc* d, y3_stream_t stream) {
   a.upsample = d->upsample;
   const long long units = static_cast<long long>(d->n) * d->h * a.g.upr;
   const long long cap = 8ll * y3::num_sms();
-  y3::bn_act_fwd_kernel<<<static_cast<unsigned>(units < cap ? units : cap), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_fwd_kernel, dim3(static_cast<unsigned>(units < cap ? units : cap)), dim3(256), 0, static_cast<cudaStream_t>(stream), a));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -821,19 +834,19 @@ extern "C" int y3_bn_act_bwd(const y3_bn_bwd_desc* d, y3_stream_t stream_) {
   const int nblk = y3_bn_partial_blocks(d->n, d->h, d->w, d->c);
   if (d->phase != 2) {
     if (d->upsample)
-      y3::bn_act_bwd_kernel<false, true><<<nblk, 256, 2 * 256 * 8 * sizeof(float), stream>>>(a);
+      Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_bwd_kernel<false, true>, dim3(nblk), dim3(256), 2 * 256 * 8 * sizeof(float), stream, a));
     else
-      y3::bn_act_bwd_kernel<false, false><<<nblk, 256, 2 * 256 * 8 * sizeof(float), stream>>>(a);
-    y3::bn_bwd_finalize_kernel<<<(2 * d->c + 31) / 32, dim3(32, 32), 0, stream>>>(d->partial, nblk, d->c, d->sums, d->dbeta_acc,
-                                                                                  d->dgamma_acc);
+      Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_bwd_kernel<false, false>, dim3(nblk), dim3(256), 2 * 256 * 8 * sizeof(float), stream, a));
+    Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_bwd_finalize_kernel, dim3((2 * d->c + 31) / 32), dim3(32, 32), 0, stream, d->partial, nblk, d->c, d->sums, d->dbeta_acc,
+                                                                                  d->dgamma_acc));
   }
   if (d->phase != 1) {
     const long long units = static_cast<long long>(d->n) * d->h * a.g.upr;
     const long long cap = 3ll * y3::num_sms();  // one wave at the kernel's 3 resident blocks per SM
     if (d->upsample)
-      y3::bn_act_bwd_kernel<true, true><<<static_cast<unsigned>(units < cap ? units : cap), 256, 0, stream>>>(a);
+      Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_bwd_kernel<true, true>, dim3(static_cast<unsigned>(units < cap ? units : cap)), dim3(256), 0, stream, a));
     else
-      y3::bn_act_bwd_kernel<true, false><<<static_cast<unsigned>(units < cap ? units : cap), 256, 0, stream>>>(a);
+      Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_bwd_kernel<true, false>, dim3(static_cast<unsigned>(units < cap ? units : cap)), dim3(256), 0, stream, a));
   }
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
@@ -842,8 +855,7 @@ extern "C" int y3_bn_act_bwd(const y3_bn_bwd_desc* d, y3_stream_t stream_) {
 extern "C" int y3_f32_to_bf16(const float* src, void* dst, int64_t n, y3_stream_t stream) {
   Y3_REQUIRE(src && dst && n > 0 && n % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
                  (reinterpret_cast<uintptr_t>(dst) & 15) == 0, "f32_to_bf16: n must be a multiple of 8, pointers 16-byte aligned");
-  y3::f32_to_bf16_kernel<<<y3::grid_for(n / 8, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, static_cast<__nv_bfloat16*>(dst), n / 8);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::f32_to_bf16_kernel, dim3(y3::grid_for(n / 8, 256, 16)), dim3(256), 0, static_cast<cudaStream_t>(stream), src, static_cast<__nv_bfloat16*>(dst), n / 8));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -852,8 +864,7 @@ extern "C" int y3_pack_dgrad_batched(const y3_pack_item* items_dev, int32_t n_it
                                      y3_stream_t stream) {
   Y3_REQUIRE(items_dev && wbf && n_items > 0 && total_tiles > 0, "pack_dgrad_batched: bad arguments");
   const int cap = 16 * y3::num_sms();
-  y3::pack_dgrad_batched_kernel<<<total_tiles < cap ? total_tiles : cap, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      items_dev, n_items, static_cast<const __nv_bfloat16*>(wbf), total_tiles);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::pack_dgrad_batched_kernel, dim3(total_tiles < cap ? total_tiles : cap), dim3(256), 0, static_cast<cudaStream_t>(stream), items_dev, n_items, static_cast<const __nv_bfloat16*>(wbf), total_tiles));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -863,8 +874,7 @@ extern "C" int y3_head_grad_pack(const float* g, int32_t n, int32_t na, int32_t 
   Y3_REQUIRE(g && dy && partial && n > 0 && na > 0 && ny > 0 && nx > 0 && no > 0 && na * no <= 256 && dy_ld - dy_coff <= 256,
              "head_grad_pack: bad arguments (na*no <= 256)");
   const int nblk = y3_bn_partial_blocks(n, ny, 0, 0);
-  y3::head_grad_pack_kernel<<<nblk, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      g, n, na, ny, nx, no, SliceW{static_cast<__nv_bfloat16*>(dy), dy_ld, dy_coff}, partial);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::head_grad_pack_kernel, dim3(nblk), dim3(256), 0, static_cast<cudaStream_t>(stream), g, n, na, ny, nx, no, SliceW{static_cast<__nv_bfloat16*>(dy), dy_ld, dy_coff}, partial));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -873,8 +883,7 @@ extern "C" int y3_pack_weights(const float* w, int32_t co, int32_t ci, int32_t k
                                y3_stream_t stream) {
   Y3_REQUIRE(w && (fwd || dgrad) && co > 0 && ci > 0 && (k == 1 || k == 3), "pack_weights: bad arguments");
   const long long total = static_cast<long long>(co) * ci * k * k;
-  y3::pack_weights_kernel<<<y3::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, co, ci, k, static_cast<__nv_bfloat16*>(fwd), static_cast<__nv_bfloat16*>(dgrad));
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::pack_weights_kernel, dim3(y3::grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), w, co, ci, k, static_cast<__nv_bfloat16*>(fwd), static_cast<__nv_bfloat16*>(dgrad)));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -883,9 +892,8 @@ extern "C" int y3_zero_stuff(const void* src, int32_t src_ld, int32_t src_coff, 
                              int32_t n, int32_t ho, int32_t wo, int32_t c, y3_stream_t stream) {
   Y3_REQUIRE(src && dst && c % 8 == 0 && n > 0 && ho > 0 && wo > 0, "zero_stuff: bad arguments");
   const long long total = static_cast<long long>(n) * ho * wo * (c / 8);
-  y3::zero_stuff_kernel<<<y3::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      Slice{static_cast<const __nv_bfloat16*>(src), src_ld, src_coff}, SliceW{static_cast<__nv_bfloat16*>(dst), dst_ld, dst_coff}, n,
-      ho, wo, c / 8);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::zero_stuff_kernel, dim3(y3::grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), Slice{static_cast<const __nv_bfloat16*>(src), src_ld, src_coff}, SliceW{static_cast<__nv_bfloat16*>(dst), dst_ld, dst_coff}, n,
+      ho, wo, c / 8));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -926,7 +934,7 @@ extern "C" int y3_conv_wgrad(const y3_wgrad_desc* d, y3_stream_t stream) {
   chunks = (a.rows + rpc - 1) / rpc;
   a.rows_per_cta = static_cast<int>(rpc);
   const dim3 grid(static_cast<unsigned>(chunks), static_cast<unsigned>(t_co * t_ci), a.taps);
-  y3::wgrad_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::wgrad_kernel, dim3(grid), dim3(128), 0, static_cast<cudaStream_t>(stream), a));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -939,7 +947,7 @@ extern "C" int y3_colsum_f32(const float* g, int32_t ld, int32_t c, int64_t rows
   Y3_REQUIRE(g && out && c > 0 && c <= 256 && rows > 0, "colsum: bad arguments");
   const int rows_per_block = 1024;
   const long long blocks = (rows + rows_per_block - 1) / rows_per_block;
-  y3::colsum_f32_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, ld, c, rows, rows_per_block, out);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::colsum_f32_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), g, ld, c, rows, rows_per_block, out));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -948,9 +956,8 @@ extern "C" int y3_add_nhwc(const void* src, int32_t src_ld, int32_t src_coff, vo
                            int32_t n, int32_t h, int32_t w, int32_t c, int32_t accumulate, y3_stream_t stream) {
   Y3_REQUIRE(src && dst && c % 8 == 0 && n > 0 && h > 0 && w > 0, "add_nhwc: bad arguments");
   const long long total = static_cast<long long>(n) * h * w * (c / 8);
-  y3::add_nhwc_kernel<<<y3::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      Slice{static_cast<const __nv_bfloat16*>(src), src_ld, src_coff}, SliceW{static_cast<__nv_bfloat16*>(dst), dst_ld, dst_coff}, n, h,
-      w, c / 8, accumulate);
+  Y3_CHECK_CUDA(::y3::launch_pdl(y3::add_nhwc_kernel, dim3(y3::grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), Slice{static_cast<const __nv_bfloat16*>(src), src_ld, src_coff}, SliceW{static_cast<__nv_bfloat16*>(dst), dst_ld, dst_coff}, n, h,
+      w, c / 8, accumulate));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }
@@ -962,11 +969,9 @@ extern "C" int y3_im2col_first(const void* in, int32_t in_dtype, float in_div, i
   const long long total = static_cast<long long>(n) * h * w;
   const SliceW o{static_cast<__nv_bfloat16*>(out), out_ld, out_coff};
   if (in_dtype == Y3_IN_U8)
-    y3::im2col_first_kernel<uint8_t><<<y3::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const uint8_t*>(in), in_div, n, h, w, o);
+    Y3_CHECK_CUDA(::y3::launch_pdl(y3::im2col_first_kernel<uint8_t>, dim3(y3::grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const uint8_t*>(in), in_div, n, h, w, o));
   else
-    y3::im2col_first_kernel<float><<<y3::grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const float*>(in), in_div, n, h, w, o);
+    Y3_CHECK_CUDA(::y3::launch_pdl(y3::im2col_first_kernel<float>, dim3(y3::grid_for(total)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const float*>(in), in_div, n, h, w, o));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
 }

@@ -91,6 +91,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // prologue above overlaps the previous kernel's tail (y3_common.cuh)
+  pdl_trigger();
 
   if (k_iters > 0) {
     if (warp == 0) {
@@ -212,8 +214,7 @@ int wgrad_tc_launch(const CUtensorMap& mdy, const CUtensorMap& mx, const WgTcArg
     Y3_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     attr_set = true;
   }
-  kern<<<grid, kWgThreads, smem, stream>>>(mdy, mx, a);
-  Y3_CHECK_CUDA(cudaGetLastError());
+  Y3_CHECK_CUDA(launch_pdl(kern, grid, dim3(kWgThreads), smem, stream, mdy, mx, a));
   return Y3_OK;
 }
 
