@@ -6,11 +6,10 @@ What is kept from the reference surface: ``Model(cfg, ch, nc, a
 ``(z, [p3, p4, p5])`` in eval mode, ``.stride .names .nc .yaml .save .hyp``, ``.model[-1]`` (Detect info:
 ``na nc nl no anchors stride``), ``.state_dict()/.load_state_dict()`` with the reference's parameter names,
 ``.fuse() .eval() .half() .float() .to()`` (no-ops or bookkeeping: BN folding and bf16 packing happen when an engine is
-built).  Training-mode forward is not part of this round's path and raises.
+built).  ``.train()`` switches forward/backward to the training engine (train.py: batch-statistics BatchNorm, saved
+activations, gradients into the flat parameter store).
 """
 from __future__ import annotations
-
-import os
 
 import ctypes as C
 import math
@@ -410,7 +409,6 @@ class Engine:
             return b
 
         op_list: list[_lib.Op] = []
-        op_node: list[int] = []  # graph node that emitted op_list[i] (filled after each node, see below)
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
 
         def emit_conv(x, prefix, c_out, k, s, act, out=None, res=None, upsample=False, out_f32=None):
@@ -510,7 +508,6 @@ class Engine:
                 tens[nd.i] = None  # fused into the producing conv's store
             elif nd.type == "Concat":
                 tens[nd.i] = bufs[nd.i]
-            op_node += [nd.i] * (len(op_list) - len(op_node))
 
         # ---- Detect: 1x1 head convs storing fp32 pixel-major [bs*ny*nx, ld], then ONE launch that transposes them
         #      into the reference's [bs,na,ny,nx,no] logits and decodes z
@@ -544,9 +541,6 @@ class Engine:
         o.decode = dec
         op_list.append(o)
 
-        op_node += [dnode.i] * (len(op_list) - len(op_node))
-        op_list = self._chunk_stacks(nodes, shp, op_list, op_node, n, L)
-
         self.tens = tens
         self.bufs = bufs
         self.n_ops = len(op_list)
@@ -559,67 +553,6 @@ class Engine:
         handle = C.c_void_p()
         _lib.check(L.y3_model_create(arr, len(op_list), C.byref(handle)), "y3_model_create")
         self.handle = handle
-
-    # L2-sized batch chunks for the high-resolution residual stacks ------------------------------------------------------
-    chunk_budget_mb = float(os.environ.get("Y3_CHUNK_MB", "72"))  # working set one chunk may occupy (B200 L2: 126 MB); 0 = off
-
-    def _chunk_stacks(self, nodes, shp, op_list, op_node, n, L):
-        """A stack of Bottlenecks (models/yolov3.yaml:17-24, models/common.py:153-165) is run chunk-major over the batch when
-        its full-batch tensors do not fit the L2: all 2 x n launches of the stack for images [0, c), then [c, 2c), ...  With c
-        chosen so that shortcut, 1x1 output and result of one chunk stay L2-resident, the residual read and the 1x1 outputs
-        stop going through HBM (at bs 32 the 80x80 stack streams 3 x 110 MB per Bottleneck otherwise).  Same kernels,
-        same descriptors — only ``n`` and the base pointers of each launch change, so results are bit-identical."""
-        budget = self.chunk_budget_mb * 1e6
-        if budget <= 0 or n < 2:
-            return op_list
-        groups = []  # (first node, last node, chunk)
-        for b in nodes[:-1]:
-            if b.type != "Bottleneck" or b.n < 2 or not (b.args[2] if len(b.args) > 2 else True):
-                continue  # only stacks with the shortcut add: that read is what a full-batch pass takes from HBM
-            c2, hh, ww = shp[b.i]
-            per_img = (hh + 2) * (ww + 2) * 2 * (2 * c2 + c2 // 2)  # shortcut + result + 1x1 output, live at any time
-            if per_img * n <= budget:
-                continue
-            c = max([d for d in range(2, n) if n % d == 0 and d * per_img <= budget], default=0)
-            # a chunk must still fill the machine (>= 2 waves of 128-row tiles) and be long enough to amortise its launch
-            # (3x3 of >= 25 GFLOP ~ 18 us): at bs 32 this selects the 80x80 stack (c = 8) and leaves 160x160 / 320x320 alone
-            if c == 0 or c * (hh + 2) * (ww + 2) < 2 * 128 * 148 or 2.0 * c * hh * ww * c2 * (c2 // 2) * 9 < 25e9:
-                continue
-            groups.append((b.i, b.i, c))
-        if not groups:
-            return op_list
-        out = []
-        i = 0
-        self.chunks = groups
-        while i < len(op_list):
-            g = next((g for g in groups if g[0] == op_node[i]), None)
-            if g is None:
-                out.append(op_list[i])
-                i += 1
-                continue
-            j = i
-            while j < len(op_list) and g[0] <= op_node[j] <= g[1]:
-                j += 1
-            assert all(o.kind == _lib.OP_CONV for o in op_list[i:j])
-            for i0 in range(0, n, g[2]):
-                out += [self._batch_slice(o, i0, g[2], L) for o in op_list[i:j]]
-            i = j
-        return out
-
-    @staticmethod
-    def _batch_slice(o, i0, cnt, L):
-        q = _lib.Op.from_buffer_copy(o)
-        d = q.conv
-        assert not d.out_f32, "fp32 head outputs are not chunked"
-        up = 2 if d.upsample else 1
-        ho, wo = d.h // d.stride * up, d.w // d.stride * up
-        d.in_ += i0 * (d.h + 2) * (d.w + 2) * d.in_ld * 2
-        d.out += i0 * (ho + 2) * (wo + 2) * d.out_ld * 2
-        if d.res:
-            d.res += i0 * (ho + 2) * (wo + 2) * d.res_ld * 2
-        d.n = cnt
-        assert L.y3_conv_weight_layout(C.byref(d)) == d.weight_layout, "chunking changed the weight layout the kernel expects"
-        return q
 
     def run(self, x: torch.Tensor | None = None):
         """Launch the whole graph on the current stream.  x: [n,ch,h,w] device tensor (fp32 or uint8 as built)."""
