@@ -398,8 +398,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     uint64_t* my_res_bar = res_bar + (kPairSync ? group * 4 + quarter : ew) * 2;
     const int pair_bar = 1 + quarter + 4 * group;  // named barrier of the two warps sharing a lane quarter (N = 64)
     constexpr uint32_t kMyResBytes = kMySlabs * 32u * C::kSlabRowBytes;
-    // accumulator row m of M tile mt -> (valid, image, unpadded output pixel)
-    auto locate = [&](int mt, bool& valid, int& img, int& oy, int& ox) {
+    int iter = 0;
+    int bias_nt = -1;  // N tile whose bias currently sits in s_bias_w
+    const bool silu = p.act == Y3_ACT_SILU;
+    const float bscale = silu ? 0.5f : 1.0f;
+    for (int tile = worker; tile < total_tiles; tile += n_workers, ++iter) {
+      if (groups == 2 && (iter & 1) != group) continue;
+      const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
+      const int li = groups == 2 ? iter >> 1 : iter;  // tiles this group has converted so far
+      const int nt = tile % p.n_tiles;
+      const int mt = PAIR ? (tile / p.n_tiles) * 2 + static_cast<int>(rank) : tile / p.n_tiles;
+      const int n0 = nt * BLOCK_N;
+
+      // ---- which output pixel does accumulator row m belong to?
+      bool valid;
+      int img, oy, ox;  // image, UNPADDED output coordinates
       if (p.mode == 0) {
         const int row = mt * kBlockM + m;
         const int plane = p.hp * p.wp;
@@ -419,62 +432,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         valid = ty < p.th && oy < p.ho && ox < p.wo;
       }
       valid = valid && active && mt < p.m_tiles;  // a pair's second CTA may own a tile past the end
-    };
-    // padded pixel index of that output pixel in the conv-output geometry (where the residual lives and `out` is written)
-    auto conv_row_of = [&](int img, int oy, int ox) -> long long {
-      const int oh = p.mode == 0 ? p.hp - 2 : p.ho, ow = p.mode == 0 ? p.wp - 2 : p.wo;
-      if (p.phase)  // one parity class of a transposed stride-2 conv: (oy, ox) -> (2 oy + a, 2 ox + b) of the 2x grid
-        return (static_cast<long long>(img) * (2 * oh + 2) + 2 * oy + p.ph_a + 1) * (2 * ow + 2) + 2 * ox + p.ph_b + 1;
-      return (static_cast<long long>(img) * (oh + 2) + oy + 1) * (ow + 2) + ox + 1;
-    };
-    // Direct-store epilogue: the residual rows of a WHOLE tile (kChunks x 64 bytes per thread) sit in registers, and chunk c of
-    // the NEXT tile is requested the moment chunk c of this one has been consumed — a full tile of MMA time to arrive.  With a
-    // one-chunk look-ahead the 128->256 3x3 +res layers at 80x80 (shortcut 110 MB at bs 32: HBM, not L2) spent most of their
-    // epilogue waiting on that load (long-scoreboard stalls, profiles/r02_ncu_conv_tc_summary.txt) and ran at 1.02-1.09 PF/s
-    // against 1.40-1.43 for the same layer without the shortcut.
-    // Only the 320-thread kernels (N = 256) have the registers for it; the others keep a one-chunk look-ahead inside the tile.
-    constexpr int kChunks = kColsPerWarp / 32;
-    constexpr bool kDeep = !STAGED && C::kMaxGroups == 1;
-    uint4 rall[STAGED ? 1 : kChunks][4];
-    auto res_row = [&](int tile_) -> const __nv_bfloat16* {  // this thread's residual row of `tile_` (nullptr: none / halo)
-      if (!kDeep || !p.res || tile_ >= total_tiles) return nullptr;
-      const int nt_ = tile_ % p.n_tiles;
-      const int mt_ = PAIR ? (tile_ / p.n_tiles) * 2 + static_cast<int>(rank) : tile_ / p.n_tiles;
-      bool v_;
-      int i_, y_, x_;
-      locate(mt_, v_, i_, y_, x_);
-      return v_ ? p.res + conv_row_of(i_, y_, x_) * p.res_ld + p.res_coff + nt_ * BLOCK_N + c_begin : nullptr;
-    };
-    const int tile_step = groups * n_workers;  // distance between two tiles of this epilogue group
-    if constexpr (kDeep) {
-      const int first_tile = worker + (groups == 2 ? group * n_workers : 0);
-      const int first_n0 = (first_tile % p.n_tiles) * BLOCK_N;
-      const __nv_bfloat16* r0 = res_row(first_tile);
-      if (r0) {
-#pragma unroll
-        for (int ch = 0; ch < kChunks; ++ch)
-          if (first_n0 + c_begin + ch * 32 < p.cout) {  // columns past c_out are never read
-#pragma unroll
-            for (int q = 0; q < 4; ++q) rall[ch][q] = __ldg(reinterpret_cast<const uint4*>(r0 + ch * 32) + q);
-          }
-      }
-    }
-    int iter = 0;
-    int bias_nt = -1;  // N tile whose bias currently sits in s_bias_w
-    const bool silu = p.act == Y3_ACT_SILU;
-    const float bscale = silu ? 0.5f : 1.0f;
-    for (int tile = worker; tile < total_tiles; tile += n_workers, ++iter) {
-      if (groups == 2 && (iter & 1) != group) continue;
-      const uint32_t as = iter & 1, aphase = (iter >> 1) & 1;
-      const int li = groups == 2 ? iter >> 1 : iter;  // tiles this group has converted so far
-      const int nt = tile % p.n_tiles;
-      const int mt = PAIR ? (tile / p.n_tiles) * 2 + static_cast<int>(rank) : tile / p.n_tiles;
-      const int n0 = nt * BLOCK_N;
-
-      // ---- which output pixel does accumulator row m belong to?
-      bool valid;
-      int img, oy, ox;  // image, UNPADDED output coordinates
-      locate(mt, valid, img, oy, ox);
       if (nt != bias_nt) {  // a layer with a single N tile loads its bias once
         if (active)
           for (int c = lane; c < kColsPerWarp; c += 32) s_bias_w[c] = bscale * __ldg(p.bias + n0 + c_begin + c);
@@ -585,8 +542,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
       const int oh = p.mode == 0 ? p.hp - 2 : p.ho;  // conv-output height/width (unpadded)
       const int ow = p.mode == 0 ? p.wp - 2 : p.wo;
-      const long long conv_row = conv_row_of(img, oy, ox);
-      const bool has_res = p.res && valid;
+      long long conv_row = (static_cast<long long>(img) * (oh + 2) + oy + 1) * (ow + 2) + ox + 1;
+      if (p.phase)  // one parity class of a transposed stride-2 conv: (oy, ox) -> (2 oy + a, 2 ox + b) of the 2x grid
+        conv_row = (static_cast<long long>(img) * (2 * oh + 2) + 2 * oy + p.ph_a + 1) * (2 * ow + 2) + 2 * ox + p.ph_b + 1;
+      const __nv_bfloat16* res_ptr = (p.res && valid) ? p.res + conv_row * p.res_ld + p.res_coff + n0 : nullptr;
       __nv_bfloat16* out_ptr = nullptr;
       float* f32_ptr = nullptr;
       long long up_row_stride = 0;
@@ -600,58 +559,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       } else {
         out_ptr = p.out + conv_row * p.out_ld + p.out_coff + n0;
       }
-      const __nv_bfloat16* res_next = res_row(tile + tile_step);  // this thread's residual row in the group's next tile
-      const int res_next_n0 = ((tile + tile_step) % p.n_tiles) * BLOCK_N;
-      const __nv_bfloat16* res_ptr = (!kDeep && has_res) ? p.res + conv_row * p.res_ld + p.res_coff + n0 + c_begin : nullptr;
-      if (res_ptr) {  // first chunk requested before the accumulator wait: its latency hides behind the MMAs
+      // residual of the first chunk is requested before waiting for the accumulator: its latency hides behind the MMAs
+      uint4 rcur[4];
+      if (res_ptr) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) rall[0][q] = __ldg(reinterpret_cast<const uint4*>(res_ptr) + q);
+        for (int q = 0; q < 4; ++q) rcur[q] = __ldg(reinterpret_cast<const uint4*>(res_ptr + c_begin) + q);
       }
 
       mbar_wait(&tfull_bar[as], aphase, p.err, 4, p.poll_ns);  // accumulator complete
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N;
       if (active) {
-#pragma unroll
-        for (int ch = 0; ch < kChunks; ++ch) {
-          const int c = c_begin + ch * 32;
+#pragma unroll 1
+        for (int c = c_begin; c < c_begin + kColsPerWarp; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32b_x32(t_addr + c, v);
-          if constexpr (!kDeep && kChunks > 1) {
-            if (res_ptr && ch + 1 < kChunks) {
+          uint4 rnext[4];
+          const bool more = c + 32 < c_begin + kColsPerWarp;
+          if (res_ptr && more) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) rall[(ch + 1) % kChunks][q] = __ldg(reinterpret_cast<const uint4*>(res_ptr + (ch + 1) * 32) + q);
-            }
+            for (int q = 0; q < 4; ++q) rnext[q] = __ldg(reinterpret_cast<const uint4*>(res_ptr + c + 32) + q);
           }
           tmem_ld_wait();
-          const bool store = valid && (f32_ptr || n0 + c < p.cout);
-          float x[32];
-          if (store) {
+          if (valid && (f32_ptr || n0 + c < p.cout)) {
+            float x[32];
             bias_act(v, s_bias_w + (c - c_begin), x, silu);
-            if (has_res) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint32_t rr[4] = {rall[ch][q].x, rall[ch][q].y, rall[ch][q].z, rall[ch][q].w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float2 f = unpack_bf16x2(rr[e]);
-                  x[q * 8 + e * 2 + 0] += f.x;
-                  x[q * 8 + e * 2 + 1] += f.y;
-                }
-              }
-            }
-          }
-          if (res_next && (res_next_n0 + c - n0) < p.cout) {  // chunk ch of the next tile: its registers are free now
-#pragma unroll
-            for (int q = 0; q < 4; ++q) rall[ch][q] = __ldg(reinterpret_cast<const uint4*>(res_next + ch * 32) + q);
-          }
-          if (store) {
             if (f32_ptr) {
               // fp32 pixel-major store (Detect heads): 128 contiguous bytes per thread and chunk
 #pragma unroll
               for (int q = 0; q < 8; ++q)
                 reinterpret_cast<float4*>(f32_ptr + c)[q] = make_float4(x[q * 4], x[q * 4 + 1], x[q * 4 + 2], x[q * 4 + 3]);
             } else {
+              if (res_ptr) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const uint32_t rr[4] = {rcur[q].x, rcur[q].y, rcur[q].z, rcur[q].w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = unpack_bf16x2(rr[e]);
+                    x[q * 8 + e * 2 + 0] += f.x;
+                    x[q * 8 + e * 2 + 1] += f.y;
+                  }
+                }
+              }
               uint4 o[4];
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -667,6 +617,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 for (int q = 0; q < 4; ++q) dst[q] = o[q];
               }
             }
+          }
+          if (res_ptr && more) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rcur[q] = rnext[q];
           }
         }
       }

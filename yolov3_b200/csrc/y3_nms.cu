@@ -595,8 +595,9 @@ __global__ void __launch_bounds__(1024) nms_compact_kernel(const NmsArgs p) {
 //   K1 candidates (unchanged)           keys (conf bits | ~id), unordered, per image
 //   K2 nms_bucket_kernel   1 CTA/image  max_nms cut (exact radix select, only when count > max_nms), xywh -> xyxy, counting
 //                                       sort of the candidates by class (shared-memory histogram + scan + scatter)
-//   K3 nms_seg_warp_kernel 1 warp/(image,class): rank the <= 512 members by key (counting in shared memory), boxes to
-//                                       registers in that order, greedy suppression (exact division-free IoU), survivors
+//   K3 nms_seg_mask_kernel 1 CTA/(image,class), <= 128 and <= 512 members: rank the members by key (counting in shared memory),
+//                                       suppression matrix (intersection bits by ballot, exact division-free IoU on the
+//                                       intersecting pairs), one warp resolves the greedy order with bit operations, survivors
 //                                       appended to the image's survivor list
 //      nms_seg_block_kernel             segments > 512 members (multi-label at low conf; agnostic / out-of-range images, whose
 //                                       single segment is ranked by all the image's CTAs and finished by the last one)
@@ -777,103 +778,8 @@ __device__ __forceinline__ void append_survivors(const NmsArgs& p, int img, bool
   }
 }
 
-// One WARP per (image, class) segment of up to kSegWarpMax members.  8 register slots (not the 16 of the v1 kernel): at 125
-// registers only 16 warps fit an SM, and 80 classes x 32 images = 17.3 warps per SM ran as two waves (93 us at conf 0.25,
-// gpurun r2j3); larger segments take the block kernel.
-constexpr int kMaskSmall = 128;  // segments up to this size take the suppression-matrix kernel (nms_seg_mask_kernel)
-constexpr int kSegSlots = 8;
-constexpr int kSegWarpMax = 32 * kSegSlots;
-
-__global__ void __launch_bounds__(256, 3) nms_seg_warp_kernel(const NmsArgs p) {
-  pdl_entry();
-  __shared__ unsigned long long s_key[8][kSegWarpMax];
-  __shared__ uint16_t s_ord[8][kSegWarpMax];
-  const unsigned full = 0xffffffffu;
-  const int img = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int seg = blockIdx.x * 8 + warp;
-  if (seg >= p.nc) return;
-  const int* off = p.seg_off + static_cast<size_t>(img) * (p.nc + 1);
-  const int lo = off[seg], hi = off[seg + 1];
-  const int m = hi - lo;
-  if (m <= kMaskSmall || m > kSegWarpMax) return;  // smaller: nms_seg_mask_kernel; larger: nms_seg_block_kernel
-  const unsigned long long* k2 = p.seg_key2 + static_cast<size_t>(img) * kRankCap + lo;
-  const float4* b4 = p.box4 + static_cast<size_t>(img) * kRankCap + lo;
-  const int slots = (m + 31) >> 5;
-  unsigned long long k[kSegSlots];
-#pragma unroll
-  for (int s = 0; s < kSegSlots; ++s) {
-    const int j = s * 32 + lane;
-    k[s] = (s < slots && j < m) ? k2[j] : 0ull;
-    if (s < slots && j < m) s_key[warp][j] = k[s];
-  }
-  __syncwarp();
-  // rank of my members = number of members with a larger key (keys are unique)
-  int r[kSegSlots];
-#pragma unroll
-  for (int s = 0; s < kSegSlots; ++s) r[s] = 0;
-  for (int t = 0; t < m; ++t) {
-    const unsigned long long kt = s_key[warp][t];  // broadcast read
-#pragma unroll
-    for (int s = 0; s < kSegSlots; ++s)
-      if (s < slots) r[s] += (kt > k[s]) ? 1 : 0;
-  }
-#pragma unroll
-  for (int s = 0; s < kSegSlots; ++s) {
-    const int j = s * 32 + lane;
-    if (s < slots && j < m) s_ord[warp][r[s]] = static_cast<uint16_t>(j);
-  }
-  __syncwarp();
-  // boxes in confidence order: rank q -> lane q % 32, slot q / 32
-  float4 b[kSegSlots];
-  uint32_t supp = 0;
-  int mj[kSegSlots];
-#pragma unroll
-  for (int s = 0; s < kSegSlots; ++s) {
-    const int q = s * 32 + lane;
-    b[s] = make_float4(0.f, 0.f, 0.f, 0.f);
-    mj[s] = 0;
-    if (s < slots && q < m) {
-      const int j = s_ord[warp][q];
-      mj[s] = j;
-      int row, cls;
-      key_to_rowcls(s_key[warp][j], p.nc, row, cls);
-      b[s] = offset_box(b4[j], cls, p);
-    } else {
-      supp |= 1u << s;
-    }
-  }
-#pragma unroll
-  for (int s = 0; s < kSegSlots; ++s) {
-    if (s * 32 >= m) break;
-    unsigned dead = __ballot_sync(full, (supp >> s) & 1u);
-    const int cnt = min(32, m - s * 32);
-    for (int l = 0; l < cnt; ++l) {
-      if ((dead >> l) & 1u) continue;
-      float4 bi;
-      bi.x = __shfl_sync(full, b[s].x, l);
-      bi.y = __shfl_sync(full, b[s].y, l);
-      bi.z = __shfl_sync(full, b[s].z, l);
-      bi.w = __shfl_sync(full, b[s].w, l);
-      const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
-      const bool hit = lane > l && !((supp >> s) & 1u) && box_suppresses(bi, ai, b[s], p);
-      if (hit) supp |= 1u << s;
-      dead |= __ballot_sync(full, hit);
-#pragma unroll
-      for (int s2 = s + 1; s2 < kSegSlots; ++s2) {
-        if (s2 * 32 >= m) break;
-        if (!((supp >> s2) & 1u) && box_suppresses(bi, ai, b[s2], p)) supp |= 1u << s2;
-      }
-    }
-  }
-#pragma unroll
-  for (int s = 0; s < kSegSlots; ++s) {
-    if (s * 32 >= m) break;
-    const int q = s * 32 + lane;
-    const bool kept = q < m && !((supp >> s) & 1u);
-    append_survivors(p, img, kept, kept ? s_key[warp][mj[s]] : 0ull, lo + mj[s], lane);
-  }
-}
+constexpr int kMaskSmall = 128;  // segments up to this size: nms_seg_mask_kernel<128, 128> (4 warps, 12 KB of shared memory)
+constexpr int kMaskLarge = 512;  // ... up to this size: nms_seg_mask_kernel<512, 256> (46 KB); larger: nms_seg_block_kernel
 
 // One CTA per (image, class) segment, suppression-matrix form: (1) rank the members by key (counting, keys in shared memory),
 // (2) boxes to shared memory in confidence order, (3) ALL pair tests in parallel — thread (i, w) builds the 32-bit word "which of
@@ -913,18 +819,54 @@ __global__ void __launch_bounds__(THREADS) nms_seg_mask_kernel(const NmsArgs p, 
   }
   __syncthreads();
   const int words = (m + 31) >> 5;
-  for (int item = threadIdx.x; item < m * words; item += THREADS) {
-    const int i = item / words, w = item - i * words;
-    uint32_t bits = 0;
-    const int j0 = w << 5;
-    if (j0 + 31 > i) {  // the word holds some j > i
+  {
+    // (3a) overlap bits: one WARP per (row i, word w): lane = member j = 32 w + lane, one ballot per word.  Only "the boxes
+    // intersect" is decided here (the first two exits of box_suppresses: 8 instructions per pair); ~9 in 10 pairs of one class
+    // leave at this point, and every lane of the warp leaves with them — a per-thread loop over the 32 pairs of a word ran the
+    // full exact test (division-free IoU in double) on every pair as soon as one lane needed it.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kWarps = THREADS / 32;
+    int i = warp / words, w = warp - i * words;
+    const int di = kWarps / words, dw = kWarps - di * words;
+    for (; i < m; i += di, w += dw) {
+      if (w >= words) {
+        w -= words;
+        if (++i >= m) break;
+      }
+      uint32_t bits = 0;
+      if ((w << 5) + 31 > i) {  // the word holds some j > i
+        const int j = (w << 5) + lane;
+        const float4 bi = s_box[i];
+        const float4 bj = s_box[j < m ? j : i];
+        const float ww = fmaxf(0.0f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
+        const float hh = fmaxf(0.0f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
+        bits = __ballot_sync(0xffffffffu, j > i && j < m && !(ww == 0.0f) && !(hh == 0.0f));  // NaN: not an exit, as in box_suppresses
+      }
+      if (lane == 0) s_mask[i * W + w] = bits;
+    }
+  }
+  __syncthreads();
+  {
+    // (3b) the exact test on the intersecting pairs only: thread = one mask word, loop over its set bits
+    int i = threadIdx.x / words, w = threadIdx.x - i * words;
+    const int di = THREADS / words, dw = THREADS - di * words;
+    for (; i < m; i += di, w += dw) {
+      if (w >= words) {
+        w -= words;
+        if (++i >= m) break;
+      }
+      uint32_t bits = s_mask[i * W + w];
+      if (!bits) continue;
       const float4 bi = s_box[i];
       const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
-      const int jb = max(j0, i + 1), je = min(j0 + 32, m);
-      for (int j = jb; j < je; ++j)
-        if (box_suppresses(bi, ai, s_box[j], p)) bits |= 1u << (j & 31);
+      uint32_t keep = 0;
+      while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        if (box_suppresses(bi, ai, s_box[(w << 5) + b], p)) keep |= 1u << b;
+      }
+      s_mask[i * W + w] = keep;
     }
-    s_mask[i * W + w] = bits;
   }
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -962,7 +904,7 @@ int launch_seg_mask(const NmsArgs& a, int m_lo, cudaStream_t stream) {
 }
 
 
-// Segments with more than kSegWarpMax members.  Class segments: one CTA ranks its members (keys tiled through shared memory) and runs
+// Segments with more than kMaskLarge members.  Class segments: one CTA ranks its members (keys tiled through shared memory) and runs
 // the greedy pass.  Single-segment images (agnostic, or boxes outside the class-offset bound): every CTA of the image ranks a
 // share of the members; the last one to finish (atomic ticket, no waiting) runs the greedy pass over the whole segment.
 constexpr int kRankTile = 1024;
@@ -978,7 +920,7 @@ __global__ void __launch_bounds__(256) nms_seg_block_kernel(const NmsArgs p) {
   const bool single = p.flags[img] & 1;
   const int lo = single ? 0 : off[seg], hi = single ? off[p.nc] : off[seg + 1];
   const int m = hi - lo;
-  if (m <= kSegWarpMax) return;  // empty, or done by the matrix / warp kernels (a single segment sits in class slot 0 there)
+  if (m <= kMaskLarge) return;  // empty, or done by the matrix kernels (a single segment sits in class slot 0 there)
   const unsigned long long* k2 = p.seg_key2 + static_cast<size_t>(img) * kRankCap + lo;
   const float4* b4 = p.box4 + static_cast<size_t>(img) * kRankCap + lo;
   uint16_t* ord = p.ord + static_cast<size_t>(img) * kRankCap + lo;
@@ -1260,11 +1202,12 @@ extern "C" int y3_nms_batched(const float* pred, const y3_nms_params* q, void* w
   }
   if (!v1) {
     Y3_CHECK_CUDA(::y3::launch_pdl(nms_bucket_kernel, dim3(a.bs), dim3(kBucketThreads), 0, stream, a));
-    // measured (gpurun r2j5 / r2j6, 32 x 25200 rows): <= 128 members per class (conf 0.25: ~65) -> suppression matrix, 37 us vs
-    // 50 us for the warp kernel; ~215 per class (conf 0.001) -> warp kernel 228 us vs 448 us for a 768-wide matrix kernel
-    // (94 KB of shared memory: 2 CTAs per SM); ~375 (multi-label) -> per-keeper block kernel 782 us vs 1178 us
+    // measured (gpurun r2j5 / r2j6, 32 x 25200 rows) with the first matrix kernel (one thread per mask word, full test on all 32
+    // pairs): <= 128 members per class (conf 0.25: ~65) 37 us vs 50 us for a warp-per-segment kernel with the boxes in registers;
+    // ~215 per class (conf 0.001) 448 us (768-wide) vs 228 us; ~375 (multi-label) 1178 us vs 782 us for the per-keeper block
+    // kernel.  The two-phase pair test (ballot of intersections, exact test on those) is what made the matrix form win there too.
     if (int rc = launch_seg_mask<kMaskSmall, 128>(a, 0, stream)) return rc;
-    Y3_CHECK_CUDA(::y3::launch_pdl(nms_seg_warp_kernel, dim3((a.nc + 7) / 8, a.bs), dim3(256), 0, stream, a));
+    if (int rc = launch_seg_mask<kMaskLarge, 256>(a, kMaskSmall, stream)) return rc;
     Y3_CHECK_CUDA(::y3::launch_pdl(nms_seg_block_kernel, dim3(a.nc, a.bs), dim3(256), 0, stream, a));
     {
       constexpr int kOutSmem = kOutSortMax * (sizeof(unsigned long long) + sizeof(uint16_t));

@@ -88,14 +88,15 @@ __device__ __forceinline__ void block_reduce_store(float (&s)[8], float (&q)[8],
 
 // ---------------------------------------------------------------------------------------------- bn_stats
 // grid: nblk blocks of 256 threads; block b walks rows b, b+nblk, ...; partial[b] = [sum(c) | sumsq(c)]
-__global__ void __launch_bounds__(256, 3) bn_stats_kernel(Slice y, Rows g, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256, 4) bn_stats_kernel(Slice y, Rows g, float* __restrict__ partial) {
   pdl_entry();
   extern __shared__ float sh[];  // [2][256][8]
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int items = g.w * g.c8, units = g.n * g.h * g.upr;
-  auto issue = [&](int u, uint4 (&v)[kUnitIters]) {
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
     const int r = u / g.upr, e0 = (u - r * g.upr) * (256 * kUnitIters) + threadIdx.x;
     const __nv_bfloat16* base = y.p + row_base(g, r) * y.ld + y.coff;
+    uint4 v[kUnitIters];
 #pragma unroll
     for (int k = 0; k < kUnitIters; ++k) {
       const int e = e0 + k * 256;
@@ -103,15 +104,6 @@ __global__ void __launch_bounds__(256, 3) bn_stats_kernel(Slice y, Rows g, float
       split_item(g, e, x, cg);
       v[k] = e < items ? __ldg(reinterpret_cast<const uint4*>(base + static_cast<long long>(x) * y.ld + cg * 8)) : make_uint4(0, 0, 0, 0);
     }
-  };
-  // one unit of look-ahead: the loads of unit u + grid are in flight while unit u is summed (the blocks of a wave otherwise
-  // all issue, all wait, all add in lock-step and HBM idles during the arithmetic)
-  uint4 v[kUnitIters], vn[kUnitIters];
-  int u = blockIdx.x;
-  if (u < units) issue(u, v);
-  for (; u < units; u += gridDim.x) {
-    const bool more = u + static_cast<int>(gridDim.x) < units;
-    if (more) issue(u + gridDim.x, vn);
 #pragma unroll
     for (int k = 0; k < kUnitIters; ++k) {
       float f[8];
@@ -121,10 +113,6 @@ __global__ void __launch_bounds__(256, 3) bn_stats_kernel(Slice y, Rows g, float
         s[i] += f[i];
         q[i] = fmaf(f[i], f[i], q[i]);
       }
-    }
-    if (more) {
-#pragma unroll
-      for (int k = 0; k < kUnitIters; ++k) v[k] = vn[k];
     }
   }
   block_reduce_store(s, q, g.c8, sh, partial + static_cast<long long>(blockIdx.x) * 2 * g.c8 * 8, g.c8 * 8);
@@ -136,9 +124,9 @@ __global__ void __launch_bounds__(256, 3) bn_stats_kernel(Slice y, Rows g, float
 // 37 us per BatchNorm layer, 2.7 ms of a 17 ms step (gpurun r2j2 launch list).
 __device__ __forceinline__ float colsum_32x32(const float* __restrict__ partial, int nblk, long long pitch, int col, bool valid,
                                               float (*sh)[33]) {
-  // all of this lane's rows are requested before the first add (kMaxPartialBlocks / 32 <= 10 independent loads in flight): as a
-  // load-add loop the L2 round trips serialised and every BatchNorm finalize cost ~4 us per column sum (gpurun r2j4)
-  constexpr int kMaxRowsPerLane = 10;
+  // all of this lane's rows are requested before the first add (kMaxPartialBlocks / 32 <= 14 independent loads in flight): as a
+  // load-add loop the 14 L2 round trips serialised and every BatchNorm finalize cost ~4 us per column sum (gpurun r2j4)
+  constexpr int kMaxRowsPerLane = 14;
   float v[kMaxRowsPerLane];
 #pragma unroll
   for (int i = 0; i < kMaxRowsPerLane; ++i) {
@@ -308,7 +296,7 @@ __device__ __forceinline__ float silu_grad(float z) {
 }
 
 template <bool APPLY, bool UPS>
-__global__ void __launch_bounds__(256, 2) bn_act_bwd_kernel(const BnBwdArgs p) {
+__global__ void __launch_bounds__(256, UPS ? 2 : 3) bn_act_bwd_kernel(const BnBwdArgs p) {
   pdl_entry();
   // block = 256 threads; thread t keeps channel group t % c8 for the whole kernel (256 % c8 == 0)
   extern __shared__ float sh[];
@@ -332,12 +320,14 @@ __global__ void __launch_bounds__(256, 2) bn_act_bwd_kernel(const BnBwdArgs p) {
       c3[k] = rs;
     }
   }
-  // raw 16-byte vectors stay packed until they are consumed (registers: the reduction pass keeps 48 per-channel values);
-  // only the 2x-upsample variant (2 layers) sums its four da replicas right away
-  auto issue = [&](int u, uint4 (&vy)[kUnitIters], uint4 (&vd)[kUnitIters], float (&du)[UPS ? kUnitIters : 1][8]) {
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
     const int r = u / g.upr, e0 = (u - r * g.upr) * (256 * kUnitIters) + threadIdx.x;
     const long long rb = row_base(g, r);
     const long long ub = p.upsample ? row_base(g, r, 2) : rb;
+    // raw 16-byte vectors stay packed until they are consumed (registers: the reduction pass keeps 48 per-channel values);
+    // only the 2x-upsample variant (2 layers) sums its four da replicas right away
+    uint4 vy[kUnitIters], vd[kUnitIters];
+    float du[UPS ? kUnitIters : 1][8];
 #pragma unroll
     for (int k = 0; k < kUnitIters; ++k) {
       const int e = e0 + k * 256;
@@ -355,19 +345,6 @@ __global__ void __launch_bounds__(256, 2) bn_act_bwd_kernel(const BnBwdArgs p) {
           vd[k] = __ldg(reinterpret_cast<const uint4*>(p.da.p + (rb + x) * p.da.ld + p.da.coff + cg * 8));
       }
     }
-  };
-  uint4 vy[kUnitIters], vd[kUnitIters], ny[kUnitIters], nd[kUnitIters];
-  float du[UPS ? kUnitIters : 1][8];
-  int u = blockIdx.x;
-  if (!UPS && u < units) issue(u, vy, vd, du);
-  for (; u < units; u += gridDim.x) {
-    // one unit of look-ahead (not for the two upsample layers, whose four-replica sums are consumed at once): the next unit's
-    // 2 x kUnitIters loads are in flight while this one goes through the MUFU-heavy arithmetic
-    const bool more = !UPS && u + static_cast<int>(gridDim.x) < units;
-    if (UPS) issue(u, vy, vd, du);
-    if (more) issue(u + gridDim.x, ny, nd, du);
-    const int r = u / g.upr, e0 = (u - r * g.upr) * (256 * kUnitIters) + threadIdx.x;
-    const long long rb = row_base(g, r);
 #pragma unroll
     for (int k = 0; k < kUnitIters; ++k) {
       const int e = e0 + k * 256;
@@ -393,13 +370,6 @@ __global__ void __launch_bounds__(256, 2) bn_act_bwd_kernel(const BnBwdArgs p) {
         }
       }
       if (APPLY && e < items) *reinterpret_cast<uint4*>(p.dy.p + (rb + x) * p.dy.ld + p.dy.coff + cg * 8) = pack8(o);
-    }
-    if (more) {
-#pragma unroll
-      for (int k = 0; k < kUnitIters; ++k) {
-        vy[k] = ny[k];
-        vd[k] = nd[k];
-      }
     }
   }
   if (!APPLY)
@@ -766,7 +736,7 @@ Rows make_rows(int n, int h, int w, int c) {
   g.upr = (w * g.c8 + 256 * kUnitIters - 1) / (256 * kUnitIters);
   return g;
 }
-constexpr int kMaxPartialBlocks = 296;  // = 2 resident 256-thread blocks per SM x 148 SMs: exactly one wave of the reduction kernels
+constexpr int kMaxPartialBlocks = 444;  // = 3 resident 256-thread blocks per SM x 148 SMs: exactly one wave of the reduction kernels
                                         // (592 ran 1.33 waves: the tail block set doubled the small layers' time); fixed: sizes stay device-independent
 
 __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __restrict__ partial, int nblk, int c,
@@ -872,7 +842,7 @@ extern "C" int y3_bn_act_bwd(const y3_bn_bwd_desc* d, y3_stream_t stream_) {
   }
   if (d->phase != 1) {
     const long long units = static_cast<long long>(d->n) * d->h * a.g.upr;
-    const long long cap = 2ll * y3::num_sms();  // one wave at the kernel's 2 resident blocks per SM
+    const long long cap = 3ll * y3::num_sms();  // one wave at the kernel's 3 resident blocks per SM
     if (d->upsample)
       Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_bwd_kernel<true, true>, dim3(static_cast<unsigned>(units < cap ? units : cap)), dim3(256), 0, stream, a));
     else
