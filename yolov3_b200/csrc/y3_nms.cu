@@ -40,6 +40,7 @@ struct NmsArgs {
   int use_mask;
   // workspace
   unsigned long long* keys;  // [bs, cap]
+  float4* cand_box;          // [bs, cap] (cx, cy, w, h) of the candidate's row, written beside its key (v2: K2 reads no pred row)
   int* count;                // [bs] candidates found (may exceed cap)
   int* flags;                // [bs] bit0: needs single-segment path; bit1: has a class segment too long for one warp
   float* det;                // [bs, kRankCap, 6]
@@ -180,10 +181,13 @@ __global__ void __launch_bounds__(32 * kCandWarps) nms_candidates_kernel(const N
   slot0 = __shfl_sync(full, slot0, 0);
   const int my_slot = slot0 + incl - my_cnt;
   unsigned long long* keys = p.keys + static_cast<size_t>(img) * p.cap;
+  float4* cbox = p.cand_box + static_cast<size_t>(img) * p.cap;
   if (!p.multi_label) {
     if (my_cnt && my_slot < p.cap) {
       const uint32_t id = static_cast<uint32_t>(my_row) * p.nc + my_c;
       keys[my_slot] = (static_cast<unsigned long long>(__float_as_uint(my_best)) << 32) | (0xFFFFFFFFu - id);
+      const float* x = base + static_cast<size_t>(my_row) * p.no;  // the row was just read by the warp: L1 / L2 hits
+      cbox[my_slot] = make_float4(__ldg(x), __ldg(x + 1), __ldg(x + 2), __ldg(x + 3));
     }
     return;
   }
@@ -192,6 +196,8 @@ __global__ void __launch_bounds__(32 * kCandWarps) nms_candidates_kernel(const N
     const float obj = __shfl_sync(full, my_obj, r);
     int slot = __shfl_sync(full, my_slot, r);
     const float* x = base + static_cast<size_t>(row0 + r) * p.no + 5;
+    const float xv = lane < 4 ? __ldg(x - 5 + lane) : 0.f;
+    const float4 rbox = make_float4(__shfl_sync(full, xv, 0), __shfl_sync(full, xv, 1), __shfl_sync(full, xv, 2), __shfl_sync(full, xv, 3));
     for (int c0 = 0; c0 < p.nc; c0 += 32) {
       const int c = c0 + lane;
       bool ok = false;
@@ -205,6 +211,7 @@ __global__ void __launch_bounds__(32 * kCandWarps) nms_candidates_kernel(const N
       if (ok && at < p.cap) {
         const uint32_t id = static_cast<uint32_t>(row0 + r) * p.nc + c;
         keys[at] = (static_cast<unsigned long long>(__float_as_uint(conf)) << 32) | (0xFFFFFFFFu - id);
+        cbox[at] = rbox;
       }
       slot += __popc(b);
     }
@@ -690,19 +697,28 @@ __global__ void __launch_bounds__(kBucketThreads) nms_bucket_kernel(const NmsArg
   }
   __syncthreads();
   const float lim = p.max_wh * 0.5f;
-  const float* base = p.pred + static_cast<size_t>(img) * p.n_rows * p.no;
+  const float4* cb = p.cand_box + static_cast<size_t>(img) * p.cap;
+  constexpr int kIlp = 4;  // candidates per thread and iteration: their loads are issued together (one CTA per image: latency-bound)
   // pass A: class histogram + "class-split is exact" check (offset boxes of different classes cannot intersect)
-  for (int i = threadIdx.x; i < c; i += blockDim.x) {
-    const unsigned long long key = keys[i];
-    if (key < thr) continue;
-    int row, cls;
-    key_to_rowcls(key, p.nc, row, cls);
-    const float* x = base + static_cast<size_t>(row) * p.no;
-    const float cx = __ldg(x), w = __ldg(x + 2);
-    const float hw = __fdiv_rn(w, 2.0f);
-    const float x1 = __fsub_rn(cx, hw), x2 = __fadd_rn(cx, hw);
-    if (!((x1 > -lim) && (x2 < lim) && (x1 <= x2))) s_outside = 1;
-    atomicAdd(&s_hist[cls], 1);
+  for (int i0 = threadIdx.x; i0 < c; i0 += kIlp * blockDim.x) {
+    unsigned long long kq[kIlp];
+    float4 bq[kIlp];
+#pragma unroll
+    for (int q = 0; q < kIlp; ++q) {
+      const int i = i0 + q * blockDim.x;
+      kq[q] = i < c ? keys[i] : 0ull;
+      bq[q] = i < c ? cb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < kIlp; ++q) {
+      if (i0 + q * static_cast<int>(blockDim.x) >= c || kq[q] < thr) continue;
+      int row, cls;
+      key_to_rowcls(kq[q], p.nc, row, cls);
+      const float hw = __fdiv_rn(bq[q].z, 2.0f);
+      const float x1 = __fsub_rn(bq[q].x, hw), x2 = __fadd_rn(bq[q].x, hw);
+      if (!((x1 > -lim) && (x2 < lim) && (x1 <= x2))) s_outside = 1;
+      atomicAdd(&s_hist[cls], 1);
+    }
   }
   __syncthreads();
   const bool single = p.agnostic || s_outside;
@@ -744,18 +760,26 @@ __global__ void __launch_bounds__(kBucketThreads) nms_bucket_kernel(const NmsArg
   // pass B: scatter (order inside a segment is arbitrary: the segment kernels rank by key)
   unsigned long long* k2 = p.seg_key2 + static_cast<size_t>(img) * kRankCap;
   float4* b4 = p.box4 + static_cast<size_t>(img) * kRankCap;
-  for (int i = threadIdx.x; i < c; i += blockDim.x) {
-    const unsigned long long key = keys[i];
-    if (key < thr) continue;
-    int row, cls;
-    key_to_rowcls(key, p.nc, row, cls);
-    const int seg = single ? 0 : cls;
-    const int pos = s_hist[seg] + atomicAdd(&s_cur[seg], 1);
-    const float* x = base + static_cast<size_t>(row) * p.no;
-    const float cx = __ldg(x), cy = __ldg(x + 1), w = __ldg(x + 2), h = __ldg(x + 3);
-    const float hw = __fdiv_rn(w, 2.0f), hh = __fdiv_rn(h, 2.0f);
-    k2[pos] = key;
-    b4[pos] = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+  for (int i0 = threadIdx.x; i0 < c; i0 += kIlp * blockDim.x) {
+    unsigned long long kq[kIlp];
+    float4 bq[kIlp];
+#pragma unroll
+    for (int q = 0; q < kIlp; ++q) {
+      const int i = i0 + q * blockDim.x;
+      kq[q] = i < c ? keys[i] : 0ull;
+      bq[q] = i < c ? cb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < kIlp; ++q) {
+      if (i0 + q * static_cast<int>(blockDim.x) >= c || kq[q] < thr) continue;
+      int row, cls;
+      key_to_rowcls(kq[q], p.nc, row, cls);
+      const int seg = single ? 0 : cls;
+      const int pos = s_hist[seg] + atomicAdd(&s_cur[seg], 1);
+      const float hw = __fdiv_rn(bq[q].z, 2.0f), hh = __fdiv_rn(bq[q].w, 2.0f);
+      k2[pos] = kq[q];
+      b4[pos] = make_float4(__fsub_rn(bq[q].x, hw), __fsub_rn(bq[q].y, hh), __fadd_rn(bq[q].x, hw), __fadd_rn(bq[q].y, hh));
+    }
   }
 }
 
@@ -819,30 +843,40 @@ __global__ void __launch_bounds__(THREADS) nms_seg_mask_kernel(const NmsArgs p, 
   }
   __syncthreads();
   const int words = (m + 31) >> 5;
+  // (3a) intersection bits.  Only "the boxes may intersect" is decided here — two comparisons per axis, a superset of the
+  // pairs that pass the first two exits of box_suppresses (NaN coordinates compare false and stay in) — and ~9 in 10 pairs of
+  // one class leave at this point, every lane of the warp with them; a per-thread loop over the 32 pairs of a word ran the full
+  // exact test (division-free IoU in double) on every pair as soon as one lane needed it.
+  // Work = the upper triangle, word column by word column: lane = member j = 32 w + lane (its box stays in registers), rows
+  // i < min(m, 32 w + 31), one ballot per (i, w); the flattened (w, i) list is cut into equal ranges, one per warp.
+  for (int t = threadIdx.x; t < m * W; t += THREADS) s_mask[t] = 0u;  // rows below the diagonal / words past `words` stay zero
+  __syncthreads();
   {
-    // (3a) overlap bits: one WARP per (row i, word w): lane = member j = 32 w + lane, one ballot per word.  Only "the boxes
-    // intersect" is decided here (the first two exits of box_suppresses: 8 instructions per pair); ~9 in 10 pairs of one class
-    // leave at this point, and every lane of the warp leaves with them — a per-thread loop over the 32 pairs of a word ran the
-    // full exact test (division-free IoU in double) on every pair as soon as one lane needed it.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kWarps = THREADS / 32;
-    int i = warp / words, w = warp - i * words;
-    const int di = kWarps / words, dw = kWarps - di * words;
-    for (; i < m; i += di, w += dw) {
-      if (w >= words) {
-        w -= words;
-        if (++i >= m) break;
+    auto rows_of = [&](int w) { return min(m, (w << 5) + 31); };
+    int total = 0;
+    for (int w = 0; w < words; ++w) total += rows_of(w);
+    const int per = (total + kWarps - 1) / kWarps;
+    int t = warp * per;
+    const int t_end = min(total, t + per);
+    int w = 0, acc = 0;
+    while (w < words && t >= acc + rows_of(w)) acc += rows_of(w++);
+    int i = t - acc;
+    const float inf = __int_as_float(0x7f800000);
+    while (t < t_end) {
+      const int j = (w << 5) + lane;
+      const float4 bj = j < m ? s_box[j] : make_float4(inf, inf, inf, inf);  // x1 = +inf: intersects nothing
+      const int i_end = min(rows_of(w), i + (t_end - t));
+      t += i_end - i;
+      for (; i < i_end; ++i) {
+        const float4 bi = s_box[i];  // broadcast
+        uint32_t bits = __ballot_sync(0xffffffffu, j < m && !(bi.z <= bj.x) && !(bj.z <= bi.x) && !(bi.w <= bj.y) && !(bj.w <= bi.y));
+        if ((i >> 5) == w) bits &= ~((2u << (i & 31)) - 1u);  // diagonal word: only j > i
+        if (lane == 0) s_mask[i * W + w] = bits;
       }
-      uint32_t bits = 0;
-      if ((w << 5) + 31 > i) {  // the word holds some j > i
-        const int j = (w << 5) + lane;
-        const float4 bi = s_box[i];
-        const float4 bj = s_box[j < m ? j : i];
-        const float ww = fmaxf(0.0f, __fsub_rn(fminf(bi.z, bj.z), fmaxf(bi.x, bj.x)));
-        const float hh = fmaxf(0.0f, __fsub_rn(fminf(bi.w, bj.w), fmaxf(bi.y, bj.y)));
-        bits = __ballot_sync(0xffffffffu, j > i && j < m && !(ww == 0.0f) && !(hh == 0.0f));  // NaN: not an exit, as in box_suppresses
-      }
-      if (lane == 0) s_mask[i * W + w] = bits;
+      ++w;
+      i = 0;
     }
   }
   __syncthreads();
@@ -1106,6 +1140,7 @@ extern "C" int64_t y3_nms_workspace_bytes(int32_t bs, int32_t cap) {
   b += y3::align_up(sizeof(unsigned long long) * size_t(bs) * y3::kRankCap, 256);
   b += y3::align_up(sizeof(int) * size_t(bs) * y3::kRankCap, 256);
   b += y3::align_up(sizeof(uint16_t) * size_t(bs) * y3::kRankCap, 256);
+  b += y3::align_up(sizeof(float4) * size_t(bs) * cap, 256);  // cand_box
   return static_cast<int64_t>(b);
 }
 
@@ -1187,6 +1222,8 @@ extern "C" int y3_nms_batched(const float* pred, const y3_nms_params* q, void* w
   a.surv_pos = reinterpret_cast<int*>(w);
   w += align_up(sizeof(int) * size_t(a.bs) * kRankCap, 256);
   a.ord = reinterpret_cast<uint16_t*>(w);
+  w += align_up(sizeof(uint16_t) * size_t(a.bs) * kRankCap, 256);
+  a.cand_box = reinterpret_cast<float4*>(w);
   a.out = out;
   a.out_src = out_src;
   a.out_count = out_count;
