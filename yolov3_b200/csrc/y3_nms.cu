@@ -143,17 +143,16 @@ __global__ void __launch_bounds__(32 * kCandWarps) nms_candidates_kernel(const N
           }
         }
       }
+      // warp arg-max with two redux.sync per row (value as an order-preserving unsigned key, then the smallest class among the
+      // lanes that hold it) instead of a 5-step butterfly of (value, class) shuffle pairs: at conf 0.001 every row comes through
+      // here and the 10 shuffles per row were a third of the kernel (one warp shuffle per clock and SM)
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int q = 0; q < kRows; ++q) {
-          const float ov = __shfl_xor_sync(full, bv[q], o);
-          const int oc = __shfl_xor_sync(full, bc[q], o);
-          if (ov > bv[q] || (ov == bv[q] && oc < bc[q])) {
-            bv[q] = ov;
-            bc[q] = oc;
-          }
-        }
+      for (int q = 0; q < kRows; ++q) {
+        uint32_t u = __float_as_uint(bv[q] + 0.0f);  // -0 -> +0: equal as floats, equal as keys
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        const uint32_t umax = __reduce_max_sync(full, u);
+        bc[q] = __reduce_min_sync(full, u == umax ? bc[q] : 0x7fffffff);  // first maximum (lowest class) wins, like torch.max
+        bv[q] = __uint_as_float((umax & 0x80000000u) ? (umax & 0x7fffffffu) : ~umax);
       }
 #pragma unroll
       for (int q = 0; q < kRows; ++q) {
@@ -820,10 +819,14 @@ __global__ void __launch_bounds__(THREADS) nms_seg_mask_kernel(const NmsArgs p, 
   float4* s_box = reinterpret_cast<float4*>(s_key + MAXM);             // [MAXM] in confidence order
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_box + MAXM);        // [MAXM][W]
   uint16_t* s_ord = reinterpret_cast<uint16_t*>(s_mask + MAXM * W);    // [MAXM] rank -> member
+  constexpr int kList = MAXM * 8;                                      // intersecting pairs tested from a compact list
+  uint32_t* s_list = reinterpret_cast<uint32_t*>(s_ord + MAXM);        // [kList] (i << 16 | j)
+  __shared__ int s_pairs;
   const int img = blockIdx.y, seg = blockIdx.x;
   const int* off = p.seg_off + static_cast<size_t>(img) * (p.nc + 1);
   const int lo = off[seg], m = off[seg + 1] - lo;
   if (m <= m_lo || m > MAXM) return;  // other instantiations / the serial block kernel own the other sizes
+  if (threadIdx.x == 0) s_pairs = 0;
   const unsigned long long* k2 = p.seg_key2 + static_cast<size_t>(img) * kRankCap + lo;
   const float4* b4 = p.box4 + static_cast<size_t>(img) * kRankCap + lo;
   for (int j = threadIdx.x; j < m; j += THREADS) s_key[j] = k2[j];
@@ -881,7 +884,11 @@ __global__ void __launch_bounds__(THREADS) nms_seg_mask_kernel(const NmsArgs p, 
   }
   __syncthreads();
   {
-    // (3b) the exact test on the intersecting pairs only: thread = one mask word, loop over its set bits
+    // (3b) the exact test on the intersecting pairs only.  The set bits are first compacted into a list of (i, j) pairs — one
+    // shared-memory atomic per non-empty word — and the list is then tested one pair per thread: every lane of a warp runs the
+    // long path (~40 instructions, double multiply) on a pair that needs it.  Looping over the bits of its own word, a thread
+    // dragged its warp through max-popcount-of-32-words rounds (~8 for ~3 useful ones).  A word that does not fit the list any
+    // more is tested in place by its owner (same result, slower).
     int i = threadIdx.x / words, w = threadIdx.x - i * words;
     const int di = THREADS / words, dw = THREADS - di * words;
     for (; i < m; i += di, w += dw) {
@@ -889,17 +896,40 @@ __global__ void __launch_bounds__(THREADS) nms_seg_mask_kernel(const NmsArgs p, 
         w -= words;
         if (++i >= m) break;
       }
+      if ((w << 5) + 31 <= i) continue;  // below the diagonal: zero
       uint32_t bits = s_mask[i * W + w];
       if (!bits) continue;
-      const float4 bi = s_box[i];
-      const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
-      uint32_t keep = 0;
-      while (bits) {
-        const int b = __ffs(bits) - 1;
-        bits &= bits - 1;
-        if (box_suppresses(bi, ai, s_box[(w << 5) + b], p)) keep |= 1u << b;
+      const int at = atomicAdd(&s_pairs, __popc(bits));
+      if (at + __popc(bits) <= kList) {
+        s_mask[i * W + w] = 0u;  // the hits come back through atomicOr below
+        int k = at;
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          s_list[k++] = (static_cast<uint32_t>(i) << 16) | static_cast<uint32_t>((w << 5) + b);
+        }
+      } else {
+        for (int k = at; k < kList; ++k) s_list[k] = 0xFFFFFFFFu;  // reserved, not used (at most one word straddles the end)
+        const float4 bi = s_box[i];
+        const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+        uint32_t keep = 0;
+        while (bits) {
+          const int b = __ffs(bits) - 1;
+          bits &= bits - 1;
+          if (box_suppresses(bi, ai, s_box[(w << 5) + b], p)) keep |= 1u << b;
+        }
+        s_mask[i * W + w] = keep;
       }
-      s_mask[i * W + w] = keep;
+    }
+    __syncthreads();
+    const int n_pairs = min(s_pairs, kList);
+    for (int k = threadIdx.x; k < n_pairs; k += THREADS) {
+      const uint32_t e = s_list[k];
+      if (e == 0xFFFFFFFFu) continue;  // slot reserved by a word that went the in-place way
+      const int pi = static_cast<int>(e >> 16), pj = static_cast<int>(e & 0xFFFFu);
+      const float4 bi = s_box[pi];
+      const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
+      if (box_suppresses(bi, ai, s_box[pj], p)) atomicOr(&s_mask[pi * W + (pj >> 5)], 1u << (pj & 31));
     }
   }
   __syncthreads();
@@ -925,7 +955,7 @@ __global__ void __launch_bounds__(THREADS) nms_seg_mask_kernel(const NmsArgs p, 
 template <int MAXM, int THREADS>
 int launch_seg_mask(const NmsArgs& a, int m_lo, cudaStream_t stream) {
   constexpr int W = MAXM / 32;
-  constexpr int kSmem = MAXM * (8 + 16 + 4 * W + 2);
+  constexpr int kSmem = MAXM * (8 + 16 + 4 * W + 2 + 4 * 8);
   auto kern = nms_seg_mask_kernel<MAXM, THREADS>;
   static bool attr_set = false;
   if (!attr_set) {
