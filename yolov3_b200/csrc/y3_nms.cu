@@ -819,7 +819,7 @@ __global__ void __launch_bounds__(THREADS) nms_seg_mask_kernel(const NmsArgs p, 
   float4* s_box = reinterpret_cast<float4*>(s_key + MAXM);             // [MAXM] in confidence order
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_box + MAXM);        // [MAXM][W]
   uint16_t* s_ord = reinterpret_cast<uint16_t*>(s_mask + MAXM * W);    // [MAXM] rank -> member
-  constexpr int kList = MAXM * 8;                                      // intersecting pairs tested from a compact list
+  constexpr int kList = MAXM * 4;                                      // intersecting pairs tested from a compact list
   uint32_t* s_list = reinterpret_cast<uint32_t*>(s_ord + MAXM);        // [kList] (i << 16 | j)
   __shared__ int s_pairs;
   const int img = blockIdx.y, seg = blockIdx.x;
@@ -934,20 +934,54 @@ __global__ void __launch_bounds__(THREADS) nms_seg_mask_kernel(const NmsArgs p, 
   }
   __syncthreads();
   if (threadIdx.x < 32) {
+    // (4) greedy order, one warp, bit operations only.  Lane l keeps word l of the removed set; `cur` (all lanes) is the word
+    // the walk is in.  Both mask words of row i are loaded whether or not the row is alive, so the loads run ahead of the
+    // 3-instruction dependency chain (test bit, OR, OR); the first version shuffled the current word out of its lane for every
+    // row and waited for each row's load: ~60 clk x m with a single warp active — with the per-32-member atomics below, most of
+    // the kernel's critical path.
     const int lane = threadIdx.x;
     uint32_t removed = 0;  // lane w holds word w of the removed set (W <= 32)
-    for (int i = 0; i < m; ++i) {
-      const uint32_t wi = __shfl_sync(0xffffffffu, removed, i >> 5);
-      if ((wi >> (i & 31)) & 1u) continue;  // uniform
-      if (lane < words) removed |= s_mask[i * W + lane];
+    for (int wb = 0; wb < words; ++wb) {
+      uint32_t cur = __shfl_sync(0xffffffffu, removed, wb);
+      const int i_end = min(m, (wb << 5) + 32);
+#pragma unroll 8
+      for (int i = wb << 5; i < i_end; ++i) {
+        const uint32_t v_own = lane < words ? s_mask[i * W + lane] : 0u;
+        const uint32_t v_cur = s_mask[i * W + wb];  // broadcast
+        if (!((cur >> (i & 31)) & 1u)) {            // uniform: member i is kept
+          removed |= v_own;
+          cur |= v_cur;
+        }
+      }
     }
-    // survivors, in rank order
+    // survivors, in rank order: ONE atomic reserves the segment's range (a dependent global round trip per 32 members before)
+    int kept_before = 0, total = 0;
+    {
+      const uint32_t valid = lane < words ? (lane == words - 1 && (m & 31) ? (1u << (m & 31)) - 1u : 0xffffffffu) : 0u;
+      const int mine = __popc(~removed & valid);
+      int incl = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      kept_before = incl - mine;  // survivors in the words before mine
+      total = __shfl_sync(0xffffffffu, incl, 31);
+    }
+    int base = 0;
+    if (lane == 0 && total) base = atomicAdd(&p.surv_cnt[img], total);
+    base = __shfl_sync(0xffffffffu, base, 0);
     for (int q0 = 0; q0 < m; q0 += 32) {
       const int q = q0 + lane;
       const uint32_t wq = __shfl_sync(0xffffffffu, removed, q0 >> 5);
-      const bool kept = q < m && !((wq >> (q & 31)) & 1u);
-      const int j = q < m ? s_ord[q] : 0;
-      append_survivors(p, img, kept, kept ? s_key[j] : 0ull, lo + j, lane);
+      const int before = __shfl_sync(0xffffffffu, kept_before, q0 >> 5);
+      const uint32_t alive = ~wq & (q0 + 32 <= m ? 0xffffffffu : (1u << (m & 31)) - 1u);
+      if ((alive >> lane) & 1u) {
+        const int j = s_ord[q];
+        const int at = base + before + __popc(alive & ((1u << lane) - 1u));
+        p.surv_key[static_cast<size_t>(img) * kRankCap + at] = s_key[j];
+        p.surv_pos[static_cast<size_t>(img) * kRankCap + at] = lo + j;
+      }
     }
   }
 }
@@ -955,7 +989,7 @@ __global__ void __launch_bounds__(THREADS) nms_seg_mask_kernel(const NmsArgs p, 
 template <int MAXM, int THREADS>
 int launch_seg_mask(const NmsArgs& a, int m_lo, cudaStream_t stream) {
   constexpr int W = MAXM / 32;
-  constexpr int kSmem = MAXM * (8 + 16 + 4 * W + 2 + 4 * 8);
+  constexpr int kSmem = MAXM * (8 + 16 + 4 * W + 2 + 4 * 4);
   auto kern = nms_seg_mask_kernel<MAXM, THREADS>;
   static bool attr_set = false;
   if (!attr_set) {
