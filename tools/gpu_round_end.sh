@@ -14,13 +14,13 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --c
 timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:conv_tc --launch-skip 74 \
   --launch-count 74 --csv --log-file ${O}_ncu_conv_tc_dram.csv python tools/run_forward.py 2 > /dev/null 2>&1
 # full captures: the largest conv group, wgrad, the BatchNorm backward reduction, the NMS segment kernel
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_tc --launch-skip 84 --launch-count 1 -f \
+timeout 400 ncu --set full --clock-control none --import-source on --source-folders yolov3_b200/csrc -k regex:conv_tc --launch-skip 84 --launch-count 1 -f \
   -o ${O}_ncu_conv_tc python tools/run_forward.py 2 > /dev/null 2>&1
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:wgrad_tc --launch-skip 140 --launch-count 2 -f \
+timeout 500 ncu --set full --clock-control none --import-source on --source-folders yolov3_b200/csrc -k regex:wgrad_tc --launch-skip 140 --launch-count 2 -f \
   -o ${O}_ncu_wgrad python tools/bench_train.py --bs 8 --steps 1 --warmup 2 --no-graphs > /dev/null 2>&1
-timeout 500 ncu --set full --clock-control none --import-source on -k regex:bn_act_bwd --launch-skip 150 --launch-count 2 -f \
+timeout 500 ncu --set full --clock-control none --import-source on --source-folders yolov3_b200/csrc -k regex:bn_act_bwd --launch-skip 150 --launch-count 2 -f \
   -o ${O}_ncu_bn_bwd python tools/bench_train.py --bs 8 --steps 1 --warmup 2 --no-graphs > /dev/null 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:nms_ --launch-skip 12 --launch-count 6 -f \
+timeout 300 ncu --set full --clock-control none --import-source on --source-folders yolov3_b200/csrc -k regex:nms_ --launch-skip 12 --launch-count 6 -f \
   -o ${O}_ncu_nms python tools/run_nms.py --iters 3 > /dev/null 2>&1
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file ${O}_train_launches.csv \
   python tools/bench_train.py --bs 8 --steps 1 --warmup 3 --no-graphs > /dev/null 2>&1

@@ -4,7 +4,8 @@
 
 Runs `cuobjdump -sass` on yolov3_b200/libyolov3_b200.so (no GPU needed) and counts, for every kernel, the instructions that
 prove which hardware path it takes: UTCHMMA (tcgen05.mma; .2CTA = cta_group::2), LDTM (tcgen05.ld), UTMALDG / UTMASTG (TMA load /
-store), UTCBAR (tcgen05.commit), SYNCS (mbarrier), HMMA / IMMA (legacy mma.sync — must be 0), MUFU, ATOM/RED (atomics).
+store), UTCBAR (tcgen05.commit), SYNCS (mbarrier), ACQBULK / PREEXIT (griddepcontrol.wait / launch_dependents: programmatic
+dependent launch), HMMA / IMMA (legacy mma.sync: only the 3-channel stem conv and the fallback wgrad), MUFU, REDUX, ATOM/ATOMS/RED.
 """
 import collections
 import re
@@ -14,7 +15,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 LIB = ROOT / "yolov3_b200" / "libyolov3_b200.so"
-KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "HMMA", "IMMA", "MUFU", "ATOM", "RED", "LDG", "STG"]
+KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "ACQBULK", "PREEXIT", "HMMA", "IMMA", "MUFU", "REDUX", "ATOM", "ATOMS", "RED", "LDG", "STG"]
 
 
 def demangle(names):
@@ -53,8 +54,8 @@ def main():
         print(" ".join(f"{c[x]:5d}" for x in KEYS) + f" | {c['_insts']:6d} | {short}")
     print("# total")
     print(" ".join(f"{total[x]:5d}" for x in KEYS) + f" | {total['_insts']:6d} | all kernels")
-    if total["HMMA"] or total["IMMA"]:
-        print("# WARNING: legacy mma.sync instructions present", file=sys.stderr)
+    legacy = [re.sub(r"\(.*$", "", names.get(k, k).replace("(anonymous namespace)::", "")) for k, c in per.items() if c["HMMA"] or c["IMMA"]]
+    print("# kernels with legacy mma.sync (HMMA): " + (", ".join(sorted(set(x.split("::")[-1].split("<")[0] for x in legacy))) or "none"))
 
 
 if __name__ == "__main__":

@@ -407,7 +407,8 @@ class TrainEngine:
         ddp = getattr(self.model, "ddp", None)
         exchange = ddp is not None and ddp.require_sync and self.world > 1
         if exchange and self.comm is None:
-            self.comm = torch.cuda.Stream(device=self.model.device)
+            # high priority: the all-reduce CTAs take the SMs the persistent conv / wgrad grids release first
+            self.comm = torch.cuda.Stream(device=self.model.device, priority=-1)
         main = torch.cuda.current_stream()
         if self.use_graphs:
             st = self._graphs.setdefault("bwd_in", {})
