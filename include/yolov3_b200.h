@@ -45,6 +45,10 @@ int64_t y3_abi_sizeof(int32_t which);
  * Results are identical either way — only the launch boundaries overlap.  Returns the previous setting.  A tuning switch with
  * no counterpart in the reference. */
 int y3_set_pdl(int32_t on);
+/* Kernel-variant switch of y3_detect_head_decode_fwd: 1 = the staged kernel (16-byte loads/stores through a shared-memory
+ * transpose; used when only z is requested and every level's plane is a multiple of 16 cells), 0 = the per-row kernel.  z is
+ * bit-identical either way.  Env Y3_DECODE2=0/1 sets the initial value.  Returns the previous setting. */
+int y3_set_decode2(int32_t on);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Conv + folded-BN + SiLU (+ residual add, + nearest-2x upsample, + concat-offset store, or fp32 head store).
