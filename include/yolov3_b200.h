@@ -49,6 +49,10 @@ int y3_set_pdl(int32_t on);
  * transpose; used when only z is requested and every level's plane is a multiple of 16 cells), 0 = the per-row kernel.  z is
  * bit-identical either way.  Env Y3_DECODE2=0/1 sets the initial value.  Returns the previous setting. */
 int y3_set_decode2(int32_t on);
+/* Kernel-variant switch of y3_bn_stats / y3_bn_act_fwd / y3_bn_act_bwd: 1 = the cp.async shared-memory-ring kernels (three work
+ * units requested ahead per thread), 0 = the register-staged ones.  Same unit order and arithmetic: results are bit-identical.
+ * Env Y3_BN_ASYNC=0/1 sets the initial value.  Returns the previous setting. */
+int y3_set_bn_async(int32_t on);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Conv + folded-BN + SiLU (+ residual add, + nearest-2x upsample, + concat-offset store, or fp32 head store).

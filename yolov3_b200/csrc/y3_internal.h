@@ -37,6 +37,9 @@ void pdl_set(int on);
 #ifndef Y3_DECODE2_DEFAULT
 #define Y3_DECODE2_DEFAULT 0
 #endif
+#ifndef Y3_BN_ASYNC_DEFAULT
+#define Y3_BN_ASYNC_DEFAULT 0
+#endif
 int decode2_enabled();  // staged Detect decode (y3_detect.cu); env Y3_DECODE2=0/1, y3_set_decode2()
 
 // ---- tcgen05 conv: kernel arguments (device view) and a prepared launch

@@ -13,6 +13,8 @@
 //                   stride-1 conv with flipped weights)
 //   wgrad           dW[co, tap, ci] = sum_p dy[p, co] * x[p + shift(tap), ci]  (warp-level bf16 MMA, split over pixels)
 //   bias_grad       Detect heads: db[co] = sum_p dy[p, co]
+#include <cstdlib>
+
 #include "y3_common.cuh"
 #include "y3_internal.h"
 
@@ -376,6 +378,245 @@ __global__ void __launch_bounds__(256, UPS ? 2 : 3) bn_act_bwd_kernel(const BnBw
     block_reduce_store(a_dz, a_dzy, g.c8, sh, p.partial + static_cast<long long>(blockIdx.x) * 2 * g.c8 * 8, g.c8 * 8);
 }
 
+// ---------------------------------------------------------------------------------------------- cp.async ring variants
+// The kernels above keep a unit's 16-byte vectors in registers between issue and use: 2-4 loads per thread in flight, three
+// or four blocks per SM = 24-48 KB per SM, with a bubble at every unit boundary — 16 us for 26 MB, long-scoreboard stalls on
+// top (profiles/r02_ncu_bn_bwd_summary.txt); a register look-ahead halved the resident blocks and gained nothing
+// (profiles/r02_experiments.md).  The variants below stage the SAME units through a per-thread shared-memory ring with
+// cp.async: a thread copies its own 16-byte items kDepth-1 units ahead into its own slots and reads them back itself, so there
+// is no barrier and no mbarrier anywhere (cp.async.wait_group cannot dead-lock), 96-144 KB per SM are in flight without
+// costing registers, and the arithmetic — unit order, item order, operations — is exactly that of the kernels above: results
+// are bit-identical (tests/diag/ab_shot.py compares them on the device).  Switch: y3_set_bn_async / Y3_BN_ASYNC.
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int kRingDepth = 4;  // units in the ring: kRingDepth - 1 requested ahead of the one being consumed
+// byte offset of (stage, stream, item k) of this thread's slots; NS = streams per unit
+template <int NS>
+__device__ __forceinline__ uint32_t ring_slot(uint32_t ring, int stage, int s, int k) {
+  return ring + ((((stage * NS + s) * kUnitIters + k) * 256 + threadIdx.x) << 4);
+}
+template <int NS>
+constexpr int ring_bytes() {
+  return kRingDepth * NS * kUnitIters * 256 * 16;
+}
+// unit i of this block -> (first item of this thread, padded pixel index of the row's x = 0)
+__device__ __forceinline__ void unit_pos(const Rows& g, int i, int& e0, long long& rb) {
+  const int u = blockIdx.x + i * gridDim.x;
+  const int r = u / g.upr;
+  e0 = (u - r * g.upr) * (256 * kUnitIters) + threadIdx.x;
+  rb = row_base(g, r);
+}
+__device__ __forceinline__ int units_of_block(const Rows& g) {
+  const int units = g.n * g.h * g.upr;
+  return static_cast<int>(blockIdx.x) < units ? (units - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x) : 0;
+}
+// request unit i of one stream into `stage`
+template <int NS>
+__device__ __forceinline__ void ring_issue(const Rows& g, const Slice& t, int s, int i, int stage, uint32_t ring) {
+  int e0;
+  long long rb;
+  unit_pos(g, i, e0, rb);
+  const int items = g.w * g.c8;
+#pragma unroll
+  for (int k = 0; k < kUnitIters; ++k) {
+    const int e = e0 + k * 256;
+    int x, cg;
+    split_item(g, e, x, cg);
+    if (e < items) cp_async16(ring_slot<NS>(ring, stage, s, k), t.p + (rb + x) * t.ld + t.coff + cg * 8);
+  }
+}
+
+__global__ void __launch_bounds__(256, 3) bn_stats_async_kernel(Slice y, Rows g, float* __restrict__ partial) {
+  pdl_entry();
+  extern __shared__ __align__(16) float ring_mem[];  // ring (32 KB); reused as [2][256][8] by the block reduction
+  float* sh = ring_mem;
+  const uint32_t ring = smem_u32(ring_mem);
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const int items = g.w * g.c8, nb = units_of_block(g);
+#pragma unroll
+  for (int i = 0; i < kRingDepth - 1; ++i) {
+    if (i < nb) ring_issue<1>(g, y, 0, i, i, ring);
+    cp_async_commit();
+  }
+  int st_c = 0, st_i = kRingDepth - 1;  // stage consumed / stage requested this iteration
+  for (int i = 0; i < nb; ++i) {
+    if (i + kRingDepth - 1 < nb) ring_issue<1>(g, y, 0, i + kRingDepth - 1, st_i, ring);
+    cp_async_commit();
+    cp_async_wait<kRingDepth - 1>();
+    int e0;
+    long long rb;
+    unit_pos(g, i, e0, rb);
+#pragma unroll
+    for (int k = 0; k < kUnitIters; ++k) {
+      const uint4 v = e0 + k * 256 < items ? lds128(ring_slot<1>(ring, st_c, 0, k)) : make_uint4(0, 0, 0, 0);
+      float f[8];
+      unpack8(v, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        q[j] = fmaf(f[j], f[j], q[j]);
+      }
+    }
+    st_c = st_c + 1 == kRingDepth ? 0 : st_c + 1;
+    st_i = st_i + 1 == kRingDepth ? 0 : st_i + 1;
+  }
+  cp_async_wait<0>();
+  __syncthreads();  // every thread is done with its ring slots: the block reduction reuses the memory
+  block_reduce_store(s, q, g.c8, sh, partial + static_cast<long long>(blockIdx.x) * 2 * g.c8 * 8, g.c8 * 8);
+}
+
+template <bool RES>
+__global__ void __launch_bounds__(256, 3) bn_act_fwd_async_kernel(const BnActArgs p) {
+  pdl_entry();
+  extern __shared__ __align__(16) float ring_mem[];
+  const uint32_t ring = smem_u32(ring_mem);
+  constexpr int NS = RES ? 2 : 1;
+  const Rows g = p.g;
+  const int items = g.w * g.c8, nb = units_of_block(g);
+  const int us = p.upsample ? 2 : 1;
+  const long long up_row = static_cast<long long>(2 * g.w + 2) * p.out.ld;
+#pragma unroll
+  for (int i = 0; i < kRingDepth - 1; ++i) {
+    if (i < nb) {
+      ring_issue<NS>(g, p.y, 0, i, i, ring);
+      if (RES) ring_issue<NS>(g, p.res, 1, i, i, ring);
+    }
+    cp_async_commit();
+  }
+  int st_c = 0, st_i = kRingDepth - 1;
+  for (int i = 0; i < nb; ++i) {
+    if (i + kRingDepth - 1 < nb) {
+      ring_issue<NS>(g, p.y, 0, i + kRingDepth - 1, st_i, ring);
+      if (RES) ring_issue<NS>(g, p.res, 1, i + kRingDepth - 1, st_i, ring);
+    }
+    cp_async_commit();
+    cp_async_wait<kRingDepth - 1>();
+    const int u = blockIdx.x + i * gridDim.x;
+    const int r = u / g.upr, e0 = (u - r * g.upr) * (256 * kUnitIters) + threadIdx.x;
+    const long long rb = row_base(g, r);
+    const long long ob = p.upsample ? row_base(g, r, 2) : rb;
+#pragma unroll
+    for (int k = 0; k < kUnitIters; ++k) {
+      const int e = e0 + k * 256;
+      if (e >= items) continue;
+      int x, cg;
+      split_item(g, e, x, cg);
+      float f[8], rr[8];
+      unpack8(lds128(ring_slot<NS>(ring, st_c, 0, k)), f);
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + cg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + cg * 8 + 4));
+      const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift + cg * 8)), h1 = __ldg(reinterpret_cast<const float4*>(p.shift + cg * 8 + 4));
+      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      const float shf[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) f[q] = silu_fast(fmaf(f[q], sc[q], shf[q]));
+      if (RES) {
+        unpack8(lds128(ring_slot<NS>(ring, st_c, 1, k)), rr);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] += rr[q];
+      }
+      const uint4 o = pack8(f);
+      __nv_bfloat16* dst = p.out.p + (ob + static_cast<long long>(x) * us) * p.out.ld + p.out.coff + cg * 8;
+      *reinterpret_cast<uint4*>(dst) = o;
+      if (p.upsample) {
+        *reinterpret_cast<uint4*>(dst + p.out.ld) = o;
+        *reinterpret_cast<uint4*>(dst + up_row) = o;
+        *reinterpret_cast<uint4*>(dst + up_row + p.out.ld) = o;
+      }
+    }
+    st_c = st_c + 1 == kRingDepth ? 0 : st_c + 1;
+    st_i = st_i + 1 == kRingDepth ? 0 : st_i + 1;
+  }
+  cp_async_wait<0>();
+}
+
+// the non-upsample reduce / apply passes (the two 2x-upsample layers stay on bn_act_bwd_kernel<*, true>)
+template <bool APPLY>
+__global__ void __launch_bounds__(256, 3) bn_act_bwd_async_kernel(const BnBwdArgs p) {
+  pdl_entry();
+  extern __shared__ __align__(16) float ring_mem[];  // ring (64 KB); the reduce pass reuses it as [2][256][8]
+  float* sh = ring_mem;
+  const uint32_t ring = smem_u32(ring_mem);
+  const Rows g = p.g;
+  const int cg = threadIdx.x % g.c8;  // fixed per thread: 256 % c8 == 0
+  const int items = g.w * g.c8, nb = units_of_block(g);
+  float a_dz[8] = {0, 0, 0, 0, 0, 0, 0, 0}, a_dzy[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float sc[8], shf[8], c2[8], c3[8];  // as in bn_act_bwd_kernel
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    sc[k] = p.scale[cg * 8 + k];
+    shf[k] = p.shift[cg * 8 + k];
+    const float mu = p.mean[cg * 8 + k], rs = p.rstd[cg * 8 + k];
+    if (APPLY) {
+      const float m_dz = p.sum_dz[cg * 8 + k] * p.inv_count, m_dzy = p.sum_dzy[cg * 8 + k] * p.inv_count;
+      c2[k] = -sc[k] * rs * m_dzy;
+      c3[k] = -sc[k] * m_dz - c2[k] * mu;
+    } else {
+      c2[k] = mu;
+      c3[k] = rs;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kRingDepth - 1; ++i) {
+    if (i < nb) {
+      ring_issue<2>(g, p.y, 0, i, i, ring);
+      ring_issue<2>(g, p.da, 1, i, i, ring);
+    }
+    cp_async_commit();
+  }
+  int st_c = 0, st_i = kRingDepth - 1;
+  for (int i = 0; i < nb; ++i) {
+    if (i + kRingDepth - 1 < nb) {
+      ring_issue<2>(g, p.y, 0, i + kRingDepth - 1, st_i, ring);
+      ring_issue<2>(g, p.da, 1, i + kRingDepth - 1, st_i, ring);
+    }
+    cp_async_commit();
+    cp_async_wait<kRingDepth - 1>();
+    int e0;
+    long long rb;
+    unit_pos(g, i, e0, rb);
+#pragma unroll
+    for (int k = 0; k < kUnitIters; ++k) {
+      const int e = e0 + k * 256;
+      const int x = g.c8_shift >= 0 ? e >> g.c8_shift : e / g.c8;
+      uint4 vy = make_uint4(0, 0, 0, 0), vd = make_uint4(0, 0, 0, 0);  // dz = 0 beyond the row: adds nothing to the sums
+      if (e < items) {
+        vy = lds128(ring_slot<2>(ring, st_c, 0, k));
+        vd = lds128(ring_slot<2>(ring, st_c, 1, k));
+      }
+      float yv[8], d[8], o[8];
+      unpack8(vy, yv);
+      unpack8(vd, d);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float z = fmaf(yv[q], sc[q], shf[q]);
+        const float dz = d[q] * silu_grad(z);
+        if (APPLY) {
+          o[q] = fmaf(sc[q], dz, fmaf(c2[q], yv[q], c3[q]));
+        } else {
+          const float yh = (yv[q] - c2[q]) * c3[q];
+          a_dz[q] += dz;
+          a_dzy[q] = fmaf(dz, yh, a_dzy[q]);
+        }
+      }
+      if (APPLY && e < items) *reinterpret_cast<uint4*>(p.dy.p + (rb + x) * p.dy.ld + p.dy.coff + cg * 8) = pack8(o);
+    }
+    st_c = st_c + 1 == kRingDepth ? 0 : st_c + 1;
+    st_i = st_i + 1 == kRingDepth ? 0 : st_i + 1;
+  }
+  cp_async_wait<0>();
+  if (!APPLY) {
+    __syncthreads();
+    block_reduce_store(a_dz, a_dzy, g.c8, sh, p.partial + static_cast<long long>(blockIdx.x) * 2 * g.c8 * 8, g.c8 * 8);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- pack_weights
 // w: fp32 [co, ci, k, k] (PyTorch layout).  fwd: bf16 [co_pad, (kh*k+kw)*ci + c];  dgrad: bf16 [ci_pad, (kh'*k+kw')*co + o]
 // with (kh', kw') = (k-1-kh, k-1-kw).  Rows beyond co / ci stay zero (buffers are zero-initialised once).
@@ -736,6 +977,25 @@ Rows make_rows(int n, int h, int w, int c) {
   g.upr = (w * g.c8 + 256 * kUnitIters - 1) / (256 * kUnitIters);
   return g;
 }
+int g_bn_async = -1;
+int bn_async_enabled() {
+  if (g_bn_async < 0) {
+    const char* e = getenv("Y3_BN_ASYNC");
+    g_bn_async = e ? (e[0] != '0') : Y3_BN_ASYNC_DEFAULT;
+  }
+  return g_bn_async;
+}
+// ring kernels: opt in to > 48 KB of dynamic shared memory and ask for the largest shared-memory carve-out, so that three
+// 64 KB blocks are resident per SM (both attributes are idempotent; the carve-out is a hint)
+template <auto Kern>
+cudaError_t allow_smem(int bytes) {
+  static bool done = false;  // per kernel; benign race: idempotent attributes.  Set on the first (eager, warm-up) launch
+  if (done) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(Kern, cudaFuncAttributePreferredSharedMemoryCarveout, static_cast<int>(cudaSharedmemCarveoutMaxShared));
+  if (e == cudaSuccess && bytes > 48 * 1024) e = cudaFuncSetAttribute(Kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  done = e == cudaSuccess;
+  return e;
+}
 constexpr int kMaxPartialBlocks = 444;  // = 3 resident 256-thread blocks per SM x 148 SMs: exactly one wave of the reduction kernels
                                         // (592 ran 1.33 waves: the tail block set doubled the small layers' time); fixed: sizes stay device-independent
 
@@ -757,6 +1017,12 @@ __global__ void __launch_bounds__(1024) bn_bwd_finalize_kernel(const float* __re
 }  // namespace
 }  // namespace y3
 
+extern "C" int y3_set_bn_async(int32_t on) {
+  const int prev = y3::bn_async_enabled();
+  y3::g_bn_async = on ? 1 : 0;
+  return prev;
+}
+
 extern "C" int32_t y3_bn_partial_blocks(int32_t n, int32_t h, int32_t w, int32_t c) {
   // work units of the streaming kernels (c == 0: one unit per image row, the Detect-head gradient pack), capped
   long long units = static_cast<long long>(n) * h;
@@ -769,6 +1035,13 @@ extern "C" int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, i
   Y3_REQUIRE(y && partial && c > 0 && c % 8 == 0 && 256 % (c / 8) == 0 && n > 0 && h > 0 && w > 0 && ld % 8 == 0 && coff % 8 == 0,
              "bn_stats: bad arguments (c must be a power of two in [8, 2048])");
   const int nblk = y3_bn_partial_blocks(n, h, w, c);
+  if (y3::bn_async_enabled()) {
+    constexpr int smem = y3::ring_bytes<1>() > 2 * 256 * 8 * 4 ? y3::ring_bytes<1>() : 2 * 256 * 8 * 4;
+    Y3_CHECK_CUDA(y3::allow_smem<y3::bn_stats_async_kernel>(smem));
+    Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_stats_async_kernel, dim3(nblk), dim3(256), smem, static_cast<cudaStream_t>(stream), Slice{static_cast<const __nv_bfloat16*>(y), ld, coff}, y3::make_rows(n, h, w, c), partial));
+    Y3_CHECK_CUDA(cudaGetLastError());
+    return Y3_OK;
+  }
   Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_stats_kernel, dim3(nblk), dim3(256), 2 * 256 * 8 * sizeof(float), static_cast<cudaStream_t>(stream), Slice{static_cast<const __nv_bfloat16*>(y), ld, coff}, y3::make_rows(n, h, w, c), partial));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
@@ -803,6 +1076,19 @@ extern "C" int y3_bn_act_fwd(const y3_bn_act_desc* d, y3_stream_t stream) {
   a.g = y3::make_rows(d->n, d->h, d->w, d->c);
   a.upsample = d->upsample;
   const long long units = static_cast<long long>(d->n) * d->h * a.g.upr;
+  if (y3::bn_async_enabled()) {
+    const long long cap3 = 3ll * y3::num_sms();  // one wave at 3 resident blocks per SM
+    const dim3 grid(static_cast<unsigned>(units < cap3 ? units : cap3));
+    if (a.res.p) {
+      Y3_CHECK_CUDA(y3::allow_smem<y3::bn_act_fwd_async_kernel<true>>(y3::ring_bytes<2>()));
+      Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_fwd_async_kernel<true>, grid, dim3(256), y3::ring_bytes<2>(), static_cast<cudaStream_t>(stream), a));
+    } else {
+      Y3_CHECK_CUDA(y3::allow_smem<y3::bn_act_fwd_async_kernel<false>>(y3::ring_bytes<1>()));
+      Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_fwd_async_kernel<false>, grid, dim3(256), y3::ring_bytes<1>(), static_cast<cudaStream_t>(stream), a));
+    }
+    Y3_CHECK_CUDA(cudaGetLastError());
+    return Y3_OK;
+  }
   const long long cap = 8ll * y3::num_sms();
   Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_fwd_kernel, dim3(static_cast<unsigned>(units < cap ? units : cap)), dim3(256), 0, static_cast<cudaStream_t>(stream), a));
   Y3_CHECK_CUDA(cudaGetLastError());
@@ -832,10 +1118,14 @@ extern "C" int y3_bn_act_bwd(const y3_bn_bwd_desc* d, y3_stream_t stream_) {
   const long long pixels = static_cast<long long>(d->n) * d->h * d->w;
   a.inv_count = 1.0f / (d->count > 0.f ? d->count : static_cast<float>(pixels));
   const int nblk = y3_bn_partial_blocks(d->n, d->h, d->w, d->c);
+  const bool async = y3::bn_async_enabled() != 0;
   if (d->phase != 2) {
     if (d->upsample)
       Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_bwd_kernel<false, true>, dim3(nblk), dim3(256), 2 * 256 * 8 * sizeof(float), stream, a));
-    else
+    else if (async) {
+      Y3_CHECK_CUDA(y3::allow_smem<y3::bn_act_bwd_async_kernel<false>>(y3::ring_bytes<2>()));
+      Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_bwd_async_kernel<false>, dim3(nblk), dim3(256), y3::ring_bytes<2>(), stream, a));
+    } else
       Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_bwd_kernel<false, false>, dim3(nblk), dim3(256), 2 * 256 * 8 * sizeof(float), stream, a));
     Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_bwd_finalize_kernel, dim3((2 * d->c + 31) / 32), dim3(32, 32), 0, stream, d->partial, nblk, d->c, d->sums, d->dbeta_acc,
                                                                                   d->dgamma_acc));
@@ -845,7 +1135,10 @@ extern "C" int y3_bn_act_bwd(const y3_bn_bwd_desc* d, y3_stream_t stream_) {
     const long long cap = 3ll * y3::num_sms();  // one wave at the kernel's 3 resident blocks per SM
     if (d->upsample)
       Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_bwd_kernel<true, true>, dim3(static_cast<unsigned>(units < cap ? units : cap)), dim3(256), 0, stream, a));
-    else
+    else if (async) {
+      Y3_CHECK_CUDA(y3::allow_smem<y3::bn_act_bwd_async_kernel<true>>(y3::ring_bytes<2>()));
+      Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_bwd_async_kernel<true>, dim3(static_cast<unsigned>(units < cap ? units : cap)), dim3(256), y3::ring_bytes<2>(), stream, a));
+    } else
       Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_bwd_kernel<true, false>, dim3(static_cast<unsigned>(units < cap ? units : cap)), dim3(256), 0, stream, a));
   }
   Y3_CHECK_CUDA(cudaGetLastError());
