@@ -182,6 +182,8 @@ section("decode", decode_ab, 32, [(80, 80), (40, 40), (20, 20)])
 section("bn", bn_ab, 8, 80, 80, 256)
 section("bn", bn_ab, 3, 13, 13, 512)      # row tail: 832 items = one full + one partial unit
 section("bn", bn_ab, 2, 5, 7, 64)         # less than one unit per row, fewer units than blocks
+section("bn", bn_ab, 2, 2, 2, 1024)       # the 64x64 test images: 256 items per row, 4 units
+section("bn", bn_ab, 2, 32, 32, 16)       # yolov3-tiny's 16-channel layer (c8 = 2)
 section("bn", bn_ab, 8, 160, 160, 128)
 section("bn", bn_ab, 8, 40, 40, 512)
 section("bn", bn_ab, 8, 20, 20, 1024)
@@ -196,20 +198,18 @@ def train_ab():
     sys.path.insert(0, str(ROOT / "tools"))
     from bench_workloads import train_step_workload
 
-    out = {}
     for flag in (0, 1, 0, 1):
         if left() <= 0:
+            emit(section="train_step", skipped="budget", flag=flag)
             break
         L.y3_set_bn_async(flag)
         L.y3_set_decode2(flag)
         r = train_step_workload(dev, 0, 1, bs=8, steps=10, warmup=3)
-        out.setdefault(f"ms_{flag}", []).append(round(r["ms_per_step"], 3))
-        out.setdefault(f"loss_{flag}", []).append(r["loss"])
-        out[f"split_{flag}"] = r.get("split_ms")
+        emit(section="train_step", flag=flag, ms_per_step=round(r["ms_per_step"], 3), img_s=round(r["value"], 1), loss=r["loss"],
+             split_ms=r.get("split_ms"))
         torch.cuda.empty_cache()
     L.y3_set_bn_async(0)
     L.y3_set_decode2(0)
-    emit(section="train_step", **out)
 
 
 if not args.skip_train:
