@@ -45,13 +45,10 @@ int64_t y3_abi_sizeof(int32_t which);
  * Results are identical either way — only the launch boundaries overlap.  Returns the previous setting.  A tuning switch with
  * no counterpart in the reference. */
 int y3_set_pdl(int32_t on);
-/* Kernel-variant switch of y3_detect_head_decode_fwd: 1 = the staged kernel (16-byte loads/stores through a shared-memory
- * transpose; used when only z is requested and every level's plane is a multiple of 16 cells), 0 = the per-row kernel.  z is
- * bit-identical either way.  Env Y3_DECODE2=0/1 sets the initial value.  Returns the previous setting. */
-int y3_set_decode2(int32_t on);
-/* Kernel-variant switch of y3_bn_stats / y3_bn_act_fwd / y3_bn_act_bwd: 1 = the cp.async shared-memory-ring kernels (three work
- * units requested ahead per thread), 0 = the register-staged ones.  Same unit order and arithmetic: results are bit-identical.
- * Env Y3_BN_ASYNC=0/1 sets the initial value.  Returns the previous setting. */
+/* Kernel-variant switch of y3_bn_act_bwd (non-upsample layers): 1 (default) = the cp.async shared-memory-ring kernels (three
+ * work units requested ahead per thread), 0 = the register-staged ones.  Same unit order and arithmetic: results are
+ * bit-identical (profiles/r02_ab_shot_kernel_variants.jsonl).  Env Y3_BN_ASYNC=0/1 sets the initial value.  Returns the
+ * previous setting.  A tuning switch with no counterpart in the reference. */
 int y3_set_bn_async(int32_t on);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -1,11 +1,12 @@
-"""On-device A/B of the kernel variants behind the run-time switches (y3_set_decode2, y3_set_bn_async): for each variant pair
-the SAME inputs go through both kernels, the outputs are compared bit for bit (the variants are meant to be bit-identical)
-and both are timed as CUDA-graph replays over buffer sets larger than L2.  Every result is appended to
+"""On-device A/B of the kernel variant behind the run-time switch y3_set_bn_async: the SAME inputs go through both kernels,
+the outputs are compared bit for bit (the variants are meant to be bit-identical) and both are timed as CUDA-graph replays
+over buffer sets larger than L2; then the whole training step with the switch off / on.  Every result is appended to
 gpurun_out/ab_shot.jsonl as soon as it exists (the GPU call this runs in may be cut short).
     python tests/diag/ab_shot.py [--budget SECONDS] [--skip-train]
+The version of this script at commit 5fd94b1 also compared a staged Detect-decode kernel and ring variants of bn_stats /
+bn_act_fwd (profiles/r02_ab_shot_kernel_variants.jsonl): bit-identical, not faster, removed (profiles/r02_experiments.md).
 Diagnostics only — not collected by pytest, not part of the product."""
 import argparse
-import ctypes as C
 import json
 import math
 import os
@@ -36,7 +37,7 @@ def emit(**kw):
 import torch  # noqa: E402
 
 from yolov3_b200 import _lib, train_ops  # noqa: E402
-from yolov3_b200.tensors import PaddedNHWC, _stream  # noqa: E402
+from yolov3_b200.tensors import PaddedNHWC  # noqa: E402
 
 emit(section="start", torch_import_s=round(time.time() - T0, 1), gpu=torch.cuda.get_device_name(0))
 L = _lib.lib()
@@ -72,46 +73,6 @@ def left():
     return args.budget - (time.time() - T0)
 
 
-# ------------------------------------------------------------------------------------------------------------ decode
-def decode_ab(bs, shapes, na=3, no=85, ld=256, nset=2):
-    gen = torch.Generator(device=dev).manual_seed(5)
-    sets = []
-    rows = sum(na * h * w for h, w in shapes)
-    for _ in range(nset):
-        heads = [torch.randn(bs * h * w, ld, device=dev, generator=gen) * 3 for h, w in shapes]
-        z = torch.zeros(bs, rows, no, device=dev)
-        d = _lib.DecodeDesc()
-        for j, (h, w) in enumerate(shapes):
-            lv = d.levels[j]
-            lv.head, lv.head_ld, lv.raw_out = heads[j].data_ptr(), ld, None
-            lv.ny, lv.nx, lv.stride = h, w, float(8 * 2 ** j)
-            for a in range(na):
-                lv.anchor_w[a], lv.anchor_h[a] = 10.0 + 7 * a + 30 * j, 13.0 + 9 * a + 20 * j
-        d.nl, d.bs, d.na, d.no, d.z = len(shapes), bs, na, no, z.data_ptr()
-        sets.append((heads, z, d))
-
-    def call(i):
-        return lambda: _lib.check(L.y3_detect_head_decode_fwd(C.byref(sets[i][2]), _stream()), "decode")
-
-    res = {}
-    outs = []
-    for flag in (0, 1):
-        L.y3_set_decode2(flag)
-        for _, z, _d in sets:
-            z.fill_(float("nan"))
-        ms = graph_time([call(i) for i in range(nset)])
-        torch.cuda.synchronize()
-        outs.append([z.clone() for _, z, _d in sets])
-        res[f"ms_{flag}"] = round(ms, 5)
-    L.y3_set_decode2(0)
-    eq = all(torch.equal(a, b) for a, b in zip(*outs))
-    fin = all(bool(torch.isfinite(b).all()) for b in outs[1])
-    md = max(float((a - b).abs().max()) for a, b in zip(*outs)) if fin else float("nan")
-    mbytes = (sum(bs * h * w for h, w in shapes) * ld * 4 + bs * rows * no * 4) / 1e6
-    emit(section="decode", bs=bs, shapes=shapes, no=no, bit_equal=eq, finite=fin, max_abs_diff=md, mbytes=round(mbytes, 1),
-         gbs_0=round(mbytes / res["ms_0"], 1), gbs_1=round(mbytes / res["ms_1"], 1), **res)
-
-
 # ------------------------------------------------------------------------------------------------------------ BatchNorm
 def rnd_act(n, h, w, c, gen, scale=1.0):
     t = PaddedNHWC.zeros(n, h, w, c, device=dev)
@@ -134,14 +95,9 @@ def bn_ab(n, h, w, c, upsample=False):
     st = dict(scale=torch.rand(c, device=dev, generator=gen) + 0.5, shift=torch.randn(c, device=dev, generator=gen) * 0.3,
               mean=torch.randn(c, device=dev, generator=gen) * 0.2, rstd=torch.rand(c, device=dev, generator=gen) + 0.5)
     ops = {
-        "stats": (lambda s: train_ops.bn_stats(s["y"], s["partial"]), lambda s: [s["partial"]]),
-        "act_fwd": (lambda s: train_ops.bn_act_fwd(s["y"], st["scale"], st["shift"], s["out"], None, upsample), lambda s: [s["out"].buf]),
         "act_bwd": (lambda s: train_ops.bn_act_bwd(s["y"], s["da"], s["dy"], st, s["sums"], s["partial"], s["dbeta"], s["dgamma"],
                                                    upsample=upsample), lambda s: [s["dy"].buf, s["sums"], s["partial"]]),
     }
-    if not upsample:
-        ops["act_fwd_res"] = (lambda s: train_ops.bn_act_fwd(s["y"], st["scale"], st["shift"], s["out"], s["res"], False),
-                              lambda s: [s["out"].buf])
     for name, (fn, outs_of) in ops.items():
         res, outs = {}, []
         for flag in (0, 1):
@@ -178,7 +134,6 @@ def section(name, fn, *a, **kw):
             sys.exit(3)
 
 
-section("decode", decode_ab, 32, [(80, 80), (40, 40), (20, 20)])
 section("bn", bn_ab, 8, 80, 80, 256)
 section("bn", bn_ab, 3, 13, 13, 512)      # row tail: 832 items = one full + one partial unit
 section("bn", bn_ab, 2, 5, 7, 64)         # less than one unit per row, fewer units than blocks
@@ -189,8 +144,6 @@ section("bn", bn_ab, 8, 40, 40, 512)
 section("bn", bn_ab, 8, 20, 20, 1024)
 section("bn", bn_ab, 8, 320, 320, 64)
 section("bn", bn_ab, 8, 20, 20, 256, upsample=True)
-section("decode", decode_ab, 8, [(80, 80), (40, 40), (20, 20)])
-section("decode", decode_ab, 2, [(8, 8), (4, 4), (2, 2)])   # planes 64/16/4: not whole tiles -> both settings run the per-row kernel
 section("bn", bn_ab, 8, 640, 640, 32)
 
 
@@ -203,13 +156,11 @@ def train_ab():
             emit(section="train_step", skipped="budget", flag=flag)
             break
         L.y3_set_bn_async(flag)
-        L.y3_set_decode2(flag)
         r = train_step_workload(dev, 0, 1, bs=8, steps=10, warmup=3)
         emit(section="train_step", flag=flag, ms_per_step=round(r["ms_per_step"], 3), img_s=round(r["value"], 1), loss=r["loss"],
              split_ms=r.get("split_ms"))
         torch.cuda.empty_cache()
     L.y3_set_bn_async(0)
-    L.y3_set_decode2(0)
 
 
 if not args.skip_train:

@@ -335,3 +335,18 @@ def test_detect_multi_backend_seam():
         save_checkpoint(src, td + "/tiny.pt")
         back = _load(td + "/tiny.pt", "cpu")
     assert back.yaml == src.yaml and all(torch.equal(v, back.state_dict()[k]) for k, v in src.state_dict().items())
+
+
+def test_package_exports_resolve_to_the_reference_seam_names():
+    """`import yolov3_b200` is lazy (no GPU, no library load); every advertised name resolves to the object in its module."""
+    import importlib
+
+    import yolov3_b200 as y
+
+    assert set(y.__all__) >= {"Model", "DetectionModel", "DetectMultiBackend", "non_max_suppression", "scale_boxes", "box_iou",
+                              "ComputeLoss", "process_batch", "letterbox", "Ensemble", "DDP", "SGD", "ModelEMA", "Pipeline"}
+    for name in y.__all__:
+        obj = getattr(y, name)
+        assert obj is getattr(importlib.import_module(obj.__module__), name)
+    with pytest.raises(AttributeError):
+        y.no_such_name

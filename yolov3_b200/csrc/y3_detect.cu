@@ -4,10 +4,7 @@
 // (= the reference's x[i]); z is fp32 [bs, sum_l na*ny*nx, no] with row = off_l + (a*ny + y)*nx + x, i.e. exactly
 // torch.cat(z, 1) of models/yolo.py:110.  Compiled without fast-math/FMA contraction: (2*s + g) * stride is evaluated
 // with the reference's operation order and rounding.
-#include <cstdlib>
-
 #include "y3_common.cuh"
-#include "y3_decode_tile.h"
 #include "y3_internal.h"
 
 namespace y3 {
@@ -59,7 +56,17 @@ __global__ void __launch_bounds__(256) decode_kernel(const DecodeArgs p) {
 // ---- fused variant used by the graph executor: reads the head convs' fp32 pixel-major output [bs*ny*nx, ld]
 // (column a*no + k), writes z AND (optionally) the reference-layout logits raw_l[bs, na, ny, nx, no].
 // One warp per (image, cell, anchor): 340-byte contiguous reads and writes.
-// (HeadDecodeArgs: y3_decode_tile.h)
+struct HeadDecodeArgs {
+  const float* head[Y3_MAX_LEVELS];
+  float* raw[Y3_MAX_LEVELS];
+  int head_ld[Y3_MAX_LEVELS];
+  int ny[Y3_MAX_LEVELS], nx[Y3_MAX_LEVELS];
+  int row_off[Y3_MAX_LEVELS + 1];
+  float stride[Y3_MAX_LEVELS];
+  float anchor_w[Y3_MAX_LEVELS][Y3_MAX_ANCHORS], anchor_h[Y3_MAX_LEVELS][Y3_MAX_ANCHORS];
+  int nl, bs, na, no;
+  float* z;
+};
 
 constexpr int kDecodeRows = 4;  // consecutive z rows per warp iteration (they are contiguous in z and in the logits)
 
@@ -192,45 +199,6 @@ __global__ void __launch_bounds__(256, NITER <= 3 ? 3 : 1) head_decode_kernel(co
   }
 }
 
-
-// ---- staged variant (inference hot path: z only, every plane a multiple of kTileCells, head_ld a power of two).
-// The kernel above moves 4 bytes per lane and instruction: 340-byte runs at a 1024-byte pitch in, 1360-byte runs out —
-// 2.5 TB/s, LSU-issue- and latency-bound (profiles/r02_per_op.json: 0.22 ms for 548 MB).  Here a block takes a tile of
-// kTileCells cells x ALL anchors = one contiguous kTileCells*head_ld*4-byte span of the head buffer, loads it with 16-byte
-// vectors, decodes, scatters the values into shared memory in z order ([anchor][cell][field]) and writes each anchor's
-// kTileCells*no contiguous floats with 16-byte vectors.  Index arithmetic: y3_decode_tile.h (shared with the host test).
-__global__ void __launch_bounds__(256) head_decode2_kernel(const HeadDecode2Args p) {
-  pdl_entry();
-  extern __shared__ float4 stage4[];
-  float* staging = reinterpret_cast<float*>(stage4);
-  const int nf4 = kTileCells << p.ld4_shift;
-  const int nout4 = p.a.na * (kTileCells / 4) * p.a.no;
-  float4* z4 = reinterpret_cast<float4*>(p.a.z);
-  const DecodeLane ln = decode_lane(p, threadIdx.x);
-  for (int t = blockIdx.x; t < p.tile_off[p.a.nl]; t += gridDim.x) {
-    const DecodeTile ti = decode_tile(p, t);
-    const float4* src = reinterpret_cast<const float4*>(p.a.head[ti.l]) + ti.src_f4;
-#pragma unroll 4
-    for (int f = threadIdx.x; f < nf4; f += 256) {
-      const float4 v = __ldg(src + f);
-      decode_stage4(p, ti, ln, f, v.x, v.y, v.z, v.w, staging);
-    }
-    __syncthreads();
-    for (int idx = threadIdx.x; idx < nout4; idx += 256) z4[decode_out4(p, ti, idx)] = stage4[idx];
-    __syncthreads();  // the next tile overwrites the staging buffer
-  }
-}
-
-int g_decode2 = -1;
-}  // namespace
-int decode2_enabled() {
-  if (g_decode2 < 0) {
-    const char* e = getenv("Y3_DECODE2");
-    g_decode2 = e ? (e[0] != '0') : Y3_DECODE2_DEFAULT;
-  }
-  return g_decode2;
-}
-namespace {
 }  // namespace
 }  // namespace y3
 
@@ -272,37 +240,9 @@ extern "C" int y3_detect_head_decode_fwd(const y3_decode_desc* d, y3_stream_t st
                "head_decode: level %d too large", l);
   }
   Y3_REQUIRE(d->na <= 8 && d->nl <= 8, "head_decode: na/nl > 8");
-  const cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (y3::decode2_enabled()) {
-    // staged kernel: z only, one power-of-two head_ld, planes in whole tiles (then every z chunk starts on a 16-byte boundary)
-    y3::HeadDecode2Args b{};
-    b.a = a;
-    bool ok = d->z != nullptr && (reinterpret_cast<uintptr_t>(d->z) & 15) == 0;
-    const int ld = d->levels[0].head_ld;
-    int sh = 0;
-    while ((4 << sh) < ld) ++sh;
-    ok = ok && (4 << sh) == ld && ld <= 1024 && ld >= d->na * d->no;  // head_ld/4 divides the block's 256 threads
-    int tiles = 0;
-    for (int l = 0; l < d->nl && ok; ++l) {
-      const y3_detect_level& lv = d->levels[l];
-      const long long pix = static_cast<long long>(d->bs) * lv.ny * lv.nx;
-      ok = !lv.raw_out && lv.head_ld == ld && (lv.ny * lv.nx) % y3::kTileCells == 0 &&
-           (reinterpret_cast<uintptr_t>(lv.head) & 15) == 0 && pix / y3::kTileCells < (1 << 24);
-      b.tile_off[l] = tiles;
-      tiles += static_cast<int>(pix / y3::kTileCells);
-    }
-    const size_t smem = static_cast<size_t>(d->na) * y3::kTileCells * d->no * sizeof(float);
-    if (ok && smem <= 48 * 1024) {
-      b.tile_off[d->nl] = tiles;
-      b.ld4_shift = sh;
-      const int cap = y3::num_sms() * 8;
-      Y3_CHECK_CUDA(::y3::launch_pdl(y3::head_decode2_kernel, dim3(tiles < cap ? tiles : cap), dim3(256), smem, st, b));
-      Y3_CHECK_CUDA(cudaGetLastError());
-      return Y3_OK;
-    }
-  }
   const int niter = (y3::kDecodeRows * d->no + 127) / 128;
   Y3_REQUIRE(niter <= 8, "head_decode: no=%d > 256 is not supported", d->no);
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
   const unsigned g = static_cast<unsigned>(blocks);
   switch (niter) {
     case 1: Y3_CHECK_CUDA(::y3::launch_pdl(y3::head_decode_kernel<1>, dim3(g), dim3(256), 0, st, a)); break;
@@ -313,12 +253,6 @@ extern "C" int y3_detect_head_decode_fwd(const y3_decode_desc* d, y3_stream_t st
   }
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
-}
-
-extern "C" int y3_set_decode2(int32_t on) {
-  const int prev = y3::decode2_enabled();
-  y3::g_decode2 = on ? 1 : 0;
-  return prev;
 }
 
 extern "C" int y3_detect_decode_fwd(const y3_detect_level* levels, int32_t nl, int32_t bs, int32_t na, int32_t no,

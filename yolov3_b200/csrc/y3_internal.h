@@ -33,14 +33,10 @@ int encode_tensor_map_bf16(CUtensorMap* out, const void* base, int rank, const u
 int num_sms();
 int pdl_enabled();   // programmatic dependent launch on (default; Y3_PDL=0 or y3_set_pdl(0) turns it off)
 void pdl_set(int on);
-// Kernel-variant switches (A/B-able at run time; results are bit-identical either way, see the setters in the public header).
-#ifndef Y3_DECODE2_DEFAULT
-#define Y3_DECODE2_DEFAULT 0
-#endif
+// Kernel-variant switch (A/B-able at run time; results are bit-identical either way, see y3_set_bn_async in the public header)
 #ifndef Y3_BN_ASYNC_DEFAULT
-#define Y3_BN_ASYNC_DEFAULT 0
+#define Y3_BN_ASYNC_DEFAULT 1
 #endif
-int decode2_enabled();  // staged Detect decode (y3_detect.cu); env Y3_DECODE2=0/1, y3_set_decode2()
 
 // ---- tcgen05 conv: kernel arguments (device view) and a prepared launch
 struct ConvTcArgs {

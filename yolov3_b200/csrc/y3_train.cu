@@ -378,15 +378,19 @@ __global__ void __launch_bounds__(256, UPS ? 2 : 3) bn_act_bwd_kernel(const BnBw
     block_reduce_store(a_dz, a_dzy, g.c8, sh, p.partial + static_cast<long long>(blockIdx.x) * 2 * g.c8 * 8, g.c8 * 8);
 }
 
-// ---------------------------------------------------------------------------------------------- cp.async ring variants
-// The kernels above keep a unit's 16-byte vectors in registers between issue and use: 2-4 loads per thread in flight, three
-// or four blocks per SM = 24-48 KB per SM, with a bubble at every unit boundary — 16 us for 26 MB, long-scoreboard stalls on
-// top (profiles/r02_ncu_bn_bwd_summary.txt); a register look-ahead halved the resident blocks and gained nothing
-// (profiles/r02_experiments.md).  The variants below stage the SAME units through a per-thread shared-memory ring with
-// cp.async: a thread copies its own 16-byte items kDepth-1 units ahead into its own slots and reads them back itself, so there
-// is no barrier and no mbarrier anywhere (cp.async.wait_group cannot dead-lock), 96-144 KB per SM are in flight without
-// costing registers, and the arithmetic — unit order, item order, operations — is exactly that of the kernels above: results
-// are bit-identical (tests/diag/ab_shot.py compares them on the device).  Switch: y3_set_bn_async / Y3_BN_ASYNC.
+// ---------------------------------------------------------------------------------------------- cp.async ring variant
+// bn_act_bwd_kernel keeps a unit's 16-byte vectors in registers between issue and use: 4 loads per thread in flight, three
+// blocks per SM, a bubble at every unit boundary, long-scoreboard stalls on top (profiles/r02_ncu_bn_bwd_summary.txt); a
+// register look-ahead halved the resident blocks and gained nothing (profiles/r02_experiments.md).  The variant below stages
+// the SAME units through a per-thread shared-memory ring with cp.async: a thread copies its own 16-byte items kRingDepth-1
+// units ahead into its own slots and reads them back itself, so there is no barrier and no mbarrier anywhere
+// (cp.async.wait_group cannot dead-lock) and 144 KB per SM are in flight without costing registers.  Unit order, item order
+// and operations are exactly those of bn_act_bwd_kernel: results are bit-identical.  Measured on the B200
+// (tests/diag/ab_shot.py, profiles/r02_ab_shot_kernel_variants.jsonl): reduce + apply passes 3-8 % faster on every layer
+// shape of the 640x640 step (e.g. 45.5 -> 43.4 us at 8x80x80x256, 136.0 -> 126.9 us at 8x320x320x64).  The same ring under
+// bn_stats gained +-5 % and under bn_act_fwd LOST 10-30 % (three 64 KB blocks per SM instead of five or six register-only
+// ones): those two were removed again — the passes are bound by resident warps x issue, not by bytes in flight.
+// Switch: y3_set_bn_async / Y3_BN_ASYNC (default on).
 __device__ __forceinline__ void cp_async16(uint32_t saddr, const void* gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gptr) : "memory");
 }
@@ -431,109 +435,6 @@ __device__ __forceinline__ void ring_issue(const Rows& g, const Slice& t, int s,
     split_item(g, e, x, cg);
     if (e < items) cp_async16(ring_slot<NS>(ring, stage, s, k), t.p + (rb + x) * t.ld + t.coff + cg * 8);
   }
-}
-
-__global__ void __launch_bounds__(256, 3) bn_stats_async_kernel(Slice y, Rows g, float* __restrict__ partial) {
-  pdl_entry();
-  extern __shared__ __align__(16) float ring_mem[];  // ring (32 KB); reused as [2][256][8] by the block reduction
-  float* sh = ring_mem;
-  const uint32_t ring = smem_u32(ring_mem);
-  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  const int items = g.w * g.c8, nb = units_of_block(g);
-#pragma unroll
-  for (int i = 0; i < kRingDepth - 1; ++i) {
-    if (i < nb) ring_issue<1>(g, y, 0, i, i, ring);
-    cp_async_commit();
-  }
-  int st_c = 0, st_i = kRingDepth - 1;  // stage consumed / stage requested this iteration
-  for (int i = 0; i < nb; ++i) {
-    if (i + kRingDepth - 1 < nb) ring_issue<1>(g, y, 0, i + kRingDepth - 1, st_i, ring);
-    cp_async_commit();
-    cp_async_wait<kRingDepth - 1>();
-    int e0;
-    long long rb;
-    unit_pos(g, i, e0, rb);
-#pragma unroll
-    for (int k = 0; k < kUnitIters; ++k) {
-      const uint4 v = e0 + k * 256 < items ? lds128(ring_slot<1>(ring, st_c, 0, k)) : make_uint4(0, 0, 0, 0);
-      float f[8];
-      unpack8(v, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += f[j];
-        q[j] = fmaf(f[j], f[j], q[j]);
-      }
-    }
-    st_c = st_c + 1 == kRingDepth ? 0 : st_c + 1;
-    st_i = st_i + 1 == kRingDepth ? 0 : st_i + 1;
-  }
-  cp_async_wait<0>();
-  __syncthreads();  // every thread is done with its ring slots: the block reduction reuses the memory
-  block_reduce_store(s, q, g.c8, sh, partial + static_cast<long long>(blockIdx.x) * 2 * g.c8 * 8, g.c8 * 8);
-}
-
-template <bool RES>
-__global__ void __launch_bounds__(256, 3) bn_act_fwd_async_kernel(const BnActArgs p) {
-  pdl_entry();
-  extern __shared__ __align__(16) float ring_mem[];
-  const uint32_t ring = smem_u32(ring_mem);
-  constexpr int NS = RES ? 2 : 1;
-  const Rows g = p.g;
-  const int items = g.w * g.c8, nb = units_of_block(g);
-  const int us = p.upsample ? 2 : 1;
-  const long long up_row = static_cast<long long>(2 * g.w + 2) * p.out.ld;
-#pragma unroll
-  for (int i = 0; i < kRingDepth - 1; ++i) {
-    if (i < nb) {
-      ring_issue<NS>(g, p.y, 0, i, i, ring);
-      if (RES) ring_issue<NS>(g, p.res, 1, i, i, ring);
-    }
-    cp_async_commit();
-  }
-  int st_c = 0, st_i = kRingDepth - 1;
-  for (int i = 0; i < nb; ++i) {
-    if (i + kRingDepth - 1 < nb) {
-      ring_issue<NS>(g, p.y, 0, i + kRingDepth - 1, st_i, ring);
-      if (RES) ring_issue<NS>(g, p.res, 1, i + kRingDepth - 1, st_i, ring);
-    }
-    cp_async_commit();
-    cp_async_wait<kRingDepth - 1>();
-    const int u = blockIdx.x + i * gridDim.x;
-    const int r = u / g.upr, e0 = (u - r * g.upr) * (256 * kUnitIters) + threadIdx.x;
-    const long long rb = row_base(g, r);
-    const long long ob = p.upsample ? row_base(g, r, 2) : rb;
-#pragma unroll
-    for (int k = 0; k < kUnitIters; ++k) {
-      const int e = e0 + k * 256;
-      if (e >= items) continue;
-      int x, cg;
-      split_item(g, e, x, cg);
-      float f[8], rr[8];
-      unpack8(lds128(ring_slot<NS>(ring, st_c, 0, k)), f);
-      const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale + cg * 8)), s1 = __ldg(reinterpret_cast<const float4*>(p.scale + cg * 8 + 4));
-      const float4 h0 = __ldg(reinterpret_cast<const float4*>(p.shift + cg * 8)), h1 = __ldg(reinterpret_cast<const float4*>(p.shift + cg * 8 + 4));
-      const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-      const float shf[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-      for (int q = 0; q < 8; ++q) f[q] = silu_fast(fmaf(f[q], sc[q], shf[q]));
-      if (RES) {
-        unpack8(lds128(ring_slot<NS>(ring, st_c, 1, k)), rr);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) f[q] += rr[q];
-      }
-      const uint4 o = pack8(f);
-      __nv_bfloat16* dst = p.out.p + (ob + static_cast<long long>(x) * us) * p.out.ld + p.out.coff + cg * 8;
-      *reinterpret_cast<uint4*>(dst) = o;
-      if (p.upsample) {
-        *reinterpret_cast<uint4*>(dst + p.out.ld) = o;
-        *reinterpret_cast<uint4*>(dst + up_row) = o;
-        *reinterpret_cast<uint4*>(dst + up_row + p.out.ld) = o;
-      }
-    }
-    st_c = st_c + 1 == kRingDepth ? 0 : st_c + 1;
-    st_i = st_i + 1 == kRingDepth ? 0 : st_i + 1;
-  }
-  cp_async_wait<0>();
 }
 
 // the non-upsample reduce / apply passes (the two 2x-upsample layers stay on bn_act_bwd_kernel<*, true>)
@@ -1035,13 +936,6 @@ extern "C" int y3_bn_stats(const void* y, int32_t ld, int32_t coff, int32_t c, i
   Y3_REQUIRE(y && partial && c > 0 && c % 8 == 0 && 256 % (c / 8) == 0 && n > 0 && h > 0 && w > 0 && ld % 8 == 0 && coff % 8 == 0,
              "bn_stats: bad arguments (c must be a power of two in [8, 2048])");
   const int nblk = y3_bn_partial_blocks(n, h, w, c);
-  if (y3::bn_async_enabled()) {
-    constexpr int smem = y3::ring_bytes<1>() > 2 * 256 * 8 * 4 ? y3::ring_bytes<1>() : 2 * 256 * 8 * 4;
-    Y3_CHECK_CUDA(y3::allow_smem<y3::bn_stats_async_kernel>(smem));
-    Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_stats_async_kernel, dim3(nblk), dim3(256), smem, static_cast<cudaStream_t>(stream), Slice{static_cast<const __nv_bfloat16*>(y), ld, coff}, y3::make_rows(n, h, w, c), partial));
-    Y3_CHECK_CUDA(cudaGetLastError());
-    return Y3_OK;
-  }
   Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_stats_kernel, dim3(nblk), dim3(256), 2 * 256 * 8 * sizeof(float), static_cast<cudaStream_t>(stream), Slice{static_cast<const __nv_bfloat16*>(y), ld, coff}, y3::make_rows(n, h, w, c), partial));
   Y3_CHECK_CUDA(cudaGetLastError());
   return Y3_OK;
@@ -1076,19 +970,6 @@ extern "C" int y3_bn_act_fwd(const y3_bn_act_desc* d, y3_stream_t stream) {
   a.g = y3::make_rows(d->n, d->h, d->w, d->c);
   a.upsample = d->upsample;
   const long long units = static_cast<long long>(d->n) * d->h * a.g.upr;
-  if (y3::bn_async_enabled()) {
-    const long long cap3 = 3ll * y3::num_sms();  // one wave at 3 resident blocks per SM
-    const dim3 grid(static_cast<unsigned>(units < cap3 ? units : cap3));
-    if (a.res.p) {
-      Y3_CHECK_CUDA(y3::allow_smem<y3::bn_act_fwd_async_kernel<true>>(y3::ring_bytes<2>()));
-      Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_fwd_async_kernel<true>, grid, dim3(256), y3::ring_bytes<2>(), static_cast<cudaStream_t>(stream), a));
-    } else {
-      Y3_CHECK_CUDA(y3::allow_smem<y3::bn_act_fwd_async_kernel<false>>(y3::ring_bytes<1>()));
-      Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_fwd_async_kernel<false>, grid, dim3(256), y3::ring_bytes<1>(), static_cast<cudaStream_t>(stream), a));
-    }
-    Y3_CHECK_CUDA(cudaGetLastError());
-    return Y3_OK;
-  }
   const long long cap = 8ll * y3::num_sms();
   Y3_CHECK_CUDA(::y3::launch_pdl(y3::bn_act_fwd_kernel, dim3(static_cast<unsigned>(units < cap ? units : cap)), dim3(256), 0, static_cast<cudaStream_t>(stream), a));
   Y3_CHECK_CUDA(cudaGetLastError());
