@@ -5,7 +5,8 @@
 Runs `cuobjdump -sass` on yolov3_b200/libyolov3_b200.so (no GPU needed) and counts, for every kernel, the instructions that
 prove which hardware path it takes: UTCHMMA (tcgen05.mma; .2CTA = cta_group::2), LDTM (tcgen05.ld), UTMALDG / UTMASTG (TMA load /
 store), UTCBAR (tcgen05.commit), SYNCS (mbarrier), ACQBULK / PREEXIT (griddepcontrol.wait / launch_dependents: programmatic
-dependent launch), HMMA / IMMA (legacy mma.sync: only the 3-channel stem conv and the fallback wgrad), MUFU, REDUX, ATOM/ATOMS/RED.
+dependent launch), HMMA / IMMA (legacy mma.sync: only the 3-channel stem conv and the fallback wgrad), MUFU, REDUX, ATOM/ATOMS/RED,
+LDGSTS (cp.async: the shared-memory ring of the BatchNorm backward passes).
 """
 import collections
 import re
@@ -15,7 +16,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
 LIB = ROOT / "yolov3_b200" / "libyolov3_b200.so"
-KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "ACQBULK", "PREEXIT", "HMMA", "IMMA", "MUFU", "REDUX", "ATOM", "ATOMS", "RED", "LDG", "STG"]
+KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "ACQBULK", "PREEXIT", "HMMA", "IMMA", "MUFU", "REDUX", "ATOM", "ATOMS", "RED", "LDG", "STG", "LDGSTS"]
 
 
 def demangle(names):
