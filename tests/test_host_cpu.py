@@ -295,12 +295,19 @@ def test_reference_arm_json_contract():
     from pathlib import Path
 
     root = Path(__file__).resolve().parents[1]
-    r = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=900, cwd=root)
+    # launched the way the driver launches the N > 1 arms (torchrun, one process per GPU): rank 0 alone runs and prints the
+    # line, the other rank exits 0 without work and without output
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29671", str(root / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=900, cwd=root,
+                       env=dict(os.environ, MASTER_ADDR="127.0.0.1"))
     assert r.returncode == 0, r.stderr[-2000:]
-    d = json.loads(r.stdout.strip().splitlines()[-1])
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"].startswith("images/sec @640 bs32 YOLOv3") and d["unit"] == "images/s"
-    assert d["higher_is_better"] is True and d["steps"] == 1 and d["value"] > 0 and d["n_gpus"] == 1
+    assert d["higher_is_better"] is True and d["steps"] == 1 and d["value"] > 0 and d["n_gpus"] == 2
+    assert d["config"]["global_batch"] == 64
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     # the reference's own Model from the staged copy (baseline/_ref) when it is there, else the oracle port — and it says which
     sys.path.insert(0, str(root / "oracle"))
