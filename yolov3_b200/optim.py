@@ -45,7 +45,12 @@ class SGD:
         self.ema = ema
         if ema is not None:
             ema._fused = True
-        self._hp_host = torch.zeros(16, dtype=torch.float32).pin_memory()
+        # hyper-parameters travel through pinned host staging: a small ring, each slot guarded by an event, so that a step
+        # issued while an earlier step's asynchronous H2D copy is still queued never rewrites the memory that copy will read
+        self._hp_ring = [torch.zeros(16, dtype=torch.float32).pin_memory() for _ in range(4)]
+        self._hp_events = [torch.cuda.Event() for _ in range(4)] if dev.type == "cuda" else [None] * 4
+        self._hp_used = [False] * 4
+        self._hp_next = 0
         self._hp = torch.zeros(16, dtype=torch.float32, device=dev)
         self._partial = torch.zeros(_lib.lib().y3_sumsq_blocks(), dtype=torch.float32, device=dev)
         self.grad_sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -58,7 +63,11 @@ class SGD:
     @torch.no_grad()
     def step(self):
         s, L = self.store, _lib.lib()
-        hp = self._hp_host
+        slot = self._hp_next
+        self._hp_next = (slot + 1) % len(self._hp_ring)
+        if self._hp_used[slot] and self._hp_events[slot] is not None:
+            self._hp_events[slot].synchronize()  # the copy that last read this staging slot has completed
+        hp = self._hp_ring[slot].zero_()
         for pg, g in zip(self.param_groups, self._slot_group_of_pg):
             hp[g] = float(pg["lr"])
             hp[3 + g] = float(pg["weight_decay"])
@@ -76,6 +85,9 @@ class SGD:
             ddp.pending_average = False
         hp[10] = scale
         self._hp.copy_(hp, non_blocking=True)
+        if self._hp_events[slot] is not None:
+            self._hp_events[slot].record()
+            self._hp_used[slot] = True
         st = _stream()
         if self.max_norm > 0:
             _lib.check(L.y3_grad_sumsq(s.G.data_ptr(), s.n_train, self._partial.data_ptr(), self.grad_sumsq.data_ptr(), st),
