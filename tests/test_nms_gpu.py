@@ -45,6 +45,24 @@ def test_nms_full_size_vs_oracle(conf, iou, ml):
         assert np.array_equal(s.cpu().numpy().astype(np.int64), rs)
 
 
+@pytest.mark.parametrize("conf,iou,ml", [(0.25, 0.45, False), (0.001, 0.6, False)])
+def test_nms_benchmarked_batch_of_32(conf, iou, ml):
+    """BASELINE config 5 at its full size (32 x 25200 x 85, the batch bench.py times): every image of the batch gets exactly
+    the rows it gets as the only image of a call (the per-image segments of the batched pipeline do not leak into each other),
+    and the first and the last image match the oracle bit for bit."""
+    from yolov3_b200.nms import non_max_suppression
+
+    pred = O.synth_predictions(32, n_rows=25200, nc=80, seed=3)
+    dev = pred.cuda()
+    outs = non_max_suppression(dev, conf, iou, multi_label=ml, max_det=300)
+    assert len(outs) == 32
+    for i in (0, 13, 31):
+        alone = non_max_suppression(dev[i:i + 1], conf, iou, multi_label=ml, max_det=300)[0]
+        assert torch.equal(outs[i], alone), i
+    ref, _ = O.non_max_suppression(pred[[0, 31]], conf, iou, multi_label=ml, max_det=300)
+    assert np.array_equal(outs[0].cpu().numpy(), ref[0]) and np.array_equal(outs[31].cpu().numpy(), ref[1])
+
+
 def test_nms_properties_and_errors():
     from yolov3_b200.nms import non_max_suppression
 
